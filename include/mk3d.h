@@ -1,0 +1,178 @@
+/*
+ * mk3d.h — C ABI of libmk3d.so: the B200 (sm_100a) sparse-convolution / masked-attention hot path
+ * behind the MinkowskiEngine surface that mvg-inatech/room-instance-segmentation-mask3d consumes.
+ *
+ * The reference has no C-level plugin interface for this path: its lower boundary is MinkowskiEngine
+ * 0.5.4's pybind11 module `MinkowskiEngineBackend._C` (un-vendored; pinned at
+ * mask3d/requirements_pip_freeze.txt:62).  Each entry point below names the reference call site whose
+ * work it replaces (paths relative to /root/reference).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); nothing synchronises;
+ *   - no allocation inside: scratch comes from the caller (`*_workspace_bytes` query functions);
+ *   - return value: 0 = ok, non-zero = error, message via mk_last_error() (thread-local);
+ *   - rows of a batch item are contiguous and batch items ascend (what ME.utils.sparse_collate yields,
+ *     mask3d/datasets/utils.py:126); `scene_offsets` are int32 [B+1] row offsets;
+ *   - dtype codes: MK_F32 = 0, MK_BF16 = 1.
+ */
+#ifndef MK3D_H_
+#define MK3D_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MK_F32 0
+#define MK_BF16 1
+#define MK_TILE_ROWS 128 /* output rows per tensor-core tile */
+
+const char* mk_last_error(void);
+int mk_version(void);
+/* 1 if the current device is sm_100 (B200); the tcgen05 entry points refuse to run otherwise. */
+int mk_device_supported(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * (1) Coordinate maps: GPU open-addressing hash table over packed 64-bit (batch,x,y,z) keys.
+ * Replaces ME CoordinateMapGPU::insert_and_map / ::stride, reached from
+ *   ME.SparseTensor(coordinates=...)            mask3d/datasets/utils.py:249-255
+ *   every stride-2 conv / pool (implicit)        mask3d/models/res16unet.py:55-63,248 ; mask3d/models/mask3d.py:297
+ *   ME.utils.sparse_quantize                     
+ * Semantics: first occurrence wins; output rows in ascending first-occurrence order (ME CPU order).
+ * ------------------------------------------------------------------------------------------- */
+int64_t mk_hash_capacity(int64_t n);                 /* power of two >= 2n */
+int64_t mk_coordmap_workspace_bytes(int64_t n);
+/* in_coords int32 [n,4] (batch,x,y,z); stride3_host: 3 ints (1,1,1 = plain insert; else coords are floored to
+ * multiples of the stride first).  Outputs: hash (keys uint64[cap], vals int32[cap]) of the NEW map,
+ * out_coords int32 [<=n,4], unique_index int32 [<=n] (source row of each new row), inverse int32 [n]
+ * (new row of every source row), n_out (device int32), status (device int32, non-zero = coordinate out of the
+ * packable range [-2^17, 2^17) or batch >= 1023). */
+int mk_coordmap_build(const int32_t* in_coords, int64_t n, const int32_t* stride3_host, uint64_t* keys, int32_t* vals,
+                      int64_t cap, int32_t* out_coords, int32_t* unique_index, int32_t* inverse, int32_t* n_out,
+                      int32_t* status, void* workspace, int64_t workspace_bytes, void* stream);
+/* rows[i] = row of query coordinate i in the map, or -1. */
+int mk_hash_query(const uint64_t* keys, const int32_t* vals, int64_t cap, const int32_t* query_coords, int64_t n,
+                  int32_t* rows, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (2) Kernel maps.  Replaces ME CoordinateMapGPU::kernel_map (implicit in every conv/pool; Python-visible as
+ * CoordinateManager.kernel_map).  Output-stationary form: nbr[k*n_out + o] = input row of
+ * (out_coords[o] + offsets[k]) or -1; offsets int32 [K,3] already scaled by dilation * input tensor stride,
+ * enumerated x-fastest.
+ * ------------------------------------------------------------------------------------------- */
+int mk_kernel_map(const uint64_t* in_keys, const int32_t* in_vals, int64_t cap, const int32_t* out_coords, int64_t n_out,
+                  const int32_t* offsets, int K, int32_t* nbr, void* stream);
+/* Per 128-slot tile, bit k set iff some slot of the tile has a neighbour for offset k (K <= 32); also the
+ * total pair count (device int64).  `n_slots` is the slot count of nbr (row stride of the table). */
+int mk_tile_kmask(const int32_t* nbr, int K, int64_t n_slots, uint32_t* tile_kmask, int64_t* pair_count, void* stream);
+/* Transposed-conv plan (coarse -> fine): given the stride-s table nbr_down [K, n_coarse] (fine row or -1) build
+ * parent[f] and koff[f] for every fine row f. */
+int mk_transpose_map(const int32_t* nbr_down, int K, int64_t n_coarse, int64_t n_fine, int32_t* parent, int32_t* koff,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (3) Sparse convolution.  Replaces ME ConvolutionForwardGPU / ConvolutionTransposeForwardGPU reached from
+ * MinkowskiConvolution.forward / MinkowskiConvolutionTranspose.forward (mask3d/models/modules/common.py:151-160,
+ * 186-195; call sites mask3d/models/res16unet.py:244-307, mask3d/models/modules/resnet_block.py:52-68).
+ *   out[o,:] = sum_k in[nbr[k,o],:] @ W[k]   (+ bias)
+ * ------------------------------------------------------------------------------------------- */
+/* fp32 CUDA-core path (exact fp32 FMA; the "fp32-accumulate parity mode").  W fp32 [K,cin,cout]. */
+int mk_conv_fwd_f32(const float* in, int cin, const float* W, int cout, const int32_t* nbr, int K, int64_t n_out,
+                    const float* bias, float* out, void* stream);
+/* Weight images for the tensor-core path: W fp32 [K,cin,cout] -> bf16 images, one per (k, 64-channel chunk),
+ * each [n_rows x 128 B] in the 128-byte-swizzled K-major shared-memory layout tcgen05.mma reads, so that a
+ * stage's B operand is one linear bulk copy.  transpose=0: rows = cout, reduction = cin (forward);
+ * transpose=1: rows = cin, reduction = cout (dgrad). */
+int64_t mk_conv_weight_image_elems(int K, int cin, int cout, int transpose);
+int mk_conv_weight_image_bf16(const float* W, int K, int cin, int cout, int transpose, void* img, void* stream);
+/* tcgen05 path: bf16 operands, fp32 accumulation in TMEM.  `in` bf16 [n_in,cin] (cin % 16 == 0), nbr int32
+ * [K,n_slots], out_rows int32 [n_slots] or NULL (slot == output row), tile_kmask from mk_tile_kmask,
+ * kidx int32 [K] or NULL: weight-image index used for table row k (dgrad passes the mirrored offset),
+ * bias fp32 [cout] or NULL, out [n_out,cout] of out_dtype.  Persistent: grid = #SMs. */
+int mk_conv_fwd_bf16(const void* in, int cin, const void* wimg, int cout, const int32_t* nbr, int K, int64_t n_slots,
+                     const int32_t* out_rows, const uint32_t* tile_kmask, const int32_t* kidx, int64_t n_out,
+                     const float* bias, void* out, int out_dtype, void* stream);
+/* Stem: Cin == 1, K up to 125 (5^3): pure lookup, CUDA cores.  in fp32 [n_in], W fp32 [K,1,cout]. */
+int mk_conv_stem_f32(const float* in, const float* W, int cout, const int32_t* nbr, int K, int64_t n_out, void* out,
+                     int out_dtype, void* stream);
+/* Backward of the fp32 path (dgrad + wgrad); CUDA cores, deterministic (no atomics on dgrad). */
+int mk_conv_dgrad_f32(const float* dout, int cout, const float* W, int cin, const int32_t* nbr_t, int K, int64_t n_in,
+                      const int32_t* kidx, float* din, void* stream);
+int mk_conv_wgrad_f32(const float* in, int cin, const float* dout, int cout, const int32_t* nbr, int K, int64_t n_out,
+                      float* dW, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (4) Normalisation / activation.  Replaces MinkowskiInstanceNorm (global avg-pool + broadcast kernels,
+ * mask3d/models/modules/common.py:24), MinkowskiBatchNorm (:22), MinkowskiReLU and SparseTensor += (resnet_block.py:65).
+ * Instance norm: per scene, per channel, biased variance, eps 1e-8.
+ * ------------------------------------------------------------------------------------------- */
+int64_t mk_instnorm_workspace_bytes(int64_t n, int C, int B);
+/* mean/rstd fp32 [B,C].  Deterministic two-stage reduction (fixed merge order, fp64 merge). */
+int mk_instnorm_stats(const void* x, int x_dtype, int64_t n, int C, const int32_t* scene_offsets, int B, float eps,
+                      float* mean, float* rstd, void* workspace, int64_t workspace_bytes, void* stream);
+/* y = (x - mean[b]) * rstd[b] * gamma + beta  (+ residual)  (relu) ; gamma/beta fp32 [C]; residual/out share out_dtype. */
+int mk_norm_apply(const void* x, int x_dtype, int64_t n, int C, const int32_t* scene_offsets, int B, const float* mean,
+                  const float* rstd, const float* gamma, const float* beta, const void* residual, int relu, void* out,
+                  int out_dtype, void* stream);
+/* dx of instance norm (ME's custom backward): given dy (already multiplied by gamma) and y_hat = (x-mean)*rstd. */
+int mk_instnorm_bwd(const float* x, const float* dy, int64_t n, int C, const int32_t* scene_offsets, int B,
+                    const float* mean, const float* rstd, const float* gamma, float* dx, float* dgamma, float* dbeta,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (5) Pooling.  Replaces MinkowskiAvgPooling / MinkowskiSumPooling (mask3d/models/mask3d.py:209,297,547).
+ * out[o] = sum over existing children / (#children if average).  nbr int32 [K,n_out].
+ * ------------------------------------------------------------------------------------------- */
+int mk_pool_fwd(const float* in, int C, const int32_t* nbr, int K, int64_t n_out, int average, float* out, void* stream);
+int mk_pool_bwd(const float* dout, int C, const int32_t* nbr, int K, int64_t n_out, int average, int64_t n_in, float* din,
+                void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (6) Decoder.  mask-logit product of Mask3D.mask_module (mask3d/models/mask3d.py:534-537), its pooled
+ * sigmoid<0.5 attention mask (:544-553) and the masked cross-attention (:397-478, CrossAttentionLayer :686-705).
+ * ------------------------------------------------------------------------------------------- */
+/* logits[n,q] = feat[n,:] . embed[b(n),q,:]   feat [n,C] (x_dtype), embed fp32 [B,Q,C], logits fp32 [n,Q]. */
+int mk_mask_logits(const void* feat, int x_dtype, int64_t n, int C, const int32_t* scene_offsets, int B,
+                   const float* embed, int Q, float* logits, void* stream);
+/* One pooling step on logits followed (optionally) by the threshold: blocked[o,q] = sigmoid(pooled) < 0.5. */
+int mk_pool_threshold(const float* pooled, int64_t n, int Q, uint8_t* blocked, void* stream);
+/* Per-scene min / max of fp32 [n,3] coordinates (input_range of the fourier embedding, mask3d.py:267-268,323-328). */
+int mk_scene_minmax(const float* xyz, const int32_t* scene_offsets, int B, float* cmin, float* cmax, void* stream);
+/* Fourier positional encoding with normalisation (mask3d/models/position_embedding.py:127-156):
+ * out[n, :] = (base[n, :] if base else 0) + [sin(p), cos(p)], p = ((xyz - min_b) / (max_b - min_b) * 2pi) @ gauss_B.
+ * gauss_B fp32 [3, D/2]; base / out [n, D]. */
+int mk_fourier_pe(const float* xyz, int64_t n, const int32_t* scene_offsets, int B, const float* cmin, const float* cmax,
+                  const float* gauss_B, int D, const void* base, int base_dtype, void* out, int out_dtype, void* stream);
+int64_t mk_xattn_workspace_bytes(int B, int Q, int H, int64_t n_keys);
+/* Masked cross-attention core of one decoder layer, all scenes, no padding (varlen over scene_offsets):
+ *   ctx[b,q,h,:] = softmax_k( scale * qp[b,q,h,:] . kp[k,h,:]  masked ) @ vp[k,h,:]
+ * qp fp32 [B,Q,D] (projected queries), kp / vp [n,D] (kv_dtype; projected keys / values of the level),
+ * blocked uint8 [n,Q] (1 = key blocked for the query).  Per (scene, query): blocked keys get -inf unless ALL keys of
+ * the scene are blocked for that query, in which case none is (mask3d/models/mask3d.py:456); pads do not exist.
+ * ctx fp32 [B,Q,D] = concatenated heads BEFORE out_proj. */
+int mk_masked_xattn_fwd(const float* qp, const void* kp, const void* vp, int kv_dtype, int64_t n, const uint8_t* blocked,
+                        const int32_t* scene_offsets, int B, int Q, int D, int H, float scale, float* ctx, void* workspace,
+                        int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (7) Furthest point sampling.  Replaces pointnet2._ext.furthest_point_sampling
+ * (mask3d/third_party/pointnet2/_ext_src/src/sampling_gpu.cu:72-176; call site mask3d/models/mask3d.py:309-317)
+ * with identical tie-breaking; all scenes in one launch.  xyz fp32 [n,3], temp fp32 [n] scratch, idx int32 [B,m]
+ * (indices local to the scene).
+ * ------------------------------------------------------------------------------------------- */
+int mk_fps(const float* xyz, const int32_t* scene_offsets, int B, int m, float* temp, int32_t* idx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Casts (plumbing between fp32 module boundaries and the bf16 tensor-core path).
+ * ------------------------------------------------------------------------------------------- */
+int mk_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n_elems, void* stream);
+/* dst[n, c_off : c_off + C] = src[n, :]  (channel concat without a separate pass over the other operand) */
+int mk_copy_channels(const void* src, int src_dtype, int C, void* dst, int dst_dtype, int C_dst, int c_off, int64_t n,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MK3D_H_ */

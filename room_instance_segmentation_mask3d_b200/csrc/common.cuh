@@ -1,0 +1,126 @@
+// Shared helpers for libmk3d.so (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <string>
+
+#include "../../include/mk3d.h"
+
+namespace mk {
+
+extern thread_local std::string g_last_error;
+
+inline int fail(const char* where, const char* what) {
+  g_last_error = std::string(where) + ": " + what;
+  return 1;
+}
+
+inline int check_launch(const char* where) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(where, cudaGetErrorString(e));
+  return 0;
+}
+
+#define MK_REQUIRE(cond, msg) \
+  do {                        \
+    if (!(cond)) return mk::fail(__func__, msg); \
+  } while (0)
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- coordinate key packing: (batch:10 | x:18 | y:18 | z:18), coordinates biased by 2^17 --------
+constexpr int kCoordBits = 18;
+constexpr int kCoordBias = 1 << 17;
+constexpr unsigned long long kEmptyKey = ~0ull;
+
+__device__ __forceinline__ bool coord_in_range(int b, int x, int y, int z) {
+  const unsigned lim = 1u << kCoordBits;
+  return (unsigned)b < 1023u && (unsigned)(x + kCoordBias) < lim && (unsigned)(y + kCoordBias) < lim &&
+         (unsigned)(z + kCoordBias) < lim;
+}
+
+__device__ __forceinline__ unsigned long long pack_key(int b, int x, int y, int z) {
+  return ((unsigned long long)(unsigned)b << (3 * kCoordBits)) |
+         ((unsigned long long)(unsigned)(x + kCoordBias) << (2 * kCoordBits)) |
+         ((unsigned long long)(unsigned)(y + kCoordBias) << kCoordBits) | (unsigned long long)(unsigned)(z + kCoordBias);
+}
+
+__device__ __forceinline__ unsigned long long hash_key(unsigned long long k) {
+  // murmur3 finaliser
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdULL;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ULL;
+  k ^= k >> 33;
+  return k;
+}
+
+// floor division for possibly negative numerators (ME floors in float; exact for |x| < 2^24)
+__device__ __forceinline__ int floor_div(int a, int s) {
+  int q = a / s;
+  return (a % s != 0 && ((a < 0) != (s < 0))) ? q - 1 : q;
+}
+
+// ---- dtype helpers ------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) {
+  return v;
+}
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) {
+  return __bfloat162float(v);
+}
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) {
+  return v;
+}
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+
+// load 4 consecutive channels as fp32
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
+  uint2 r = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&r.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&r.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t*>(&a);
+  r.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = r;
+}
+
+// scene of a row: largest b with offsets[b] <= row  (B is small; linear scan of a broadcast-cached array)
+__device__ __forceinline__ int scene_of_row(const int32_t* __restrict__ offsets, int B, int64_t row) {
+  int b = 0;
+  while (b + 1 < B && row >= offsets[b + 1]) ++b;
+  return b;
+}
+
+}  // namespace mk

@@ -1,0 +1,346 @@
+// Mask3D decoder kernels: mask-logit product, fourier positional encoding, masked cross-attention core.
+//
+// Replaces, for one decoder layer (reference: mask3d/models/mask3d.py:397-478, 520-561):
+//   * the per-scene Python loop `decomposed_features[i] @ mask_embed[i].T` (:534-535)      -> mk_mask_logits
+//   * get_pos_encs' per-scene fourier embedding (:261-278, position_embedding.py:127-156)  -> mk_scene_minmax + mk_fourier_pe
+//   * pad-to-max-K + dense [B*8,Q,K] bool mask + stock MHA with materialised weights (:400-478)
+//       -> mk_masked_xattn_fwd: varlen over scenes (no pads exist), split over keys (flash-decoding style),
+//          online softmax per (query, head) in registers, "query blocks every key => unblock all" rule (:456)
+//          resolved by a per-(scene, query) any-open flag computed in the same launch sequence.
+// All three are HBM/L2-bound (Q = 25 queries => <= 25 FLOP per K/V byte).
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace mk {
+
+// ---------------------------------------------------------------------------------------------------
+// mask logits: logits[n, q] = feat[n, :] . embed[b, q, :]
+// ---------------------------------------------------------------------------------------------------
+constexpr int kMlRows = 64;
+constexpr int kMlThreads = 256;
+constexpr int kMlMaxQPerThread = 32;  // Q <= 128
+
+template <typename T>
+__global__ void __launch_bounds__(kMlThreads) k_mask_logits(const T* __restrict__ feat, int C, const int32_t* __restrict__ scene_offsets,
+                                                           const float* __restrict__ embed, int Q, float* __restrict__ logits) {
+  extern __shared__ float sm[];
+  float* sE = sm;                 // [Q][C]
+  float* sF = sm + (size_t)Q * C; // [kMlRows][C + 1]
+  const int b = blockIdx.y;
+  const int64_t start = (int64_t)scene_offsets[b] + (int64_t)blockIdx.x * kMlRows;
+  const int64_t end = min((int64_t)scene_offsets[b + 1], start + kMlRows);
+  if (start >= end) return;
+  const int nrows = (int)(end - start);
+  for (int i = threadIdx.x; i < Q * C; i += kMlThreads) sE[i] = embed[(int64_t)b * Q * C + i];
+  const int CV = C >> 2;
+  for (int i = threadIdx.x; i < nrows * CV; i += kMlThreads) {
+    const int r = i / CV, c = (i - r * CV) * 4;
+    float4 v = load4(feat + (start + r) * C + c);
+    float* d = sF + r * (C + 1) + c;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  __syncthreads();
+  const int r = threadIdx.x % kMlRows, qg = threadIdx.x / kMlRows;  // 4 query groups
+  if (r >= nrows) return;
+  float acc[kMlMaxQPerThread];
+#pragma unroll
+  for (int j = 0; j < kMlMaxQPerThread; ++j) acc[j] = 0.f;
+  const float* f = sF + r * (C + 1);
+  const int nq = (Q - qg + 3) / 4;  // queries qg, qg+4, ...
+  for (int c = 0; c < C; ++c) {
+    const float x = f[c];
+#pragma unroll
+    for (int j = 0; j < kMlMaxQPerThread; ++j)
+      if (j < nq) acc[j] = fmaf(x, sE[(qg + 4 * j) * C + c], acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < kMlMaxQPerThread; ++j)
+    if (j < nq) logits[(start + r) * Q + qg + 4 * j] = acc[j];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// per-scene min / max of fp32 [n,3] coordinates
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_scene_minmax(const float* __restrict__ xyz, const int32_t* __restrict__ scene_offsets,
+                                                      float* __restrict__ cmin, float* __restrict__ cmax) {
+  const int b = blockIdx.x;
+  const int64_t s = scene_offsets[b], e = scene_offsets[b + 1];
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int64_t r = s + threadIdx.x; r < e; r += blockDim.x) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float v = xyz[r * 3 + a];
+      mn[a] = fminf(mn[a], v);
+      mx[a] = fmaxf(mx[a], v);
+    }
+  }
+  __shared__ float smn[8][3], smx[8][3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_down_sync(0xffffffffu, mn[a], d));
+      mx[a] = fmaxf(mx[a], __shfl_down_sync(0xffffffffu, mx[a], d));
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      smn[threadIdx.x >> 5][a] = mn[a];
+      smx[threadIdx.x >> 5][a] = mx[a];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float lo = FLT_MAX, hi = -FLT_MAX;
+    for (int w = 0; w < 8; ++w) {
+      lo = fminf(lo, smn[w][threadIdx.x]);
+      hi = fmaxf(hi, smx[w][threadIdx.x]);
+    }
+    cmin[b * 3 + threadIdx.x] = lo;
+    cmax[b * 3 + threadIdx.x] = hi;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fourier PE: out[n, j] = sin(p_j), out[n, D/2 + j] = cos(p_j), p = ((xyz - min) / (max - min) * 2pi) @ gauss_B
+// optionally out = base + pe (the attention key input `src + pos`)
+// ---------------------------------------------------------------------------------------------------
+template <typename TB, typename TO>
+__global__ void __launch_bounds__(256) k_fourier_pe(const float* __restrict__ xyz, int64_t n, const int32_t* __restrict__ scene_offsets,
+                                                    int B, const float* __restrict__ cmin, const float* __restrict__ cmax,
+                                                    const float* __restrict__ gauss_B, int D, const TB* __restrict__ base,
+                                                    TO* __restrict__ out) {
+  const int half = D >> 1;
+  const int64_t total = n * half;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / half;
+    const int j = (int)(i - r * half);
+    const int b = scene_of_row(scene_offsets, B, r);
+    float p = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float lo = cmin[b * 3 + a], hi = cmax[b * 3 + a];
+      // same association as position_embedding.py:33-43,146: ((x - lo) * 1) / (hi - lo) + 0, then * 2pi
+      float x = ((xyz[r * 3 + a] - lo) * 1.0f) / (hi - lo) + 0.0f;
+      x *= 6.283185307179586f;
+      p = fmaf(x, gauss_B[a * half + j], p);
+    }
+    float s, c;
+    sincosf(p, &s, &c);
+    if (base) {
+      s += to_f32<TB>(base[r * D + j]);
+      c += to_f32<TB>(base[r * D + half + j]);
+    }
+    out[r * D + j] = from_f32<TO>(s);
+    out[r * D + half + j] = from_f32<TO>(c);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// masked cross-attention core
+// ---------------------------------------------------------------------------------------------------
+// any_open[b, q] = 1 iff some key of scene b is not blocked for query q
+__global__ void __launch_bounds__(256) k_any_open(const uint8_t* __restrict__ blocked, int64_t n, int Q,
+                                                  const int32_t* __restrict__ scene_offsets, int B, int32_t* __restrict__ any_open) {
+  const int64_t total = n * Q;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    if (!blocked[i]) {
+      const int64_t r = i / Q;
+      const int q = (int)(i - r * Q);
+      any_open[scene_of_row(scene_offsets, B, r) * Q + q] = 1;  // benign race: every writer stores 1
+    }
+  }
+}
+
+constexpr int kXaKeysPerTile = 32;
+constexpr int kXaMaxHd = 32;  // head dim <= 32 (partial record stride)
+
+// grid (splits, B); block = Q*H threads rounded up to a warp multiple; thread = (query, head).
+// partial[(b*splits + split)][q*H + h] = {m, l, acc[hd]}
+template <typename T, int HD>
+__global__ void __launch_bounds__(1024) k_xattn_partial(const float* __restrict__ qp, const T* __restrict__ kp, const T* __restrict__ vp,
+                                                        const uint8_t* __restrict__ blocked, const int32_t* __restrict__ any_open,
+                                                        const int32_t* __restrict__ scene_offsets, int Q, int D, int H, float scale,
+                                                        int keys_per_split, float* __restrict__ partial) {
+  extern __shared__ float sm[];
+  const int hd = D / H;
+  float* sK = sm;                                   // [tile][D]
+  float* sV = sm + (size_t)kXaKeysPerTile * D;      // [tile][D]
+  uint8_t* sM = (uint8_t*)(sV + (size_t)kXaKeysPerTile * D);  // [tile][Q]
+  const int b = blockIdx.y, split = blockIdx.x, nsplit = gridDim.x;
+  const int64_t s0 = (int64_t)scene_offsets[b] + (int64_t)split * keys_per_split;
+  const int64_t s1 = min((int64_t)scene_offsets[b + 1], s0 + keys_per_split);
+  const int t = threadIdx.x;
+  const bool active = t < Q * H;
+  const int q = active ? t / H : 0, h = active ? t % H : 0;
+  float qv[HD], acc[HD];
+#pragma unroll
+  for (int j = 0; j < HD; ++j) {
+    qv[j] = (active && j < hd) ? qp[((int64_t)b * Q + q) * D + h * hd + j] * scale : 0.f;
+    acc[j] = 0.f;
+  }
+  const bool use_mask = active && any_open[b * Q + q] != 0;
+  float m = -INFINITY, l = 0.f;
+  for (int64_t k0 = s0; k0 < s1; k0 += kXaKeysPerTile) {
+    const int nk = (int)min((int64_t)kXaKeysPerTile, s1 - k0);
+    __syncthreads();
+    for (int i = t; i < nk * (D >> 2); i += blockDim.x) {
+      const int r = i / (D >> 2), c = (i - r * (D >> 2)) * 4;
+      store4(sK + r * D + c, load4(kp + (k0 + r) * D + c));
+      store4(sV + r * D + c, load4(vp + (k0 + r) * D + c));
+    }
+    for (int i = t; i < nk * Q; i += blockDim.x) sM[i] = blocked[k0 * Q + i];
+    __syncthreads();
+    if (active) {
+      for (int r = 0; r < nk; ++r) {
+        if (use_mask && sM[r * Q + q]) continue;
+        const float* kr = sK + r * D + h * hd;
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < HD; ++j)
+          if (j < hd) s = fmaf(qv[j], kr[j], s);
+        const float mn = fmaxf(m, s);
+        const float corr = expf(m - mn);  // m = -inf on the first key: exp(-inf) = 0
+        const float pw = expf(s - mn);
+        l = l * corr + pw;
+        const float* vr = sV + r * D + h * hd;
+#pragma unroll
+        for (int j = 0; j < HD; ++j)
+          if (j < hd) acc[j] = fmaf(acc[j], corr, pw * vr[j]);
+        m = mn;
+      }
+    }
+  }
+  if (active) {
+    float* o = partial + (((int64_t)b * nsplit + split) * Q * H + t) * (2 + kXaMaxHd);
+    o[0] = m;
+    o[1] = l;
+#pragma unroll
+    for (int j = 0; j < HD; ++j)
+      if (j < hd) o[2 + j] = acc[j];
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_xattn_combine(const float* __restrict__ partial, int nsplit, int Q, int D, int H,
+                                                        float* __restrict__ ctx) {
+  const int b = blockIdx.x, t = threadIdx.x;
+  if (t >= Q * H) return;
+  const int hd = D / H, q = t / H, h = t % H;
+  float m = -INFINITY;
+  for (int s = 0; s < nsplit; ++s) m = fmaxf(m, partial[(((int64_t)b * nsplit + s) * Q * H + t) * (2 + kXaMaxHd)]);
+  float l = 0.f, acc[kXaMaxHd];
+#pragma unroll
+  for (int j = 0; j < kXaMaxHd; ++j) acc[j] = 0.f;
+  for (int s = 0; s < nsplit; ++s) {  // fixed order
+    const float* p = partial + (((int64_t)b * nsplit + s) * Q * H + t) * (2 + kXaMaxHd);
+    if (p[1] == 0.f) continue;
+    const float w = expf(p[0] - m);
+    l += p[1] * w;
+#pragma unroll
+    for (int j = 0; j < kXaMaxHd; ++j)
+      if (j < hd) acc[j] = fmaf(p[2 + j], w, acc[j]);
+  }
+  const float inv = 1.f / l;
+#pragma unroll
+  for (int j = 0; j < kXaMaxHd; ++j)
+    if (j < hd) ctx[((int64_t)b * Q + q) * D + h * hd + j] = acc[j] * inv;
+}
+
+inline int xattn_splits(int64_t n, int B) {
+  // ~2 blocks per SM over the batch, at least 256 keys per split
+  int64_t s = ceil_div(2 * (int64_t)num_sms(), B > 0 ? B : 1);
+  int64_t by_keys = ceil_div(n > 0 ? n : 1, 256);
+  if (s > by_keys) s = by_keys;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+
+}  // namespace mk
+
+using namespace mk;
+
+extern "C" {
+
+int mk_mask_logits(const void* feat, int x_dtype, int64_t n, int C, const int32_t* scene_offsets, int B, const float* embed,
+                   int Q, float* logits, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  MK_REQUIRE(C % 4 == 0, "C must be a multiple of 4");
+  MK_REQUIRE(Q >= 1 && Q <= 4 * kMlMaxQPerThread, "Q must be <= 128");
+  if (n == 0) return 0;
+  const size_t smem = ((size_t)Q * C + (size_t)kMlRows * (C + 1)) * sizeof(float);
+  MK_REQUIRE(smem <= 200 * 1024, "Q*C too large for shared memory");
+  dim3 grid((unsigned)ceil_div(n, kMlRows), (unsigned)B);
+  if (x_dtype == MK_F32) {
+    cudaFuncSetAttribute(k_mask_logits<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_mask_logits<float><<<grid, kMlThreads, smem, st>>>((const float*)feat, C, scene_offsets, embed, Q, logits);
+  } else {
+    cudaFuncSetAttribute(k_mask_logits<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_mask_logits<__nv_bfloat16><<<grid, kMlThreads, smem, st>>>((const __nv_bfloat16*)feat, C, scene_offsets, embed, Q, logits);
+  }
+  return check_launch(__func__);
+}
+
+int mk_scene_minmax(const float* xyz, const int32_t* scene_offsets, int B, float* cmin, float* cmax, void* stream_) {
+  k_scene_minmax<<<B, 256, 0, (cudaStream_t)stream_>>>(xyz, scene_offsets, cmin, cmax);
+  return check_launch(__func__);
+}
+
+int mk_fourier_pe(const float* xyz, int64_t n, const int32_t* scene_offsets, int B, const float* cmin, const float* cmax,
+                  const float* gauss_B, int D, const void* base, int base_dtype, void* out, int out_dtype, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  MK_REQUIRE(D % 2 == 0, "D must be even");
+  if (n == 0) return 0;
+  int64_t blocks = ceil_div(n * (D / 2), 256);
+  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+#define MK_PE(TB, TO) \
+  k_fourier_pe<TB, TO><<<(unsigned)blocks, 256, 0, st>>>(xyz, n, scene_offsets, B, cmin, cmax, gauss_B, D, (const TB*)base, (TO*)out)
+  if (base_dtype == MK_F32 && out_dtype == MK_F32) MK_PE(float, float);
+  else if (base_dtype == MK_F32 && out_dtype == MK_BF16) MK_PE(float, __nv_bfloat16);
+  else if (base_dtype == MK_BF16 && out_dtype == MK_F32) MK_PE(__nv_bfloat16, float);
+  else MK_PE(__nv_bfloat16, __nv_bfloat16);
+#undef MK_PE
+  return check_launch(__func__);
+}
+
+int64_t mk_xattn_workspace_bytes(int B, int Q, int H, int64_t n_keys) {
+  const int splits = xattn_splits(n_keys, B);
+  return ((int64_t)B * splits * Q * H * (2 + kXaMaxHd)) * (int64_t)sizeof(float) + (int64_t)B * Q * sizeof(int32_t) + 256;
+}
+
+int mk_masked_xattn_fwd(const float* qp, const void* kp, const void* vp, int kv_dtype, int64_t n, const uint8_t* blocked,
+                        const int32_t* scene_offsets, int B, int Q, int D, int H, float scale, float* ctx, void* workspace,
+                        int64_t workspace_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  MK_REQUIRE(D % H == 0 && D / H <= kXaMaxHd && D % 4 == 0, "head dim must be <= 32 and D a multiple of 4");
+  MK_REQUIRE(Q * H <= 1024, "Q*H must be <= 1024");
+  MK_REQUIRE(workspace_bytes >= mk_xattn_workspace_bytes(B, Q, H, n), "workspace too small");
+  const int splits = xattn_splits(n, B);
+  int32_t* any_open = (int32_t*)workspace;
+  float* partial = (float*)((uint8_t*)workspace + (((int64_t)B * Q * sizeof(int32_t) + 255) / 256) * 256);
+  cudaMemsetAsync(any_open, 0, (size_t)B * Q * sizeof(int32_t), st);
+  if (n > 0) {
+    int64_t blocks = ceil_div(n * Q, 256);
+    if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+    k_any_open<<<(unsigned)blocks, 256, 0, st>>>(blocked, n, Q, scene_offsets, B, any_open);
+  }
+  const int keys_per_split = (int)ceil_div(n > 0 ? n : 1, splits);  // upper bound on any scene's size / splits
+  const int threads = ((Q * H + 31) / 32) * 32;
+  const size_t smem = (size_t)2 * kXaKeysPerTile * D * sizeof(float) + (size_t)kXaKeysPerTile * Q;
+  dim3 grid((unsigned)splits, (unsigned)B);
+#define MK_XA(T, HD)                                                                                                        \
+  k_xattn_partial<T, HD><<<grid, threads, smem, st>>>(qp, (const T*)kp, (const T*)vp, blocked, any_open, scene_offsets, Q, D, H, \
+                                                      scale, keys_per_split, partial)
+  const bool hd16 = D / H <= 16;
+  if (kv_dtype == MK_F32) {
+    if (hd16) MK_XA(float, 16); else MK_XA(float, 32);
+  } else {
+    if (hd16) MK_XA(__nv_bfloat16, 16); else MK_XA(__nv_bfloat16, 32);
+  }
+#undef MK_XA
+  k_xattn_combine<<<B, threads, 0, st>>>(partial, splits, Q, D, H, ctx);
+  return check_launch(__func__);
+}
+
+}  // extern "C"

@@ -1,0 +1,263 @@
+// Instance norm (per scene, per channel) + affine + residual + ReLU, and its backward.
+//
+// Replaces MinkowskiInstanceNorm's 2 global-avg-pool + 2 broadcast launches (4 full passes over [N,C],
+// SURVEY.md section 8a-a9) and the separate MinkowskiReLU / `out += residual` passes (a11) with
+//   stats:  one read of x   (chunked, shifted sums, deterministic fp64 merge in fixed order)
+//   apply:  one read of x (+ residual), one write, fused affine + residual + ReLU + dtype cast.
+// HBM-bound: vectorised 4-channel loads, coalesced along channels, grid sized in multiples of the SM count.
+#include "common.cuh"
+
+namespace mk {
+
+constexpr int kNormThreads = 256;
+
+// partial layout: [chunk][3][C] = {count (as float), shifted sum, shifted sum of squares}, shift[chunk][C]
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads) k_in_stats_partial(const T* __restrict__ x, int C,
+                                                                   const int32_t* __restrict__ scene_offsets, int rows_per_chunk,
+                                                                   int chunks_per_scene, float* __restrict__ partial) {
+  const int b = blockIdx.y;
+  const int chunk = blockIdx.x;
+  const int64_t start = (int64_t)scene_offsets[b] + (int64_t)chunk * rows_per_chunk;
+  const int64_t end = min((int64_t)scene_offsets[b + 1], start + rows_per_chunk);
+  const int CV = C >> 2;                 // 4-channel vectors per row
+  const int RL = kNormThreads / CV;      // row lanes
+  const int cv = threadIdx.x % CV, rl = threadIdx.x / CV;
+  float* out = partial + ((int64_t)(b * chunks_per_scene + chunk)) * 4 * C;
+  extern __shared__ float sm[];  // [RL][2][C]
+  float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0), shift = make_float4(0, 0, 0, 0);
+  if (start < end) shift = load4(x + start * C + 4 * cv);
+  if (rl < RL) {
+    for (int64_t r = start + rl; r < end; r += RL) {
+      float4 v = load4(x + r * C + 4 * cv);
+      v.x -= shift.x; v.y -= shift.y; v.z -= shift.z; v.w -= shift.w;
+      s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+      s2.x = fmaf(v.x, v.x, s2.x); s2.y = fmaf(v.y, v.y, s2.y); s2.z = fmaf(v.z, v.z, s2.z); s2.w = fmaf(v.w, v.w, s2.w);
+    }
+    float* p = sm + (int64_t)rl * 2 * C;
+    store4(p + 4 * cv, s1);
+    store4(p + C + 4 * cv, s2);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kNormThreads) {
+    float a = 0.f, q = 0.f;
+    for (int l = 0; l < RL; ++l) {  // fixed order
+      a += sm[l * 2 * C + c];
+      q += sm[l * 2 * C + C + c];
+    }
+    out[c] = (float)(end > start ? end - start : 0);
+    out[C + c] = a;
+    out[2 * C + c] = q;
+  }
+  if (rl == 0) store4(out + 3 * C + 4 * cv, shift);
+}
+
+__global__ void k_in_stats_final(const float* __restrict__ partial, int C, int chunks_per_scene, float eps,
+                                 float* __restrict__ mean, float* __restrict__ rstd) {
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double n = 0, mu = 0, m2 = 0;  // Chan et al. parallel merge, chunks in ascending order
+    for (int ch = 0; ch < chunks_per_scene; ++ch) {
+      const float* p = partial + ((int64_t)(b * chunks_per_scene + ch)) * 4 * C;
+      double nb = p[c];
+      if (nb <= 0) continue;
+      double s1 = p[C + c], s2 = p[2 * C + c], sh = p[3 * C + c];
+      double mub = sh + s1 / nb;
+      double m2b = s2 - s1 * s1 / nb;
+      if (m2b < 0) m2b = 0;
+      double d = mub - mu, nt = n + nb;
+      mu += d * nb / nt;
+      m2 += m2b + d * d * n * nb / nt;
+      n = nt;
+    }
+    double var = n > 0 ? m2 / n : 0.0;
+    mean[b * C + c] = (float)mu;
+    rstd[b * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) k_norm_apply(const TIn* __restrict__ x, int64_t n, int C,
+                                                    const int32_t* __restrict__ scene_offsets, int B,
+                                                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                    const TOut* __restrict__ residual, int relu, TOut* __restrict__ out) {
+  const int CV = C >> 2;
+  const int64_t total = n * CV;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / CV;
+    const int c = (int)(i - r * CV) * 4;
+    float4 v = load4(x + r * C + c);
+    if (mean) {
+      const int b = scene_of_row(scene_offsets, B, r);
+      const float4 m = load4(mean + b * C + c), s = load4(rstd + b * C + c);
+      v.x = (v.x - m.x) * s.x; v.y = (v.y - m.y) * s.y; v.z = (v.z - m.z) * s.z; v.w = (v.w - m.w) * s.w;
+    }
+    if (gamma) {
+      const float4 g = load4(gamma + c), be = load4(beta + c);
+      v.x = fmaf(v.x, g.x, be.x); v.y = fmaf(v.y, g.y, be.y); v.z = fmaf(v.z, g.z, be.z); v.w = fmaf(v.w, g.w, be.w);
+    }
+    if (residual) {
+      const float4 q = load4(residual + r * C + c);
+      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    }
+    if (relu) {
+      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    }
+    store4(out + r * C + c, v);
+  }
+}
+
+// ---- backward: per (scene, channel) sums of dy*gamma and dy*gamma*yhat, then dx -------------------
+// partial [chunk][2][C]
+__global__ void __launch_bounds__(kNormThreads) k_in_bwd_partial(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                 int C, const int32_t* __restrict__ scene_offsets,
+                                                                 int rows_per_chunk, int chunks_per_scene,
+                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                 float* __restrict__ partial) {
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int64_t start = (int64_t)scene_offsets[b] + (int64_t)chunk * rows_per_chunk;
+  const int64_t end = min((int64_t)scene_offsets[b + 1], start + rows_per_chunk);
+  float* out = partial + ((int64_t)(b * chunks_per_scene + chunk)) * 2 * C;
+  for (int c = threadIdx.x; c < C; c += kNormThreads) {
+    const float m = mean[b * C + c], s = rstd[b * C + c];
+    float a = 0.f, q = 0.f;
+    for (int64_t r = start; r < end; ++r) {
+      const float g = dy[r * C + c];
+      const float yh = (x[r * C + c] - m) * s;
+      a += g;
+      q = fmaf(g, yh, q);
+    }
+    out[c] = a;
+    out[C + c] = q;
+  }
+}
+
+__global__ void k_in_bwd_final(const float* __restrict__ partial, int C, int chunks_per_scene, int B,
+                               const int32_t* __restrict__ scene_offsets, float* __restrict__ sum_dy,
+                               float* __restrict__ sum_dyy, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  // one block; thread per channel; deterministic order
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double tg = 0, tb = 0;
+    for (int b = 0; b < B; ++b) {
+      double a = 0, q = 0;
+      for (int ch = 0; ch < chunks_per_scene; ++ch) {
+        const float* p = partial + ((int64_t)(b * chunks_per_scene + ch)) * 2 * C;
+        a += p[c];
+        q += p[C + c];
+      }
+      sum_dy[b * C + c] = (float)a;
+      sum_dyy[b * C + c] = (float)q;
+      tb += a;
+      tg += q;
+    }
+    if (dgamma) dgamma[c] = (float)tg;
+    if (dbeta) dbeta[c] = (float)tb;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_in_bwd_dx(const float* __restrict__ x, const float* __restrict__ dy, int64_t n, int C,
+                                                   const int32_t* __restrict__ scene_offsets, int B,
+                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                   const float* __restrict__ gamma, const float* __restrict__ sum_dy,
+                                                   const float* __restrict__ sum_dyy, float* __restrict__ dx) {
+  const int64_t total = n * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / C;
+    const int c = (int)(i - r * C);
+    const int b = scene_of_row(scene_offsets, B, r);
+    const float nb = (float)(scene_offsets[b + 1] - scene_offsets[b]);
+    const float s = rstd[b * C + c];
+    const float yh = (x[i] - mean[b * C + c]) * s;
+    const float g = gamma ? gamma[c] : 1.f;
+    // dy here is the gradient w.r.t. the affine output; dgamma/dbeta sums were taken on dy directly
+    dx[i] = g * s * (dy[i] - sum_dy[b * C + c] / nb - yh * sum_dyy[b * C + c] / nb);
+  }
+}
+
+inline void norm_chunking(int64_t n, int B, int* rows_per_chunk, int* chunks_per_scene) {
+  // target ~4 chunks per SM over the whole batch; chunks are per scene, sized for the largest possible scene (n)
+  int64_t target = 4 * (int64_t)num_sms();
+  int64_t rpc = ceil_div(n > 0 ? n : 1, target);
+  if (rpc < 64) rpc = 64;
+  *rows_per_chunk = (int)rpc;
+  *chunks_per_scene = (int)ceil_div(n > 0 ? n : 1, rpc);
+  (void)B;
+}
+
+}  // namespace mk
+
+using namespace mk;
+
+extern "C" {
+
+int64_t mk_instnorm_workspace_bytes(int64_t n, int C, int B) {
+  int rpc, cps;
+  norm_chunking(n, B, &rpc, &cps);
+  return ((int64_t)B * cps * 4 * C + 2 * (int64_t)B * C + 64) * (int64_t)sizeof(float);
+}
+
+int mk_instnorm_stats(const void* x, int x_dtype, int64_t n, int C, const int32_t* scene_offsets, int B, float eps,
+                      float* mean, float* rstd, void* workspace, int64_t workspace_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  MK_REQUIRE(C % 4 == 0 && C >= 4 && C <= 4 * kNormThreads, "C must be a multiple of 4, <= 1024");
+  MK_REQUIRE(workspace_bytes >= mk_instnorm_workspace_bytes(n, C, B), "workspace too small");
+  MK_REQUIRE(B >= 1, "B must be >= 1");
+  int rpc, cps;
+  norm_chunking(n, B, &rpc, &cps);
+  float* partial = (float*)workspace;
+  const int CV = C / 4, RL = kNormThreads / CV;
+  size_t smem = (size_t)RL * 2 * C * sizeof(float);
+  dim3 grid((unsigned)cps, (unsigned)B);
+  if (x_dtype == MK_F32)
+    k_in_stats_partial<float><<<grid, kNormThreads, smem, st>>>((const float*)x, C, scene_offsets, rpc, cps, partial);
+  else
+    k_in_stats_partial<__nv_bfloat16><<<grid, kNormThreads, smem, st>>>((const __nv_bfloat16*)x, C, scene_offsets, rpc, cps, partial);
+  k_in_stats_final<<<B, 128, 0, st>>>(partial, C, cps, eps, mean, rstd);
+  return check_launch(__func__);
+}
+
+int mk_norm_apply(const void* x, int x_dtype, int64_t n, int C, const int32_t* scene_offsets, int B, const float* mean,
+                  const float* rstd, const float* gamma, const float* beta, const void* residual, int relu, void* out,
+                  int out_dtype, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  MK_REQUIRE(C % 4 == 0, "C must be a multiple of 4");
+  if (n == 0) return 0;
+  int64_t total = n * (C / 4);
+  int64_t blocks = ceil_div(total, 256);
+  int64_t cap = 8 * (int64_t)num_sms();
+  if (blocks > cap) blocks = cap;
+#define MK_APPLY(TI, TO)                                                                                              \
+  k_norm_apply<TI, TO><<<(unsigned)blocks, 256, 0, st>>>((const TI*)x, n, C, scene_offsets, B, mean, rstd, gamma, beta, \
+                                                         (const TO*)residual, relu, (TO*)out)
+  if (x_dtype == MK_F32 && out_dtype == MK_F32) MK_APPLY(float, float);
+  else if (x_dtype == MK_F32 && out_dtype == MK_BF16) MK_APPLY(float, __nv_bfloat16);
+  else if (x_dtype == MK_BF16 && out_dtype == MK_F32) MK_APPLY(__nv_bfloat16, float);
+  else MK_APPLY(__nv_bfloat16, __nv_bfloat16);
+#undef MK_APPLY
+  return check_launch(__func__);
+}
+
+int mk_instnorm_bwd(const float* x, const float* dy, int64_t n, int C, const int32_t* scene_offsets, int B,
+                    const float* mean, const float* rstd, const float* gamma, float* dx, float* dgamma, float* dbeta,
+                    void* workspace, int64_t workspace_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  MK_REQUIRE(workspace_bytes >= mk_instnorm_workspace_bytes(n, C, B), "workspace too small");
+  int rpc, cps;
+  norm_chunking(n, B, &rpc, &cps);
+  float* partial = (float*)workspace;
+  float* sum_dy = partial + (int64_t)B * cps * 4 * C;
+  float* sum_dyy = sum_dy + (int64_t)B * C;
+  dim3 grid((unsigned)cps, (unsigned)B);
+  k_in_bwd_partial<<<grid, kNormThreads, 0, st>>>(x, dy, C, scene_offsets, rpc, cps, mean, rstd, partial);
+  k_in_bwd_final<<<1, 256, 0, st>>>(partial, C, cps, B, scene_offsets, sum_dy, sum_dyy, dgamma, dbeta);
+  if (n > 0) {
+    int64_t blocks = ceil_div(n * C, 256);
+    int64_t cap = 8 * (int64_t)num_sms();
+    if (blocks > cap) blocks = cap;
+    k_in_bwd_dx<<<(unsigned)blocks, 256, 0, st>>>(x, dy, n, C, scene_offsets, B, mean, rstd, gamma, sum_dy, sum_dyy, dx);
+  }
+  return check_launch(__func__);
+}
+
+}  // extern "C"

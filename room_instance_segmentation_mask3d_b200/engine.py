@@ -1,0 +1,285 @@
+"""Coordinate manager: coordinate maps, kernel maps and tensor-core tile plans on the GPU.
+
+Mirrors MinkowskiEngine 0.5.4's CoordinateManager as the reference uses it: one manager per
+input SparseTensor, shared by every tensor derived from it; coordinate maps cached by (tensor_stride, string_id),
+kernel maps cached by (in_key, out_key, kernel_size, dilation).  All arithmetic runs in libmk3d.so
+(csrc/coords.cu); torch supplies device memory and the stream.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import lib
+
+I32 = torch.int32
+
+
+def _tuple3(v, D=3) -> Tuple[int, ...]:
+    if isinstance(v, int):
+        return (v,) * D
+    if isinstance(v, torch.Tensor):
+        v = v.tolist()
+    v = tuple(int(x) for x in v)
+    assert len(v) == D, f"expected {D} values, got {v}"
+    return v
+
+
+class CoordinateMapKey:
+    """(tensor_stride, string_id)."""
+
+    __slots__ = ("tensor_stride", "string_id")
+
+    def __init__(self, tensor_stride, string_id: str = ""):
+        self.tensor_stride = _tuple3(tensor_stride)
+        self.string_id = string_id
+
+    def get_key(self):
+        return (list(self.tensor_stride), self.string_id)
+
+    def get_tensor_stride(self):
+        return list(self.tensor_stride)
+
+    def get_coordinate_size(self):
+        return len(self.tensor_stride) + 1
+
+    def __hash__(self):
+        return hash((self.tensor_stride, self.string_id))
+
+    def __eq__(self, o):
+        return isinstance(o, CoordinateMapKey) and self.tensor_stride == o.tensor_stride and self.string_id == o.string_id
+
+    def __repr__(self):
+        return f"CoordinateMapKey(stride={list(self.tensor_stride)}, id={self.string_id!r})"
+
+
+class CoordMap:
+    """One coordinate map: rows + its hash table + the per-scene row ranges."""
+
+    def __init__(self, coords: torch.Tensor, keys: torch.Tensor, vals: torch.Tensor, cap: int):
+        self.coords, self.keys, self.vals, self.cap = coords, keys, vals, cap
+        self.n = coords.shape[0]
+        self._offsets: Optional[torch.Tensor] = None
+        self._offsets_host: Optional[List[int]] = None
+
+    def scene_offsets(self, B: int) -> torch.Tensor:
+        """int32 [B+1]: rows of scene b are [off[b], off[b+1]) — batch items are contiguous and ascending."""
+        if self._offsets is None or self._offsets.numel() != B + 1:
+            b = self.coords[:, 0].contiguous()
+            bounds = torch.arange(B + 1, device=b.device, dtype=I32)
+            self._offsets = torch.searchsorted(b, bounds, right=False).to(I32)
+            self._offsets_host = None
+        return self._offsets
+
+    def scene_offsets_host(self, B: int) -> List[int]:
+        if self._offsets_host is None:
+            self._offsets_host = self.scene_offsets(B).tolist()
+        return self._offsets_host
+
+
+class KernelMap:
+    """Output-stationary kernel map nbr[K, n_slots] (+ what the tensor-core kernel needs)."""
+
+    def __init__(self, nbr: torch.Tensor, K: int, n_out: int, out_rows: Optional[torch.Tensor] = None):
+        self.nbr = nbr                    # int32 [K, n_slots]
+        self.K = K
+        self.n_slots = nbr.shape[1]
+        self.n_out = n_out
+        self.out_rows = out_rows          # int32 [n_slots] or None (slot == row)
+        self._kmask: Optional[torch.Tensor] = None
+        self._pairs_dev: Optional[torch.Tensor] = None
+        self._pairs: Optional[int] = None
+
+    def _build_kmask(self):
+        ntiles = (self.n_slots + lib.TILE - 1) // lib.TILE
+        self._kmask = torch.empty(max(ntiles, 1), dtype=I32, device=self.nbr.device)
+        self._pairs_dev = torch.zeros(1, dtype=torch.int64, device=self.nbr.device)
+        lib.call("mk_tile_kmask", lib.p(self.nbr), self.K, self.n_slots, lib.p(self._kmask) if self.K <= 32 else None,
+                 lib.p(self._pairs_dev), lib.stream())
+
+    @property
+    def tile_kmask(self) -> torch.Tensor:
+        if self._kmask is None:
+            self._build_kmask()
+        return self._kmask
+
+    @property
+    def num_pairs(self) -> int:
+        """Actual pair count P = sum_k n_k (the algorithmic-FLOP figure).  Host sync."""
+        if self._pairs is None:
+            if self._pairs_dev is None:
+                self._build_kmask()
+            self._pairs = int(self._pairs_dev.item())
+        return self._pairs
+
+
+def kernel_offsets(kernel_size: Sequence[int], dilation: Sequence[int], tensor_stride: Sequence[int]) -> List[List[int]]:
+    """HYPER_CUBE offsets, x fastest; odd K centred, even K anchored at the output coordinate."""
+    out = []
+    for iz in range(kernel_size[2]):
+        for iy in range(kernel_size[1]):
+            for ix in range(kernel_size[0]):
+                o = []
+                for a, i in enumerate((ix, iy, iz)):
+                    off = (i - kernel_size[a] // 2) if kernel_size[a] % 2 == 1 else i
+                    o.append(off * dilation[a] * tensor_stride[a])
+                out.append(o)
+    return out
+
+
+class CoordinateManager:
+    def __init__(self, D: int = 3, device=None, **_):
+        lib.require_cuda()
+        assert D == 3, "the hot path is 3-D (SURVEY.md section 8)"
+        self.D = D
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._maps: Dict[CoordinateMapKey, CoordMap] = {}
+        self._kmaps: Dict[tuple, KernelMap] = {}
+        self._tplans: Dict[tuple, KernelMap] = {}
+        self._offs_cache: Dict[tuple, torch.Tensor] = {}
+        self._B: Optional[int] = None
+
+    # ------------------------------------------------------------------ coordinate maps
+    def _build_map(self, in_coords: torch.Tensor, stride: Tuple[int, int, int]):
+        n = in_coords.shape[0]
+        dev = in_coords.device
+        cap = lib.query("mk_hash_capacity", n)
+        keys = torch.empty(cap, dtype=torch.int64, device=dev)
+        vals = torch.empty(cap, dtype=I32, device=dev)
+        out_coords = torch.empty((n, 4), dtype=I32, device=dev)
+        uniq = torch.empty(n, dtype=I32, device=dev)
+        inv = torch.empty(n, dtype=I32, device=dev)
+        meta = torch.zeros(2, dtype=I32, device=dev)  # [n_out, status]
+        wsb = lib.query("mk_coordmap_workspace_bytes", n)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        stride_host = (ctypes.c_int32 * 3)(*stride)
+        lib.call("mk_coordmap_build", lib.p(in_coords), n, ctypes.cast(stride_host, ctypes.c_void_p), lib.p(keys), lib.p(vals), cap,
+                 lib.p(out_coords), lib.p(uniq), lib.p(inv), ctypes.c_void_p(meta.data_ptr()), ctypes.c_void_p(meta.data_ptr() + 4),
+                 lib.p(ws), wsb, lib.stream())
+        n_out, status = meta.tolist()  # one host sync per map: sizes are data-dependent
+        if status != 0:
+            raise RuntimeError("coordinate out of the packable range [-2^17, 2^17) or batch index >= 1023")
+        return CoordMap(out_coords[:n_out], keys, vals, cap), uniq[:n_out], inv
+
+    def insert_and_map(self, coords: torch.Tensor, tensor_stride=1, string_id: str = ""):
+        key = CoordinateMapKey(_tuple3(tensor_stride), string_id)
+        if key in self._maps:
+            raise RuntimeError(f"coordinate map {key} already exists")
+        c = coords.to(device=self.device, dtype=I32).contiguous()
+        assert c.dim() == 2 and c.shape[1] == 4, "coordinates must be [N, 4] = (batch, x, y, z)"
+        cmap, uniq, inv = self._build_map(c, (1, 1, 1))
+        self._maps[key] = cmap
+        return key, (uniq.long(), inv.long())
+
+    def stride(self, in_key: CoordinateMapKey, stride) -> CoordinateMapKey:
+        s = _tuple3(stride)
+        if all(x == 1 for x in s):
+            return in_key
+        out_ts = tuple(a * b for a, b in zip(in_key.tensor_stride, s))
+        key = CoordinateMapKey(out_ts, "")
+        if key not in self._maps:
+            cmap, _, _ = self._build_map(self._maps[in_key].coords, out_ts)
+            self._maps[key] = cmap
+        return key
+
+    def exists(self, key) -> bool:
+        return key in self._maps
+
+    def get_coordinates(self, key) -> torch.Tensor:
+        return self._maps[key].coords
+
+    def size(self, key) -> int:
+        return self._maps[key].n
+
+    def coord_map(self, key) -> CoordMap:
+        return self._maps[key]
+
+    def number_of_unique_batch_indices(self) -> int:
+        if self._B is None:
+            k0 = next(iter(self._maps))
+            c = self._maps[k0].coords
+            self._B = int(c[-1, 0].item()) + 1 if c.shape[0] else 0  # batch indices ascend (sparse_collate)
+        return self._B
+
+    def scene_offsets(self, key) -> torch.Tensor:
+        return self._maps[key].scene_offsets(self.number_of_unique_batch_indices())
+
+    def scene_offsets_host(self, key) -> List[int]:
+        return self._maps[key].scene_offsets_host(self.number_of_unique_batch_indices())
+
+    def origin_map(self, key) -> List[torch.Tensor]:
+        off = self.scene_offsets_host(key)
+        return [torch.arange(off[b], off[b + 1], device=self.device) for b in range(len(off) - 1)]
+
+    # ------------------------------------------------------------------ kernel maps
+    def _offsets_dev(self, ks, dil, ts) -> torch.Tensor:
+        ck = (ks, dil, ts)
+        if ck not in self._offs_cache:
+            self._offs_cache[ck] = torch.tensor(kernel_offsets(ks, dil, ts), dtype=I32, device=self.device).contiguous()
+        return self._offs_cache[ck]
+
+    def neighbor_table(self, in_key, out_key, kernel_size, dilation=1) -> KernelMap:
+        ks, dl = _tuple3(kernel_size), _tuple3(dilation)
+        ck = (in_key, out_key, ks, dl)
+        km = self._kmaps.get(ck)
+        if km is None:
+            im, om = self._maps[in_key], self._maps[out_key]
+            K = ks[0] * ks[1] * ks[2]
+            nbr = torch.empty((K, om.n), dtype=I32, device=self.device)
+            offs = self._offsets_dev(ks, dl, in_key.tensor_stride)
+            lib.call("mk_kernel_map", lib.p(im.keys), lib.p(im.vals), im.cap, lib.p(om.coords), om.n, lib.p(offs), K, lib.p(nbr), lib.stream())
+            km = KernelMap(nbr, K, om.n)
+            self._kmaps[ck] = km
+        return km
+
+    def transpose_plan(self, coarse_key, fine_key, kernel_size, dilation=1) -> KernelMap:
+        """Tile plan of the transposed conv coarse -> fine.  Every fine row has exactly one (offset k, parent) pair, so
+        slots are the fine rows stably sorted by k and padded per k to a multiple of 128: every tile then has a single
+        active offset and the tensor-core kernel does no wasted MMA work."""
+        ks, dl = _tuple3(kernel_size), _tuple3(dilation)
+        ck = (coarse_key, fine_key, ks, dl)
+        plan = self._tplans.get(ck)
+        if plan is None:
+            down = self.neighbor_table(fine_key, coarse_key, ks, dl)  # nbr_down[k, coarse] = fine row
+            n_fine, n_coarse, K = self._maps[fine_key].n, self._maps[coarse_key].n, down.K
+            parent = torch.empty(n_fine, dtype=I32, device=self.device)
+            koff = torch.empty(n_fine, dtype=I32, device=self.device)
+            lib.call("mk_transpose_map", lib.p(down.nbr), K, n_coarse, n_fine, lib.p(parent), lib.p(koff), lib.stream())
+            order = torch.sort(koff, stable=True).indices  # fine rows grouped by k, ascending inside a group
+            counts = torch.bincount(koff.clamp_min(0), minlength=K)[:K]
+            counts_h = counts.tolist()
+            padded = [((c + lib.TILE - 1) // lib.TILE) * lib.TILE for c in counts_h]
+            n_slots = max(sum(padded), lib.TILE)
+            out_rows = torch.full((n_slots,), -1, dtype=I32, device=self.device)
+            nbr_t = torch.full((K, n_slots), -1, dtype=I32, device=self.device)
+            src0, dst0 = 0, 0
+            for k in range(K):
+                c = counts_h[k]
+                if c:
+                    rows = order[src0:src0 + c].to(I32)
+                    out_rows[dst0:dst0 + c] = rows
+                    nbr_t[k, dst0:dst0 + c] = parent[rows.long()]
+                src0 += c
+                dst0 += padded[k]
+            plan = KernelMap(nbr_t, K, n_fine, out_rows)
+            plan.parent, plan.koff = parent, koff
+            self._tplans[ck] = plan
+        return plan
+
+    def kernel_map(self, in_key, out_key, stride=1, kernel_size=3, dilation=1, region_type=None, region_offset=None,
+                   is_transpose: bool = False, is_pool: bool = False) -> Dict[int, torch.Tensor]:
+        """ME-visible kernel map {k: int32 [2, n_k]} rows (in, out), pairs of each k sorted by out row (the canonical
+        form of SURVEY.md section 8a-a6); transposed = the forward map of the same two coordinate maps, columns swapped."""
+        km = self.neighbor_table(out_key, in_key, kernel_size, dilation) if is_transpose else \
+            self.neighbor_table(in_key, out_key, kernel_size, dilation)
+        res = {}
+        present = km.nbr >= 0
+        for k in range(km.K):
+            o = torch.nonzero(present[k]).flatten().to(I32)
+            if o.numel() == 0:
+                continue
+            i = km.nbr[k, o.long()]
+            res[k] = torch.stack([o, i] if is_transpose else [i, o]).to(I32)
+        return res

@@ -1,0 +1,126 @@
+"""ctypes binding of libmk3d.so (include/mk3d.h).  Fails loudly: there is no CPU / eager fallback.
+
+Every wrapper takes torch CUDA tensors, checks dtype / contiguity, and passes raw device pointers plus the
+current torch CUDA stream to the C ABI.  PyTorch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+from typing import Optional
+
+import torch
+
+from . import build as _build
+
+F32, BF16 = 0, 1
+TILE = 128
+
+_lib = None
+
+_SIGS = {
+    "mk_last_error": (c_char_p, []),
+    "mk_version": (c_int, []),
+    "mk_device_supported": (c_int, []),
+    "mk_hash_capacity": (c_int64, [c_int64]),
+    "mk_coordmap_workspace_bytes": (c_int64, [c_int64]),
+    "mk_coordmap_build": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_int64, c_void_p]),
+    "mk_hash_query": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "mk_kernel_map": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
+    "mk_tile_kmask": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
+    "mk_transpose_map": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "mk_conv_fwd_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
+    "mk_conv_weight_image_elems": (c_int64, [c_int, c_int, c_int, c_int]),
+    "mk_conv_weight_image_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "mk_conv_fwd_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
+                                 c_void_p, c_void_p, c_int, c_void_p]),
+    "mk_conv_stem_f32": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_int, c_void_p]),
+    "mk_conv_dgrad_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
+    "mk_conv_wgrad_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "mk_instnorm_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
+    "mk_instnorm_stats": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "mk_norm_apply": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                              c_void_p, c_int, c_void_p]),
+    "mk_instnorm_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_int64, c_void_p]),
+    "mk_pool_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
+    "mk_pool_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_int64, c_void_p, c_void_p]),
+    "mk_mask_logits": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "mk_pool_threshold": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "mk_scene_minmax": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "mk_fourier_pe": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
+                              c_void_p]),
+    "mk_xattn_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int64]),
+    "mk_masked_xattn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
+                                    c_void_p, c_void_p, c_int64, c_void_p]),
+    "mk_fps": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "mk_cast": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p]),
+    "mk_copy_channels": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def load(build_if_missing: bool = True) -> ctypes.CDLL:
+    """Load (building with nvcc first if the .so is absent or stale).  Raises if it cannot."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing and _build.needs_build():
+        _build.build()
+    if not os.path.exists(_build.LIB):
+        raise RuntimeError(f"libmk3d.so not found at {_build.LIB}; run `python -m room_instance_segmentation_mask3d_b200.build`")
+    lib = ctypes.CDLL(_build.LIB)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed: {load().mk_last_error().decode()}")
+
+
+def require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError("room_instance_segmentation_mask3d_b200 needs a CUDA device: the hot path has no CPU fallback")
+
+
+def dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def tdtype(code: int) -> torch.dtype:
+    return torch.float32 if code == F32 else torch.bfloat16
+
+
+def p(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
+    return c_void_p(t.data_ptr())
+
+
+def stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def call(name: str, *args) -> None:
+    _check(getattr(load(), name)(*args), name)
+
+
+def query(name: str, *args) -> int:
+    return int(getattr(load(), name)(*args))

@@ -1,0 +1,219 @@
+"""Functional wrappers over the C ABI: one Python function per kernel family, raw torch tensors in and out.
+
+Two compute modes for the convolution (BASELINE.json north_star):
+  "fp32"  exact-fp32 CUDA-core path (mk_conv_fwd_f32) — the parity mode (<= 1e-3 relative vs the oracle);
+  "bf16"  tcgen05 tensor-core path (mk_conv_fwd_bf16): bf16 operands, fp32 accumulation in TMEM.
+"""
+from __future__ import annotations
+
+import weakref
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import lib
+from .engine import KernelMap
+
+_MODE = "bf16"
+
+
+def set_compute_mode(mode: str) -> None:
+    global _MODE
+    assert mode in ("fp32", "bf16")
+    _MODE = mode
+
+
+def get_compute_mode() -> str:
+    return _MODE
+
+
+# ----------------------------------------------------------------------------------------------------
+# weight images (bf16, pre-swizzled) — cached per parameter version
+# ----------------------------------------------------------------------------------------------------
+_wimg_cache: Dict[Tuple[int, int], Tuple[int, torch.Tensor, "weakref.ref"]] = {}
+
+
+def weight_image(W: torch.Tensor, transpose: bool = False) -> torch.Tensor:
+    """bf16 weight image of W fp32 [K, cin, cout] (or [cin, cout]) for mk_conv_fwd_bf16."""
+    key = (W.data_ptr(), int(transpose), tuple(W.shape))
+    ent = _wimg_cache.get(key)
+    if ent is not None and ent[0] == W._version and ent[2]() is not None:
+        return ent[1]
+    W3 = W.detach()
+    if W3.dim() == 2:
+        W3 = W3.unsqueeze(0)
+    W3 = W3.contiguous().float()
+    K, cin, cout = W3.shape
+    n = lib.query("mk_conv_weight_image_elems", K, cin, cout, int(transpose))
+    img = torch.empty(n, dtype=torch.bfloat16, device=W.device)
+    lib.call("mk_conv_weight_image_bf16", lib.p(W3), K, cin, cout, int(transpose), lib.p(img), lib.stream())
+    if len(_wimg_cache) > 4096:
+        _wimg_cache.clear()
+    _wimg_cache[key] = (W._version, img, weakref.ref(W))
+    return img
+
+
+def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    if x.dtype == dtype:
+        return x
+    out = torch.empty(x.shape, dtype=dtype, device=x.device)
+    lib.call("mk_cast", lib.p(x.contiguous()), lib.dt(x), lib.p(out), lib.dt(out), x.numel(), lib.stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# convolution
+# ----------------------------------------------------------------------------------------------------
+def conv_forward(x: torch.Tensor, W: torch.Tensor, km: KernelMap, bias: Optional[torch.Tensor] = None, mode: Optional[str] = None,
+                 out_dtype: Optional[torch.dtype] = None, kidx: Optional[torch.Tensor] = None, transpose_w: bool = False) -> torch.Tensor:
+    """out[o] = sum_k x[nbr[k, o]] @ W[k] (+ bias).  W fp32 [K, cin, cout]; x [n_in, cin] fp32 or bf16."""
+    mode = mode or _MODE
+    W3 = W if W.dim() == 3 else W.unsqueeze(0)
+    K, cin, cout = W3.shape
+    if transpose_w:
+        cin, cout = cout, cin
+    assert K == km.K and x.shape[1] == cin, f"shape mismatch: W {tuple(W3.shape)}, x {tuple(x.shape)}, K {km.K}"
+    bias_flat = bias.detach().reshape(-1).float().contiguous() if bias is not None else None
+    if cin == 1 and not transpose_w and km.out_rows is None:
+        out_dtype = out_dtype or (torch.float32 if mode == "fp32" else torch.bfloat16)
+        out = torch.empty((km.n_out, cout), dtype=out_dtype, device=x.device)
+        lib.call("mk_conv_stem_f32", lib.p(cast(x, torch.float32).contiguous()), lib.p(W3.detach().float().contiguous()), cout, lib.p(km.nbr),
+                 K, km.n_out, lib.p(out), lib.dt(out), lib.stream())
+        if bias_flat is not None:
+            out += bias_flat.to(out.dtype)
+        return out
+    if mode == "fp32":
+        assert km.out_rows is None and not transpose_w
+        out = torch.empty((km.n_out, cout), dtype=torch.float32, device=x.device)
+        lib.call("mk_conv_fwd_f32", lib.p(cast(x, torch.float32).contiguous()), cin, lib.p(W3.detach().float().contiguous()), cout,
+                 lib.p(km.nbr), K, km.n_out, lib.p(bias_flat), lib.p(out), lib.stream())
+        return out if out_dtype in (None, torch.float32) else cast(out, out_dtype)
+    out_dtype = out_dtype or torch.bfloat16
+    xb = cast(x.contiguous(), torch.bfloat16)
+    img = weight_image(W, transpose=transpose_w)
+    out = torch.empty((km.n_out, cout), dtype=out_dtype, device=x.device)
+    lib.call("mk_conv_fwd_bf16", lib.p(xb), cin, lib.p(img), cout, lib.p(km.nbr), K, km.n_slots, lib.p(km.out_rows), lib.p(km.tile_kmask),
+             lib.p(kidx), km.n_out, lib.p(bias_flat), lib.p(out), lib.dt(out), lib.stream())
+    return out
+
+
+def conv_transpose_forward_fp32(x: torch.Tensor, W: torch.Tensor, plan: KernelMap, bias=None) -> torch.Tensor:
+    """fp32 parity path of the transposed conv: out[f] = x[parent[f]] @ W[koff[f]], expressed through the generic
+    output-stationary kernel with the plan's table restricted to real rows (slot -> row permutation undone)."""
+    W3 = W if W.dim() == 3 else W.unsqueeze(0)
+    K, cin, cout = W3.shape
+    # identity-ordered table [K, n_fine]: nbr[k, f] = parent[f] if koff[f] == k else -1
+    ks = torch.arange(K, device=x.device, dtype=torch.int32)[:, None]
+    nbr = torch.where(plan.koff[None, :] == ks, plan.parent[None, :], torch.full_like(plan.parent[None, :], -1)).contiguous()
+    out = torch.empty((plan.n_out, cout), dtype=torch.float32, device=x.device)
+    bias_flat = bias.detach().reshape(-1).float().contiguous() if bias is not None else None
+    lib.call("mk_conv_fwd_f32", lib.p(cast(x, torch.float32).contiguous()), cin, lib.p(W3.detach().float().contiguous()), cout, lib.p(nbr), K,
+             plan.n_out, lib.p(bias_flat), lib.p(out), lib.stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# normalisation
+# ----------------------------------------------------------------------------------------------------
+def instance_norm_stats(x: torch.Tensor, scene_offsets: torch.Tensor, B: int, eps: float = 1e-8):
+    n, C = x.shape
+    mean = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    rstd = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    wsb = lib.query("mk_instnorm_workspace_bytes", n, C, B)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
+    lib.call("mk_instnorm_stats", lib.p(x), lib.dt(x), n, C, lib.p(scene_offsets), B, eps, lib.p(mean), lib.p(rstd), lib.p(ws), wsb, lib.stream())
+    return mean, rstd
+
+
+def norm_apply(x, scene_offsets, B, mean, rstd, gamma, beta, residual=None, relu=False, out_dtype=None) -> torch.Tensor:
+    n, C = x.shape
+    out_dtype = out_dtype or x.dtype
+    out = torch.empty((n, C), dtype=out_dtype, device=x.device)
+    if residual is not None:
+        residual = cast(residual.contiguous(), out_dtype)
+    g = gamma.detach().reshape(-1).float().contiguous() if gamma is not None else None
+    b = beta.detach().reshape(-1).float().contiguous() if beta is not None else None
+    lib.call("mk_norm_apply", lib.p(x), lib.dt(x), n, C, lib.p(scene_offsets), B, lib.p(mean), lib.p(rstd), lib.p(g), lib.p(b), lib.p(residual),
+             int(relu), lib.p(out), lib.dt(out), lib.stream())
+    return out
+
+
+def instance_norm(x, scene_offsets, B, gamma, beta, residual=None, relu=False, out_dtype=None, eps=1e-8) -> torch.Tensor:
+    x = x.contiguous()
+    mean, rstd = instance_norm_stats(x, scene_offsets, B, eps)
+    return norm_apply(x, scene_offsets, B, mean, rstd, gamma, beta, residual, relu, out_dtype)
+
+
+# ----------------------------------------------------------------------------------------------------
+# pooling, decoder pieces, FPS
+# ----------------------------------------------------------------------------------------------------
+def pool_forward(x: torch.Tensor, km: KernelMap, average: bool = True) -> torch.Tensor:
+    x = cast(x, torch.float32).contiguous()
+    out = torch.empty((km.n_out, x.shape[1]), dtype=torch.float32, device=x.device)
+    lib.call("mk_pool_fwd", lib.p(x), x.shape[1], lib.p(km.nbr), km.K, km.n_out, int(average), lib.p(out), lib.stream())
+    return out
+
+
+def pool_backward(dout: torch.Tensor, km: KernelMap, n_in: int, average: bool = True) -> torch.Tensor:
+    dout = dout.contiguous().float()
+    din = torch.empty((n_in, dout.shape[1]), dtype=torch.float32, device=dout.device)
+    lib.call("mk_pool_bwd", lib.p(dout), dout.shape[1], lib.p(km.nbr), km.K, km.n_out, int(average), n_in, lib.p(din), lib.stream())
+    return din
+
+
+def mask_logits(feat: torch.Tensor, scene_offsets: torch.Tensor, B: int, embed: torch.Tensor) -> torch.Tensor:
+    """logits[n, q] = feat[n] . embed[b(n), q]   (mask3d.py:534-537)."""
+    n, C = feat.shape
+    Q = embed.shape[1]
+    out = torch.empty((n, Q), dtype=torch.float32, device=feat.device)
+    lib.call("mk_mask_logits", lib.p(feat.contiguous()), lib.dt(feat), n, C, lib.p(scene_offsets), B, lib.p(embed.detach().float().contiguous()),
+             Q, lib.p(out), lib.stream())
+    return out
+
+
+def threshold_blocked(pooled: torch.Tensor) -> torch.Tensor:
+    """uint8 [n, Q]: sigmoid(pooled) < 0.5   (mask3d.py:550)."""
+    out = torch.empty(pooled.shape, dtype=torch.uint8, device=pooled.device)
+    lib.call("mk_pool_threshold", lib.p(pooled.contiguous()), pooled.shape[0], pooled.shape[1], lib.p(out), lib.stream())
+    return out
+
+
+def scene_minmax(xyz: torch.Tensor, scene_offsets: torch.Tensor, B: int):
+    cmin = torch.empty((B, 3), dtype=torch.float32, device=xyz.device)
+    cmax = torch.empty((B, 3), dtype=torch.float32, device=xyz.device)
+    lib.call("mk_scene_minmax", lib.p(xyz.contiguous()), lib.p(scene_offsets), B, lib.p(cmin), lib.p(cmax), lib.stream())
+    return cmin, cmax
+
+
+def fourier_pe(xyz, scene_offsets, B, cmin, cmax, gauss_B, base: Optional[torch.Tensor] = None, out_dtype=torch.float32) -> torch.Tensor:
+    n = xyz.shape[0]
+    D = gauss_B.shape[1] * 2
+    out = torch.empty((n, D), dtype=out_dtype, device=xyz.device)
+    lib.call("mk_fourier_pe", lib.p(xyz.contiguous()), n, lib.p(scene_offsets), B, lib.p(cmin), lib.p(cmax), lib.p(gauss_B.detach().float().contiguous()), D,
+             lib.p(base.contiguous()) if base is not None else None, lib.dt(base) if base is not None else lib.F32, lib.p(out), lib.dt(out),
+             lib.stream())
+    return out
+
+
+def masked_cross_attention(qp: torch.Tensor, kp: torch.Tensor, vp: torch.Tensor, blocked: torch.Tensor, scene_offsets: torch.Tensor,
+                           num_heads: int) -> torch.Tensor:
+    """ctx [B, Q, D] (heads concatenated, before out_proj)."""
+    B, Q, D = qp.shape
+    n = kp.shape[0]
+    assert kp.dtype == vp.dtype
+    wsb = lib.query("mk_xattn_workspace_bytes", B, Q, num_heads, n)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=qp.device)
+    ctx = torch.empty((B, Q, D), dtype=torch.float32, device=qp.device)
+    scale = float((D // num_heads) ** -0.5)
+    lib.call("mk_masked_xattn_fwd", lib.p(qp.detach().float().contiguous()), lib.p(kp.contiguous()), lib.p(vp.contiguous()), lib.dt(kp), n,
+             lib.p(blocked.contiguous()), lib.p(scene_offsets), B, Q, D, num_heads, scale, lib.p(ctx), lib.p(ws), wsb, lib.stream())
+    return ctx
+
+
+def furthest_point_sample(xyz: torch.Tensor, scene_offsets: torch.Tensor, B: int, m: int) -> torch.Tensor:
+    """int32 [B, m] scene-local indices; tie-breaking identical to pointnet2's kernel (csrc/fps.cu)."""
+    xyz = xyz.float().contiguous()
+    temp = torch.empty(xyz.shape[0], dtype=torch.float32, device=xyz.device)
+    idx = torch.zeros((B, m), dtype=torch.int32, device=xyz.device)
+    lib.call("mk_fps", lib.p(xyz), lib.p(scene_offsets), B, m, lib.p(temp), lib.p(idx), lib.stream())
+    return idx
