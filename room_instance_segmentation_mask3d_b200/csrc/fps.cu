@@ -3,8 +3,10 @@
 // Replaces pointnet2._ext.furthest_point_sampling (reference: mask3d/third_party/pointnet2/_ext_src/src/
 // sampling_gpu.cu:72-176, one 512-thread block per call, called once per scene from mask3d/models/mask3d.py:309-317).
 // The reference's result is a function of its block size Bv = min(2^floor(log2 n), 512) (cuda_utils.h:17-21):
-// per-thread strict '>' scan (lines 111-112) followed by a left-biased shared-memory tree (lines 62-68) selects
-//     argmax over candidates of (d2 descending, k mod Bv ascending, k ascending).
+// per-thread strict '>' scan (lines 111-112) followed by a left-biased shared-memory tree (lines 62-68: at stride s
+// position p keeps its own value on ties with p+s, s = Bv/2 ... 1) selects
+//     argmax over candidates of (d2 descending, bitreverse(k mod Bv) ascending, k ascending)
+// — the last tree level prefers even threads, the one before threads = 0 mod 4, and so on.
 // This kernel evaluates that total order directly, so any thread count / scan order gives the same indices.
 // Points with |p|^2 <= 1e-3 are skipped exactly as line 104 does; temp starts at 1e10 (sampling.cpp:76-78).
 #include "common.cuh"
@@ -13,7 +15,7 @@ namespace mk {
 
 struct Cand {
   float d;
-  int kmod;
+  unsigned kmod;  // __brev(k mod Bv): only the relative order matters
   int k;
 };
 
@@ -54,7 +56,7 @@ __global__ void __launch_bounds__(kFpsThreads) k_fps(const float* __restrict__ x
   __syncthreads();
   for (int j = 1; j < m; ++j) {
     const float x1 = pts[old * 3 + 0], y1 = pts[old * 3 + 1], z1 = pts[old * 3 + 2];
-    Cand best{-1.f, 0, 0};  // a reference thread that saw no candidate contributes (best = -1, besti = 0)
+    Cand best{-1.f, 0u, 0};  // a reference thread that saw no candidate contributes (best = -1, besti = 0)
     for (int k = threadIdx.x; k < n; k += kFpsThreads) {
       const float x2 = pts[k * 3 + 0], y2 = pts[k * 3 + 1], z2 = pts[k * 3 + 2];
       const float mag = (x2 * x2) + (y2 * y2) + (z2 * z2);
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(kFpsThreads) k_fps(const float* __restrict__ x
       const float d = (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1) + (z2 - z1) * (z2 - z1);
       const float d2 = fminf(d, tmp[k]);
       tmp[k] = d2;
-      Cand c{d2, k % Bv, k};
+      Cand c{d2, __brev((unsigned)(k % Bv)), k};
       if (better(c, best)) best = c;
     }
 #pragma unroll

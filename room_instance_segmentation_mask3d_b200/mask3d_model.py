@@ -1,0 +1,320 @@
+"""Host-side mirror of the reference model on the hot path: Res16UNet34C backbone + Mask3D query decoder.
+
+State-dict names and shapes are identical to the reference's modules (reference: mask3d/models/res16unet.py:28-314,
+mask3d/models/resnet.py:99-152, mask3d/models/modules/resnet_block.py:7-68, mask3d/models/mask3d.py:73-259), so a
+reference checkpoint loads with `load_state_dict`.  Two execution paths:
+
+  * `forward`        composes the MinkowskiEngine-compatible modules of `me_api` exactly like the reference does
+                     (autograd-capable; what the unmodified reference code would execute on the shim);
+  * `forward_fused`  inference fast path: calls the kernels directly, keeps activations in the compute dtype
+                     (bf16 on the tcgen05 path), fuses InstanceNorm + residual + ReLU + cast into one pass, replaces the
+                     decoder's per-scene Python loops / padding / dense masks by varlen kernels.
+
+The architecture is written from the layer table, not from the reference's source text.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import me_api as ME
+from . import ops
+from .engine import CoordinateMapKey
+
+LAYERS = (2, 3, 4, 6, 2, 2, 2, 2)
+PLANES = (32, 64, 128, 256, 256, 128, 96, 96)
+INIT_DIM = 32
+
+
+def _conv(cin, cout, k, stride=1, bias=False):
+    return ME.MinkowskiConvolution(cin, cout, kernel_size=k, stride=stride, dilation=1, bias=bias, dimension=3)
+
+
+def _conv_tr(cin, cout):
+    return ME.MinkowskiConvolutionTranspose(cin, cout, kernel_size=2, stride=2, dilation=1, bias=False, dimension=3)
+
+
+class BasicBlock(nn.Module):
+    """conv3 -> IN -> ReLU -> conv3 -> IN -> (+ 1x1 conv + IN of the input when widths differ) -> ReLU."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv1, self.norm1 = _conv(cin, cout, 3), ME.MinkowskiInstanceNorm(cout)
+        self.conv2, self.norm2 = _conv(cout, cout, 3), ME.MinkowskiInstanceNorm(cout)
+        self.relu = ME.MinkowskiReLU(inplace=True)
+        self.downsample = nn.Sequential(_conv(cin, cout, 1), ME.MinkowskiInstanceNorm(cout)) if cin != cout else None
+
+    def forward(self, x):
+        out = self.relu(self.norm1(self.conv1(x)))
+        out = self.norm2(self.conv2(out))
+        out += x if self.downsample is None else self.downsample(x)
+        return self.relu(out)
+
+
+def _stage(cin, cout, n):
+    return nn.Sequential(*[BasicBlock(cin if i == 0 else cout, cout) for i in range(n)])
+
+
+class Res16UNet34C(nn.Module):
+    """Sparse U-Net: 4 stride-2 encoder levels, 4 transposed-conv decoder levels with skip concatenation."""
+
+    PLANES, LAYERS = PLANES, LAYERS
+
+    def __init__(self, in_channels=1, out_channels=1, conv1_kernel_size=5, out_fpn=True):
+        super().__init__()
+        self.out_fpn, self.D = out_fpn, 3
+        P, L = PLANES, LAYERS
+        self.conv0p1s1, self.bn0 = _conv(in_channels, INIT_DIM, conv1_kernel_size), ME.MinkowskiInstanceNorm(INIT_DIM)
+        widths = [INIT_DIM, P[0], P[1], P[2], P[3]]  # block output width per level 0..4
+        for lvl in range(1, 5):
+            cin = widths[lvl - 1]
+            setattr(self, f"conv{lvl}p{2 ** (lvl - 1)}s2", _conv(cin, cin, 2, stride=2))
+            setattr(self, f"bn{lvl}", ME.MinkowskiInstanceNorm(cin))
+            setattr(self, f"block{lvl}", _stage(cin, P[lvl - 1], L[lvl - 1]))
+        cur = P[3]
+        for j, lvl in enumerate(range(4, 0, -1)):
+            up = P[4 + j]
+            setattr(self, f"convtr{4 + j}p{2 ** lvl}s2", _conv_tr(cur, up))
+            setattr(self, f"bntr{4 + j}", ME.MinkowskiInstanceNorm(up))
+            setattr(self, f"block{5 + j}", _stage(up + widths[lvl - 1], up, L[4 + j]))
+            cur = up
+        self.final = _conv(P[7], out_channels, 1, bias=True)  # constructed, never called (res16unet.py:231-238)
+        self.relu = ME.MinkowskiReLU(inplace=True)
+
+    # ---- module path (reference composition, res16unet.py:241-314)
+    def forward(self, x):
+        skips = [self.relu(self.bn0(self.conv0p1s1(x)))]
+        out = skips[0]
+        for lvl in range(1, 5):
+            out = self.relu(getattr(self, f"bn{lvl}")(getattr(self, f"conv{lvl}p{2 ** (lvl - 1)}s2")(out)))
+            out = getattr(self, f"block{lvl}")(out)
+            skips.append(out)
+        fmaps = [out]
+        for j, lvl in enumerate(range(4, 0, -1)):
+            out = self.relu(getattr(self, f"bntr{4 + j}")(getattr(self, f"convtr{4 + j}p{2 ** lvl}s2")(out)))
+            out = ME.cat(out, skips[lvl - 1])
+            out = getattr(self, f"block{5 + j}")(out)
+            fmaps.append(out)
+        return (out, fmaps) if self.out_fpn else out
+
+    # ---- fused inference path
+    @torch.no_grad()
+    def forward_fused(self, x: ME.SparseTensor):
+        mgr = x.coordinate_manager
+        mode = ops.get_compute_mode()
+        act = torch.float32 if mode == "fp32" else torch.bfloat16
+        B = mgr.number_of_unique_batch_indices()
+        keys = [x.coordinate_map_key]
+        for _ in range(4):
+            keys.append(mgr.stride(keys[-1], 2))
+        offs = [mgr.scene_offsets(k) for k in keys]
+
+        def cn(f, conv, norm, km, lvl, relu=True, residual=None, kind=0):
+            if kind == 2 and mode == "fp32":
+                y = ops.conv_transpose_forward_fp32(f, conv.kernel, km)
+            else:
+                y = ops.conv_forward(f, conv.kernel, km, bias=conv.bias, mode=mode, out_dtype=act)
+            return ops.instance_norm(y, offs[lvl], B, norm.weight, norm.bias, residual=residual, relu=relu, out_dtype=act)
+
+        def block(f, blk, lvl):
+            km3 = mgr.neighbor_table(keys[lvl], keys[lvl], 3, 1)
+            h = cn(f, blk.conv1, blk.norm1, km3, lvl)
+            res = f
+            if blk.downsample is not None:
+                res = cn(f, blk.downsample[0], blk.downsample[1], mgr.neighbor_table(keys[lvl], keys[lvl], 1, 1), lvl, relu=False)
+            return cn(h, blk.conv2, blk.norm2, km3, lvl, relu=True, residual=res)
+
+        ks0 = self.conv0p1s1.kernel_generator.kernel_size
+        f = cn(x.F, self.conv0p1s1, self.bn0, mgr.neighbor_table(keys[0], keys[0], ks0, 1), 0)
+        skips = [f]
+        for lvl in range(1, 5):
+            km = mgr.neighbor_table(keys[lvl - 1], keys[lvl], 2, 1)
+            f = cn(f, getattr(self, f"conv{lvl}p{2 ** (lvl - 1)}s2"), getattr(self, f"bn{lvl}"), km, lvl)
+            for blk in getattr(self, f"block{lvl}"):
+                f = block(f, blk, lvl)
+            skips.append(f)
+        fmaps = [f]
+        for j, lvl in enumerate(range(4, 0, -1)):
+            plan = mgr.transpose_plan(keys[lvl], keys[lvl - 1], 2, 1)
+            f = cn(f, getattr(self, f"convtr{4 + j}p{2 ** lvl}s2"), getattr(self, f"bntr{4 + j}"), plan, lvl - 1, kind=2)
+            f = torch.cat([f, skips[lvl - 1]], dim=1)
+            for blk in getattr(self, f"block{5 + j}"):
+                f = block(f, blk, lvl - 1)
+            fmaps.append(f)
+        wrap = lambda t, k: ME.SparseTensor(t, coordinate_map_key=k, coordinate_manager=mgr)
+        out = wrap(f, keys[0])
+        fm = [wrap(t, keys[4 - i]) for i, t in enumerate(fmaps)]
+        return (out, fm) if self.out_fpn else out
+
+
+# ----------------------------------------------------------------------------------------------------
+# decoder
+# ----------------------------------------------------------------------------------------------------
+class _GaussPE(nn.Module):
+    """Holds the `pos_enc.gauss_B` buffer [3, 64] (position_embedding.py:72-74)."""
+
+    def __init__(self, d_pos=128, gauss_scale=1.0):
+        super().__init__()
+        self.register_buffer("gauss_B", torch.empty(3, d_pos // 2).normal_() * gauss_scale)
+
+
+class _MLP(nn.Module):
+    """GenericMLP(use_conv=True, hidden=[d], output_use_activation=True): Conv1d-ReLU-Conv1d-ReLU under `.layers`."""
+
+    def __init__(self, d):
+        super().__init__()
+        self.layers = nn.Sequential(nn.Conv1d(d, d, 1, bias=True), nn.ReLU(), nn.Conv1d(d, d, 1, bias=True), nn.ReLU())
+
+
+class CrossAttentionLayer(nn.Module):
+    def __init__(self, d, h):
+        super().__init__()
+        self.multihead_attn, self.norm = nn.MultiheadAttention(d, h, dropout=0.0), nn.LayerNorm(d)
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+
+
+class SelfAttentionLayer(nn.Module):
+    def __init__(self, d, h):
+        super().__init__()
+        self.self_attn, self.norm = nn.MultiheadAttention(d, h, dropout=0.0), nn.LayerNorm(d)
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+
+
+class FFNLayer(nn.Module):
+    def __init__(self, d, dff):
+        super().__init__()
+        self.linear1, self.linear2, self.norm = nn.Linear(d, dff), nn.Linear(dff, d), nn.LayerNorm(d)
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+
+
+class Mask3D(nn.Module):
+    """Default reference configuration (mask3d/conf/model/mask3d.yaml): non-parametric queries (FPS + fourier PE), shared
+    decoder, post-norm, dropout 0, no level embedding, is_eval=True (keys never subsampled, trainer.py:274)."""
+
+    def __init__(self, backbone: Optional[Res16UNet34C] = None, hidden_dim=128, num_queries=25, num_heads=8, dim_feedforward=1024,
+                 num_classes=1, num_decoders=3, hlevels=(0, 1, 2, 3), gauss_scale=1.0):
+        super().__init__()
+        self.backbone = backbone if backbone is not None else Res16UNet34C()
+        self.mask_dim, self.num_queries, self.num_heads = hidden_dim, num_queries, num_heads
+        self.num_decoders, self.hlevels, self.num_classes = num_decoders, tuple(hlevels), num_classes
+        sizes = PLANES[-5:]
+        d = hidden_dim
+        self.mask_features_head = _conv(PLANES[7], d, 1, bias=True)
+        self.query_projection = _MLP(d)
+        self.mask_embed_head = nn.Sequential(nn.Linear(d, d), nn.ReLU(), nn.Linear(d, d))
+        self.class_embed_head = nn.Linear(d, num_classes + 1)
+        self.pos_enc = _GaussPE(d, gauss_scale)
+        self.pooling = ME.MinkowskiAvgPooling(kernel_size=2, stride=2, dimension=3)
+        mk = lambda f: nn.ModuleList([nn.ModuleList([f(i) for i in range(len(self.hlevels))])])
+        self.cross_attention = mk(lambda i: CrossAttentionLayer(d, num_heads))
+        self.self_attention = mk(lambda i: SelfAttentionLayer(d, num_heads))
+        self.ffn_attention = mk(lambda i: FFNLayer(d, dim_feedforward))
+        self.lin_squeeze = mk(lambda i: nn.Linear(sizes[self.hlevels[i]], d))
+        self.decoder_norm = nn.LayerNorm(d)
+        self._derived: Dict[Tuple[int, str], Tuple[int, torch.Tensor]] = {}
+
+    def _d(self, p: torch.Tensor, tag: str, fn):
+        """cache of derived weight layouts (transposes / slices), invalidated by the parameter's version counter"""
+        k = (p.data_ptr(), tag)
+        e = self._derived.get(k)
+        if e is None or e[0] != p._version:
+            e = (p._version, fn(p.detach()).contiguous())
+            self._derived[k] = e
+        return e[1]
+
+    @torch.no_grad()
+    def forward(self, x: ME.SparseTensor, is_eval: bool = True) -> dict:
+        """Fused inference forward.  Returns the fields of the reference's ModelOutput (mask3d.py:28-47)."""
+        mgr = x.coordinate_manager
+        mode = ops.get_compute_mode()
+        act = torch.float32 if mode == "fp32" else torch.bfloat16
+        B, Q, H, D = mgr.number_of_unique_batch_indices(), self.num_queries, self.num_heads, self.mask_dim
+        backbone_out, fmaps = self.backbone.forward_fused(x)
+        keys = [fm.coordinate_map_key for fm in fmaps]  # coarse -> fine (L4 .. L0)
+        nl = len(fmaps)
+        offs = [mgr.scene_offsets(k) for k in keys]
+        gB = self.pos_enc.gauss_B
+
+        # coordinate pyramid (avg-pooled voxel coordinates, mask3d.py:286-299) and per-level fourier PE (:261-278)
+        cf = [None] * nl
+        cf[nl - 1] = x.C[:, 1:4].float().contiguous()
+        pool_km = [None] * nl  # pool_km[i]: level i+1 (finer) -> level i
+        for i in range(nl - 2, -1, -1):
+            pool_km[i] = mgr.neighbor_table(keys[i + 1], keys[i], 2, 1)
+            cf[i] = ops.pool_forward(cf[i + 1], pool_km[i], average=True)
+        pe = []
+        for i in range(nl):
+            cmin, cmax = ops.scene_minmax(cf[i], offs[i], B)
+            pe.append(ops.fourier_pe(cf[i], offs[i], B, cmin, cmax, gB, out_dtype=torch.float32))
+            if i == nl - 1:
+                mins0, maxs0 = cmin, cmax
+
+        km1 = mgr.neighbor_table(keys[-1], keys[-1], 1, 1)
+        mask_features = ops.conv_forward(backbone_out.F, self.mask_features_head.kernel, km1, bias=self.mask_features_head.bias,
+                                         mode=mode, out_dtype=act)
+
+        # non-parametric queries: FPS over the input voxel coordinates + fourier PE of the sampled points (:308-338)
+        fps_idx = ops.furthest_point_sample(cf[nl - 1], offs[-1], B, Q).long()  # scene-local
+        sampled = cf[nl - 1][(fps_idx + offs[-1][:B, None].long()).reshape(-1)]  # [B*Q, 3]
+        q_off = torch.arange(0, (B + 1) * Q, Q, dtype=torch.int32, device=sampled.device)
+        qpos = ops.fourier_pe(sampled, q_off, B, mins0, maxs0, gB, out_dtype=torch.float32)  # [B*Q, D]
+        l0, l2 = self.query_projection.layers[0], self.query_projection.layers[2]
+        qpos = F.relu(F.linear(F.relu(F.linear(qpos, l0.weight.squeeze(-1), l0.bias)), l2.weight.squeeze(-1), l2.bias))
+        query_pos = qpos.view(B, Q, D)
+        queries = torch.zeros_like(query_pos)
+
+        pred_class, pred_masks = [], []
+
+        def mask_module(queries, n_pool, want_mask):
+            qn = self.decoder_norm(queries)
+            emb = self.mask_embed_head(qn)
+            cls = self.class_embed_head(qn)
+            logits = ops.mask_logits(mask_features, offs[-1], B, emb)  # [N0, Q] fp32
+            blocked = None
+            if want_mask:
+                pooled = logits
+                for s in range(n_pool):
+                    pooled = ops.pool_forward(pooled, pool_km[nl - 2 - s], average=True)
+                blocked = ops.threshold_blocked(pooled)
+            return cls, logits, blocked
+
+        for _ in range(self.num_decoders):
+            for i, hl in enumerate(self.hlevels):
+                cls, logits, blocked = mask_module(queries, nl - hl - 1, True)
+                ca, sa, ff, sq = self.cross_attention[0][i], self.self_attention[0][i], self.ffn_attention[0][i], self.lin_squeeze[0][i]
+                kml = mgr.neighbor_table(keys[hl], keys[hl], 1, 1)
+                mha = ca.multihead_attn
+                Wsq = self._d(sq.weight, "T", lambda w: w.t())                                  # [C_l, D]
+                Wk = self._d(mha.in_proj_weight, "k", lambda w: w[D:2 * D].t())                   # [D, D] (in, out)
+                Wv = self._d(mha.in_proj_weight, "v", lambda w: w[2 * D:].t())
+                src = ops.conv_forward(fmaps[hl].F, Wsq, kml, bias=sq.bias, mode=mode, out_dtype=torch.float32)
+                kin = src + pe[hl]
+                kp = ops.conv_forward(kin, Wk, kml, bias=mha.in_proj_bias[D:2 * D], mode=mode, out_dtype=act)
+                vp = ops.conv_forward(src, Wv, kml, bias=mha.in_proj_bias[2 * D:], mode=mode, out_dtype=act)
+                qp = F.linear(queries + query_pos, mha.in_proj_weight[:D], mha.in_proj_bias[:D])
+                ctx = ops.masked_cross_attention(qp, kp, vp, blocked, offs[hl], H)
+                out = ca.norm(queries + F.linear(ctx, mha.out_proj.weight, mha.out_proj.bias))
+                # self-attention over the Q queries of each scene + FFN: [B, Q, D]-sized, stock torch
+                qk = (out + query_pos).transpose(0, 1)
+                t2, _ = sa.self_attn(qk, qk, out.transpose(0, 1), need_weights=False)
+                out = sa.norm(out + t2.transpose(0, 1))
+                queries = ff.norm(out + ff.linear2(F.relu(ff.linear1(out))))
+                pred_class.append(cls)
+                pred_masks.append(logits)
+        cls, logits, _ = mask_module(queries, 0, False)
+        pred_class.append(cls)
+        pred_masks.append(logits)
+        off0 = mgr.scene_offsets_host(keys[-1])
+        split = lambda t: [t[off0[b]:off0[b + 1]] for b in range(B)]
+        return dict(pred_class=pred_class[-1], pred_class_all_decoders=pred_class, pred_mask=split(pred_masks[-1]),
+                    pred_mask_all_decoders=pred_masks, sampled_coords=sampled.view(B, Q, 3), backbone_features=backbone_out,
+                    queries=queries, fps_idx=fps_idx)

@@ -1,0 +1,97 @@
+"""CPU-side checks (no GPU): oracle vs golden fixture, state-dict compatibility, C-ABI symbol export, host logic."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "mask3d_tiny2.npz")
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    from room_instance_segmentation_mask3d_b200 import build, lib
+
+    path = build.build()
+    assert os.path.exists(path)
+    cdll = ctypes.CDLL(path)
+    header = open(os.path.join(ROOT, "include", "mk3d.h")).read()
+    declared = set(re.findall(r"\b(mk_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(cdll, name), f"libmk3d.so does not export {name}"
+    assert declared == set(lib.EXPORTED_SYMBOLS), declared ^ set(lib.EXPORTED_SYMBOLS)
+    lib.load()
+    assert lib.query("mk_version") == 1
+    assert lib.query("mk_hash_capacity", 1000) == 2048
+
+
+def test_product_fails_loudly_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from room_instance_segmentation_mask3d_b200 import me_api
+
+    with pytest.raises(RuntimeError):
+        me_api.SparseTensor(features=torch.ones(3, 1), coordinates=torch.zeros(3, 4, dtype=torch.int32))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "room_instance_segmentation_mask3d_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+                assert "/root/reference" not in src, f"{f} names the reference path"
+
+
+def test_state_dict_matches_reference_names_and_shapes():
+    from room_instance_segmentation_mask3d_b200 import mask3d_model
+
+    g = np.load(GOLD)
+    ref = {n: tuple(int(d) for d in s.split(",") if d) for n, s in zip(g["names"], g["shapes"])}
+    sd = mask3d_model.Mask3D().state_dict()
+    mine = {k: tuple(v.shape) for k, v in sd.items()}
+    assert set(mine) == set(ref), (set(mine) ^ set(ref))
+    for k in ref:
+        assert mine[k] == ref[k], (k, mine[k], ref[k])
+    assert sum(int(np.prod(s)) for s in ref.values() if True) > 39_000_000
+
+
+def test_oracle_replays_reference_golden():
+    """oracle/mask3d_oracle.py (the functional restatement that travels to the GPU box) against the fixture written by the
+    reference's unmodified modules."""
+    from oracle import mask3d_oracle, me_oracle
+    from room_instance_segmentation_mask3d_b200 import weights
+
+    g = np.load(GOLD)
+    spec = [(n, tuple(int(d) for d in s.split(",") if d)) for n, s in zip(g["names"], g["shapes"])]
+    sd = {k: torch.from_numpy(v) for k, v in weights.synth_state_dict(spec).items()}
+    x = me_oracle.SparseTensor(features=torch.from_numpy(g["feats"]), coordinates=torch.from_numpy(g["coords"]))
+    with torch.no_grad():
+        o = mask3d_oracle.mask3d_forward(sd, x)
+    assert np.array_equal(o["backbone_out"].F.numpy(), g["backbone_out"])
+    assert np.array_equal(o["sampled_coords"].numpy(), g["sampled_coords"])
+    assert np.abs(torch.cat(o["pred_masks"][-1]).numpy() - g["pred_mask_last"]).max() < 1e-3 * np.abs(g["pred_mask_last"]).max()
+    assert np.abs(torch.stack(o["pred_class"]).numpy() - g["pred_class"]).max() < 1e-3 * np.abs(g["pred_class"]).max()
+    mgr = x.coordinate_manager
+    for lvl, ts in enumerate((1, 2, 4, 8, 16)):
+        assert np.array_equal(mgr.get_coordinates(me_oracle.CoordinateMapKey((ts,) * 3)).numpy(), g[f"coords_l{lvl}"])
+
+
+def test_s200k_scene_statistics():
+    """SURVEY.md section 8 header figures, regenerated from the repo's own generator + oracle."""
+    from oracle import me_oracle as O
+    from room_instance_segmentation_mask3d_b200 import scenes
+
+    s = scenes.box_room()
+    assert len(s) == 223_648
+    c, _ = scenes.collate([s])
+    sizes = [len(c)]
+    cur = c
+    for lvl in range(1, 5):
+        cur = O.stride_coords(cur, (2 ** lvl,) * 3)
+        sizes.append(len(cur))
+    assert sizes == [223_648, 55_328, 13_626, 3_360, 794]

@@ -1,0 +1,328 @@
+"""GPU parity: every kernel family of libmk3d.so (called through the C ABI) against the CPU oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): maps / indices bit-exact; conv, norm, pooling, mask logits, attention within
+1e-3 relative in fp32 mode; bf16 tensor-core mode is compared (a) against the oracle fed the SAME bf16-rounded operands
+(tests the kernel: tolerance 2e-3 of the output scale, fp32 accumulation order differs) and (b) against the fp32 oracle
+with the stated bf16 tolerance 3e-2.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fps_oracle, me_oracle as O
+from room_instance_segmentation_mask3d_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def R():
+    from room_instance_segmentation_mask3d_b200 import engine, lib, me_api, ops
+
+    lib.load()
+
+    class NS:
+        pass
+
+    ns = NS()
+    ns.engine, ns.lib, ns.me, ns.ops = engine, lib, me_api, ops
+    return ns
+
+
+def make_batch(seed=0, with_dups=False):
+    sc = [scenes.tiny_scene(seed), scenes.tiny_scene(seed + 1, (20, 16, 10)), scenes.tiny_scene(seed + 2, (9, 30, 7), 1)]
+    coords, feats = scenes.collate(sc)
+    if with_dups:
+        rng = np.random.default_rng(seed)
+        dup = rng.integers(0, len(coords), size=len(coords) // 3)
+        coords = np.concatenate([coords, coords[dup]], 0)
+        order = np.argsort(coords[:, 0], kind="stable")  # keep batches contiguous, duplicates interleaved at the end of each
+        coords = coords[order]
+    return coords
+
+
+# ------------------------------------------------------------------------------------------ coordinate maps
+@pytest.mark.parametrize("with_dups", [False, True])
+def test_insert_and_map_bit_exact(R, with_dups):
+    coords = make_batch(3, with_dups)
+    mgr = R.engine.CoordinateManager(D=3)
+    key, (uniq, inv) = mgr.insert_and_map(torch.from_numpy(coords).cuda())
+    u_ref, inv_ref = O.insert_and_map(coords)
+    assert np.array_equal(uniq.cpu().numpy(), u_ref)
+    assert np.array_equal(inv.cpu().numpy(), inv_ref)
+    assert np.array_equal(mgr.get_coordinates(key).cpu().numpy(), coords[u_ref])
+
+
+def test_empty_and_single(R):
+    mgr = R.engine.CoordinateManager(D=3)
+    key, (uniq, inv) = mgr.insert_and_map(torch.zeros((0, 4), dtype=torch.int32).cuda())
+    assert mgr.size(key) == 0 and uniq.numel() == 0
+    mgr = R.engine.CoordinateManager(D=3)
+    key, _ = mgr.insert_and_map(torch.tensor([[0, -5, 7, 9]], dtype=torch.int32).cuda())
+    assert mgr.size(key) == 1
+
+
+def test_out_of_range_coordinate_raises(R):
+    mgr = R.engine.CoordinateManager(D=3)
+    with pytest.raises(RuntimeError):
+        mgr.insert_and_map(torch.tensor([[0, 1 << 17, 0, 0]], dtype=torch.int32).cuda())
+
+
+def test_stride_maps_bit_exact(R):
+    coords = make_batch(5)
+    mgr = R.engine.CoordinateManager(D=3)
+    key, _ = mgr.insert_and_map(torch.from_numpy(coords).cuda())
+    ref = coords
+    for lvl in range(1, 5):
+        key = mgr.stride(key, 2)
+        ts = (2 ** lvl,) * 3
+        ref = O.stride_coords(ref, ts)
+        assert key.tensor_stride == ts
+        assert np.array_equal(mgr.get_coordinates(key).cpu().numpy(), ref), f"level {lvl}"
+
+
+@pytest.mark.parametrize("ksize,stride", [(3, 1), (5, 1), (2, 2), (1, 1)])
+def test_kernel_map_bit_exact(R, ksize, stride):
+    coords = make_batch(7)
+    mgr = R.engine.CoordinateManager(D=3)
+    k_in, _ = mgr.insert_and_map(torch.from_numpy(coords).cuda())
+    k_out = mgr.stride(k_in, stride)
+    km = mgr.neighbor_table(k_in, k_out, ksize, 1)
+    out_coords = mgr.get_coordinates(k_out).cpu().numpy()
+    ref = O.neighbor_table(coords, out_coords, O.kernel_offsets((ksize,) * 3, (1,) * 3, (1,) * 3))
+    assert np.array_equal(km.nbr.cpu().numpy(), ref)
+    assert km.num_pairs == int((ref >= 0).sum())
+    # ME-visible dict form (canonical: sorted by out row)
+    d = mgr.kernel_map(k_in, k_out, stride=stride, kernel_size=ksize)
+    dref = O.kernel_map_from_table(ref)
+    assert sorted(d) == sorted(dref)
+    for k in dref:
+        assert np.array_equal(d[k].cpu().numpy(), dref[k])
+    # per-tile offset masks
+    if ksize ** 3 <= 32:
+        kmask = km.tile_kmask.cpu().numpy().view(np.uint32)
+        for t in range(len(kmask)):
+            sl = ref[:, t * 128:(t + 1) * 128]
+            want = sum(1 << k for k in range(ref.shape[0]) if (sl[k] >= 0).any())
+            assert int(kmask[t]) == want
+
+
+def test_kernel_map_on_strided_level(R):
+    coords = make_batch(9)
+    mgr = R.engine.CoordinateManager(D=3)
+    k0, _ = mgr.insert_and_map(torch.from_numpy(coords).cuda())
+    k1 = mgr.stride(k0, 2)
+    k2 = mgr.stride(k1, 2)
+    c1, c2 = mgr.get_coordinates(k1).cpu().numpy(), mgr.get_coordinates(k2).cpu().numpy()
+    km = mgr.neighbor_table(k1, k1, 3, 1)
+    assert np.array_equal(km.nbr.cpu().numpy(), O.neighbor_table(c1, c1, O.kernel_offsets((3,) * 3, (1,) * 3, (2,) * 3)))
+    km = mgr.neighbor_table(k1, k2, 2, 1)
+    assert np.array_equal(km.nbr.cpu().numpy(), O.neighbor_table(c1, c2, O.kernel_offsets((2,) * 3, (1,) * 3, (2,) * 3)))
+
+
+def test_hash_query(R):
+    coords = make_batch(1)
+    mgr = R.engine.CoordinateManager(D=3)
+    key, _ = mgr.insert_and_map(torch.from_numpy(coords).cuda())
+    cm = mgr.coord_map(key)
+    q = np.concatenate([coords[::7], coords[::11] + np.array([0, 1000, 0, 0], dtype=np.int32)])
+    rows = torch.empty(len(q), dtype=torch.int32, device="cuda")
+    R.lib.call("mk_hash_query", R.lib.p(cm.keys), R.lib.p(cm.vals), cm.cap, R.lib.p(torch.from_numpy(q).cuda()), len(q), R.lib.p(rows), R.lib.stream())
+    want = np.concatenate([np.arange(len(coords))[::7], -np.ones(len(coords[::11]), dtype=np.int64)])
+    assert np.array_equal(rows.cpu().numpy(), want)
+
+
+# ------------------------------------------------------------------------------------------ convolution
+def _conv_setup(R, cin, cout, ksize, stride=1, seed=0):
+    coords = make_batch(seed)
+    mgr = R.engine.CoordinateManager(D=3)
+    k_in, _ = mgr.insert_and_map(torch.from_numpy(coords).cuda())
+    k_out = mgr.stride(k_in, stride)
+    km = mgr.neighbor_table(k_in, k_out, ksize, 1)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(len(coords), cin, generator=g)
+    W = torch.randn(ksize ** 3, cin, cout, generator=g) / np.sqrt(cin * ksize ** 3)
+    bias = torch.randn(1, cout, generator=g) * 0.1
+    return mgr, k_in, k_out, km, x, W, bias
+
+
+@pytest.mark.parametrize("cin,cout,ksize,stride", [(32, 32, 3, 1), (96, 96, 3, 1), (128, 96, 3, 1), (32, 64, 2, 2), (48, 16, 3, 1)])
+def test_conv_fp32_parity(R, cin, cout, ksize, stride):
+    mgr, k_in, k_out, km, x, W, bias = _conv_setup(R, cin, cout, ksize, stride)
+    ref = O.conv_from_table(x, W, km.nbr.cpu().numpy(), km.n_out) + bias
+    out = R.ops.conv_forward(x.cuda(), W.cuda(), km, bias=bias.cuda(), mode="fp32")
+    assert rel_err(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("cin,cout,ksize,stride", [(32, 32, 3, 1), (64, 64, 3, 1), (96, 96, 3, 1), (128, 96, 3, 1), (192, 128, 3, 1),
+                                                  (384, 256, 3, 1), (256, 256, 3, 1), (32, 32, 2, 2), (128, 128, 2, 2), (96, 128, 1, 1),
+                                                  (16, 16, 3, 1)])
+def test_conv_bf16_tensor_core_parity(R, cin, cout, ksize, stride):
+    mgr, k_in, k_out, km, x, W, bias = _conv_setup(R, cin, cout, ksize, stride, seed=cin + cout)
+    xb, Wb = x.bfloat16().float(), W.bfloat16().float()
+    ref_same_operands = O.conv_from_table(xb, Wb, km.nbr.cpu().numpy(), km.n_out) + bias
+    ref_fp32 = O.conv_from_table(x, W, km.nbr.cpu().numpy(), km.n_out) + bias
+    out = R.ops.conv_forward(x.cuda(), W.cuda(), km, bias=bias.cuda(), mode="bf16", out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert rel_err(out, ref_same_operands) < 2e-3, "tcgen05 kernel disagrees with the oracle on identical bf16 operands"
+    assert rel_err(out, ref_fp32) < 3e-2
+    out_b = R.ops.conv_forward(x.cuda(), W.cuda(), km, bias=bias.cuda(), mode="bf16", out_dtype=torch.bfloat16)
+    assert rel_err(out_b.float(), ref_same_operands) < 1e-2
+
+
+def test_conv_stem_5x5x5(R):
+    mgr, k_in, k_out, km, x, W, bias = _conv_setup(R, 1, 32, 5, 1)
+    ref = O.conv_from_table(x, W, km.nbr.cpu().numpy(), km.n_out)
+    out = R.ops.conv_forward(x.cuda(), W.cuda(), km, mode="fp32")
+    assert rel_err(out, ref) < 1e-5
+    out = R.ops.conv_forward(x.cuda(), W.cuda(), km, mode="bf16", out_dtype=torch.float32)
+    assert rel_err(out, ref) < 1e-5  # the stem always runs in fp32 on CUDA cores
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-5), ("bf16", 3e-2)])
+def test_conv_transpose_parity(R, mode, tol):
+    coords = make_batch(11)
+    mgr = R.engine.CoordinateManager(D=3)
+    k0, _ = mgr.insert_and_map(torch.from_numpy(coords).cuda())
+    k1 = mgr.stride(k0, 2)
+    g = torch.Generator().manual_seed(1)
+    n1 = mgr.size(k1)
+    x = torch.randn(n1, 64, generator=g)
+    W = torch.randn(8, 64, 32, generator=g) / np.sqrt(64 * 8)
+    nbr_down = mgr.neighbor_table(k0, k1, 2, 1).nbr.cpu().numpy()
+    ref = O.conv_transpose_from_table(x if mode == "fp32" else x.bfloat16().float(), W if mode == "fp32" else W.bfloat16().float(), nbr_down, len(coords))
+    plan = mgr.transpose_plan(k1, k0, 2, 1)
+    if mode == "fp32":
+        out = R.ops.conv_transpose_forward_fp32(x.cuda(), W.cuda(), plan)
+    else:
+        out = R.ops.conv_forward(x.cuda(), W.cuda(), plan, mode="bf16", out_dtype=torch.float32)
+    assert rel_err(out, ref) < (tol if mode == "fp32" else 2e-3)
+
+
+# ------------------------------------------------------------------------------------------ norm / pool
+@pytest.mark.parametrize("C", [32, 96, 256, 384])
+def test_instance_norm_parity(R, C):
+    coords = make_batch(13)
+    mgr = R.engine.CoordinateManager(D=3)
+    key, _ = mgr.insert_and_map(torch.from_numpy(coords).cuda())
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(len(coords), C, generator=g) * 3 + 5  # large mean: exercises the shifted-sum statistics
+    gamma, beta = torch.randn(1, C, generator=g), torch.randn(1, C, generator=g)
+    res = torch.randn(len(coords), C, generator=g)
+    rows = [np.nonzero(coords[:, 0] == b)[0] for b in range(int(coords[:, 0].max()) + 1)]
+    ref = torch.relu(O.instance_norm(x, rows, gamma, beta) + res)
+    off, B = mgr.scene_offsets(key), mgr.number_of_unique_batch_indices()
+    out = R.ops.instance_norm(x.cuda(), off, B, gamma.cuda(), beta.cuda(), residual=res.cuda(), relu=True)
+    assert rel_err(out, ref) < 1e-4
+    out_b = R.ops.instance_norm(x.cuda().bfloat16(), off, B, gamma.cuda(), beta.cuda(), relu=False, out_dtype=torch.float32)
+    ref_b = O.instance_norm(x.bfloat16().float(), rows, gamma, beta)
+    assert rel_err(out_b, ref_b) < 1e-4
+
+
+def test_avg_pool_parity(R):
+    coords = make_batch(17)
+    mgr = R.engine.CoordinateManager(D=3)
+    k0, _ = mgr.insert_and_map(torch.from_numpy(coords).cuda())
+    k1 = mgr.stride(k0, 2)
+    km = mgr.neighbor_table(k0, k1, 2, 1)
+    x = torch.randn(len(coords), 25)
+    for avg in (True, False):
+        ref = O.avg_pool_from_table(x, km.nbr.cpu().numpy(), km.n_out, average=avg)
+        out = R.ops.pool_forward(x.cuda(), km, average=avg)
+        assert rel_err(out, ref) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------ decoder pieces
+def test_mask_logits_and_threshold(R):
+    coords = make_batch(19)
+    mgr = R.engine.CoordinateManager(D=3)
+    key, _ = mgr.insert_and_map(torch.from_numpy(coords).cuda())
+    off, B = mgr.scene_offsets(key), mgr.number_of_unique_batch_indices()
+    g = torch.Generator().manual_seed(3)
+    feat = torch.randn(len(coords), 128, generator=g)
+    for Q in (25, 100):
+        emb = torch.randn(B, Q, 128, generator=g)
+        ref = torch.cat([feat[coords[:, 0] == b] @ emb[b].T for b in range(B)])
+        out = R.ops.mask_logits(feat.cuda(), off, B, emb.cuda())
+        assert rel_err(out, ref) < 1e-5
+        blocked = R.ops.threshold_blocked(out)
+        assert torch.equal(blocked.cpu().bool(), out.cpu().sigmoid() < 0.5)
+
+
+def test_fourier_pe_parity(R):
+    from oracle.mask3d_oracle import fourier_pos_enc
+
+    coords = make_batch(23)
+    mgr = R.engine.CoordinateManager(D=3)
+    key, _ = mgr.insert_and_map(torch.from_numpy(coords).cuda())
+    off, B = mgr.scene_offsets(key), mgr.number_of_unique_batch_indices()
+    xyz = torch.from_numpy(coords[:, 1:]).float()
+    gB = torch.randn(3, 64, generator=torch.Generator().manual_seed(5))
+    cmin, cmax = R.ops.scene_minmax(xyz.cuda(), off, B)
+    pe = R.ops.fourier_pe(xyz.cuda(), off, B, cmin, cmax, gB.cuda())
+    for b in range(B):
+        sel = coords[:, 0] == b
+        c = xyz[sel]
+        ref = fourier_pos_enc(c[None], gB, c.min(0)[0][None], c.max(0)[0][None])[0].T
+        assert torch.equal(cmin[b].cpu(), c.min(0)[0]) and torch.equal(cmax[b].cpu(), c.max(0)[0])
+        assert (pe.cpu()[sel] - ref).abs().max() < 2e-4  # sin/cos of arguments up to ~50 rad: a few ulp of the argument
+
+
+@pytest.mark.parametrize("Q", [25, 100])
+def test_masked_cross_attention_vs_stock_mha(R, Q):
+    """Reference formulation: pad to max K, dense bool mask, all-blocked rule, stock MHA (mask3d.py:400-478)."""
+    torch.manual_seed(Q)
+    D, H, B = 128, 8, 3
+    sizes = [700, 37, 1300]
+    off = torch.tensor([0] + list(np.cumsum(sizes)), dtype=torch.int32)
+    n = sum(sizes)
+    mha = torch.nn.MultiheadAttention(D, H)
+    query = torch.randn(Q, B, D)
+    key_in = torch.randn(n, D)
+    val_in = torch.randn(n, D)
+    blocked = torch.rand(n, Q) < 0.6
+    blocked[off[1]:off[2], 3] = True  # query 3 blocks every key of scene 1 -> must attend to all of them
+    blocked[:, 5] = True              # query 5 blocks everything everywhere
+    Kmax = max(sizes)
+    kpad, vpad, mpad = torch.zeros(Kmax, B, D), torch.zeros(Kmax, B, D), torch.ones(B, Kmax, Q, dtype=torch.bool)
+    for b in range(B):
+        s, e = int(off[b]), int(off[b + 1])
+        idx = torch.zeros(Kmax, dtype=torch.long)
+        idx[: e - s] = torch.arange(e - s)
+        kpad[:, b], vpad[:, b] = key_in[s:e][idx], val_in[s:e][idx]
+        m = blocked[s:e][idx].clone()
+        mpad[b] = m
+    mpad.permute(0, 2, 1)[mpad.sum(1) == Kmax] = False
+    pad = torch.stack([torch.arange(Kmax) >= sz for sz in sizes])
+    mpad = torch.logical_or(mpad, pad[..., None])
+    with torch.no_grad():
+        ref, _ = mha(query, kpad, vpad, attn_mask=mpad.repeat_interleave(H, dim=0).permute(0, 2, 1))
+        Wq, Wk, Wv = mha.in_proj_weight.chunk(3)
+        bq, bk, bv = mha.in_proj_bias.chunk(3)
+        qp = (query.permute(1, 0, 2) @ Wq.T + bq).cuda()
+        kp = (key_in @ Wk.T + bk).cuda()
+        vp = (val_in @ Wv.T + bv).cuda()
+        ctx = R.ops.masked_cross_attention(qp, kp, vp, blocked.to(torch.uint8).cuda(), off.cuda(), H)
+        out = (ctx.cpu() @ mha.out_proj.weight.T + mha.out_proj.bias).permute(1, 0, 2)
+    # NOTE the reference pads with copies of row 0 but masks them, and its all-blocked test counts pads as blocked
+    # (sum == Kmax only if every real key is blocked too), so semantics coincide with the varlen kernel.
+    assert rel_err(out, ref) < 1e-4
+
+
+def test_fps_matches_reference_tie_breaking(R):
+    sc = [scenes.tiny_scene(0), scenes.tiny_scene(1, (20, 16, 10)), scenes.box_room((1.0, 1.2, 0.6), 0.02), scenes.tiny_scene(5, (7, 5, 4), 0)]
+    coords, _ = scenes.collate(sc)
+    off = torch.tensor([0] + list(np.cumsum([len(s) for s in sc])), dtype=torch.int32)
+    xyz = torch.from_numpy(coords[:, 1:]).float()
+    for m in (25, 100):
+        idx = R.ops.furthest_point_sample(xyz.cuda(), off.cuda(), len(sc), m).cpu().numpy()
+        for b, s in enumerate(sc):
+            if len(s) <= m:
+                continue
+            ref = fps_oracle.furthest_point_sample(s.astype(np.float32), m)
+            assert np.array_equal(idx[b], ref), f"scene {b}, m {m}"
