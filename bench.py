@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Benchmark of the Mask3D hot path on B200 (contract: see the task brief; one JSON line on stdout from rank 0).
+
+Workload (BASELINE.json configs[1]): full Mask3D inference — Res16UNet34C sparse-conv backbone + 12 masked-attention
+query-refinement layers, 25 queries — on a synthetic single-floor 6-room Structured3D-shaped scene voxelised at 2 cm
+(~0.89 M voxels), one scene per step per GPU, bf16 tensor-core mode (fp32 accumulate).  A step includes everything that
+depends on the scene: coordinate hashing, 4 strided coordinate maps, 14 kernel maps, backbone, decoder.
+
+  value   voxels/s with the scene's coordinates already resident in HBM
+  e2e     voxels/s through the public API from pinned HOST buffers, H2D of coordinates/features and D2H of the class
+          logits + final mask logits inside the timed region
+  --impl reference   the CPU restatement of the reference's MinkowskiEngine + PyTorch path (oracle/, "port": ME 0.5.4 is
+          not installable here) on all host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mask3D inference throughput (Res16UNet34C sparse-conv backbone + 12-layer masked-attention decoder)"
+UNIT = "voxels/s"
+
+
+def workload_config(voxel_m: float, n_scenes: int):
+    return {"workload": "BASELINE.json configs[1]: Mask3D full inference, synthetic single-floor 6-room scene "
+                        f"(10x8x2.8 m, surfaces + furniture), {voxel_m * 100:.0f} cm voxels, 25 queries, 1 scene per step per GPU",
+            "voxel_cm": voxel_m * 100, "scenes_cycled": n_scenes, "queries": 25, "decoder_layers": 12,
+            "l2_policy": "inputs larger than L2: ~0.9 M voxels x 96..384 channels per layer (>170 MB activations per layer), "
+                         "a different scene every step"}
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi, as the profiling recipe prescribes)
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        import subprocess
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port of the reference's ME + PyTorch path)
+# ----------------------------------------------------------------------------------------------------
+def cpu_forward_factory(num_queries=25):
+    import torch
+    from oracle import mask3d_oracle, me_oracle
+    from room_instance_segmentation_mask3d_b200 import mask3d_model, weights
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec = [(k, tuple(v.shape)) for k, v in mask3d_model.Mask3D(num_queries=num_queries).state_dict().items()]
+    sd = {k: torch.from_numpy(v) for k, v in weights.synth_state_dict(spec).items()}
+
+    def run(coords, feats):
+        x = me_oracle.SparseTensor(features=torch.from_numpy(feats), coordinates=torch.from_numpy(coords))
+        with torch.no_grad():
+            o = mask3d_oracle.mask3d_forward(sd, x, num_queries=num_queries)
+        return o
+
+    return run
+
+
+def cpu_sample_scene(target_voxels: float):
+    """The same floor-plan generator at the finest voxel size whose voxel count stays under `target_voxels`."""
+    from room_instance_segmentation_mask3d_b200 import scenes
+
+    n15 = 14633.0  # floor_plan(seed=1000) at 15 cm
+    for v in (0.02, 0.03, 0.04, 0.05, 0.06, 0.08, 0.10, 0.15):
+        if n15 * (0.15 / v) ** 2 * 1.1 <= target_voxels or v == 0.15:
+            s = scenes.floor_plan(1000, voxel_m=v)
+            return v, scenes.collate([s])
+
+
+def time_cpu(budget_s: float, steps: int, warmup: int):
+    run = cpu_forward_factory()
+    from room_instance_segmentation_mask3d_b200 import scenes
+
+    c, f = scenes.collate([scenes.floor_plan(1000, voxel_m=0.15)])
+    t0 = time.perf_counter(); run(c, f); t_cal = time.perf_counter() - t0  # calibration: ~15 k voxels
+    thr = len(c) / t_cal
+    per_step = budget_s / max(steps + warmup, 1)
+    v, (coords, feats) = cpu_sample_scene(max(thr * per_step * 1.5, 15000))  # larger scenes run at better voxels/s than the calibration
+    for _ in range(warmup):
+        run(coords, feats)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter(); run(coords, feats); ts.append(time.perf_counter() - t0)
+    t = float(np.median(ts))
+    return len(coords) / t, t, v, len(coords)
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    steps, warmup = args.steps, args.warmup
+    val, t, v, n = time_cpu(150.0, steps, warmup)
+    cores = os.cpu_count() or 1
+    sample = f"floor_plan(seed=1000) at {v * 100:.0f} cm voxels = {n} voxels, one full Mask3D forward per step (median of {steps})"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(0.02, 3),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "note": "CPU restatement of the reference's MinkowskiEngine-CPU algorithm (hash maps, per-offset index_select -> "
+                                     f"mm -> index_add_) + stock PyTorch decoder; torch threads = {torch.get_num_threads()}"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from room_instance_segmentation_mask3d_b200 import lib, mask3d_model, me_api, ops, scenes, weights
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib.load()
+    ops.set_compute_mode(args.mode)
+    voxel = args.voxel_cm / 100.0
+    n_scenes = 3
+    host_scenes = [scenes.collate([scenes.floor_plan(1000 + rank * 16 + i, voxel_m=voxel)]) for i in range(n_scenes)]
+    model = mask3d_model.Mask3D().eval()
+    weights.load_synth(model, seed=0)
+    model = model.to(dev)
+
+    pinned = [(torch.from_numpy(c).pin_memory(), torch.from_numpy(f).pin_memory()) for c, f in host_scenes]
+    resident = [(c.to(dev), f.to(dev)) for c, f in pinned]
+    nvox = [c.shape[0] for c, _ in host_scenes]
+
+    def step_resident(i):
+        c, f = resident[i % n_scenes]
+        return model(me_api.SparseTensor(features=f, coordinates=c))
+
+    h_cls = torch.empty((13, 1, 25, 2), dtype=torch.float32).pin_memory()
+    h_mask = [torch.empty((n, 25), dtype=torch.float32).pin_memory() for n in nvox]
+
+    def step_e2e(i):
+        c, f = pinned[i % n_scenes]
+        cd, fd = c.to(dev, non_blocking=True), f.to(dev, non_blocking=True)
+        o = model(me_api.SparseTensor(features=fd, coordinates=cd))
+        h_cls.copy_(torch.stack(o["pred_class_all_decoders"]), non_blocking=True)
+        h_mask[i % n_scenes].copy_(o["pred_mask_all_decoders"][-1], non_blocking=True)
+        return o
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.kernel_launches
+    ms = timed(step_resident, args.steps)
+    launches = lib.kernel_launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    vox_per_step = float(np.mean([nvox[i % n_scenes] for i in range(args.steps)]))
+    value = world * vox_per_step * args.steps / (ms * 1e-3)
+
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = world * vox_per_step * args.steps / (ms_e2e * 1e-3)
+    h2d = int(np.mean([c.numel() * 4 + f.numel() * 4 for c, f in pinned]))
+    d2h = int(h_cls.numel() * 4 + np.mean([m.numel() * 4 for m in h_mask]))
+
+    # per-launch CUDA events around the dominant kernel (k_conv_umma) over extra instrumented steps
+    roofline = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+        ev = lib.instrument(["mk_conv_fwd_bf16"])
+        isteps = min(args.steps, 3)
+        torch.cuda.synchronize()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for i in range(isteps):
+            step_resident(i)
+        t1.record()
+        torch.cuda.synchronize()
+        lib.instrument(None)
+        recs = ev["mk_conv_fwd_bf16"]
+        tot_ms = sum(s.elapsed_time(e) for s, e, _ in recs)
+        tot_flops = sum(t[0] for _, _, t in recs)
+        n_launch = len(recs)
+        by_shape = {}
+        for s, e, t in recs:
+            k = f"K{t[1]}_{t[2]}x{t[3]}"
+            a = by_shape.setdefault(k, [0.0, 0.0, 0])
+            a[0] += t[0]; a[1] += s.elapsed_time(e); a[2] += 1
+        top = sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:6]
+        achieved = tot_flops / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
+        roofline = {"kernel": "k_conv_umma (tcgen05 gather-GEMM sparse conv)", "bound": "tensor", "achieved": achieved, "peak": peak,
+                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "launches_per_step": n_launch / isteps, "flops_per_launch_avg": tot_flops / max(n_launch, 1),
+                    "ms_per_launch_avg": tot_ms / max(n_launch, 1), "share_of_step": tot_ms / t0.elapsed_time(t1),
+                    "by_shape_tflops": {k: round(v[0] / (v[1] * 1e-3) / 1e12, 1) for k, v in top},
+                    "by_shape_ms_per_step": {k: round(v[1] / isteps, 3) for k, v in top}}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        val, t, v, n = time_cpu(25.0, 1, 0)
+        cpu_baseline = {"value": val, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                        "sample": f"floor_plan(seed=1000) at {v * 100:.0f} cm voxels = {n} voxels, one full Mask3D forward ({t:.1f} s)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic", "config": workload_config(voxel, n_scenes),
+                "scenes_per_sec": world * args.steps / (ms * 1e-3), "voxels_per_scene": vox_per_step,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--voxel-cm", type=float, default=2.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_ours(a)

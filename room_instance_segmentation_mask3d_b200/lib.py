@@ -118,7 +118,35 @@ def stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# kernels launched per C-ABI call (memsets not counted) — bench.py reports the total as `gpu_launches`
+_KERNELS_PER_CALL = {"mk_coordmap_build": 7, "mk_instnorm_stats": 2, "mk_masked_xattn_fwd": 3, "mk_instnorm_bwd": 3}
+kernel_launches = 0
+_timed = None  # optional {entry-point name: [(start_event, end_event, tag), ...]} filled when bench.py instruments a step
+_tag = None
+
+
+def instrument(names=None):
+    """Start collecting CUDA-event pairs around the named entry points (None = stop)."""
+    global _timed
+    _timed = {n: [] for n in names} if names else None
+    return _timed
+
+
+def set_tag(tag) -> None:
+    global _tag
+    _tag = tag
+
+
 def call(name: str, *args) -> None:
+    global kernel_launches
+    kernel_launches += _KERNELS_PER_CALL.get(name, 1)
+    if _timed is not None and name in _timed:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        _check(getattr(load(), name)(*args), name)
+        e.record()
+        _timed[name].append((s, e, _tag))
+        return
     _check(getattr(load(), name)(*args), name)
 
 

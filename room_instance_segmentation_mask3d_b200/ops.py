@@ -92,6 +92,8 @@ def conv_forward(x: torch.Tensor, W: torch.Tensor, km: KernelMap, bias: Optional
     xb = cast(x.contiguous(), torch.bfloat16)
     img = weight_image(W, transpose=transpose_w)
     out = torch.empty((km.n_out, cout), dtype=out_dtype, device=x.device)
+    if lib._timed is not None:  # bench.py instrumentation: algorithmic FLOPs = 2 * P * Cin * Cout
+        lib.set_tag((2 * km.num_pairs * cin * cout, K, cin, cout, km.n_out))
     lib.call("mk_conv_fwd_bf16", lib.p(xb), cin, lib.p(img), cout, lib.p(km.nbr), K, km.n_slots, lib.p(km.out_rows), lib.p(km.tile_kmask),
              lib.p(kidx), km.n_out, lib.p(bias_flat), lib.p(out), lib.dt(out), lib.stream())
     return out
