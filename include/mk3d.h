@@ -71,6 +71,11 @@ int mk_tile_kmask(const int32_t* nbr, int K, int64_t n_slots, uint32_t* tile_kma
  * parent[f] and koff[f] for every fine row f. */
 int mk_transpose_map(const int32_t* nbr_down, int K, int64_t n_coarse, int64_t n_fine, int32_t* parent, int32_t* koff,
                      void* stream);
+/* Mask-sorted tile plans: masks[o] = bitmask over k of present neighbours of slot o (K <= 32); the host sorts slots by
+ * (coarse row chunk, mask) so that every 128-slot tile has (almost) a single mask, then permutes the table:
+ * out[k, s] = nbr[k, order[s]]  (order[s] < 0 -> -1, a padding slot). */
+int mk_row_kmask(const int32_t* nbr, int K, int64_t n, uint32_t* masks, void* stream);
+int mk_permute_table(const int32_t* nbr, int K, int64_t n, const int32_t* order, int64_t n_slots, int32_t* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (3) Sparse convolution.  Replaces ME ConvolutionForwardGPU / ConvolutionTransposeForwardGPU reached from
@@ -90,10 +95,12 @@ int mk_conv_weight_image_bf16(const float* W, int K, int cin, int cout, int tran
 /* tcgen05 path: bf16 operands, fp32 accumulation in TMEM.  `in` bf16 [n_in,cin] (cin % 16 == 0), nbr int32
  * [K,n_slots], out_rows int32 [n_slots] or NULL (slot == output row), tile_kmask from mk_tile_kmask,
  * kidx int32 [K] or NULL: weight-image index used for table row k (dgrad passes the mirrored offset),
- * bias fp32 [cout] or NULL, out [n_out,cout] of out_dtype.  Persistent: grid = #SMs. */
+ * bias fp32 [cout] or NULL, out [n_out,out_stride] of out_dtype of which the first out_cols (<= cout) columns are
+ * written (0 = cout; used by the mask-logit product whose Q = 25 queries are padded to 32 accumulator columns).
+ * Persistent: grid = #SMs. */
 int mk_conv_fwd_bf16(const void* in, int cin, const void* wimg, int cout, const int32_t* nbr, int K, int64_t n_slots,
                      const int32_t* out_rows, const uint32_t* tile_kmask, const int32_t* kidx, int64_t n_out,
-                     const float* bias, void* out, int out_dtype, void* stream);
+                     const float* bias, void* out, int out_dtype, int out_cols, int out_stride, void* stream);
 /* Stem: Cin == 1, K up to 125 (5^3): pure lookup, CUDA cores.  in fp32 [n_in], W fp32 [K,1,cout]. */
 int mk_conv_stem_f32(const float* in, const float* W, int cout, const int32_t* nbr, int K, int64_t n_out, void* out,
                      int out_dtype, void* stream);
@@ -139,7 +146,7 @@ int mk_mask_logits(const void* feat, int x_dtype, int64_t n, int C, const int32_
 /* One pooling step on logits followed (optionally) by the threshold: blocked[o,q] = sigmoid(pooled) < 0.5. */
 int mk_pool_threshold(const float* pooled, int64_t n, int Q, uint8_t* blocked, void* stream);
 /* Per-scene min / max of fp32 [n,3] coordinates (input_range of the fourier embedding, mask3d.py:267-268,323-328). */
-int mk_scene_minmax(const float* xyz, const int32_t* scene_offsets, int B, float* cmin, float* cmax, void* stream);
+int mk_scene_minmax(const float* xyz, int64_t n, const int32_t* scene_offsets, int B, float* cmin, float* cmax, void* stream);
 /* Fourier positional encoding with normalisation (mask3d/models/position_embedding.py:127-156):
  * out[n, :] = (base[n, :] if base else 0) + [sin(p), cos(p)], p = ((xyz - min_b) / (max_b - min_b) * 2pi) @ gauss_B.
  * gauss_B fp32 [3, D/2]; base / out [n, D]. */
@@ -159,10 +166,12 @@ int mk_masked_xattn_fwd(const float* qp, const void* kp, const void* vp, int kv_
 /* ---------------------------------------------------------------------------------------------
  * (7) Furthest point sampling.  Replaces pointnet2._ext.furthest_point_sampling
  * (mask3d/third_party/pointnet2/_ext_src/src/sampling_gpu.cu:72-176; call site mask3d/models/mask3d.py:309-317)
- * with identical tie-breaking; all scenes in one launch.  xyz fp32 [n,3], temp fp32 [n] scratch, idx int32 [B,m]
- * (indices local to the scene).
+ * with identical tie-breaking; all scenes together, many CTAs per scene, one launch per sampling round.
+ * xyz fp32 [n_total,3], temp fp32 [n_total] scratch, idx int32 [B,m] (indices local to the scene).
  * ------------------------------------------------------------------------------------------- */
-int mk_fps(const float* xyz, const int32_t* scene_offsets, int B, int m, float* temp, int32_t* idx, void* stream);
+int64_t mk_fps_workspace_bytes(int B, int m);
+int mk_fps(const float* xyz, const int32_t* scene_offsets, int B, int m, int64_t n_total, float* temp, int32_t* idx,
+           void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Casts (plumbing between fp32 module boundaries and the bf16 tensor-core path).

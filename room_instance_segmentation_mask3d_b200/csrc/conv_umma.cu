@@ -32,7 +32,6 @@ constexpr int kMmaWarp = 4;
 constexpr int kLoadWarp = 5;
 constexpr int kFirstEpiWarp = 6;
 constexpr int kNumThreads = 320;
-constexpr int kLag = 2;                    // cp.async groups in flight per producer thread before it signals
 constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
 
@@ -152,6 +151,8 @@ struct ConvParams {
   int num_tiles;
   int num_stages;
   int nchunks;
+  int out_cols;    // columns actually stored (<= cout; the rest of the accumulator is padding)
+  int out_stride;  // elements between consecutive output rows
 };
 
 struct Ring {
@@ -167,7 +168,8 @@ struct Ring {
   }
 };
 
-template <typename TOut>
+// kLag: cp.async groups a producer thread keeps in flight before it signals the oldest one (gather latency hiding)
+template <typename TOut, int kLag>
 __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x A 16 KB][stages x B cout*128][barriers]
@@ -327,12 +329,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
       int64_t orow = -1;
       if (slot < p.n_slots) orow = p.out_rows ? (int64_t)p.out_rows[slot] : slot;
       if (orow >= p.n_out) orow = -1;
-      TOut* optr = orow >= 0 ? (TOut*)p.out + orow * p.cout : nullptr;
+      TOut* optr = orow >= 0 ? (TOut*)p.out + orow * p.out_stride : nullptr;
+      const bool vec_ok = ((p.out_stride * (int)sizeof(TOut)) & 15) == 0;
       if (kmask != 0) {
         mbar_wait(smem_u32(&tmem_full[acc_buf]), acc_phase);
         tc_fence_after();
       }
-      for (int c0 = 0; c0 < p.cout; c0 += 16) {
+      for (int c0 = 0; c0 < p.out_cols; c0 += 16) {
         float v[16];
         if (kmask != 0) {
           uint32_t r[16];
@@ -346,11 +349,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
         }
         if (p.bias) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += p.bias[c0 + j];
+          for (int j = 0; j < 16; ++j) v[j] += (c0 + j < p.out_cols) ? p.bias[c0 + j] : 0.f;
         }
         if (optr) {
+          if (vec_ok && c0 + 16 <= p.out_cols) {
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) store4(optr + c0 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+            for (int j = 0; j < 16; j += 4) store4(optr + c0 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < p.out_cols) optr[c0 + j] = from_f32<TOut>(v[j]);
+          }
         }
       }
       if (kmask != 0) {
@@ -423,11 +432,14 @@ int mk_conv_weight_image_bf16(const float* W, int K, int cin, int cout, int tran
 
 int mk_conv_fwd_bf16(const void* in, int cin, const void* wimg, int cout, const int32_t* nbr, int K, int64_t n_slots,
                      const int32_t* out_rows, const uint32_t* tile_kmask, const int32_t* kidx, int64_t n_out,
-                     const float* bias, void* out, int out_dtype, void* stream_) {
+                     const float* bias, void* out, int out_dtype, int out_cols, int out_stride, void* stream_) {
   MK_REQUIRE(mk_device_supported(), "tcgen05 path needs an sm_100 device (B200)");
   MK_REQUIRE(cin % 16 == 0 && cin >= 16, "cin must be a multiple of 16");
   MK_REQUIRE(cout % 16 == 0 && cout >= 16 && cout <= 256, "cout must be a multiple of 16 in [16,256]");
   MK_REQUIRE(K >= 1 && K <= 32, "K must be <= 32 (per-tile offset bitmask)");
+  if (out_cols <= 0) out_cols = cout;
+  if (out_stride <= 0) out_stride = out_cols;
+  MK_REQUIRE(out_cols <= cout && out_stride >= out_cols, "out_cols <= cout and out_stride >= out_cols required");
   MK_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)wimg & 15) == 0 && ((uintptr_t)out & 15) == 0, "16-byte alignment");
   if (n_slots == 0) return 0;
   ConvParams p;
@@ -446,21 +458,37 @@ int mk_conv_fwd_bf16(const void* in, int cin, const void* wimg, int cout, const 
   p.K = K;
   p.num_tiles = (int)ceil_div(n_slots, kTileM);
   p.nchunks = (cin + kChunkElems - 1) / kChunkElems;
+  p.out_cols = out_cols;
+  p.out_stride = out_stride;
   int stages = kMaxStages;
-  while (stages > kLag + 1 && conv_smem_bytes(cout, stages) > 200 * 1024) --stages;
+  while (stages > 3 && conv_smem_bytes(cout, stages) > 210 * 1024) --stages;
   MK_REQUIRE(conv_smem_bytes(cout, stages) <= 227 * 1024, "shared memory budget exceeded");
   p.num_stages = stages;
   const size_t smem = conv_smem_bytes(cout, stages);
   int grid = num_sms();
   if (grid > p.num_tiles) grid = p.num_tiles;
   cudaStream_t st = (cudaStream_t)stream_;
-  if (out_dtype == MK_F32) {
-    cudaFuncSetAttribute(k_conv_umma<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_conv_umma<float><<<grid, kNumThreads, smem, st>>>(p);
-  } else {
-    cudaFuncSetAttribute(k_conv_umma<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_conv_umma<__nv_bfloat16><<<grid, kNumThreads, smem, st>>>(p);
-  }
+  // producers keep (lag + 1) stages of gathers in flight; the ring must be strictly deeper than that
+  const int lag = stages >= 8 ? 5 : (stages >= 6 ? 4 : (stages >= 5 ? 3 : (stages >= 4 ? 2 : 1)));
+#define MK_LAUNCH(T, L)                                                                                     \
+  do {                                                                                                      \
+    cudaFuncSetAttribute(k_conv_umma<T, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+    k_conv_umma<T, L><<<grid, kNumThreads, smem, st>>>(p);                                                  \
+  } while (0)
+#define MK_LAUNCH_T(T)              \
+  do {                              \
+    switch (lag) {                  \
+      case 5: MK_LAUNCH(T, 5); break; \
+      case 4: MK_LAUNCH(T, 4); break; \
+      case 3: MK_LAUNCH(T, 3); break; \
+      case 2: MK_LAUNCH(T, 2); break; \
+      default: MK_LAUNCH(T, 1); break; \
+    }                               \
+  } while (0)
+  if (out_dtype == MK_F32) MK_LAUNCH_T(float);
+  else MK_LAUNCH_T(__nv_bfloat16);
+#undef MK_LAUNCH_T
+#undef MK_LAUNCH
   return check_launch(__func__);
 }
 

@@ -233,6 +233,26 @@ __global__ void __launch_bounds__(MK_TILE_ROWS) k_tile_kmask(const int32_t* __re
   }
 }
 
+// per-slot offset bitmask: bit k set iff nbr[k, slot] >= 0  (K <= 32).  Slots with equal masks are grouped into the same
+// tensor-core tiles by the host (mask-sorted tile plan) so a tile's active-offset set equals its rows' set.
+__global__ void k_row_kmask(const int32_t* __restrict__ nbr, int K, int64_t n, uint32_t* __restrict__ masks) {
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t m = 0;
+    for (int k = 0; k < K; ++k) m |= (nbr[(int64_t)k * n + o] >= 0 ? 1u : 0u) << k;
+    masks[o] = m;
+  }
+}
+
+// nbr_sorted[k, s] = nbr[k, order[s]]
+__global__ void k_permute_table(const int32_t* __restrict__ nbr, int64_t n, const int32_t* __restrict__ order, int64_t n_slots,
+                                int32_t* __restrict__ out) {
+  const int k = blockIdx.y;
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += (int64_t)gridDim.x * blockDim.x) {
+    const int o = order[s];
+    out[(int64_t)k * n_slots + s] = o >= 0 ? nbr[(int64_t)k * n + o] : -1;
+  }
+}
+
 __global__ void k_transpose_map(const int32_t* __restrict__ nbr_down, int K, int64_t n_coarse,
                                 int32_t* __restrict__ parent, int32_t* __restrict__ koff) {
   const int k = blockIdx.y;
@@ -335,6 +355,24 @@ int mk_tile_kmask(const int32_t* nbr, int K, int64_t n_slots, uint32_t* tile_kma
   if (n_slots == 0) return check_launch(__func__);
   k_tile_kmask<<<(unsigned)ceil_div(n_slots, MK_TILE_ROWS), MK_TILE_ROWS, 0, st>>>(nbr, K, n_slots, tile_kmask,
                                                                                    (unsigned long long*)pair_count);
+  return check_launch(__func__);
+}
+
+int mk_row_kmask(const int32_t* nbr, int K, int64_t n, uint32_t* masks, void* stream_) {
+  MK_REQUIRE(K >= 1 && K <= 32, "K must be <= 32");
+  if (n == 0) return 0;
+  int64_t bx = ceil_div(n, 256);
+  if (bx > 8 * num_sms()) bx = 8 * num_sms();
+  k_row_kmask<<<(unsigned)bx, 256, 0, (cudaStream_t)stream_>>>(nbr, K, n, masks);
+  return check_launch(__func__);
+}
+
+int mk_permute_table(const int32_t* nbr, int K, int64_t n, const int32_t* order, int64_t n_slots, int32_t* out, void* stream_) {
+  if (n_slots == 0) return 0;
+  int64_t bx = ceil_div(n_slots, 256);
+  if (bx > 8 * num_sms()) bx = 8 * num_sms();
+  dim3 grid((unsigned)bx, (unsigned)K);
+  k_permute_table<<<grid, 256, 0, (cudaStream_t)stream_>>>(nbr, n, order, n_slots, out);
   return check_launch(__func__);
 }
 

@@ -62,10 +62,28 @@ __global__ void __launch_bounds__(kMlThreads) k_mask_logits(const T* __restrict_
 // ---------------------------------------------------------------------------------------------------
 // per-scene min / max of fp32 [n,3] coordinates
 // ---------------------------------------------------------------------------------------------------
+// order-preserving float <-> uint map so that min / max can use integer atomics
+__device__ __forceinline__ unsigned f2ord(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o); }
+
+__global__ void k_minmax_init(unsigned* __restrict__ omin, unsigned* __restrict__ omax, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    omin[i] = 0xffffffffu;
+    omax[i] = 0u;
+  }
+}
+
+// grid (chunks, B)
 __global__ void __launch_bounds__(256) k_scene_minmax(const float* __restrict__ xyz, const int32_t* __restrict__ scene_offsets,
-                                                      float* __restrict__ cmin, float* __restrict__ cmax) {
-  const int b = blockIdx.x;
-  const int64_t s = scene_offsets[b], e = scene_offsets[b + 1];
+                                                      int rows_per_chunk, unsigned* __restrict__ omin, unsigned* __restrict__ omax) {
+  const int b = blockIdx.y;
+  const int64_t s = (int64_t)scene_offsets[b] + (int64_t)blockIdx.x * rows_per_chunk;
+  const int64_t e = min((int64_t)scene_offsets[b + 1], s + rows_per_chunk);
+  if (s >= e) return;
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   for (int64_t r = s + threadIdx.x; r < e; r += blockDim.x) {
 #pragma unroll
@@ -75,7 +93,6 @@ __global__ void __launch_bounds__(256) k_scene_minmax(const float* __restrict__ 
       mx[a] = fmaxf(mx[a], v);
     }
   }
-  __shared__ float smn[8][3], smx[8][3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
 #pragma unroll
@@ -87,19 +104,17 @@ __global__ void __launch_bounds__(256) k_scene_minmax(const float* __restrict__ 
   if ((threadIdx.x & 31) == 0) {
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      smn[threadIdx.x >> 5][a] = mn[a];
-      smx[threadIdx.x >> 5][a] = mx[a];
+      atomicMin(&omin[b * 3 + a], f2ord(mn[a]));
+      atomicMax(&omax[b * 3 + a], f2ord(mx[a]));
     }
   }
-  __syncthreads();
-  if (threadIdx.x < 3) {
-    float lo = FLT_MAX, hi = -FLT_MAX;
-    for (int w = 0; w < 8; ++w) {
-      lo = fminf(lo, smn[w][threadIdx.x]);
-      hi = fmaxf(hi, smx[w][threadIdx.x]);
-    }
-    cmin[b * 3 + threadIdx.x] = lo;
-    cmax[b * 3 + threadIdx.x] = hi;
+}
+
+__global__ void k_minmax_finish(unsigned* __restrict__ omin, unsigned* __restrict__ omax, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    reinterpret_cast<float*>(omin)[i] = ord2f(omin[i]);
+    reinterpret_cast<float*>(omax)[i] = ord2f(omax[i]);
   }
 }
 
@@ -223,29 +238,48 @@ __global__ void __launch_bounds__(1024) k_xattn_partial(const float* __restrict_
   }
 }
 
-__global__ void __launch_bounds__(1024) k_xattn_combine(const float* __restrict__ partial, int nsplit, int Q, int D, int H,
-                                                        float* __restrict__ ctx) {
-  const int b = blockIdx.x, t = threadIdx.x;
+// grid (ceil(Q*H / 8), B), block 256: warp w handles (query, head) pair 8*blockIdx.x + w; its 32 lanes fold the splits
+// lane, lane+32, ... in ascending order (online-softmax merge), then the lanes are merged by a fixed shuffle tree.
+__global__ void __launch_bounds__(256) k_xattn_combine(const float* __restrict__ partial, int nsplit, int Q, int D, int H,
+                                                       float* __restrict__ ctx) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (t >= Q * H) return;
   const int hd = D / H, q = t / H, h = t % H;
-  float m = -INFINITY;
-  for (int s = 0; s < nsplit; ++s) m = fmaxf(m, partial[(((int64_t)b * nsplit + s) * Q * H + t) * (2 + kXaMaxHd)]);
-  float l = 0.f, acc[kXaMaxHd];
+  float m = -INFINITY, l = 0.f, acc[kXaMaxHd];
 #pragma unroll
   for (int j = 0; j < kXaMaxHd; ++j) acc[j] = 0.f;
-  for (int s = 0; s < nsplit; ++s) {  // fixed order
+  for (int s = lane; s < nsplit; s += 32) {
     const float* p = partial + (((int64_t)b * nsplit + s) * Q * H + t) * (2 + kXaMaxHd);
-    if (p[1] == 0.f) continue;
-    const float w = expf(p[0] - m);
-    l += p[1] * w;
+    const float pm = p[0], pl = p[1];
+    if (pl == 0.f) continue;
+    const float mn = fmaxf(m, pm);
+    const float c0 = expf(m - mn), c1 = expf(pm - mn);
+    l = l * c0 + pl * c1;
 #pragma unroll
     for (int j = 0; j < kXaMaxHd; ++j)
-      if (j < hd) acc[j] = fmaf(p[2 + j], w, acc[j]);
+      if (j < hd) acc[j] = acc[j] * c0 + p[2 + j] * c1;
+    m = mn;
   }
-  const float inv = 1.f / l;
 #pragma unroll
-  for (int j = 0; j < kXaMaxHd; ++j)
-    if (j < hd) ctx[((int64_t)b * Q + q) * D + h * hd + j] = acc[j] * inv;
+  for (int d = 16; d > 0; d >>= 1) {
+    const float om = __shfl_down_sync(0xffffffffu, m, d), ol = __shfl_down_sync(0xffffffffu, l, d);
+    const float mn = fmaxf(m, om);
+    const float c0 = (m == -INFINITY) ? 0.f : expf(m - mn), c1 = (om == -INFINITY) ? 0.f : expf(om - mn);
+    l = l * c0 + ol * c1;
+#pragma unroll
+    for (int j = 0; j < kXaMaxHd; ++j) {
+      const float oa = __shfl_down_sync(0xffffffffu, acc[j], d);
+      if (j < hd) acc[j] = acc[j] * c0 + oa * c1;
+    }
+    m = mn;
+  }
+  if (lane == 0) {
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int j = 0; j < kXaMaxHd; ++j)
+      if (j < hd) ctx[((int64_t)b * Q + q) * D + h * hd + j] = acc[j] * inv;
+  }
 }
 
 inline int xattn_splits(int64_t n, int B) {
@@ -282,8 +316,16 @@ int mk_mask_logits(const void* feat, int x_dtype, int64_t n, int C, const int32_
   return check_launch(__func__);
 }
 
-int mk_scene_minmax(const float* xyz, const int32_t* scene_offsets, int B, float* cmin, float* cmax, void* stream_) {
-  k_scene_minmax<<<B, 256, 0, (cudaStream_t)stream_>>>(xyz, scene_offsets, cmin, cmax);
+int mk_scene_minmax(const float* xyz, int64_t n, const int32_t* scene_offsets, int B, float* cmin, float* cmax, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (B <= 0) return 0;
+  int64_t chunks = ceil_div(2 * (int64_t)num_sms(), B);
+  int64_t rpc = ceil_div(n > 0 ? n : 1, chunks);
+  if (rpc < 1024) rpc = 1024;
+  chunks = ceil_div(n > 0 ? n : 1, rpc);
+  k_minmax_init<<<(unsigned)ceil_div(3 * B, 128), 128, 0, st>>>((unsigned*)cmin, (unsigned*)cmax, 3 * B);
+  k_scene_minmax<<<dim3((unsigned)chunks, (unsigned)B), 256, 0, st>>>(xyz, scene_offsets, (int)rpc, (unsigned*)cmin, (unsigned*)cmax);
+  k_minmax_finish<<<(unsigned)ceil_div(3 * B, 128), 128, 0, st>>>((unsigned*)cmin, (unsigned*)cmax, 3 * B);
   return check_launch(__func__);
 }
 
@@ -339,7 +381,7 @@ int mk_masked_xattn_fwd(const float* qp, const void* kp, const void* vp, int kv_
     if (hd16) MK_XA(__nv_bfloat16, 16); else MK_XA(__nv_bfloat16, 32);
   }
 #undef MK_XA
-  k_xattn_combine<<<B, threads, 0, st>>>(partial, splits, Q, D, H, ctx);
+  k_xattn_combine<<<dim3((unsigned)ceil_div(Q * H, 8), (unsigned)B), 256, 0, st>>>(partial, splits, Q, D, H, ctx);
   return check_launch(__func__);
 }
 

@@ -52,25 +52,45 @@ __global__ void __launch_bounds__(kNormThreads) k_in_stats_partial(const T* __re
   if (rl == 0) store4(out + 3 * C + 4 * cv, shift);
 }
 
-__global__ void k_in_stats_final(const float* __restrict__ partial, int C, int chunks_per_scene, float eps,
-                                 float* __restrict__ mean, float* __restrict__ rstd) {
-  const int b = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    double n = 0, mu = 0, m2 = 0;  // Chan et al. parallel merge, chunks in ascending order
-    for (int ch = 0; ch < chunks_per_scene; ++ch) {
+// grid (C / 32, B), block 256 = 32 channels x 8 chunk lanes.  Chunk statistics are merged with Chan's parallel formula in
+// fp64: lane l folds chunks l, l+8, ... in ascending order, then the 8 lanes are folded in ascending lane order by the
+// channel's lane-0 thread => a fixed merge tree, bit-reproducible.
+__global__ void __launch_bounds__(256) k_in_stats_final(const float* __restrict__ partial, int C, int chunks_per_scene, float eps,
+                                                        float* __restrict__ mean, float* __restrict__ rstd) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int lane = threadIdx.x >> 5;  // 0..7
+  __shared__ double sn[8][32], smu[8][32], sm2[8][32];
+  double n = 0, mu = 0, m2 = 0;
+  if (c < C) {
+    for (int ch = lane; ch < chunks_per_scene; ch += 8) {
       const float* p = partial + ((int64_t)(b * chunks_per_scene + ch)) * 4 * C;
-      double nb = p[c];
+      const double nb = p[c];
       if (nb <= 0) continue;
-      double s1 = p[C + c], s2 = p[2 * C + c], sh = p[3 * C + c];
-      double mub = sh + s1 / nb;
+      const double s1 = p[C + c], s2 = p[2 * C + c], sh = p[3 * C + c];
+      const double mub = sh + s1 / nb;
       double m2b = s2 - s1 * s1 / nb;
       if (m2b < 0) m2b = 0;
-      double d = mub - mu, nt = n + nb;
+      const double d = mub - mu, nt = n + nb;
       mu += d * nb / nt;
       m2 += m2b + d * d * n * nb / nt;
       n = nt;
     }
-    double var = n > 0 ? m2 / n : 0.0;
+  }
+  sn[lane][threadIdx.x & 31] = n;
+  smu[lane][threadIdx.x & 31] = mu;
+  sm2[lane][threadIdx.x & 31] = m2;
+  __syncthreads();
+  if (lane == 0 && c < C) {
+    for (int l = 1; l < 8; ++l) {
+      const double nb = sn[l][threadIdx.x], mub = smu[l][threadIdx.x], m2b = sm2[l][threadIdx.x];
+      if (nb <= 0) continue;
+      const double d = mub - mu, nt = n + nb;
+      mu += d * nb / nt;
+      m2 += m2b + d * d * n * nb / nt;
+      n = nt;
+    }
+    const double var = n > 0 ? m2 / n : 0.0;
     mean[b * C + c] = (float)mu;
     rstd[b * C + c] = (float)(1.0 / sqrt(var + (double)eps));
   }
@@ -177,7 +197,7 @@ __global__ void __launch_bounds__(256) k_in_bwd_dx(const float* __restrict__ x, 
 
 inline void norm_chunking(int64_t n, int B, int* rows_per_chunk, int* chunks_per_scene) {
   // target ~4 chunks per SM over the whole batch; chunks are per scene, sized for the largest possible scene (n)
-  int64_t target = 4 * (int64_t)num_sms();
+  int64_t target = 2 * (int64_t)num_sms();
   int64_t rpc = ceil_div(n > 0 ? n : 1, target);
   if (rpc < 64) rpc = 64;
   *rows_per_chunk = (int)rpc;
@@ -213,7 +233,7 @@ int mk_instnorm_stats(const void* x, int x_dtype, int64_t n, int C, const int32_
     k_in_stats_partial<float><<<grid, kNormThreads, smem, st>>>((const float*)x, C, scene_offsets, rpc, cps, partial);
   else
     k_in_stats_partial<__nv_bfloat16><<<grid, kNormThreads, smem, st>>>((const __nv_bfloat16*)x, C, scene_offsets, rpc, cps, partial);
-  k_in_stats_final<<<B, 128, 0, st>>>(partial, C, cps, eps, mean, rstd);
+  k_in_stats_final<<<dim3((unsigned)ceil_div(C, 32), (unsigned)B), 256, 0, st>>>(partial, C, cps, eps, mean, rstd);
   return check_launch(__func__);
 }
 

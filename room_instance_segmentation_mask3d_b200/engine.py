@@ -91,6 +91,7 @@ class KernelMap:
         self._kmask: Optional[torch.Tensor] = None
         self._pairs_dev: Optional[torch.Tensor] = None
         self._pairs: Optional[int] = None
+        self._sorted: Optional["KernelMap"] = None
 
     def _build_kmask(self):
         ntiles = (self.n_slots + lib.TILE - 1) // lib.TILE
@@ -98,6 +99,26 @@ class KernelMap:
         self._pairs_dev = torch.zeros(1, dtype=torch.int64, device=self.nbr.device)
         lib.call("mk_tile_kmask", lib.p(self.nbr), self.K, self.n_slots, lib.p(self._kmask) if self.K <= 32 else None,
                  lib.p(self._pairs_dev), lib.stream())
+
+    def sorted_plan(self, chunk_rows: int = 1 << 17) -> "KernelMap":
+        """Mask-sorted tile plan: output slots are reordered so that rows with the same set of present offsets share
+        tensor-core tiles (a lexicographic tile of a surface scene touches ~23 of 27 offsets, a mask-sorted one ~10, i.e.
+        2.3x less gather + MMA work).  Sorting is done inside chunks of `chunk_rows` consecutive rows so that a chunk's
+        gather working set stays L2-resident.  Slots map back to rows through `out_rows`."""
+        if self._sorted is None:
+            if self.K == 1 or self.K > 32 or self.out_rows is not None or self.n_out == 0:
+                self._sorted = self
+            else:
+                n, dev = self.n_out, self.nbr.device
+                masks = torch.empty(n, dtype=I32, device=dev)
+                lib.call("mk_row_kmask", lib.p(self.nbr), self.K, n, lib.p(masks), lib.stream())
+                key = (torch.arange(n, device=dev, dtype=torch.int64) // chunk_rows << 32) | (masks.long() & 0xFFFFFFFF)
+                order = torch.sort(key, stable=True).indices.to(I32)
+                nbr_s = torch.empty_like(self.nbr)
+                lib.call("mk_permute_table", lib.p(self.nbr), self.K, n, lib.p(order), n, lib.p(nbr_s), lib.stream())
+                self._sorted = KernelMap(nbr_s, self.K, n, order)
+                self._sorted._sorted = self._sorted
+        return self._sorted
 
     @property
     def tile_kmask(self) -> torch.Tensor:
@@ -231,6 +252,25 @@ class CoordinateManager:
             offs = self._offsets_dev(ks, dl, in_key.tensor_stride)
             lib.call("mk_kernel_map", lib.p(im.keys), lib.p(im.vals), im.cap, lib.p(om.coords), om.n, lib.p(offs), K, lib.p(nbr), lib.stream())
             km = KernelMap(nbr, K, om.n)
+            self._kmaps[ck] = km
+        return km
+
+    def scene_select_table(self, key) -> KernelMap:
+        """Table with one "offset" per scene: nbr[b, r] = r if row r belongs to scene b else -1.  Lets the tensor-core conv
+        kernel apply a different weight per scene (the mask-logit product, mask3d.py:534-535) with its per-tile offset mask."""
+        ck = ("scene_select", key)
+        km = self._kmaps.get(ck)
+        if km is None:
+            cm = self._maps[key]
+            B = self.number_of_unique_batch_indices()
+            rows = torch.arange(cm.n, device=self.device, dtype=I32)
+            if B <= 1:
+                nbr = rows[None, :].contiguous()
+            else:
+                b_of = cm.coords[:, 0]
+                nbr = torch.where(b_of[None, :] == torch.arange(B, device=self.device, dtype=I32)[:, None], rows[None, :],
+                                  torch.full((1, 1), -1, dtype=I32, device=self.device)).contiguous()
+            km = KernelMap(nbr, max(B, 1), cm.n)
             self._kmaps[ck] = km
         return km
 

@@ -35,7 +35,9 @@ _SIGS = {
     "mk_conv_weight_image_elems": (c_int64, [c_int, c_int, c_int, c_int]),
     "mk_conv_weight_image_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mk_conv_fwd_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
-                                 c_void_p, c_void_p, c_int, c_void_p]),
+                                 c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "mk_row_kmask": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "mk_permute_table": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "mk_conv_stem_f32": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_int, c_void_p]),
     "mk_conv_dgrad_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "mk_conv_wgrad_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
@@ -49,13 +51,14 @@ _SIGS = {
     "mk_pool_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_int64, c_void_p, c_void_p]),
     "mk_mask_logits": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "mk_pool_threshold": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
-    "mk_scene_minmax": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "mk_scene_minmax": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "mk_fourier_pe": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
                               c_void_p]),
     "mk_xattn_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int64]),
     "mk_masked_xattn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
                                     c_void_p, c_void_p, c_int64, c_void_p]),
-    "mk_fps": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "mk_fps_workspace_bytes": (c_int64, [c_int, c_int]),
+    "mk_fps": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "mk_cast": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p]),
     "mk_copy_channels": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
 }
@@ -119,7 +122,8 @@ def stream():
 
 
 # kernels launched per C-ABI call (memsets not counted) — bench.py reports the total as `gpu_launches`
-_KERNELS_PER_CALL = {"mk_coordmap_build": 7, "mk_instnorm_stats": 2, "mk_masked_xattn_fwd": 3, "mk_instnorm_bwd": 3}
+_KERNELS_PER_CALL = {"mk_coordmap_build": 7, "mk_instnorm_stats": 2, "mk_masked_xattn_fwd": 3, "mk_instnorm_bwd": 3, "mk_scene_minmax": 3,
+                     "mk_fps": 25}
 kernel_launches = 0
 _timed = None  # optional {entry-point name: [(start_event, end_event, tag), ...]} filled when bench.py instruments a step
 _tag = None

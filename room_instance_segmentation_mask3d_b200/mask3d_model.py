@@ -273,12 +273,13 @@ class Mask3D(nn.Module):
         queries = torch.zeros_like(query_pos)
 
         pred_class, pred_masks = [], []
+        sel0 = mgr.scene_select_table(keys[-1])
 
         def mask_module(queries, n_pool, want_mask):
             qn = self.decoder_norm(queries)
             emb = self.mask_embed_head(qn)
             cls = self.class_embed_head(qn)
-            logits = ops.mask_logits(mask_features, offs[-1], B, emb)  # [N0, Q] fp32
+            logits = ops.mask_logits(mask_features, offs[-1], B, emb, select=sel0)  # [N0, Q] fp32
             blocked = None
             if want_mask:
                 pooled = logits

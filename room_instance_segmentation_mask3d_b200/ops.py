@@ -15,6 +15,7 @@ from . import lib
 from .engine import KernelMap
 
 _MODE = "bf16"
+SORT_TILES = True  # mask-sorted tile plans for the tensor-core conv (engine.KernelMap.sorted_plan)
 
 
 def set_compute_mode(mode: str) -> None:
@@ -65,7 +66,8 @@ def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 # convolution
 # ----------------------------------------------------------------------------------------------------
 def conv_forward(x: torch.Tensor, W: torch.Tensor, km: KernelMap, bias: Optional[torch.Tensor] = None, mode: Optional[str] = None,
-                 out_dtype: Optional[torch.dtype] = None, kidx: Optional[torch.Tensor] = None, transpose_w: bool = False) -> torch.Tensor:
+                 out_dtype: Optional[torch.dtype] = None, kidx: Optional[torch.Tensor] = None, transpose_w: bool = False,
+                 out_cols: int = 0) -> torch.Tensor:
     """out[o] = sum_k x[nbr[k, o]] @ W[k] (+ bias).  W fp32 [K, cin, cout]; x [n_in, cin] fp32 or bf16."""
     mode = mode or _MODE
     W3 = W if W.dim() == 3 else W.unsqueeze(0)
@@ -91,11 +93,13 @@ def conv_forward(x: torch.Tensor, W: torch.Tensor, km: KernelMap, bias: Optional
     out_dtype = out_dtype or torch.bfloat16
     xb = cast(x.contiguous(), torch.bfloat16)
     img = weight_image(W, transpose=transpose_w)
-    out = torch.empty((km.n_out, cout), dtype=out_dtype, device=x.device)
+    ocols = out_cols or cout
+    out = torch.empty((km.n_out, ocols), dtype=out_dtype, device=x.device)
     if lib._timed is not None:  # bench.py instrumentation: algorithmic FLOPs = 2 * P * Cin * Cout
-        lib.set_tag((2 * km.num_pairs * cin * cout, K, cin, cout, km.n_out))
-    lib.call("mk_conv_fwd_bf16", lib.p(xb), cin, lib.p(img), cout, lib.p(km.nbr), K, km.n_slots, lib.p(km.out_rows), lib.p(km.tile_kmask),
-             lib.p(kidx), km.n_out, lib.p(bias_flat), lib.p(out), lib.dt(out), lib.stream())
+        lib.set_tag((2 * km.num_pairs * cin * ocols, K, cin, cout, km.n_out))
+    plan = km.sorted_plan() if SORT_TILES else km
+    lib.call("mk_conv_fwd_bf16", lib.p(xb), cin, lib.p(img), cout, lib.p(plan.nbr), K, plan.n_slots, lib.p(plan.out_rows), lib.p(plan.tile_kmask),
+             lib.p(kidx), km.n_out, lib.p(bias_flat), lib.p(out), lib.dt(out), ocols, ocols, lib.stream())
     return out
 
 
@@ -163,10 +167,19 @@ def pool_backward(dout: torch.Tensor, km: KernelMap, n_in: int, average: bool = 
     return din
 
 
-def mask_logits(feat: torch.Tensor, scene_offsets: torch.Tensor, B: int, embed: torch.Tensor) -> torch.Tensor:
-    """logits[n, q] = feat[n] . embed[b(n), q]   (mask3d.py:534-537)."""
+def mask_logits(feat: torch.Tensor, scene_offsets: torch.Tensor, B: int, embed: torch.Tensor, select: Optional[KernelMap] = None) -> torch.Tensor:
+    """logits[n, q] = feat[n] . embed[b(n), q]   (mask3d.py:534-537).
+
+    bf16 features + a scene-select table (engine.CoordinateManager.scene_select_table): the product runs on the tcgen05
+    kernel as a conv with one "offset" per scene, W[b] = embed[b]^T zero-padded to 32 accumulator columns per 32 queries,
+    storing only the Q real columns.  fp32 features: exact-fp32 CUDA-core kernel (parity mode)."""
     n, C = feat.shape
     Q = embed.shape[1]
+    if feat.dtype == torch.bfloat16 and select is not None and select.K <= 32 and C % 16 == 0 and Q <= 256:
+        Qp = ((Q + 15) // 16) * 16
+        W = torch.zeros((embed.shape[0], C, Qp), dtype=torch.float32, device=feat.device)
+        W[:, :, :Q] = embed.detach().float().transpose(1, 2)
+        return conv_forward(feat, W, select, mode="bf16", out_dtype=torch.float32, out_cols=Q)
     out = torch.empty((n, Q), dtype=torch.float32, device=feat.device)
     lib.call("mk_mask_logits", lib.p(feat.contiguous()), lib.dt(feat), n, C, lib.p(scene_offsets), B, lib.p(embed.detach().float().contiguous()),
              Q, lib.p(out), lib.stream())
@@ -183,7 +196,7 @@ def threshold_blocked(pooled: torch.Tensor) -> torch.Tensor:
 def scene_minmax(xyz: torch.Tensor, scene_offsets: torch.Tensor, B: int):
     cmin = torch.empty((B, 3), dtype=torch.float32, device=xyz.device)
     cmax = torch.empty((B, 3), dtype=torch.float32, device=xyz.device)
-    lib.call("mk_scene_minmax", lib.p(xyz.contiguous()), lib.p(scene_offsets), B, lib.p(cmin), lib.p(cmax), lib.stream())
+    lib.call("mk_scene_minmax", lib.p(xyz.contiguous()), xyz.shape[0], lib.p(scene_offsets), B, lib.p(cmin), lib.p(cmax), lib.stream())
     return cmin, cmax
 
 
@@ -216,6 +229,8 @@ def furthest_point_sample(xyz: torch.Tensor, scene_offsets: torch.Tensor, B: int
     """int32 [B, m] scene-local indices; tie-breaking identical to pointnet2's kernel (csrc/fps.cu)."""
     xyz = xyz.float().contiguous()
     temp = torch.empty(xyz.shape[0], dtype=torch.float32, device=xyz.device)
-    idx = torch.zeros((B, m), dtype=torch.int32, device=xyz.device)
-    lib.call("mk_fps", lib.p(xyz), lib.p(scene_offsets), B, m, lib.p(temp), lib.p(idx), lib.stream())
+    idx = torch.empty((B, m), dtype=torch.int32, device=xyz.device)
+    wsb = lib.query("mk_fps_workspace_bytes", B, m)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=xyz.device)
+    lib.call("mk_fps", lib.p(xyz), lib.p(scene_offsets), B, m, xyz.shape[0], lib.p(temp), lib.p(idx), lib.p(ws), wsb, lib.stream())
     return idx

@@ -254,6 +254,38 @@ def test_mask_logits_and_threshold(R):
         assert torch.equal(blocked.cpu().bool(), out.cpu().sigmoid() < 0.5)
 
 
+def test_mask_logits_tensor_core_path(R):
+    """bf16 features: the product runs on the tcgen05 conv kernel with one weight per scene (scene-select table)."""
+    coords = make_batch(29)
+    mgr = R.engine.CoordinateManager(D=3)
+    key, _ = mgr.insert_and_map(torch.from_numpy(coords).cuda())
+    off, B = mgr.scene_offsets(key), mgr.number_of_unique_batch_indices()
+    g = torch.Generator().manual_seed(4)
+    feat = torch.randn(len(coords), 128, generator=g)
+    sel = mgr.scene_select_table(key)
+    for Q in (25, 100):
+        emb = torch.randn(B, Q, 128, generator=g)
+        ref = torch.cat([feat.bfloat16().float()[coords[:, 0] == b] @ emb[b].bfloat16().float().T for b in range(B)])
+        out = R.ops.mask_logits(feat.cuda().bfloat16(), off, B, emb.cuda(), select=sel)
+        assert out.shape == (len(coords), Q) and out.dtype == torch.float32
+        assert rel_err(out, ref) < 2e-3
+
+
+def test_sorted_tile_plan_is_a_permutation(R):
+    coords = make_batch(31)
+    mgr = R.engine.CoordinateManager(D=3)
+    key, _ = mgr.insert_and_map(torch.from_numpy(coords).cuda())
+    km = mgr.neighbor_table(key, key, 3, 1)
+    sp = km.sorted_plan(chunk_rows=1024)
+    order = sp.out_rows.cpu().numpy()
+    assert np.array_equal(np.sort(order), np.arange(km.n_out))
+    assert np.array_equal(sp.nbr.cpu().numpy(), km.nbr.cpu().numpy()[:, order])
+    assert np.array_equal(order // 1024, np.sort(order // 1024)), "rows must stay inside their chunk"
+    # fewer active (tile, offset) pairs than the lexicographic plan
+    pop = lambda t: sum(bin(int(v) & 0xFFFFFFFF).count("1") for v in t.cpu().numpy())
+    assert pop(sp.tile_kmask) <= pop(km.tile_kmask)
+
+
 def test_fourier_pe_parity(R):
     from oracle.mask3d_oracle import fourier_pos_enc
 
