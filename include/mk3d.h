@@ -71,10 +71,11 @@ int mk_tile_kmask(const int32_t* nbr, int K, int64_t n_slots, uint32_t* tile_kma
  * parent[f] and koff[f] for every fine row f. */
 int mk_transpose_map(const int32_t* nbr_down, int K, int64_t n_coarse, int64_t n_fine, int32_t* parent, int32_t* koff,
                      void* stream);
-/* Mask-sorted tile plans: masks[o] = bitmask over k of present neighbours of slot o (K <= 32); the host sorts slots by
- * (coarse row chunk, mask) so that every 128-slot tile has (almost) a single mask, then permutes the table:
- * out[k, s] = nbr[k, order[s]]  (order[s] < 0 -> -1, a padding slot). */
-int mk_row_kmask(const int32_t* nbr, int K, int64_t n, uint32_t* masks, void* stream);
+/* Mask-sorted tile plans: keys[o] = (bitmask over k of present neighbours of slot o, K <= 32) << 32 | (batch & 3) << 30 |
+ * 30-bit Morton code of the slot's coordinate / stride.  The host sorts slots by key so that every 128-slot tile has (almost)
+ * a single mask and is a compact spatial patch, then permutes the table: out[k, s] = nbr[k, order[s]]  (order[s] < 0 -> -1). */
+int mk_row_sort_keys(const int32_t* nbr, int K, int64_t n, const int32_t* coords, const int32_t* stride3_host, uint64_t* keys,
+                     void* stream);
 int mk_permute_table(const int32_t* nbr, int K, int64_t n, const int32_t* order, int64_t n_slots, int32_t* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -98,9 +99,12 @@ int mk_conv_weight_image_bf16(const float* W, int K, int cin, int cout, int tran
  * bias fp32 [cout] or NULL, out [n_out,out_stride] of out_dtype of which the first out_cols (<= cout) columns are
  * written (0 = cout; used by the mask-logit product whose Q = 25 queries are padded to 32 accumulator columns).
  * Persistent: grid = #SMs. */
-int mk_conv_fwd_bf16(const void* in, int cin, const void* wimg, int cout, const int32_t* nbr, int K, int64_t n_slots,
+int mk_conv_fwd_bf16(const void* in, int64_t n_in, int cin, const void* wimg, int cout, const int32_t* nbr, int K, int64_t n_slots,
                      const int32_t* out_rows, const uint32_t* tile_kmask, const int32_t* kidx, int64_t n_out,
                      const float* bias, void* out, int out_dtype, int out_cols, int out_stride, void* stream);
+/* A-operand producer of mk_conv_fwd_bf16: 0 = LSU (LDG.128 -> registers -> swizzled STS.128, default), 1 = TMA gather4
+ * (also env MK3D_GATHER=tma). */
+int mk_set_gather_mode(int mode);
 /* Stem: Cin == 1, K up to 125 (5^3): pure lookup, CUDA cores.  in fp32 [n_in], W fp32 [K,1,cout]. */
 int mk_conv_stem_f32(const float* in, const float* W, int cout, const int32_t* nbr, int K, int64_t n_out, void* out,
                      int out_dtype, void* stream);

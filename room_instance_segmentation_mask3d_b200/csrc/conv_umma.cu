@@ -19,154 +19,12 @@
 //
 // Warp roles (320 threads): warps 0-3 gather producers, warp 4 MMA issuer (one elected lane), warp 5 weight
 // loader + TMEM allocator, warps 6-9 epilogue (TMEM lane quarter = warp % 4).
-#include "common.cuh"
+#include <cstdlib>
+#include <vector>
+
+#include "umma.cuh"
 
 namespace mk {
-
-constexpr int kTileM = MK_TILE_ROWS;       // 128
-constexpr int kChunkElems = 64;            // bf16 elements per 128-byte swizzle row
-constexpr int kABytes = kTileM * 128;      // 16 KB per stage
-constexpr int kNumProducerWarps = 4;
-constexpr int kNumProducerThreads = kNumProducerWarps * 32;
-constexpr int kMmaWarp = 4;
-constexpr int kLoadWarp = 5;
-constexpr int kFirstEpiWarp = 6;
-constexpr int kNumThreads = 320;
-constexpr int kMaxStages = 8;
-constexpr int kTmemCols = 512;
-
-// ---------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "DONE:\n"
-      "}\n" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread (thread = lane = accumulator row)
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, 128-byte swizzle shared-memory matrix descriptor (sm_100 format, version 1):
-//   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major, 1) | [32,46) SBO >> 4 (1024 B between
-//   8-row groups) | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// instruction descriptor, kind::f16: D fp32 (bits 4-5 = 1), A/B bf16 (bits 7-9, 10-12 = 1), both K-major,
-// N >> 3 at bits 17-22, M >> 4 at bits 24-28.
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-struct ConvParams {
-  const __nv_bfloat16* in;
-  const __nv_bfloat16* wimg;
-  const int32_t* nbr;
-  const int32_t* out_rows;
-  const uint32_t* tile_kmask;
-  const int32_t* kidx;
-  const float* bias;
-  void* out;
-  int64_t n_slots;
-  int64_t n_out;
-  int cin;
-  int cout;
-  int K;
-  int num_tiles;
-  int num_stages;
-  int nchunks;
-  int out_cols;    // columns actually stored (<= cout; the rest of the accumulator is padding)
-  int out_stride;  // elements between consecutive output rows
-};
-
-struct Ring {
-  int stage = 0;
-  uint32_t phase = 0;
-  int n;
-  __device__ explicit Ring(int n_) : n(n_) {}
-  __device__ void advance() {
-    if (++stage == n) {
-      stage = 0;
-      phase ^= 1;
-    }
-  }
-};
 
 // kLag: cp.async groups a producer thread keeps in flight before it signals the oldest one (gather latency hiding)
 template <typename TOut, int kLag>
@@ -189,7 +47,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), kNumProducerThreads + 1);
+      mbar_init(smem_u32(&full_bar[s]), ((p.debug & 32) ? kNumProducerWarps : kNumProducerThreads) + 1);  // every producer thread's completion-triggered arrive + the weight loader
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -211,71 +69,78 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
 
   if (warp < kNumProducerWarps) {
     // ===================== gather producers =====================
+    // 16-byte cp.async (LDGSTS) with completion-triggered mbarrier arrives: no thread-side wait, all S stages stay in flight.
+    // Alternatives measured on B200 (profiles/): register-staged LDG.128 + STS.128 (~1.3x slower) and TMA gather4 (~2.5x slower).
     Ring ring(S);
-    int issued = 0, arrived = 0;
-    int arr_stage = 0;
     const int piece = lane & 7;     // 16-byte piece of the 128-byte row
     const int rsub = lane >> 3;     // 4 rows per warp instruction
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const uint32_t kmask = p.tile_kmask[tile];
-      const int64_t slot = (int64_t)tile * kTileM + warp * 32 + lane;
-      for (uint32_t m = kmask; m; m &= m - 1) {
-        const int k = __ffs(m) - 1;
-        const int my_idx = slot < p.n_slots ? p.nbr[(int64_t)k * p.n_slots + slot] : -1;
-        int idxs[8];  // input rows of the 8 tile rows this lane copies a piece of (rows 4j + rsub of the warp)
+    const int slot_in_tile = warp * 32 + lane;
+    auto load_idx = [&](const WorkCursor& c) -> int {
+      const int64_t slot = (int64_t)c.tile * kTileM + slot_in_tile;
+      return (c.valid() && slot < p.n_slots) ? __ldg(p.nbr + (int64_t)c.k() * p.n_slots + slot) : -1;
+    };
+    // neighbour indices are prefetched 4 work items ahead: the dependent global load (index -> gather address) would
+    // otherwise expose one L2 round trip per (tile, offset)
+    long long t_wait = 0, t_start = clock64();
+    WorkCursor cur(p.tile_kmask, blockIdx.x, gridDim.x, p.num_tiles), pf = cur;
+    int q0 = load_idx(pf); pf.next();
+    int q1 = load_idx(pf); pf.next();
+    int q2 = load_idx(pf); pf.next();
+    int q3 = load_idx(pf); pf.next();
+    while (cur.valid()) {
+      const int my_idx = q0;
+      q0 = q1; q1 = q2; q2 = q3;
+      q3 = (p.debug & 16) ? 0 : load_idx(pf);
+      pf.next();
+      int idxs[8];  // input rows of the 8 tile rows this lane copies a piece of (rows 4j + rsub of the warp)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) idxs[j] = __shfl_sync(0xffffffffu, my_idx, 4 * j + rsub);
-        for (int ch = 0; ch < nchunks; ++ch) {
-          const int width = min(kChunkElems, p.cin - ch * kChunkElems);  // valid elements in this chunk
-          mbar_wait(smem_u32(&empty_bar[ring.stage]), ring.phase ^ 1);
-          const uint32_t a_base = smem_u32(sA + (size_t)ring.stage * kABytes);
-          if (piece * 8 < width) {
+      for (int j = 0; j < 8; ++j) idxs[j] = (p.debug & 16) ? 0 : __shfl_sync(0xffffffffu, my_idx, 4 * j + rsub);
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int width = min(kChunkElems, p.cin - ch * kChunkElems);  // valid elements in this chunk
+        if (lane == 0) {
+          const long long t0 = clock64();
+          mbar_wait(smem_u32(&empty_bar[ring.stage]), ring.phase ^ 1);  // one poller per warp
+          t_wait += clock64() - t0;
+        }
+        __syncwarp();
+        const uint32_t a_base = smem_u32(sA + (size_t)ring.stage * kABytes);
+        if (piece * 8 < width && !(p.debug & 1)) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int idx = idxs[j];
-              const int row = warp * 32 + 4 * j + rsub;  // row within the tile
-              const uint32_t dst = a_base + (uint32_t)(row * 128 + ((piece ^ (row & 7)) << 4));
-              const __nv_bfloat16* src = p.in + (int64_t)(idx < 0 ? 0 : idx) * p.cin + ch * kChunkElems + piece * 8;
-              cp_async_16(dst, src, idx < 0 ? 0u : 16u);
-            }
-          }
-          cp_async_commit();
-          ++issued;
-          ring.advance();
-          if (issued - arrived > kLag) {
-            cp_async_wait<kLag>();
-            fence_proxy_async();
-            mbar_arrive(smem_u32(&full_bar[arr_stage]));
-            ++arrived;
-            if (++arr_stage == S) arr_stage = 0;
+          for (int j = 0; j < 8; ++j) {
+            const int idx = idxs[j];
+            const int row = warp * 32 + 4 * j + rsub;  // row within the tile
+            const uint32_t dst = a_base + (uint32_t)(row * 128 + ((piece ^ (row & 7)) << 4));
+            const __nv_bfloat16* src = p.in + (int64_t)(idx < 0 ? 0 : idx) * p.cin + ch * kChunkElems + piece * 8;
+            cp_async_16(dst, src, idx < 0 ? 0u : 16u);
           }
         }
+        // completion-triggered arrive: no wait_group / fence in the producer (a producer-side fence.proxy.async would drain
+        // every outstanding cp.async of the thread); the generic->async proxy fence is executed by the MMA thread after it
+        // has acquired the full barrier
+        if (!(p.debug & 32) || lane == 0) cp_async_arrive_noinc(smem_u32(&full_bar[ring.stage]));
+        ring.advance();
       }
+      cur.next();
     }
     cp_async_wait<0>();
-    fence_proxy_async();
-    while (arrived < issued) {
-      mbar_arrive(smem_u32(&full_bar[arr_stage]));
-      ++arrived;
-      if (++arr_stage == S) arr_stage = 0;
-    }
   } else if (warp == kLoadWarp) {
     // ===================== weight loader (one lane) =====================
     if (lane == 0) {
       Ring ring(S);
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const uint32_t kmask = p.tile_kmask[tile];
-        for (uint32_t m = kmask; m; m &= m - 1) {
-          const int k = __ffs(m) - 1;
-          const int kw = p.kidx ? p.kidx[k] : k;
-          for (int ch = 0; ch < nchunks; ++ch) {
-            mbar_wait(smem_u32(&empty_bar[ring.stage]), ring.phase ^ 1);
-            const uint32_t bar = smem_u32(&full_bar[ring.stage]);
+      for (WorkCursor cur(p.tile_kmask, blockIdx.x, gridDim.x, p.num_tiles); cur.valid(); cur.next()) {
+        const int k = cur.k();
+        const int kw = p.kidx ? p.kidx[k] : k;
+        for (int ch = 0; ch < nchunks; ++ch) {
+          mbar_wait(smem_u32(&empty_bar[ring.stage]), ring.phase ^ 1);
+          const uint32_t bar = smem_u32(&full_bar[ring.stage]);
+          if (p.debug & 2) {
+            mbar_arrive(bar);
+          } else {
             mbar_arrive_expect_tx(bar, (uint32_t)b_bytes);
             const __nv_bfloat16* src = p.wimg + ((int64_t)kw * nchunks + ch) * (int64_t)p.cout * kChunkElems;
             bulk_copy_g2s(smem_u32(sB + (size_t)ring.stage * b_bytes), src, (uint32_t)b_bytes, bar);
-            ring.advance();
           }
+          ring.advance();
         }
       }
     }
@@ -287,34 +152,51 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
       const uint32_t idesc = make_idesc(kTileM, p.cout);
       int acc_buf = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const uint32_t kmask = p.tile_kmask[tile];
-        if (kmask == 0) continue;
-        mbar_wait(smem_u32(&tmem_empty[acc_buf]), acc_phase ^ 1);
-        tc_fence_after();
+      bool tile_open = false;
+      uint32_t accumulate = 0;
+      long long tw_full = 0, tw_tmem = 0, t_start = clock64(), n_it = 0;
+      for (WorkCursor cur(p.tile_kmask, blockIdx.x, gridDim.x, p.num_tiles); cur.valid(); cur.next()) {
+        if (!tile_open) {
+          const long long t0 = clock64();
+          mbar_wait(smem_u32(&tmem_empty[acc_buf]), acc_phase ^ 1);
+          tw_tmem += clock64() - t0;
+          tc_fence_after();
+          tile_open = true;
+          accumulate = 0;
+        }
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc_buf * 256);
-        uint32_t accumulate = 0;
-        for (uint32_t m = kmask; m; m &= m - 1) {
-          for (int ch = 0; ch < nchunks; ++ch) {
-            const int width = min(kChunkElems, p.cin - ch * kChunkElems);
-            mbar_wait(smem_u32(&full_bar[ring.stage]), ring.phase);
-            tc_fence_after();
-            const uint64_t adesc = make_smem_desc(smem_u32(sA + (size_t)ring.stage * kABytes));
-            const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)ring.stage * b_bytes));
-            for (int kk = 0; kk < width / 16; ++kk) {
-              // +32 bytes along K inside the 128-byte swizzle row == +2 in the (addr >> 4) field
-              umma_bf16(tmem_d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, accumulate);
-              accumulate = 1;
-            }
-            umma_commit(smem_u32(&empty_bar[ring.stage]));  // frees the stage when these MMAs retire
-            ring.advance();
+        for (int ch = 0; ch < nchunks; ++ch) {
+          const int width = min(kChunkElems, p.cin - ch * kChunkElems);
+          const long long t1 = clock64();
+          mbar_wait(smem_u32(&full_bar[ring.stage]), ring.phase);
+          tw_full += clock64() - t1;
+          ++n_it;
+          if (!(p.debug & 64)) fence_proxy_async();  // producers' cp.async (generic proxy) writes -> visible to tcgen05.mma (async proxy)
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(smem_u32(sA + (size_t)ring.stage * kABytes));
+          const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)ring.stage * b_bytes));
+          for (int kk = 0; kk < ((p.debug & 4) ? (accumulate ? 0 : 1) : width / 16); ++kk) {
+            // +32 bytes along K inside the 128-byte swizzle row == +2 in the (addr >> 4) field
+            umma_bf16(tmem_d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, accumulate);
+            accumulate = 1;
+          }
+          umma_commit(smem_u32(&empty_bar[ring.stage]));  // frees the stage when these MMAs retire
+          ring.advance();
+        }
+        if (cur.last_k_of_tile()) {
+          umma_commit(smem_u32(&tmem_full[acc_buf]));
+          tile_open = false;
+          if (++acc_buf == 2) {
+            acc_buf = 0;
+            acc_phase ^= 1;
           }
         }
-        umma_commit(smem_u32(&tmem_full[acc_buf]));
-        if (++acc_buf == 2) {
-          acc_buf = 0;
-          acc_phase ^= 1;
-        }
+      }
+      if (p.trace) {
+        p.trace[blockIdx.x * 8 + 2] = (unsigned long long)tw_full;
+        p.trace[blockIdx.x * 8 + 3] = (unsigned long long)tw_tmem;
+        p.trace[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_start);
+        p.trace[blockIdx.x * 8 + 5] = (unsigned long long)n_it;
       }
     }
     __syncwarp();
@@ -323,16 +205,26 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     int acc_buf = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const uint32_t kmask = p.tile_kmask[tile];
+    auto load_row = [&](int tile) -> int64_t {
       const int64_t slot = (int64_t)tile * kTileM + q * 32 + lane;
-      int64_t orow = -1;
-      if (slot < p.n_slots) orow = p.out_rows ? (int64_t)p.out_rows[slot] : slot;
-      if (orow >= p.n_out) orow = -1;
+      int64_t r = -1;
+      if (tile < p.num_tiles && slot < p.n_slots) r = p.out_rows ? (int64_t)__ldg(p.out_rows + slot) : slot;
+      return r >= p.n_out ? -1 : r;
+    };
+    uint32_t kmask_next = blockIdx.x < p.num_tiles ? p.tile_kmask[blockIdx.x] : 0u;
+    int64_t orow_next = load_row(blockIdx.x);
+    long long te_wait = 0, te_start = clock64();
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const uint32_t kmask = kmask_next;
+      const int64_t orow = orow_next;
+      if (tile + (int)gridDim.x < p.num_tiles) kmask_next = p.tile_kmask[tile + gridDim.x];
+      orow_next = load_row(tile + gridDim.x);
       TOut* optr = orow >= 0 ? (TOut*)p.out + orow * p.out_stride : nullptr;
       const bool vec_ok = ((p.out_stride * (int)sizeof(TOut)) & 15) == 0;
       if (kmask != 0) {
+        const long long t0 = clock64();
         mbar_wait(smem_u32(&tmem_full[acc_buf]), acc_phase);
+        te_wait += clock64() - t0;
         tc_fence_after();
       }
       for (int c0 = 0; c0 < p.out_cols; c0 += 16) {
@@ -351,7 +243,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] += (c0 + j < p.out_cols) ? p.bias[c0 + j] : 0.f;
         }
-        if (optr) {
+        if (optr && !(p.debug & 8)) {
           if (vec_ok && c0 + 16 <= p.out_cols) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4) store4(optr + c0 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
@@ -371,8 +263,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
         }
       }
     }
+    if (p.trace && warp == kFirstEpiWarp && lane == 0) {
+      p.trace[blockIdx.x * 8 + 6] = (unsigned long long)te_wait;
+      p.trace[blockIdx.x * 8 + 7] = (unsigned long long)(clock64() - te_start);
+    }
   }
 
+  if (p.trace && warp == kFirstEpiWarp && lane == 0) {
+    // (epilogue timers live in the epilogue branch's scope; written there)
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == kLoadWarp) {
@@ -411,11 +310,29 @@ inline size_t conv_smem_bytes(int cout, int stages) {
   return 1024 + (size_t)stages * (kABytes + (size_t)cout * 128) + (2 * kMaxStages + 4) * sizeof(uint64_t) + 16;
 }
 
+int conv_tma_launch(const ConvParams& p, int64_t n_in, int out_dtype, cudaStream_t st);  // conv_tma.cu
+
+// 0 = LSU producer: LDG.128 -> registers -> swizzled STS.128 (default); 1 = TMA gather4 producer (MK3D_GATHER=tma; measured
+// ~2.5x slower on random rows, kept for A/B measurements)
+static int g_gather_mode = -1;
+inline int gather_mode() {
+  if (g_gather_mode < 0) {
+    const char* e = getenv("MK3D_GATHER");
+    g_gather_mode = (e && e[0] == 't') ? 1 : 0;
+  }
+  return g_gather_mode;
+}
+
 }  // namespace mk
 
 using namespace mk;
 
 extern "C" {
+
+int mk_set_gather_mode(int mode) {
+  g_gather_mode = mode ? 1 : 0;
+  return 0;
+}
 
 int64_t mk_conv_weight_image_elems(int K, int cin, int cout, int transpose) {
   const int red = transpose ? cout : cin, rows = transpose ? cin : cout;
@@ -430,7 +347,7 @@ int mk_conv_weight_image_bf16(const float* W, int K, int cin, int cout, int tran
   return check_launch(__func__);
 }
 
-int mk_conv_fwd_bf16(const void* in, int cin, const void* wimg, int cout, const int32_t* nbr, int K, int64_t n_slots,
+int mk_conv_fwd_bf16(const void* in, int64_t n_in, int cin, const void* wimg, int cout, const int32_t* nbr, int K, int64_t n_slots,
                      const int32_t* out_rows, const uint32_t* tile_kmask, const int32_t* kidx, int64_t n_out,
                      const float* bias, void* out, int out_dtype, int out_cols, int out_stride, void* stream_) {
   MK_REQUIRE(mk_device_supported(), "tcgen05 path needs an sm_100 device (B200)");
@@ -460,6 +377,13 @@ int mk_conv_fwd_bf16(const void* in, int cin, const void* wimg, int cout, const 
   p.nchunks = (cin + kChunkElems - 1) / kChunkElems;
   p.out_cols = out_cols;
   p.out_stride = out_stride;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("MK3D_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;  // timing ablations only (results are wrong when non-zero): 1 skip gathers, 2 skip weight copies, 4 one MMA per tile, 8 skip stores
+  }
+  p.trace = nullptr;
+  if (gather_mode() == 1) return conv_tma_launch(p, n_in, out_dtype, (cudaStream_t)stream_);
   int stages = kMaxStages;
   while (stages > 3 && conv_smem_bytes(cout, stages) > 210 * 1024) --stages;
   MK_REQUIRE(conv_smem_bytes(cout, stages) <= 227 * 1024, "shared memory budget exceeded");
@@ -485,8 +409,25 @@ int mk_conv_fwd_bf16(const void* in, int cin, const void* wimg, int cout, const 
       default: MK_LAUNCH(T, 1); break; \
     }                               \
   } while (0)
+  static int trace_on = -1;
+  if (trace_on < 0) trace_on = getenv("MK3D_TRACE") ? 1 : 0;
+  if (trace_on) {
+    cudaMalloc(&p.trace, (size_t)grid * 8 * sizeof(unsigned long long));
+    cudaMemset(p.trace, 0, (size_t)grid * 8 * sizeof(unsigned long long));
+  }
   if (out_dtype == MK_F32) MK_LAUNCH_T(float);
   else MK_LAUNCH_T(__nv_bfloat16);
+  if (trace_on) {
+    std::vector<unsigned long long> h((size_t)grid * 8);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h.data(), p.trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(p.trace);
+    double a[8] = {0};
+    for (int b = 0; b < grid; ++b)
+      for (int j = 0; j < 8; ++j) a[j] += (double)h[(size_t)b * 8 + j] / grid;
+    fprintf(stderr, "[mk3d trace] cin %d cout %d K %d tiles %d stages %d | producer: wait_empty %.0f / total %.0f | mma: wait_full %.0f wait_tmem %.0f / total %.0f, iters %.0f | epilogue: wait_full %.0f / total %.0f (cycles, CTA mean)\n",
+            cin, cout, K, p.num_tiles, stages, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+  }
 #undef MK_LAUNCH_T
 #undef MK_LAUNCH
   return check_launch(__func__);

@@ -233,13 +233,28 @@ __global__ void __launch_bounds__(MK_TILE_ROWS) k_tile_kmask(const int32_t* __re
   }
 }
 
-// per-slot offset bitmask: bit k set iff nbr[k, slot] >= 0  (K <= 32).  Slots with equal masks are grouped into the same
-// tensor-core tiles by the host (mask-sorted tile plan) so a tile's active-offset set equals its rows' set.
-__global__ void k_row_kmask(const int32_t* __restrict__ nbr, int K, int64_t n, uint32_t* __restrict__ masks) {
+// per-slot sort key for mask-sorted tile plans:  (offset bitmask) << 32 | (batch & 3) << 30 | 30-bit Morton code.
+// bit k of the mask is set iff nbr[k, slot] >= 0 (K <= 32).  Slots with equal masks are grouped into the same tensor-core
+// tiles (a tile's active-offset set then equals its rows' set) and, inside a mask group, ordered along a Z-curve so that a
+// tile is a compact spatial patch whose neighbour gathers overlap (L1 / L2 reuse).
+__device__ __forceinline__ unsigned spread3(unsigned v) {  // 10 bits -> every third bit
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+__global__ void k_row_sort_keys(const int32_t* __restrict__ nbr, int K, int64_t n, const int4* __restrict__ coords, int sx, int sy,
+                                int sz, unsigned long long* __restrict__ keys) {
   for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
-    uint32_t m = 0;
+    unsigned m = 0;
     for (int k = 0; k < K; ++k) m |= (nbr[(int64_t)k * n + o] >= 0 ? 1u : 0u) << k;
-    masks[o] = m;
+    const int4 c = coords[o];
+    const unsigned morton = spread3((unsigned)floor_div(c.y, sx)) | (spread3((unsigned)floor_div(c.z, sy)) << 1) |
+                            (spread3((unsigned)floor_div(c.w, sz)) << 2);
+    keys[o] = ((unsigned long long)m << 32) | ((unsigned long long)((unsigned)c.x & 3u) << 30) | (unsigned long long)morton;
   }
 }
 
@@ -358,12 +373,15 @@ int mk_tile_kmask(const int32_t* nbr, int K, int64_t n_slots, uint32_t* tile_kma
   return check_launch(__func__);
 }
 
-int mk_row_kmask(const int32_t* nbr, int K, int64_t n, uint32_t* masks, void* stream_) {
+int mk_row_sort_keys(const int32_t* nbr, int K, int64_t n, const int32_t* coords, const int32_t* stride3_host, uint64_t* keys,
+                     void* stream_) {
   MK_REQUIRE(K >= 1 && K <= 32, "K must be <= 32");
   if (n == 0) return 0;
   int64_t bx = ceil_div(n, 256);
   if (bx > 8 * num_sms()) bx = 8 * num_sms();
-  k_row_kmask<<<(unsigned)bx, 256, 0, (cudaStream_t)stream_>>>(nbr, K, n, masks);
+  const int sx = stride3_host ? stride3_host[0] : 1, sy = stride3_host ? stride3_host[1] : 1, sz = stride3_host ? stride3_host[2] : 1;
+  k_row_sort_keys<<<(unsigned)bx, 256, 0, (cudaStream_t)stream_>>>(nbr, K, n, (const int4*)coords, sx, sy, sz,
+                                                                  (unsigned long long*)keys);
   return check_launch(__func__);
 }
 

@@ -1,0 +1,194 @@
+// Shared device helpers for the tcgen05 kernels: PTX wrappers (mbarrier, cp.async, bulk copies, TMEM, tcgen05.mma),
+// shared-memory / instruction descriptors, the pipeline ring and the (tile, offset) work cursor.
+#pragma once
+
+#include "common.cuh"
+
+namespace mk {
+
+
+constexpr int kTileM = MK_TILE_ROWS;       // 128
+constexpr int kChunkElems = 64;            // bf16 elements per 128-byte swizzle row
+constexpr int kABytes = kTileM * 128;      // 16 KB per stage
+constexpr int kNumProducerWarps = 4;
+constexpr int kNumProducerThreads = kNumProducerWarps * 32;
+constexpr int kMmaWarp = 4;
+constexpr int kLoadWarp = 5;
+constexpr int kFirstEpiWarp = 6;
+constexpr int kNumThreads = 320;
+constexpr int kMaxStages = 8;
+constexpr int kTmemCols = 512;
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  // .ca: allocate in L1 — a tile is a compact spatial patch (mask + Z-curve sorted), so the neighbour rows gathered for its
+  // different offsets overlap heavily and are re-read from L1 instead of L2
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// arrive on `bar` when all cp.async issued so far by this thread have landed (no thread-side wait: the stage stays in flight)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread (thread = lane = accumulator row)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (sm_100 format, version 1):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major, 1) | [32,46) SBO >> 4 (1024 B between
+//   8-row groups) | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor, kind::f16: D fp32 (bits 4-5 = 1), A/B bf16 (bits 7-9, 10-12 = 1), both K-major,
+// N >> 3 at bits 17-22, M >> 4 at bits 24-28.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct ConvParams {
+  const __nv_bfloat16* in;
+  const __nv_bfloat16* wimg;
+  const int32_t* nbr;
+  const int32_t* out_rows;
+  const uint32_t* tile_kmask;
+  const int32_t* kidx;
+  const float* bias;
+  void* out;
+  int64_t n_slots;
+  int64_t n_out;
+  int cin;
+  int cout;
+  int K;
+  int num_tiles;
+  int num_stages;
+  int nchunks;
+  int out_cols;    // columns actually stored (<= cout; the rest of the accumulator is padding)
+  int out_stride;  // elements between consecutive output rows
+  int debug;       // timing ablation flags (MK3D_DEBUG), 0 in production
+  unsigned long long* trace;  // MK3D_TRACE: per-CTA role timers [grid][8], nullptr in production
+};
+
+struct Ring {
+  int stage = 0;
+  uint32_t phase = 0;
+  int n;
+  __device__ explicit Ring(int n_) : n(n_) {}
+  __device__ void advance() {
+    if (++stage == n) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+};
+
+
+// Enumerates this CTA's (tile, offset k) work items in execution order: tiles blockIdx.x, +gridDim.x, ...; inside a tile the
+// set bits of its offset mask, ascending.  The mask of the NEXT tile is loaded when the current one is entered, so the
+// global-load latency of tile_kmask never sits on a role's critical path.
+struct WorkCursor {
+  const uint32_t* kmask;
+  int tile, stride, num_tiles;
+  uint32_t m, m_next;
+  __device__ WorkCursor(const uint32_t* kmask_, int first, int stride_, int num_tiles_)
+      : kmask(kmask_), tile(first), stride(stride_), num_tiles(num_tiles_) {
+    m = tile < num_tiles ? kmask[tile] : 0u;
+    m_next = tile + stride < num_tiles ? kmask[tile + stride] : 0u;
+    skip_empty();
+  }
+  __device__ void skip_empty() {
+    while (m == 0u && tile < num_tiles) {
+      tile += stride;
+      m = m_next;
+      m_next = tile + stride < num_tiles ? kmask[tile + stride] : 0u;
+    }
+  }
+  __device__ bool valid() const { return tile < num_tiles; }
+  __device__ int k() const { return __ffs(m) - 1; }
+  __device__ bool last_k_of_tile() const { return (m & (m - 1)) == 0u; }
+  __device__ void next() {
+    m &= m - 1;
+    skip_empty();
+  }
+};
+
+
+}  // namespace mk

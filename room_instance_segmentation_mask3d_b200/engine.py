@@ -82,7 +82,9 @@ class CoordMap:
 class KernelMap:
     """Output-stationary kernel map nbr[K, n_slots] (+ what the tensor-core kernel needs)."""
 
-    def __init__(self, nbr: torch.Tensor, K: int, n_out: int, out_rows: Optional[torch.Tensor] = None):
+    def __init__(self, nbr: torch.Tensor, K: int, n_out: int, out_rows: Optional[torch.Tensor] = None,
+                 out_coords: Optional[torch.Tensor] = None, out_stride: Tuple[int, int, int] = (1, 1, 1)):
+        self.out_coords, self.out_stride = out_coords, out_stride  # coordinates of the output rows (for spatial tile sorting)
         self.nbr = nbr                    # int32 [K, n_slots]
         self.K = K
         self.n_slots = nbr.shape[1]
@@ -100,20 +102,21 @@ class KernelMap:
         lib.call("mk_tile_kmask", lib.p(self.nbr), self.K, self.n_slots, lib.p(self._kmask) if self.K <= 32 else None,
                  lib.p(self._pairs_dev), lib.stream())
 
-    def sorted_plan(self, chunk_rows: int = 1 << 17) -> "KernelMap":
+    def sorted_plan(self) -> "KernelMap":
         """Mask-sorted tile plan: output slots are reordered so that rows with the same set of present offsets share
         tensor-core tiles (a lexicographic tile of a surface scene touches ~23 of 27 offsets, a mask-sorted one ~10, i.e.
-        2.3x less gather + MMA work).  Sorting is done inside chunks of `chunk_rows` consecutive rows so that a chunk's
-        gather working set stays L2-resident.  Slots map back to rows through `out_rows`."""
+        2.3x less gather + MMA work) and, inside a mask group, follow a Z-curve so that a tile is a compact spatial patch
+        whose neighbour gathers overlap.  Slots map back to rows through `out_rows`."""
         if self._sorted is None:
-            if self.K == 1 or self.K > 32 or self.out_rows is not None or self.n_out == 0:
+            if self.K == 1 or self.K > 32 or self.out_rows is not None or self.n_out == 0 or self.out_coords is None:
                 self._sorted = self
             else:
                 n, dev = self.n_out, self.nbr.device
-                masks = torch.empty(n, dtype=I32, device=dev)
-                lib.call("mk_row_kmask", lib.p(self.nbr), self.K, n, lib.p(masks), lib.stream())
-                key = (torch.arange(n, device=dev, dtype=torch.int64) // chunk_rows << 32) | (masks.long() & 0xFFFFFFFF)
-                order = torch.sort(key, stable=True).indices.to(I32)
+                keys = torch.empty(n, dtype=torch.int64, device=dev)
+                st = (ctypes.c_int32 * 3)(*self.out_stride)
+                lib.call("mk_row_sort_keys", lib.p(self.nbr), self.K, n, lib.p(self.out_coords), ctypes.cast(st, ctypes.c_void_p), lib.p(keys),
+                         lib.stream())
+                order = torch.sort(keys, stable=True).indices.to(I32)
                 nbr_s = torch.empty_like(self.nbr)
                 lib.call("mk_permute_table", lib.p(self.nbr), self.K, n, lib.p(order), n, lib.p(nbr_s), lib.stream())
                 self._sorted = KernelMap(nbr_s, self.K, n, order)
@@ -251,7 +254,7 @@ class CoordinateManager:
             nbr = torch.empty((K, om.n), dtype=I32, device=self.device)
             offs = self._offsets_dev(ks, dl, in_key.tensor_stride)
             lib.call("mk_kernel_map", lib.p(im.keys), lib.p(im.vals), im.cap, lib.p(om.coords), om.n, lib.p(offs), K, lib.p(nbr), lib.stream())
-            km = KernelMap(nbr, K, om.n)
+            km = KernelMap(nbr, K, om.n, out_coords=om.coords, out_stride=out_key.tensor_stride)
             self._kmaps[ck] = km
         return km
 

@@ -34,9 +34,10 @@ _SIGS = {
     "mk_conv_fwd_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "mk_conv_weight_image_elems": (c_int64, [c_int, c_int, c_int, c_int]),
     "mk_conv_weight_image_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "mk_conv_fwd_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
+    "mk_conv_fwd_bf16": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
                                  c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "mk_row_kmask": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "mk_set_gather_mode": (c_int, [c_int]),
+    "mk_row_sort_keys": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mk_permute_table": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "mk_conv_stem_f32": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_int, c_void_p]),
     "mk_conv_dgrad_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),

@@ -98,7 +98,7 @@ def conv_forward(x: torch.Tensor, W: torch.Tensor, km: KernelMap, bias: Optional
     if lib._timed is not None:  # bench.py instrumentation: algorithmic FLOPs = 2 * P * Cin * Cout
         lib.set_tag((2 * km.num_pairs * cin * ocols, K, cin, cout, km.n_out))
     plan = km.sorted_plan() if SORT_TILES else km
-    lib.call("mk_conv_fwd_bf16", lib.p(xb), cin, lib.p(img), cout, lib.p(plan.nbr), K, plan.n_slots, lib.p(plan.out_rows), lib.p(plan.tile_kmask),
+    lib.call("mk_conv_fwd_bf16", lib.p(xb), xb.shape[0], cin, lib.p(img), cout, lib.p(plan.nbr), K, plan.n_slots, lib.p(plan.out_rows), lib.p(plan.tile_kmask),
              lib.p(kidx), km.n_out, lib.p(bias_flat), lib.p(out), lib.dt(out), ocols, ocols, lib.stream())
     return out
 

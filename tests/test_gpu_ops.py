@@ -276,11 +276,12 @@ def test_sorted_tile_plan_is_a_permutation(R):
     mgr = R.engine.CoordinateManager(D=3)
     key, _ = mgr.insert_and_map(torch.from_numpy(coords).cuda())
     km = mgr.neighbor_table(key, key, 3, 1)
-    sp = km.sorted_plan(chunk_rows=1024)
+    sp = km.sorted_plan()
     order = sp.out_rows.cpu().numpy()
     assert np.array_equal(np.sort(order), np.arange(km.n_out))
     assert np.array_equal(sp.nbr.cpu().numpy(), km.nbr.cpu().numpy()[:, order])
-    assert np.array_equal(order // 1024, np.sort(order // 1024)), "rows must stay inside their chunk"
+    masks = ((km.nbr.cpu().numpy() >= 0).astype(np.int64) * (1 << np.arange(27))[:, None]).sum(0)
+    assert np.array_equal(masks[order], np.sort(masks)), "slots must be grouped by neighbour mask"
     # fewer active (tile, offset) pairs than the lexicographic plan
     pop = lambda t: sum(bin(int(v) & 0xFFFFFFFF).count("1") for v in t.cpu().numpy())
     assert pop(sp.tile_kmask) <= pop(km.tile_kmask)
