@@ -4,10 +4,9 @@
 // section 3.4) with ONE persistent, warp-specialised, output-stationary kernel:
 //
 //   tile      = 128 output slots (rows of the accumulator = TMEM lanes)
-//   iteration = (kernel offset k with at least one neighbour in the tile, 64-channel chunk of Cin)
-//   A operand = the 128 gathered input rows of the chunk, staged by 4 producer warps with 16-byte
-//               cp.async (zero-fill for absent neighbours) straight into the 128B-swizzled K-major
-//               shared-memory layout that tcgen05.mma reads
+//   iteration = (kernel offset k with at least one neighbour in the tile, 64-channel chunk of Cin) = one pipeline stage
+//   A operand = the 128 gathered input rows of the chunk, staged with 16-byte cp.async (LDGSTS, zero-fill for absent
+//               neighbours) straight into the 128B-swizzled K-major shared-memory layout that tcgen05.mma reads
 //   B operand = W[k] chunk, pre-swizzled on the device once per weight ("weight image"), so a stage is one
 //               linear cp.async.bulk (TMA engine, UBLKCP) completing on the stage's mbarrier
 //   D         = fp32 accumulator in TMEM, two buffers of `cout` columns: the epilogue of tile t
@@ -17,8 +16,17 @@
 // Offsets whose neighbour column is empty for the whole tile are skipped via the per-tile bitmask from
 // mk_tile_kmask, which is what keeps the MMA work close to the algorithmic 2*P*Cin*Cout on surface data.
 //
-// Warp roles (320 threads): warps 0-3 gather producers, warp 4 MMA issuer (one elected lane), warp 5 weight
-// loader + TMEM allocator, warps 6-9 epilogue (TMEM lane quarter = warp % 4).
+// Warp roles (320 threads): warps 0-3 and 5 are PRODUCERS, warp 4 the MMA issuer (one elected lane), warps 6-9 the
+// epilogue (TMEM lane quarter = warp % 4); warp 5 also owns the TMEM allocation.
+//
+// Producers own whole stages round-robin (stage i belongs to producer i mod 5): ncu's per-instruction stall samples of the
+// previous design (all 4 producer warps cooperating on EVERY stage, profiles/r01_conv96_*) showed the producer loop —
+// mbarrier try_wait, index shuffles, LDGSTS issue throttling, exposed index loads — at ~1100 cycles per stage on every
+// producer warp, i.e. the gather front-end, not the tensor pipe or L2, bounded the kernel.  With stage ownership the same
+// fixed costs overlap across five stages in flight.  Per stage the owning warp: waits for the stage to be free, gathers
+// 128 rows x 128 B with 32 LDGSTS per lane (neighbour indices held 4 per lane, distributed by shuffle, prefetched two of its
+// own stages ahead), lets the copies arrive on the stage's full barrier (cp.async.mbarrier.arrive.noinc: no thread-side
+// wait), and lane 0 adds the weight-image bulk copy with its expect_tx on the same barrier.
 #include <cstdlib>
 #include <vector>
 
@@ -26,8 +34,26 @@
 
 namespace mk {
 
-// kLag: cp.async groups a producer thread keeps in flight before it signals the oldest one (gather latency hiding)
-template <typename TOut, int kLag>
+constexpr int kMaxProducers = 5;  // warps 0-3 and 5
+
+// (item = (tile, offset), 64-channel chunk) iteration space of one CTA, in execution order
+struct IterCursor {
+  WorkCursor c;
+  int ch, nchunks;
+  __device__ IterCursor(const uint32_t* kmask, int first, int stride, int num_tiles, int nchunks_)
+      : c(kmask, first, stride, num_tiles), ch(0), nchunks(nchunks_) {}
+  __device__ bool valid() const { return c.valid(); }
+  __device__ void advance(int n) {
+    for (int i = 0; i < n && c.valid(); ++i) {
+      if (++ch == nchunks) {
+        ch = 0;
+        c.next();
+      }
+    }
+  }
+};
+
+template <typename TOut, bool kDbg>
 __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x A 16 KB][stages x B cout*128][barriers]
@@ -37,17 +63,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)S * kABytes;
   uint64_t* bars = (uint64_t*)(sB + (size_t)S * b_bytes);
-  uint64_t* full_bar = bars;                       // [S]  producers (128) + weight loader (1, with tx bytes)
+  uint64_t* full_bar = bars;                       // [S]  32 producer lanes (copy completion) + 1 expect_tx arrive
   uint64_t* empty_bar = bars + kMaxStages;         // [S]  one tcgen05.commit
   uint64_t* tmem_full = bars + 2 * kMaxStages;     // [2]  one tcgen05.commit
   uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;  // [2]  128 epilogue threads
   uint32_t* tmem_base_slot = (uint32_t*)(bars + 2 * kMaxStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int dbg = kDbg ? p.debug : 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), ((p.debug & 32) ? kNumProducerWarps : kNumProducerThreads) + 1);  // every producer thread's completion-triggered arrive + the weight loader
+      mbar_init(smem_u32(&full_bar[s]), 32 + 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -67,84 +94,88 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
 
   const int nchunks = p.nchunks;
 
-  if (warp < kNumProducerWarps) {
-    // ===================== gather producers =====================
-    // 16-byte cp.async (LDGSTS) with completion-triggered mbarrier arrives: no thread-side wait, all S stages stay in flight.
-    // Alternatives measured on B200 (profiles/): register-staged LDG.128 + STS.128 (~1.3x slower) and TMA gather4 (~2.5x slower).
-    Ring ring(S);
-    const int piece = lane & 7;     // 16-byte piece of the 128-byte row
-    const int rsub = lane >> 3;     // 4 rows per warp instruction
-    const int slot_in_tile = warp * 32 + lane;
-    auto load_idx = [&](const WorkCursor& c) -> int {
-      const int64_t slot = (int64_t)c.tile * kTileM + slot_in_tile;
-      return (c.valid() && slot < p.n_slots) ? __ldg(p.nbr + (int64_t)c.k() * p.n_slots + slot) : -1;
+  if (warp < kNumProducerWarps || warp == kLoadWarp) {
+    // ===================== producers (5 warps, one stage each, round-robin) =====================
+    const int pi = warp < kNumProducerWarps ? warp : kNumProducerWarps;
+    // Stage ownership: iteration i is staged by producer i mod NP into ring slot i mod S.  NP < S is required: the
+    // parity wait on a slot's empty barrier is only unambiguous while a producer can be at most ONE ring phase ahead of
+    // the consumer, which holds iff everything before iteration i - NP - S being consumed implies i - 2S is (S > NP).
+    const int NP = p.num_producers;
+    const int piece = lane & 7;  // 16-byte piece of the 128-byte row
+    const int rsub = lane >> 3;  // 4 rows per warp instruction
+    // swizzled piece offset inside the row: row & 7 == 4 * (jj & 1) + rsub for row = 4 * jj + rsub
+    const uint32_t sw_even = (uint32_t)((piece ^ rsub) << 4), sw_odd = (uint32_t)((piece ^ (4 + rsub)) << 4);
+    struct Idx {
+      int r[4];  // input rows gathered into tile rows lane, lane + 32, lane + 64, lane + 96
+      int kw;    // weight-image index of the item's offset
     };
-    // neighbour indices are prefetched 4 work items ahead: the dependent global load (index -> gather address) would
-    // otherwise expose one L2 round trip per (tile, offset)
-    long long t_wait = 0, t_start = clock64();
-    WorkCursor cur(p.tile_kmask, blockIdx.x, gridDim.x, p.num_tiles), pf = cur;
-    int q0 = load_idx(pf); pf.next();
-    int q1 = load_idx(pf); pf.next();
-    int q2 = load_idx(pf); pf.next();
-    int q3 = load_idx(pf); pf.next();
-    while (cur.valid()) {
-      const int my_idx = q0;
-      q0 = q1; q1 = q2; q2 = q3;
-      q3 = (p.debug & 16) ? 0 : load_idx(pf);
-      pf.next();
-      int idxs[8];  // input rows of the 8 tile rows this lane copies a piece of (rows 4j + rsub of the warp)
+    auto load_idx = [&](const IterCursor& c) -> Idx {
+      Idx x;
+      const int k = c.valid() ? c.c.k() : 0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) idxs[j] = (p.debug & 16) ? 0 : __shfl_sync(0xffffffffu, my_idx, 4 * j + rsub);
-      for (int ch = 0; ch < nchunks; ++ch) {
-        const int width = min(kChunkElems, p.cin - ch * kChunkElems);  // valid elements in this chunk
-        if (lane == 0) {
-          const long long t0 = clock64();
-          mbar_wait(smem_u32(&empty_bar[ring.stage]), ring.phase ^ 1);  // one poller per warp
-          t_wait += clock64() - t0;
-        }
-        __syncwarp();
-        const uint32_t a_base = smem_u32(sA + (size_t)ring.stage * kABytes);
-        if (piece * 8 < width && !(p.debug & 1)) {
+      for (int g = 0; g < 4; ++g) {
+        const int64_t slot = (int64_t)c.c.tile * kTileM + g * 32 + lane;
+        x.r[g] = (c.valid() && slot < p.n_slots) ? __ldg(p.nbr + (int64_t)k * p.n_slots + slot) : -1;
+      }
+      x.kw = (c.valid() && p.kidx) ? __ldg(p.kidx + k) : k;
+      return x;
+    };
+    IterCursor cur(p.tile_kmask, blockIdx.x, gridDim.x, p.num_tiles, nchunks);
+    const bool active = pi < NP;  // surplus producer warps idle
+    if (active) cur.advance(pi);
+    IterCursor nxt = cur;
+    nxt.advance(NP);
+    Idx ci = load_idx(cur), ni = load_idx(nxt);
+    int stage = pi % S;
+    uint32_t phase = (uint32_t)((pi / S) & 1);
+    while (active && cur.valid()) {
+      IterCursor nn = nxt;
+      nn.advance(NP);
+      const Idx nni = load_idx(nn);  // consumed two of this warp's stages later
+      const int ch = cur.ch;
+      const int width = min(kChunkElems, p.cin - ch * kChunkElems);  // valid elements in this chunk
+      mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+      const uint32_t a_base = smem_u32(sA + (size_t)stage * kABytes);
+      const uint32_t bar = smem_u32(&full_bar[stage]);
+      {
+        // lanes whose piece lies beyond a narrow chunk (or all lanes in the gather-off ablation) still take part in the shuffles
+        const bool act = piece * 8 < width && !(dbg & 1);
+        const __nv_bfloat16* src0 = p.in + ch * kChunkElems + piece * 8;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int idx = idxs[j];
-            const int row = warp * 32 + 4 * j + rsub;  // row within the tile
-            const uint32_t dst = a_base + (uint32_t)(row * 128 + ((piece ^ (row & 7)) << 4));
-            const __nv_bfloat16* src = p.in + (int64_t)(idx < 0 ? 0 : idx) * p.cin + ch * kChunkElems + piece * 8;
-            cp_async_16(dst, src, idx < 0 ? 0u : 16u);
+        for (int g = 0; g < 4; ++g) {
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int idx = __shfl_sync(0xffffffffu, ci.r[g], 4 * jj + rsub);
+            const int row = g * 32 + 4 * jj + rsub;  // row within the tile
+            const uint32_t dst = a_base + (uint32_t)(row * 128) + ((jj & 1) ? sw_odd : sw_even);
+            if (act) cp_async_16(dst, src0 + (int64_t)(idx < 0 ? 0 : idx) * p.cin, idx < 0 ? 0u : 16u);
           }
         }
-        // completion-triggered arrive: no wait_group / fence in the producer (a producer-side fence.proxy.async would drain
-        // every outstanding cp.async of the thread); the generic->async proxy fence is executed by the MMA thread after it
-        // has acquired the full barrier
-        if (!(p.debug & 32) || lane == 0) cp_async_arrive_noinc(smem_u32(&full_bar[ring.stage]));
-        ring.advance();
       }
-      cur.next();
+      // completion-triggered arrive: no wait_group / fence in the producer; the proxy hand-over is completed by the MMA
+      // thread's acquire fence after it has observed the barrier phase
+      cp_async_arrive_noinc(bar);
+      if (lane == 0) {
+        if (dbg & 2) {
+          mbar_arrive(bar);
+        } else {
+          mbar_arrive_expect_tx(bar, (uint32_t)b_bytes);
+          const __nv_bfloat16* wsrc = p.wimg + ((int64_t)ci.kw * nchunks + ch) * (int64_t)p.cout * kChunkElems;
+          bulk_copy_g2s(smem_u32(sB + (size_t)stage * b_bytes), wsrc, (uint32_t)b_bytes, bar);
+        }
+      }
+      __syncwarp();
+      ci = ni;
+      ni = nni;
+      cur = nxt;
+      nxt = nn;
+      stage += NP;
+      while (stage >= S) {
+        stage -= S;
+        phase ^= 1;
+      }
     }
     cp_async_wait<0>();
-  } else if (warp == kLoadWarp) {
-    // ===================== weight loader (one lane) =====================
-    if (lane == 0) {
-      Ring ring(S);
-      for (WorkCursor cur(p.tile_kmask, blockIdx.x, gridDim.x, p.num_tiles); cur.valid(); cur.next()) {
-        const int k = cur.k();
-        const int kw = p.kidx ? p.kidx[k] : k;
-        for (int ch = 0; ch < nchunks; ++ch) {
-          mbar_wait(smem_u32(&empty_bar[ring.stage]), ring.phase ^ 1);
-          const uint32_t bar = smem_u32(&full_bar[ring.stage]);
-          if (p.debug & 2) {
-            mbar_arrive(bar);
-          } else {
-            mbar_arrive_expect_tx(bar, (uint32_t)b_bytes);
-            const __nv_bfloat16* src = p.wimg + ((int64_t)kw * nchunks + ch) * (int64_t)p.cout * kChunkElems;
-            bulk_copy_g2s(smem_u32(sB + (size_t)ring.stage * b_bytes), src, (uint32_t)b_bytes, bar);
-          }
-          ring.advance();
-        }
-      }
-    }
-    __syncwarp();
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (one lane) =====================
     if (lane == 0) {
@@ -154,12 +185,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
       uint32_t acc_phase = 0;
       bool tile_open = false;
       uint32_t accumulate = 0;
-      long long tw_full = 0, tw_tmem = 0, t_start = clock64(), n_it = 0;
+      long long tw_full = 0, tw_tmem = 0, t_start = kDbg ? clock64() : 0, n_it = 0;
       for (WorkCursor cur(p.tile_kmask, blockIdx.x, gridDim.x, p.num_tiles); cur.valid(); cur.next()) {
         if (!tile_open) {
-          const long long t0 = clock64();
+          const long long t0 = kDbg ? clock64() : 0;
           mbar_wait(smem_u32(&tmem_empty[acc_buf]), acc_phase ^ 1);
-          tw_tmem += clock64() - t0;
+          if (kDbg) tw_tmem += clock64() - t0;
           tc_fence_after();
           tile_open = true;
           accumulate = 0;
@@ -167,15 +198,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc_buf * 256);
         for (int ch = 0; ch < nchunks; ++ch) {
           const int width = min(kChunkElems, p.cin - ch * kChunkElems);
-          const long long t1 = clock64();
+          const long long t1 = kDbg ? clock64() : 0;
           mbar_wait(smem_u32(&full_bar[ring.stage]), ring.phase);
-          tw_full += clock64() - t1;
-          ++n_it;
-          if (!(p.debug & 64)) fence_proxy_async();  // producers' cp.async (generic proxy) writes -> visible to tcgen05.mma (async proxy)
+          if (kDbg) {
+            tw_full += clock64() - t1;
+            ++n_it;
+          }
+          if (dbg & 64) fence_proxy_async();  // A/B only: the bidirectional fence (MEMBAR.ALL.CTA) the acquire form replaces
+          else fence_proxy_async_acquire();   // producers' cp.async (generic proxy) writes -> visible to tcgen05.mma (async proxy)
           tc_fence_after();
           const uint64_t adesc = make_smem_desc(smem_u32(sA + (size_t)ring.stage * kABytes));
           const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)ring.stage * b_bytes));
-          for (int kk = 0; kk < ((p.debug & 4) ? (accumulate ? 0 : 1) : width / 16); ++kk) {
+          const int nk = (dbg & 4) ? (accumulate ? 0 : 1) : width / 16;
+          for (int kk = 0; kk < nk; ++kk) {
             // +32 bytes along K inside the 128-byte swizzle row == +2 in the (addr >> 4) field
             umma_bf16(tmem_d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, accumulate);
             accumulate = 1;
@@ -192,11 +227,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
           }
         }
       }
-      if (p.trace) {
-        p.trace[blockIdx.x * 8 + 2] = (unsigned long long)tw_full;
-        p.trace[blockIdx.x * 8 + 3] = (unsigned long long)tw_tmem;
-        p.trace[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_start);
-        p.trace[blockIdx.x * 8 + 5] = (unsigned long long)n_it;
+      if (kDbg && p.trace) {
+        p.trace[blockIdx.x * 16 + 2] = (unsigned long long)tw_full;
+        p.trace[blockIdx.x * 16 + 3] = (unsigned long long)tw_tmem;
+        p.trace[blockIdx.x * 16 + 4] = (unsigned long long)(clock64() - t_start);
+        p.trace[blockIdx.x * 16 + 5] = (unsigned long long)n_it;
       }
     }
     __syncwarp();
@@ -213,7 +248,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
     };
     uint32_t kmask_next = blockIdx.x < p.num_tiles ? p.tile_kmask[blockIdx.x] : 0u;
     int64_t orow_next = load_row(blockIdx.x);
-    long long te_wait = 0, te_start = clock64();
+    long long te_wait = 0, te_start = kDbg ? clock64() : 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const uint32_t kmask = kmask_next;
       const int64_t orow = orow_next;
@@ -222,9 +257,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
       TOut* optr = orow >= 0 ? (TOut*)p.out + orow * p.out_stride : nullptr;
       const bool vec_ok = ((p.out_stride * (int)sizeof(TOut)) & 15) == 0;
       if (kmask != 0) {
-        const long long t0 = clock64();
+        const long long t0 = kDbg ? clock64() : 0;
         mbar_wait(smem_u32(&tmem_full[acc_buf]), acc_phase);
-        te_wait += clock64() - t0;
+        if (kDbg) te_wait += clock64() - t0;
         tc_fence_after();
       }
       for (int c0 = 0; c0 < p.out_cols; c0 += 16) {
@@ -243,7 +278,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] += (c0 + j < p.out_cols) ? p.bias[c0 + j] : 0.f;
         }
-        if (optr && !(p.debug & 8)) {
+        if (optr && !(dbg & 8)) {
           if (vec_ok && c0 + 16 <= p.out_cols) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4) store4(optr + c0 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
@@ -263,15 +298,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
         }
       }
     }
-    if (p.trace && warp == kFirstEpiWarp && lane == 0) {
-      p.trace[blockIdx.x * 8 + 6] = (unsigned long long)te_wait;
-      p.trace[blockIdx.x * 8 + 7] = (unsigned long long)(clock64() - te_start);
+    if (kDbg && p.trace && warp == kFirstEpiWarp && lane == 0) {
+      p.trace[blockIdx.x * 16 + 6] = (unsigned long long)te_wait;
+      p.trace[blockIdx.x * 16 + 7] = (unsigned long long)(clock64() - te_start);
     }
   }
 
-  if (p.trace && warp == kFirstEpiWarp && lane == 0) {
-    // (epilogue timers live in the epilogue branch's scope; written there)
-  }
   tc_fence_before();
   __syncthreads();
   if (warp == kLoadWarp) {
@@ -387,48 +419,49 @@ int mk_conv_fwd_bf16(const void* in, int64_t n_in, int cin, const void* wimg, in
   int stages = kMaxStages;
   while (stages > 3 && conv_smem_bytes(cout, stages) > 210 * 1024) --stages;
   MK_REQUIRE(conv_smem_bytes(cout, stages) <= 227 * 1024, "shared memory budget exceeded");
+  {
+    static int st_env = -1, np_env = -1;
+    if (st_env < 0) { const char* e = getenv("MK3D_STAGES"); st_env = e ? atoi(e) : 0; }
+    if (np_env < 0) { const char* e = getenv("MK3D_PRODUCERS"); np_env = e ? atoi(e) : 0; }
+    if (st_env >= 2 && st_env < stages) stages = st_env;  // tuning sweeps only
+    p.num_producers = stages - 1 < kMaxProducers ? stages - 1 : kMaxProducers;
+    if (np_env >= 1 && np_env < p.num_producers) p.num_producers = np_env;
+  }
   p.num_stages = stages;
   const size_t smem = conv_smem_bytes(cout, stages);
   int grid = num_sms();
   if (grid > p.num_tiles) grid = p.num_tiles;
   cudaStream_t st = (cudaStream_t)stream_;
-  // producers keep (lag + 1) stages of gathers in flight; the ring must be strictly deeper than that
-  const int lag = stages >= 8 ? 5 : (stages >= 6 ? 4 : (stages >= 5 ? 3 : (stages >= 4 ? 2 : 1)));
-#define MK_LAUNCH(T, L)                                                                                     \
+#define MK_LAUNCH(T, D)                                                                                     \
   do {                                                                                                      \
-    cudaFuncSetAttribute(k_conv_umma<T, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
-    k_conv_umma<T, L><<<grid, kNumThreads, smem, st>>>(p);                                                  \
-  } while (0)
-#define MK_LAUNCH_T(T)              \
-  do {                              \
-    switch (lag) {                  \
-      case 5: MK_LAUNCH(T, 5); break; \
-      case 4: MK_LAUNCH(T, 4); break; \
-      case 3: MK_LAUNCH(T, 3); break; \
-      case 2: MK_LAUNCH(T, 2); break; \
-      default: MK_LAUNCH(T, 1); break; \
-    }                               \
+    cudaFuncSetAttribute(k_conv_umma<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+    k_conv_umma<T, D><<<grid, kNumThreads, smem, st>>>(p);                                                  \
   } while (0)
   static int trace_on = -1;
   if (trace_on < 0) trace_on = getenv("MK3D_TRACE") ? 1 : 0;
   if (trace_on) {
-    cudaMalloc(&p.trace, (size_t)grid * 8 * sizeof(unsigned long long));
-    cudaMemset(p.trace, 0, (size_t)grid * 8 * sizeof(unsigned long long));
+    cudaMalloc(&p.trace, (size_t)grid * 16 * sizeof(unsigned long long));
+    cudaMemset(p.trace, 0, (size_t)grid * 16 * sizeof(unsigned long long));
   }
-  if (out_dtype == MK_F32) MK_LAUNCH_T(float);
-  else MK_LAUNCH_T(__nv_bfloat16);
+  const bool dbg_build = trace_on || p.debug != 0;
+  if (out_dtype == MK_F32) {
+    if (dbg_build) MK_LAUNCH(float, true);
+    else MK_LAUNCH(float, false);
+  } else {
+    if (dbg_build) MK_LAUNCH(__nv_bfloat16, true);
+    else MK_LAUNCH(__nv_bfloat16, false);
+  }
   if (trace_on) {
-    std::vector<unsigned long long> h((size_t)grid * 8);
+    std::vector<unsigned long long> h((size_t)grid * 16);
     cudaStreamSynchronize(st);
     cudaMemcpy(h.data(), p.trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     cudaFree(p.trace);
-    double a[8] = {0};
+    double a[16] = {0};
     for (int b = 0; b < grid; ++b)
-      for (int j = 0; j < 8; ++j) a[j] += (double)h[(size_t)b * 8 + j] / grid;
-    fprintf(stderr, "[mk3d trace] cin %d cout %d K %d tiles %d stages %d | producer: wait_empty %.0f / total %.0f | mma: wait_full %.0f wait_tmem %.0f / total %.0f, iters %.0f | epilogue: wait_full %.0f / total %.0f (cycles, CTA mean)\n",
-            cin, cout, K, p.num_tiles, stages, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+      for (int j = 0; j < 16; ++j) a[j] += (double)h[(size_t)b * 16 + j] / grid;
+    fprintf(stderr, "[mk3d trace] cin %d cout %d K %d tiles %d stages %d | mma: wait_full %.0f wait_tmem %.0f / total %.0f, iters %.0f | epilogue: wait_full %.0f / total %.0f (cycles, CTA mean)\n",
+            cin, cout, K, p.num_tiles, stages, a[2], a[3], a[4], a[5], a[6], a[7]);
   }
-#undef MK_LAUNCH_T
 #undef MK_LAUNCH
   return check_launch(__func__);
 }

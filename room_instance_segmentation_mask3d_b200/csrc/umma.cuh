@@ -48,6 +48,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// Consumer-side (acquire) half of the generic -> async proxy hand-over: executed by the MMA thread after it has observed the
+// stage's mbarrier phase, before tcgen05.mma reads the tile through the async proxy.  The bidirectional fence.proxy.async
+// compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC; the MEMBAR queues behind every in-flight LDGSTS of the SM's LSU FIFO
+// (~500-1000 cycles per pipeline stage, measured with clock64 around it), which serialised the whole gather pipeline.
+// The unidirectional acquire form needs no instruction on sm_100a: the release half is the completion-triggered
+// cp.async.mbarrier.arrive (the arrive fires after the copies have been written to shared memory).
+__device__ __forceinline__ void fence_proxy_async_acquire() {
+  asm volatile("fence.proxy.async::generic.acquire.sync_restrict::shared::cluster.cluster;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -140,6 +149,7 @@ struct ConvParams {
   int K;
   int num_tiles;
   int num_stages;
+  int num_producers;  // active producer warps (<= 5 and < num_stages: a producer may be at most one ring phase ahead)
   int nchunks;
   int out_cols;    // columns actually stored (<= cout; the rest of the accumulator is padding)
   int out_stride;  // elements between consecutive output rows
