@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
       // completion-triggered arrive: no wait_group / fence in the producer; the proxy hand-over is completed by the MMA
       // thread's acquire fence after it has observed the barrier phase
       cp_async_arrive_noinc(bar);
-      if (lane == 0) {
+      if (elect_one_sync()) {
         if (dbg & 2) {
           mbar_arrive(bar);
         } else {
@@ -177,64 +177,67 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
     }
     cp_async_wait<0>();
   } else if (warp == kMmaWarp) {
-    // ===================== MMA issuer (one lane) =====================
-    if (lane == 0) {
-      Ring ring(S);
-      const uint32_t idesc = make_idesc(kTileM, p.cout);
-      int acc_buf = 0;
-      uint32_t acc_phase = 0;
-      bool tile_open = false;
-      uint32_t accumulate = 0;
-      long long tw_full = 0, tw_tmem = 0, t_start = kDbg ? clock64() : 0, n_it = 0;
-      for (WorkCursor cur(p.tile_kmask, blockIdx.x, gridDim.x, p.num_tiles); cur.valid(); cur.next()) {
-        if (!tile_open) {
-          const long long t0 = kDbg ? clock64() : 0;
-          mbar_wait(smem_u32(&tmem_empty[acc_buf]), acc_phase ^ 1);
-          if (kDbg) tw_tmem += clock64() - t0;
-          tc_fence_after();
-          tile_open = true;
-          accumulate = 0;
+    // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+    // Every lane runs the loop so that all control flow and descriptor arithmetic stays warp-uniform; only the tcgen05
+    // instructions sit under elect_one_sync() (see umma.cuh).
+    Ring ring(S);
+    const uint32_t idesc = make_idesc(kTileM, p.cout);
+    int acc_buf = 0;
+    uint32_t acc_phase = 0;
+    bool tile_open = false;
+    uint32_t accumulate = 0;
+    long long tw_full = 0, tw_tmem = 0, t_start = kDbg ? clock64() : 0, n_it = 0;
+    for (WorkCursor cur(p.tile_kmask, blockIdx.x, gridDim.x, p.num_tiles); cur.valid(); cur.next()) {
+      if (!tile_open) {
+        const long long t0 = kDbg ? clock64() : 0;
+        mbar_wait(smem_u32(&tmem_empty[acc_buf]), acc_phase ^ 1);
+        if (kDbg) tw_tmem += clock64() - t0;
+        tc_fence_after();
+        tile_open = true;
+        accumulate = 0;
+      }
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc_buf * 256);
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int width = min(kChunkElems, p.cin - ch * kChunkElems);
+        const long long t1 = kDbg ? clock64() : 0;
+        mbar_wait(smem_u32(&full_bar[ring.stage]), ring.phase);
+        if (kDbg) {
+          tw_full += clock64() - t1;
+          ++n_it;
         }
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc_buf * 256);
-        for (int ch = 0; ch < nchunks; ++ch) {
-          const int width = min(kChunkElems, p.cin - ch * kChunkElems);
-          const long long t1 = kDbg ? clock64() : 0;
-          mbar_wait(smem_u32(&full_bar[ring.stage]), ring.phase);
-          if (kDbg) {
-            tw_full += clock64() - t1;
-            ++n_it;
-          }
-          if (dbg & 64) fence_proxy_async();  // A/B only: the bidirectional fence (MEMBAR.ALL.CTA) the acquire form replaces
-          else fence_proxy_async_acquire();   // producers' cp.async (generic proxy) writes -> visible to tcgen05.mma (async proxy)
-          tc_fence_after();
-          const uint64_t adesc = make_smem_desc(smem_u32(sA + (size_t)ring.stage * kABytes));
-          const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)ring.stage * b_bytes));
-          const int nk = (dbg & 4) ? (accumulate ? 0 : 1) : width / 16;
+        if (dbg & 64) fence_proxy_async();  // A/B only: the bidirectional fence (MEMBAR.ALL.CTA) the acquire form replaces
+        else fence_proxy_async_acquire();   // producers' cp.async (generic proxy) writes -> visible to tcgen05.mma (async proxy)
+        tc_fence_after();
+        const uint64_t adesc = make_smem_desc(smem_u32(sA + (size_t)ring.stage * kABytes));
+        const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)ring.stage * b_bytes));
+        const int nk = (dbg & 4) ? (accumulate ? 0 : 1) : width / 16;
+        if (elect_one_sync()) {
           for (int kk = 0; kk < nk; ++kk) {
             // +32 bytes along K inside the 128-byte swizzle row == +2 in the (addr >> 4) field
-            umma_bf16(tmem_d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, accumulate);
-            accumulate = 1;
+            umma_bf16(tmem_d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (kk > 0) ? 1u : accumulate);
           }
           umma_commit(smem_u32(&empty_bar[ring.stage]));  // frees the stage when these MMAs retire
-          ring.advance();
         }
-        if (cur.last_k_of_tile()) {
-          umma_commit(smem_u32(&tmem_full[acc_buf]));
-          tile_open = false;
-          if (++acc_buf == 2) {
-            acc_buf = 0;
-            acc_phase ^= 1;
-          }
-        }
+        __syncwarp();
+        if (nk > 0) accumulate = 1;
+        ring.advance();
       }
-      if (kDbg && p.trace) {
-        p.trace[blockIdx.x * 16 + 2] = (unsigned long long)tw_full;
-        p.trace[blockIdx.x * 16 + 3] = (unsigned long long)tw_tmem;
-        p.trace[blockIdx.x * 16 + 4] = (unsigned long long)(clock64() - t_start);
-        p.trace[blockIdx.x * 16 + 5] = (unsigned long long)n_it;
+      if (cur.last_k_of_tile()) {
+        if (elect_one_sync()) umma_commit(smem_u32(&tmem_full[acc_buf]));
+        __syncwarp();
+        tile_open = false;
+        if (++acc_buf == 2) {
+          acc_buf = 0;
+          acc_phase ^= 1;
+        }
       }
     }
-    __syncwarp();
+    if (kDbg && p.trace && lane == 0) {
+      p.trace[blockIdx.x * 16 + 2] = (unsigned long long)tw_full;
+      p.trace[blockIdx.x * 16 + 3] = (unsigned long long)tw_tmem;
+      p.trace[blockIdx.x * 16 + 4] = (unsigned long long)(clock64() - t_start);
+      p.trace[blockIdx.x * 16 + 5] = (unsigned long long)n_it;
+    }
   } else {
     // ===================== epilogue (4 warps) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access

@@ -60,6 +60,22 @@ __device__ __forceinline__ void fence_proxy_async_acquire() {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// true on exactly one lane of a converged warp.  A branch on this predicate is how single-thread tcgen05 / bulk-copy
+// instructions must be issued: the compiler then keeps their operands on the uniform datapath and emits ONE UTCHMMA / UTCBAR /
+// UBLKCP per warp.  Guarding with `lane == 0` instead makes it treat the code as divergent and wrap every such instruction in
+// an ELECT / BRA.U.ANY waterfall loop with R2UR moves (~15 dependent instructions, ~100 cycles per MMA on the issuing thread).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
   // .ca: allocate in L1 — a tile is a compact spatial patch (mask + Z-curve sorted), so the neighbour rows gathered for its
   // different offsets overlap heavily and are re-read from L1 instead of L2
