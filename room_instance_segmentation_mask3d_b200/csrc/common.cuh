@@ -116,6 +116,22 @@ __device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
   *reinterpret_cast<uint2*>(p) = r;
 }
 
+// 16 consecutive channels from fp32 registers: 4 x 16-byte stores (fp32) or 2 x 16-byte stores (bf16)
+__device__ __forceinline__ void store16(float* p, const float (&v)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(p + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+}
+__device__ __forceinline__ void store16(__nv_bfloat16* p, const float (&v)[16]) {
+  uint32_t w[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    w[j] = *reinterpret_cast<uint32_t*>(&t);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  *reinterpret_cast<uint4*>(p + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
 // scene of a row: largest b with offsets[b] <= row  (B is small; linear scan of a broadcast-cached array)
 __device__ __forceinline__ int scene_of_row(const int32_t* __restrict__ offsets, int B, int64_t row) {
   int b = 0;

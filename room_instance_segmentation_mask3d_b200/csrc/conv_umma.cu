@@ -36,18 +36,51 @@ namespace mk {
 
 constexpr int kMaxProducers = 5;  // warps 0-3 and 5
 
-// (item = (tile, offset), 64-channel chunk) iteration space of one CTA, in execution order
-struct IterCursor {
-  WorkCursor c;
+// Work enumeration of one CTA.  A "super-tile" is G consecutive 128-slot tiles (G = 2 when cout <= 128: the two accumulators
+// share every weight chunk, which halves the weight traffic and the per-stage bookkeeping of all three roles; mask-sorted
+// plans give neighbouring tiles the same offset set, so the union costs nothing).  Items are the set bits of the union of the
+// member tiles' offset masks, ascending; an iteration is (item, 64-channel chunk).
+struct SuperCursor {
+  const uint32_t* kmask;
+  int G, st, stride, num_st, num_tiles;
+  uint32_t m0, m1, mu;      // member masks of the current super-tile, remaining union bits
+  uint32_t n0, n1;          // masks of the next super-tile (prefetched)
   int ch, nchunks;
-  __device__ IterCursor(const uint32_t* kmask, int first, int stride, int num_tiles, int nchunks_)
-      : c(kmask, first, stride, num_tiles), ch(0), nchunks(nchunks_) {}
-  __device__ bool valid() const { return c.valid(); }
-  __device__ void advance(int n) {
-    for (int i = 0; i < n && c.valid(); ++i) {
+  __device__ uint32_t mask_of(int t) const { return t < num_tiles ? kmask[t] : 0u; }
+  __device__ SuperCursor(const uint32_t* kmask_, int G_, int first, int stride_, int num_tiles_, int nchunks_)
+      : kmask(kmask_), G(G_), st(first), stride(stride_), num_tiles(num_tiles_), ch(0), nchunks(nchunks_) {
+    num_st = (num_tiles + G - 1) / G;
+    load(st, m0, m1);
+    load(st + stride, n0, n1);
+    mu = m0 | m1;
+    skip_empty();
+  }
+  __device__ void load(int s, uint32_t& a, uint32_t& b) const {
+    a = s < num_st ? mask_of(G * s) : 0u;
+    b = (s < num_st && G == 2) ? mask_of(2 * s + 1) : 0u;
+  }
+  __device__ void skip_empty() {
+    while (mu == 0u && st < num_st) {
+      st += stride;
+      m0 = n0;
+      m1 = n1;
+      mu = m0 | m1;
+      load(st + stride, n0, n1);
+    }
+  }
+  __device__ bool valid() const { return st < num_st; }
+  __device__ int k() const { return __ffs(mu) - 1; }
+  __device__ bool has(int g) const { return (((g ? m1 : m0) >> k()) & 1u) != 0u; }
+  __device__ bool last_k() const { return (mu & (mu - 1)) == 0u; }
+  __device__ void next_item() {
+    mu &= mu - 1;
+    skip_empty();
+  }
+  __device__ void advance(int n) {  // n iterations
+    for (int i = 0; i < n && valid(); ++i) {
       if (++ch == nchunks) {
         ch = 0;
-        c.next();
+        next_item();
       }
     }
   }
@@ -56,12 +89,14 @@ struct IterCursor {
 template <typename TOut, bool kDbg>
 __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages x A 16 KB][stages x B cout*128][barriers]
+  // carve: [stages x G x A 16 KB][stages x B cout*128][barriers]
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int S = p.num_stages;
+  const int G = p.group;
+  const int a_bytes = G * kABytes;
   const int b_bytes = p.cout * 128;
   uint8_t* sA = smem;
-  uint8_t* sB = smem + (size_t)S * kABytes;
+  uint8_t* sB = smem + (size_t)S * a_bytes;
   uint64_t* bars = (uint64_t*)(sB + (size_t)S * b_bytes);
   uint64_t* full_bar = bars;                       // [S]  32 producer lanes (copy completion) + 1 expect_tx arrive
   uint64_t* empty_bar = bars + kMaxStages;         // [S]  one tcgen05.commit
@@ -71,6 +106,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dbg = kDbg ? p.debug : 0;
+  const int acc_cols = G == 2 ? 128 : 256;  // TMEM columns per accumulator: [buffer][member tile] x acc_cols = 512
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
@@ -95,60 +131,73 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
   const int nchunks = p.nchunks;
 
   if (warp < kNumProducerWarps || warp == kLoadWarp) {
-    // ===================== producers (5 warps, one stage each, round-robin) =====================
+    // ===================== producers (up to 5 warps, one stage each, round-robin) =====================
     const int pi = warp < kNumProducerWarps ? warp : kNumProducerWarps;
-    // Stage ownership: iteration i is staged by producer i mod NP into ring slot i mod S.  NP < S is required: the
-    // parity wait on a slot's empty barrier is only unambiguous while a producer can be at most ONE ring phase ahead of
-    // the consumer, which holds iff everything before iteration i - NP - S being consumed implies i - 2S is (S > NP).
+    // Stage ownership: iteration i is staged by producer i mod NP into ring slot i mod S.  NP <= S is required: the
+    // parity wait on a slot's empty barrier is only unambiguous while a producer is at most ONE ring phase ahead of the
+    // consumer; having passed the wait of iteration i - NP it knows i - NP - S and everything earlier was consumed, which
+    // covers i - 2S iff S >= NP.
     const int NP = p.num_producers;
     const int piece = lane & 7;  // 16-byte piece of the 128-byte row
     const int rsub = lane >> 3;  // 4 rows per warp instruction
     // swizzled piece offset inside the row: row & 7 == 4 * (jj & 1) + rsub for row = 4 * jj + rsub
     const uint32_t sw_even = (uint32_t)((piece ^ rsub) << 4), sw_odd = (uint32_t)((piece ^ (4 + rsub)) << 4);
     struct Idx {
-      int r[4];  // input rows gathered into tile rows lane, lane + 32, lane + 64, lane + 96
-      int kw;    // weight-image index of the item's offset
+      int r[2][4];  // per member tile: input rows gathered into tile rows lane, lane + 32, lane + 64, lane + 96
+      int kw;       // weight-image index of the item's offset
+      uint32_t has; // bit g: member tile g has this offset
     };
-    auto load_idx = [&](const IterCursor& c) -> Idx {
+    auto load_idx = [&](const SuperCursor& c) -> Idx {
       Idx x;
-      const int k = c.valid() ? c.c.k() : 0;
+      const bool v = c.valid();
+      const int k = v ? c.k() : 0;
+      x.has = v ? ((c.has(0) ? 1u : 0u) | (c.has(1) ? 2u : 0u)) : 0u;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int64_t slot = (int64_t)c.c.tile * kTileM + g * 32 + lane;
-        x.r[g] = (c.valid() && slot < p.n_slots) ? __ldg(p.nbr + (int64_t)k * p.n_slots + slot) : -1;
+      for (int g = 0; g < 2; ++g) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int64_t slot = ((int64_t)c.st * G + g) * kTileM + q * 32 + lane;
+          x.r[g][q] = (((x.has >> g) & 1u) && slot < p.n_slots) ? __ldg(p.nbr + (int64_t)k * p.n_slots + slot) : -1;
+        }
       }
-      x.kw = (c.valid() && p.kidx) ? __ldg(p.kidx + k) : k;
+      x.kw = (v && p.kidx) ? __ldg(p.kidx + k) : k;
       return x;
     };
-    IterCursor cur(p.tile_kmask, blockIdx.x, gridDim.x, p.num_tiles, nchunks);
+    SuperCursor cur(p.tile_kmask, G, blockIdx.x, gridDim.x, p.num_tiles, nchunks);
     const bool active = pi < NP;  // surplus producer warps idle
     if (active) cur.advance(pi);
-    IterCursor nxt = cur;
+    SuperCursor nxt = cur;
     nxt.advance(NP);
     Idx ci = load_idx(cur), ni = load_idx(nxt);
     int stage = pi % S;
     uint32_t phase = (uint32_t)((pi / S) & 1);
+    long long tp_wait = 0, tp_start = kDbg ? clock64() : 0;
     while (active && cur.valid()) {
-      IterCursor nn = nxt;
+      SuperCursor nn = nxt;
       nn.advance(NP);
       const Idx nni = load_idx(nn);  // consumed two of this warp's stages later
       const int ch = cur.ch;
       const int width = min(kChunkElems, p.cin - ch * kChunkElems);  // valid elements in this chunk
+      const long long tp0 = kDbg ? clock64() : 0;
       mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-      const uint32_t a_base = smem_u32(sA + (size_t)stage * kABytes);
+      if (kDbg) tp_wait += clock64() - tp0;
       const uint32_t bar = smem_u32(&full_bar[stage]);
-      {
-        // lanes whose piece lies beyond a narrow chunk (or all lanes in the gather-off ablation) still take part in the shuffles
-        const bool act = piece * 8 < width && !(dbg & 1);
-        const __nv_bfloat16* src0 = p.in + ch * kChunkElems + piece * 8;
+      // lanes whose piece lies beyond a narrow chunk (or all lanes in the gather-off ablation) still take part in the shuffles
+      const bool act = piece * 8 < width && !(dbg & 1);
+      const __nv_bfloat16* src0 = p.in + ch * kChunkElems + piece * 8;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+      for (int g = 0; g < 2; ++g) {
+        if ((ci.has >> g) & 1u) {  // warp-uniform
+          const uint32_t a_base = smem_u32(sA + (size_t)stage * a_bytes + (size_t)g * kABytes);
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const int idx = __shfl_sync(0xffffffffu, ci.r[g], 4 * jj + rsub);
-            const int row = g * 32 + 4 * jj + rsub;  // row within the tile
-            const uint32_t dst = a_base + (uint32_t)(row * 128) + ((jj & 1) ? sw_odd : sw_even);
-            if (act) cp_async_16(dst, src0 + (int64_t)(idx < 0 ? 0 : idx) * p.cin, idx < 0 ? 0u : 16u);
+          for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const int idx = __shfl_sync(0xffffffffu, ci.r[g][q], 4 * jj + rsub);
+              const int row = q * 32 + 4 * jj + rsub;  // row within the tile
+              const uint32_t dst = a_base + (uint32_t)(row * 128) + ((jj & 1) ? sw_odd : sw_even);
+              if (act) cp_async_16(dst, src0 + (int64_t)(idx < 0 ? 0 : idx) * p.cin, idx < 0 ? 0u : 16u);
+            }
           }
         }
       }
@@ -175,6 +224,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
         phase ^= 1;
       }
     }
+    if (kDbg && p.trace && warp == 0 && lane == 0) {
+      p.trace[blockIdx.x * 16 + 0] = (unsigned long long)tp_wait;
+      p.trace[blockIdx.x * 16 + 1] = (unsigned long long)(clock64() - tp_start);
+    }
     cp_async_wait<0>();
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
@@ -185,18 +238,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
     int acc_buf = 0;
     uint32_t acc_phase = 0;
     bool tile_open = false;
-    uint32_t accumulate = 0;
+    uint32_t started = 0;  // bit g: accumulator of member tile g holds a partial sum
     long long tw_full = 0, tw_tmem = 0, t_start = kDbg ? clock64() : 0, n_it = 0;
-    for (WorkCursor cur(p.tile_kmask, blockIdx.x, gridDim.x, p.num_tiles); cur.valid(); cur.next()) {
+    for (SuperCursor cur(p.tile_kmask, G, blockIdx.x, gridDim.x, p.num_tiles, nchunks); cur.valid(); cur.next_item()) {
       if (!tile_open) {
         const long long t0 = kDbg ? clock64() : 0;
         mbar_wait(smem_u32(&tmem_empty[acc_buf]), acc_phase ^ 1);
         if (kDbg) tw_tmem += clock64() - t0;
         tc_fence_after();
         tile_open = true;
-        accumulate = 0;
+        started = 0;
       }
-      const uint32_t tmem_d = tmem_base + (uint32_t)(acc_buf * 256);
+      const uint32_t has = (cur.has(0) ? 1u : 0u) | (cur.has(1) ? 2u : 0u);
       for (int ch = 0; ch < nchunks; ++ch) {
         const int width = min(kChunkElems, p.cin - ch * kChunkElems);
         const long long t1 = kDbg ? clock64() : 0;
@@ -208,21 +261,29 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
         if (dbg & 64) fence_proxy_async();  // A/B only: the bidirectional fence (MEMBAR.ALL.CTA) the acquire form replaces
         else fence_proxy_async_acquire();   // producers' cp.async (generic proxy) writes -> visible to tcgen05.mma (async proxy)
         tc_fence_after();
-        const uint64_t adesc = make_smem_desc(smem_u32(sA + (size_t)ring.stage * kABytes));
         const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)ring.stage * b_bytes));
-        const int nk = (dbg & 4) ? (accumulate ? 0 : 1) : width / 16;
+        const int nk = width / 16;
         if (elect_one_sync()) {
-          for (int kk = 0; kk < nk; ++kk) {
-            // +32 bytes along K inside the 128-byte swizzle row == +2 in the (addr >> 4) field
-            umma_bf16(tmem_d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (kk > 0) ? 1u : accumulate);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if ((has >> g) & 1u) {
+              const uint64_t adesc = make_smem_desc(smem_u32(sA + (size_t)ring.stage * a_bytes + (size_t)g * kABytes));
+              const uint32_t tmem_d = tmem_base + (uint32_t)((acc_buf * G + g) * acc_cols);
+              const uint32_t first_acc = (started >> g) & 1u;
+              const int nkg = (dbg & 4) ? (first_acc ? 0 : 1) : nk;
+              for (int kk = 0; kk < nkg; ++kk) {
+                // +32 bytes along K inside the 128-byte swizzle row == +2 in the (addr >> 4) field
+                umma_bf16(tmem_d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (kk > 0) ? 1u : first_acc);
+              }
+            }
           }
           umma_commit(smem_u32(&empty_bar[ring.stage]));  // frees the stage when these MMAs retire
         }
         __syncwarp();
-        if (nk > 0) accumulate = 1;
+        started |= has;
         ring.advance();
       }
-      if (cur.last_k_of_tile()) {
+      if (cur.last_k()) {
         if (elect_one_sync()) umma_commit(smem_u32(&tmem_full[acc_buf]));
         __syncwarp();
         tile_open = false;
@@ -243,56 +304,76 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     int acc_buf = 0;
     uint32_t acc_phase = 0;
+    const int num_st = (p.num_tiles + G - 1) / G;
     auto load_row = [&](int tile) -> int64_t {
       const int64_t slot = (int64_t)tile * kTileM + q * 32 + lane;
       int64_t r = -1;
       if (tile < p.num_tiles && slot < p.n_slots) r = p.out_rows ? (int64_t)__ldg(p.out_rows + slot) : slot;
       return r >= p.n_out ? -1 : r;
     };
-    uint32_t kmask_next = blockIdx.x < p.num_tiles ? p.tile_kmask[blockIdx.x] : 0u;
-    int64_t orow_next = load_row(blockIdx.x);
+    auto load_mask = [&](int tile) -> uint32_t { return tile < p.num_tiles ? p.tile_kmask[tile] : 0u; };
+    uint32_t km_next[2];
+    int64_t orow_next[2];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int t = g < G ? (int)blockIdx.x * G + g : p.num_tiles;
+      km_next[g] = (int)blockIdx.x < num_st ? load_mask(t) : 0u;
+      orow_next[g] = (int)blockIdx.x < num_st ? load_row(t) : -1;
+    }
+    const bool vec_ok = ((p.out_stride * (int)sizeof(TOut)) & 15) == 0;
     long long te_wait = 0, te_start = kDbg ? clock64() : 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const uint32_t kmask = kmask_next;
-      const int64_t orow = orow_next;
-      if (tile + (int)gridDim.x < p.num_tiles) kmask_next = p.tile_kmask[tile + gridDim.x];
-      orow_next = load_row(tile + gridDim.x);
-      TOut* optr = orow >= 0 ? (TOut*)p.out + orow * p.out_stride : nullptr;
-      const bool vec_ok = ((p.out_stride * (int)sizeof(TOut)) & 15) == 0;
-      if (kmask != 0) {
+    for (int st = blockIdx.x; st < num_st; st += gridDim.x) {
+      uint32_t km[2];
+      int64_t orow[2];
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        km[g] = km_next[g];
+        orow[g] = orow_next[g];
+        const int tn = g < G ? (st + (int)gridDim.x) * G + g : p.num_tiles;
+        const bool vn = st + (int)gridDim.x < num_st;
+        km_next[g] = vn ? load_mask(tn) : 0u;
+        orow_next[g] = vn ? load_row(tn) : -1;
+      }
+      const bool any = (km[0] | km[1]) != 0u;
+      if (any) {
         const long long t0 = kDbg ? clock64() : 0;
         mbar_wait(smem_u32(&tmem_full[acc_buf]), acc_phase);
         if (kDbg) te_wait += clock64() - t0;
         tc_fence_after();
       }
-      for (int c0 = 0; c0 < p.out_cols; c0 += 16) {
-        float v[16];
-        if (kmask != 0) {
-          uint32_t r[16];
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_buf * 256 + c0), r);
-          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-        } else {
+      for (int g = 0; g < 2; ++g) {
+        if (g >= G || st * G + g >= p.num_tiles) continue;
+        TOut* optr = orow[g] >= 0 ? (TOut*)p.out + orow[g] * p.out_stride : nullptr;
+        const uint32_t tcol = (uint32_t)((acc_buf * G + g) * acc_cols);
+        for (int c0 = 0; c0 < p.out_cols; c0 += 16) {
+          float v[16];
+          if (km[g] != 0u) {
+            uint32_t r[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + tcol + (uint32_t)c0, r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = 0.f;
-        }
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += (c0 + j < p.out_cols) ? p.bias[c0 + j] : 0.f;
-        }
-        if (optr && !(dbg & 8)) {
-          if (vec_ok && c0 + 16 <= p.out_cols) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) store4(optr + c0 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (c0 + j < p.out_cols) optr[c0 + j] = from_f32<TOut>(v[j]);
+            for (int j = 0; j < 16; ++j) v[j] = 0.f;
+          }
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += (c0 + j < p.out_cols) ? p.bias[c0 + j] : 0.f;
+          }
+          if (optr && !(dbg & 8)) {
+            if (vec_ok && c0 + 16 <= p.out_cols) {
+              store16(optr + c0, v);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < p.out_cols) optr[c0 + j] = from_f32<TOut>(v[j]);
+            }
           }
         }
       }
-      if (kmask != 0) {
+      if (any) {
         tc_fence_before();
         mbar_arrive(smem_u32(&tmem_empty[acc_buf]));
         if (++acc_buf == 2) {
@@ -341,8 +422,8 @@ __global__ void __launch_bounds__(256) k_weight_image(const float* __restrict__ 
   }
 }
 
-inline size_t conv_smem_bytes(int cout, int stages) {
-  return 1024 + (size_t)stages * (kABytes + (size_t)cout * 128) + (2 * kMaxStages + 4) * sizeof(uint64_t) + 16;
+inline size_t conv_smem_bytes(int cout, int stages, int group = 1) {
+  return 1024 + (size_t)stages * ((size_t)group * kABytes + (size_t)cout * 128) + (2 * kMaxStages + 4) * sizeof(uint64_t) + 16;
 }
 
 int conv_tma_launch(const ConvParams& p, int64_t n_in, int out_dtype, cudaStream_t st);  // conv_tma.cu
@@ -419,21 +500,29 @@ int mk_conv_fwd_bf16(const void* in, int64_t n_in, int cin, const void* wimg, in
   }
   p.trace = nullptr;
   if (gather_mode() == 1) return conv_tma_launch(p, n_in, out_dtype, (cudaStream_t)stream_);
+  // super-tiles of two tiles when both accumulators fit next to their double buffer (4 x 128 TMEM columns) and there are
+  // enough tiles to keep every SM busy with the coarser work unit
+  static int grp_env = -1;
+  if (grp_env < 0) { const char* e = getenv("MK3D_GROUP"); grp_env = e ? atoi(e) : 0; }
+  int group = (cout <= 128 && p.num_tiles >= 4 * num_sms()) ? 2 : 1;
+  if (grp_env == 1 || (grp_env == 2 && cout <= 128)) group = grp_env;
+  p.group = group;
   int stages = kMaxStages;
-  while (stages > 3 && conv_smem_bytes(cout, stages) > 210 * 1024) --stages;
-  MK_REQUIRE(conv_smem_bytes(cout, stages) <= 227 * 1024, "shared memory budget exceeded");
+  while (stages > 2 && conv_smem_bytes(cout, stages, group) > 222 * 1024) --stages;
+  MK_REQUIRE(conv_smem_bytes(cout, stages, group) <= 227 * 1024, "shared memory budget exceeded");
   {
     static int st_env = -1, np_env = -1;
     if (st_env < 0) { const char* e = getenv("MK3D_STAGES"); st_env = e ? atoi(e) : 0; }
     if (np_env < 0) { const char* e = getenv("MK3D_PRODUCERS"); np_env = e ? atoi(e) : 0; }
     if (st_env >= 2 && st_env < stages) stages = st_env;  // tuning sweeps only
-    p.num_producers = stages - 1 < kMaxProducers ? stages - 1 : kMaxProducers;
+    p.num_producers = stages < kMaxProducers ? stages : kMaxProducers;
     if (np_env >= 1 && np_env < p.num_producers) p.num_producers = np_env;
   }
   p.num_stages = stages;
-  const size_t smem = conv_smem_bytes(cout, stages);
+  const size_t smem = conv_smem_bytes(cout, stages, group);
   int grid = num_sms();
-  if (grid > p.num_tiles) grid = p.num_tiles;
+  const int num_super = (p.num_tiles + group - 1) / group;
+  if (grid > num_super) grid = num_super;
   cudaStream_t st = (cudaStream_t)stream_;
 #define MK_LAUNCH(T, D)                                                                                     \
   do {                                                                                                      \
@@ -462,8 +551,8 @@ int mk_conv_fwd_bf16(const void* in, int64_t n_in, int cin, const void* wimg, in
     double a[16] = {0};
     for (int b = 0; b < grid; ++b)
       for (int j = 0; j < 16; ++j) a[j] += (double)h[(size_t)b * 16 + j] / grid;
-    fprintf(stderr, "[mk3d trace] cin %d cout %d K %d tiles %d stages %d | mma: wait_full %.0f wait_tmem %.0f / total %.0f, iters %.0f | epilogue: wait_full %.0f / total %.0f (cycles, CTA mean)\n",
-            cin, cout, K, p.num_tiles, stages, a[2], a[3], a[4], a[5], a[6], a[7]);
+    fprintf(stderr, "[mk3d trace] cin %d cout %d K %d tiles %d stages %d | producer0: wait_empty %.0f / total %.0f | mma: wait_full %.0f wait_tmem %.0f / total %.0f, iters %.0f | epilogue: wait_full %.0f / total %.0f (cycles, CTA mean)\n",
+            cin, cout, K, p.num_tiles, stages, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
   }
 #undef MK_LAUNCH
   return check_launch(__func__);

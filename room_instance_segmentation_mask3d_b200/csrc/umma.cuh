@@ -165,6 +165,7 @@ struct ConvParams {
   int K;
   int num_tiles;
   int num_stages;
+  int group;       // member tiles per super-tile (1 or 2)
   int num_producers;  // active producer warps (<= 5 and < num_stages: a producer may be at most one ring phase ahead)
   int nchunks;
   int out_cols;    // columns actually stored (<= cout; the rest of the accumulator is padding)
