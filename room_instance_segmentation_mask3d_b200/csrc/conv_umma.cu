@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
     const int rsub = lane >> 3;  // 4 rows per warp instruction
     // swizzled piece offset inside the row: row & 7 == 4 * (jj & 1) + rsub for row = 4 * jj + rsub
     const uint32_t sw_even = (uint32_t)((piece ^ rsub) << 4), sw_odd = (uint32_t)((piece ^ (4 + rsub)) << 4);
+    const uint32_t row_bytes = (uint32_t)p.cin * (uint32_t)sizeof(__nv_bfloat16);
     struct Idx {
       int r[2][4];  // per member tile: input rows gathered into tile rows lane, lane + 32, lane + 64, lane + 96
       int kw;       // weight-image index of the item's offset
@@ -184,7 +185,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
       const uint32_t bar = smem_u32(&full_bar[stage]);
       // lanes whose piece lies beyond a narrow chunk (or all lanes in the gather-off ablation) still take part in the shuffles
       const bool act = piece * 8 < width && !(dbg & 1);
-      const __nv_bfloat16* src0 = p.in + ch * kChunkElems + piece * 8;
+      // source address = per-lane 64-bit base + row * row_bytes as ONE 32x32+64 multiply-add (IMAD.WIDE.U32)
+      uint64_t src0 = (uint64_t)p.in + (uint64_t)(ch * kChunkElems + piece * 8) * sizeof(__nv_bfloat16);
+      asm volatile("" : "+l"(src0));  // keep the base in one register pair (otherwise it is re-derived from the constant bank per copy)
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
         if ((ci.has >> g) & 1u) {  // warp-uniform
@@ -196,7 +199,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
               const int idx = __shfl_sync(0xffffffffu, ci.r[g][q], 4 * jj + rsub);
               const int row = q * 32 + 4 * jj + rsub;  // row within the tile
               const uint32_t dst = a_base + (uint32_t)(row * 128) + ((jj & 1) ? sw_odd : sw_even);
-              if (act) cp_async_16(dst, src0 + (int64_t)(idx < 0 ? 0 : idx) * p.cin, idx < 0 ? 0u : 16u);
+              const uint32_t idxc = idx < 0 ? 0u : (uint32_t)idx;
+              if (act) cp_async_16(dst, (const void*)(src0 + (uint64_t)idxc * row_bytes), idx < 0 ? 0u : 16u);
             }
           }
         }
@@ -261,19 +265,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
         if (dbg & 64) fence_proxy_async();  // A/B only: the bidirectional fence (MEMBAR.ALL.CTA) the acquire form replaces
         else fence_proxy_async_acquire();   // producers' cp.async (generic proxy) writes -> visible to tcgen05.mma (async proxy)
         tc_fence_after();
-        const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)ring.stage * b_bytes));
-        const int nk = width / 16;
+        const uint32_t b_lo = smem_desc_lo(smem_u32(sB) + (uint32_t)(ring.stage * b_bytes));
+        const uint32_t a_lo0 = smem_desc_lo(smem_u32(sA) + (uint32_t)(ring.stage * a_bytes));
+        const int nk = width >> 4;
         if (elect_one_sync()) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             if ((has >> g) & 1u) {
-              const uint64_t adesc = make_smem_desc(smem_u32(sA + (size_t)ring.stage * a_bytes + (size_t)g * kABytes));
+              const uint32_t a_lo = a_lo0 + (uint32_t)(g * (kABytes >> 4));
               const uint32_t tmem_d = tmem_base + (uint32_t)((acc_buf * G + g) * acc_cols);
               const uint32_t first_acc = (started >> g) & 1u;
               const int nkg = (dbg & 4) ? (first_acc ? 0 : 1) : nk;
               for (int kk = 0; kk < nkg; ++kk) {
                 // +32 bytes along K inside the 128-byte swizzle row == +2 in the (addr >> 4) field
-                umma_bf16(tmem_d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (kk > 0) ? 1u : first_acc);
+                umma_bf16_lohi(tmem_d, a_lo + 2u * kk, b_lo + 2u * kk, kSmemDescHi, idesc, (kk > 0) ? 1u : first_acc);
               }
             }
           }
