@@ -52,44 +52,40 @@ __global__ void __launch_bounds__(kNormThreads) k_in_stats_partial(const T* __re
   if (rl == 0) store4(out + 3 * C + 4 * cv, shift);
 }
 
-// grid (C / 32, B), block 256 = 32 channels x 8 chunk lanes.  Chunk statistics are merged with Chan's parallel formula in
-// fp64: lane l folds chunks l, l+8, ... in ascending order, then the 8 lanes are folded in ascending lane order by the
-// channel's lane-0 thread => a fixed merge tree, bit-reproducible.
+// grid (ceil(C / 8), B), block 256 = 8 warps, one channel per warp.  Chunk statistics are merged with Chan's parallel formula in
+// fp64: lane l folds chunks l, l+32, ... in ascending order, then the 32 lanes are folded by a fixed shuffle tree (lane i
+// absorbs lane i + d, d = 16 .. 1) => a fixed merge order, bit-reproducible run to run.
+__device__ __forceinline__ void chan_merge(double& n, double& mu, double& m2, double nb, double mub, double m2b) {
+  if (nb <= 0) return;
+  const double nt = n + nb, d = mub - mu, f = nb / nt;
+  mu += d * f;
+  m2 += m2b + d * d * n * f;
+  n = nt;
+}
+
 __global__ void __launch_bounds__(256) k_in_stats_final(const float* __restrict__ partial, int C, int chunks_per_scene, float eps,
                                                         float* __restrict__ mean, float* __restrict__ rstd) {
   const int b = blockIdx.y;
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int lane = threadIdx.x >> 5;  // 0..7
-  __shared__ double sn[8][32], smu[8][32], sm2[8][32];
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= C) return;  // whole warp
   double n = 0, mu = 0, m2 = 0;
-  if (c < C) {
-    for (int ch = lane; ch < chunks_per_scene; ch += 8) {
-      const float* p = partial + ((int64_t)(b * chunks_per_scene + ch)) * 4 * C;
-      const double nb = p[c];
-      if (nb <= 0) continue;
-      const double s1 = p[C + c], s2 = p[2 * C + c], sh = p[3 * C + c];
-      const double mub = sh + s1 / nb;
-      double m2b = s2 - s1 * s1 / nb;
-      if (m2b < 0) m2b = 0;
-      const double d = mub - mu, nt = n + nb;
-      mu += d * nb / nt;
-      m2 += m2b + d * d * n * nb / nt;
-      n = nt;
-    }
+  for (int ch = lane; ch < chunks_per_scene; ch += 32) {
+    const float* p = partial + ((int64_t)(b * chunks_per_scene + ch)) * 4 * C;
+    const double nb = p[c];
+    if (nb <= 0) continue;
+    const double s1 = p[C + c], s2 = p[2 * C + c], sh = p[3 * C + c];
+    double m2b = s2 - s1 * s1 / nb;
+    if (m2b < 0) m2b = 0;
+    chan_merge(n, mu, m2, nb, sh + s1 / nb, m2b);
   }
-  sn[lane][threadIdx.x & 31] = n;
-  smu[lane][threadIdx.x & 31] = mu;
-  sm2[lane][threadIdx.x & 31] = m2;
-  __syncthreads();
-  if (lane == 0 && c < C) {
-    for (int l = 1; l < 8; ++l) {
-      const double nb = sn[l][threadIdx.x], mub = smu[l][threadIdx.x], m2b = sm2[l][threadIdx.x];
-      if (nb <= 0) continue;
-      const double d = mub - mu, nt = n + nb;
-      mu += d * nb / nt;
-      m2 += m2b + d * d * n * nb / nt;
-      n = nt;
-    }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const double nb = __shfl_down_sync(0xffffffffu, n, d), mub = __shfl_down_sync(0xffffffffu, mu, d),
+                 m2b = __shfl_down_sync(0xffffffffu, m2, d);
+    chan_merge(n, mu, m2, nb, mub, m2b);
+  }
+  if (lane == 0) {
     const double var = n > 0 ? m2 / n : 0.0;
     mean[b * C + c] = (float)mu;
     rstd[b * C + c] = (float)(1.0 / sqrt(var + (double)eps));
@@ -233,7 +229,7 @@ int mk_instnorm_stats(const void* x, int x_dtype, int64_t n, int C, const int32_
     k_in_stats_partial<float><<<grid, kNormThreads, smem, st>>>((const float*)x, C, scene_offsets, rpc, cps, partial);
   else
     k_in_stats_partial<__nv_bfloat16><<<grid, kNormThreads, smem, st>>>((const __nv_bfloat16*)x, C, scene_offsets, rpc, cps, partial);
-  k_in_stats_final<<<dim3((unsigned)ceil_div(C, 32), (unsigned)B), 256, 0, st>>>(partial, C, cps, eps, mean, rstd);
+  k_in_stats_final<<<dim3((unsigned)ceil_div(C, 8), (unsigned)B), 256, 0, st>>>(partial, C, cps, eps, mean, rstd);
   return check_launch(__func__);
 }
 

@@ -153,6 +153,9 @@ def kernel_offsets(kernel_size: Sequence[int], dilation: Sequence[int], tensor_s
     return out
 
 
+_OFFSETS_CACHE: Dict[tuple, torch.Tensor] = {}  # (kernel_size, dilation, tensor_stride, device) -> int32 [K, 3]; scene independent
+
+
 class CoordinateManager:
     def __init__(self, D: int = 3, device=None, **_):
         lib.require_cuda()
@@ -239,10 +242,11 @@ class CoordinateManager:
 
     # ------------------------------------------------------------------ kernel maps
     def _offsets_dev(self, ks, dil, ts) -> torch.Tensor:
-        ck = (ks, dil, ts)
-        if ck not in self._offs_cache:
-            self._offs_cache[ck] = torch.tensor(kernel_offsets(ks, dil, ts), dtype=I32, device=self.device).contiguous()
-        return self._offs_cache[ck]
+        ck = (ks, dil, ts, self.device)
+        t = _OFFSETS_CACHE.get(ck)
+        if t is None:
+            t = _OFFSETS_CACHE[ck] = torch.tensor(kernel_offsets(ks, dil, ts), dtype=I32, device=self.device).contiguous()
+        return t
 
     def neighbor_table(self, in_key, out_key, kernel_size, dilation=1) -> KernelMap:
         ks, dl = _tuple3(kernel_size), _tuple3(dilation)
@@ -290,26 +294,42 @@ class CoordinateManager:
             parent = torch.empty(n_fine, dtype=I32, device=self.device)
             koff = torch.empty(n_fine, dtype=I32, device=self.device)
             lib.call("mk_transpose_map", lib.p(down.nbr), K, n_coarse, n_fine, lib.p(parent), lib.p(koff), lib.stream())
-            order = torch.sort(koff, stable=True).indices  # fine rows grouped by k, ascending inside a group
-            counts = torch.bincount(koff.clamp_min(0), minlength=K)[:K]
-            counts_h = counts.tolist()
-            padded = [((c + lib.TILE - 1) // lib.TILE) * lib.TILE for c in counts_h]
-            n_slots = max(sum(padded), lib.TILE)
+            # slots = fine rows grouped by k (stable: ascending row inside a group), every group padded to a multiple of 128.
+            # No host sync: the slot count is the upper bound ceil(n_fine / 128) + K tiles; surplus tiles have an empty offset
+            # mask and are skipped by the kernel.
+            order = torch.sort(koff, stable=True).indices
+            k_sorted = koff[order].long()
+            ks_ = torch.arange(K, device=self.device)
+            start = torch.searchsorted(k_sorted, ks_)  # k_sorted ascends: group boundaries without a host sync
+            counts = torch.searchsorted(k_sorted, ks_, right=True) - start
+            padded = (counts + (lib.TILE - 1)) // lib.TILE * lib.TILE
+            pstart = torch.cumsum(padded, 0) - padded
+            slot = pstart[k_sorted] + (torch.arange(n_fine, device=self.device) - start[k_sorted])
+            n_slots = ((n_fine + lib.TILE - 1) // lib.TILE + K) * lib.TILE
             out_rows = torch.full((n_slots,), -1, dtype=I32, device=self.device)
+            out_rows[slot] = order.to(I32)
             nbr_t = torch.full((K, n_slots), -1, dtype=I32, device=self.device)
-            src0, dst0 = 0, 0
-            for k in range(K):
-                c = counts_h[k]
-                if c:
-                    rows = order[src0:src0 + c].to(I32)
-                    out_rows[dst0:dst0 + c] = rows
-                    nbr_t[k, dst0:dst0 + c] = parent[rows.long()]
-                src0 += c
-                dst0 += padded[k]
+            nbr_t[k_sorted, slot] = parent[order]
             plan = KernelMap(nbr_t, K, n_fine, out_rows)
             plan.parent, plan.koff = parent, koff
             self._tplans[ck] = plan
         return plan
+
+    def prebuild(self, in_key, levels: int = 5, first_kernel: int = 5) -> List[CoordinateMapKey]:
+        """Build every coordinate map, kernel map and tile plan a Res16UNet-style network needs, up front: the host syncs
+        of the data-dependent map sizes then happen while the GPU queue is still empty instead of draining it mid-network."""
+        keys = [in_key]
+        for _ in range(levels - 1):
+            keys.append(self.stride(keys[-1], 2))
+        self.neighbor_table(keys[0], keys[0], first_kernel, 1)
+        for lvl, k in enumerate(keys):
+            self.neighbor_table(k, k, 3, 1).sorted_plan().tile_kmask
+            self.neighbor_table(k, k, 1, 1).tile_kmask
+            self.scene_offsets(k)
+            if lvl > 0:
+                self.neighbor_table(keys[lvl - 1], k, 2, 1).sorted_plan().tile_kmask
+                self.transpose_plan(k, keys[lvl - 1], 2, 1).tile_kmask
+        return keys
 
     def kernel_map(self, in_key, out_key, stride=1, kernel_size=3, dilation=1, region_type=None, region_offset=None,
                    is_transpose: bool = False, is_pool: bool = False) -> Dict[int, torch.Tensor]:

@@ -48,6 +48,9 @@ _SIGS = {
                               c_void_p, c_int, c_void_p]),
     "mk_instnorm_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_int64, c_void_p]),
+    "mk_conv_instnorm_bf16": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
+                                      c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_int, c_void_p, c_int64, c_void_p]),
     "mk_pool_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
     "mk_pool_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_int64, c_void_p, c_void_p]),
     "mk_mask_logits": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
@@ -112,19 +115,41 @@ def tdtype(code: int) -> torch.dtype:
 
 
 def p(t: Optional[torch.Tensor]):
+    """Device pointer of a contiguous CUDA tensor as a plain int (ctypes converts it for c_void_p parameters)."""
     if t is None:
         return None
     assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
-    return c_void_p(t.data_ptr())
+    return t.data_ptr()
+
+
+_stream_cache = None  # (cuda_stream handle) pinned for the duration of a `stream_scope`
 
 
 def stream():
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+    if _stream_cache is not None:
+        return _stream_cache
+    return torch.cuda.current_stream().cuda_stream
+
+
+class stream_scope:
+    """Resolve the current torch CUDA stream once for a whole forward pass (torch.cuda.current_stream() costs several
+    microseconds per call, i.e. milliseconds per step at ~2000 launches).  Callers must not switch streams inside."""
+
+    def __enter__(self):
+        global _stream_cache
+        self.prev = _stream_cache
+        _stream_cache = torch.cuda.current_stream().cuda_stream
+        return self
+
+    def __exit__(self, *exc):
+        global _stream_cache
+        _stream_cache = self.prev
+        return False
 
 
 # kernels launched per C-ABI call (memsets not counted) — bench.py reports the total as `gpu_launches`
 _KERNELS_PER_CALL = {"mk_coordmap_build": 7, "mk_instnorm_stats": 2, "mk_masked_xattn_fwd": 3, "mk_instnorm_bwd": 3, "mk_scene_minmax": 3,
-                     "mk_fps": 25}
+                     "mk_fps": 25, "mk_conv_instnorm_bf16": 4}
 kernel_launches = 0
 _timed = None  # optional {entry-point name: [(start_event, end_event, tag), ...]} filled when bench.py instruments a step
 _tag = None
@@ -142,17 +167,35 @@ def set_tag(tag) -> None:
     _tag = tag
 
 
+_fns = {}
+_scratch = {}
+
+
+def scratch(nbytes: int, device) -> torch.Tensor:
+    """Reusable per-device scratch buffer for kernels that need a workspace only for the duration of one C-ABI call
+    (stream-ordered: the next user is enqueued behind the previous one on the same stream)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream())
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = _scratch[key] = torch.empty(max(int(nbytes * 1.5), 1 << 20), dtype=torch.uint8, device=device)
+    return buf
+
+
 def call(name: str, *args) -> None:
     global kernel_launches
-    kernel_launches += _KERNELS_PER_CALL.get(name, 1)
+    fn = _fns.get(name)
+    if fn is None:
+        fn = _fns[name] = (getattr(load(), name), _KERNELS_PER_CALL.get(name, 1))
+    kernel_launches += fn[1]
     if _timed is not None and name in _timed:
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        _check(getattr(load(), name)(*args), name)
+        _check(fn[0](*args), name)
         e.record()
         _timed[name].append((s, e, _tag))
         return
-    _check(getattr(load(), name)(*args), name)
+    if fn[0](*args) != 0:
+        _check(1, name)
 
 
 def query(name: str, *args) -> int:

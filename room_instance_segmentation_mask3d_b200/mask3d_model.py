@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import lib
 from . import me_api as ME
 from . import ops
 from .engine import CoordinateMapKey
@@ -103,16 +104,21 @@ class Res16UNet34C(nn.Module):
     # ---- fused inference path
     @torch.no_grad()
     def forward_fused(self, x: ME.SparseTensor):
+        with lib.stream_scope():
+            return self._forward_fused(x)
+
+    def _forward_fused(self, x: ME.SparseTensor):
         mgr = x.coordinate_manager
         mode = ops.get_compute_mode()
         act = torch.float32 if mode == "fp32" else torch.bfloat16
         B = mgr.number_of_unique_batch_indices()
-        keys = [x.coordinate_map_key]
-        for _ in range(4):
-            keys.append(mgr.stride(keys[-1], 2))
+        keys = mgr.prebuild(x.coordinate_map_key, 5, self.conv0p1s1.kernel_generator.kernel_size[0])
         offs = [mgr.scene_offsets(k) for k in keys]
 
         def cn(f, conv, norm, km, lvl, relu=True, residual=None, kind=0):
+            if mode == "bf16" and f.dtype == torch.bfloat16 and f.shape[1] % 16 == 0:
+                return ops.conv_instnorm_bf16(f, conv.kernel, km, offs[lvl], B, norm.weight, norm.bias, bias=conv.bias,
+                                              residual=residual, relu=relu, out_dtype=act)
             if kind == 2 and mode == "fp32":
                 y = ops.conv_transpose_forward_fp32(f, conv.kernel, km)
             else:
@@ -234,6 +240,10 @@ class Mask3D(nn.Module):
     @torch.no_grad()
     def forward(self, x: ME.SparseTensor, is_eval: bool = True) -> dict:
         """Fused inference forward.  Returns the fields of the reference's ModelOutput (mask3d.py:28-47)."""
+        with lib.stream_scope():
+            return self._forward(x)
+
+    def _forward(self, x: ME.SparseTensor) -> dict:
         mgr = x.coordinate_manager
         mode = ops.get_compute_mode()
         act = torch.float32 if mode == "fp32" else torch.bfloat16
@@ -288,26 +298,43 @@ class Mask3D(nn.Module):
                 blocked = ops.threshold_blocked(pooled)
             return cls, logits, blocked
 
+        # keys / values of every level do not depend on the queries and the decoder weights are shared between the
+        # `num_decoders` repetitions (shared_decoder: true, conf/model/mask3d.yaml:28): project them once per level instead of
+        # once per layer (the reference recomputes them 3x, mask3d.py:467-478)
+        kv = {}
+        for i, hl in enumerate(self.hlevels):
+            ca, sq = self.cross_attention[0][i], self.lin_squeeze[0][i]
+            kml = mgr.neighbor_table(keys[hl], keys[hl], 1, 1)
+            mha = ca.multihead_attn
+            Wsq = self._d(sq.weight, "T", lambda w: w.t())                                  # [C_l, D]
+            Wk = self._d(mha.in_proj_weight, "k", lambda w: w[D:2 * D].t())                   # [D, D] (in, out)
+            Wv = self._d(mha.in_proj_weight, "v", lambda w: w[2 * D:].t())
+            src = ops.conv_forward(fmaps[hl].F, Wsq, kml, bias=sq.bias, mode=mode, out_dtype=torch.float32)
+            kin = src + pe[hl]
+            kv[i] = (ops.conv_forward(kin, Wk, kml, bias=mha.in_proj_bias[D:2 * D], mode=mode, out_dtype=act),
+                     ops.conv_forward(src, Wv, kml, bias=mha.in_proj_bias[2 * D:], mode=mode, out_dtype=act))
+
+        hd = D // H
         for _ in range(self.num_decoders):
             for i, hl in enumerate(self.hlevels):
                 cls, logits, blocked = mask_module(queries, nl - hl - 1, True)
-                ca, sa, ff, sq = self.cross_attention[0][i], self.self_attention[0][i], self.ffn_attention[0][i], self.lin_squeeze[0][i]
-                kml = mgr.neighbor_table(keys[hl], keys[hl], 1, 1)
+                ca, sa, ff = self.cross_attention[0][i], self.self_attention[0][i], self.ffn_attention[0][i]
                 mha = ca.multihead_attn
-                Wsq = self._d(sq.weight, "T", lambda w: w.t())                                  # [C_l, D]
-                Wk = self._d(mha.in_proj_weight, "k", lambda w: w[D:2 * D].t())                   # [D, D] (in, out)
-                Wv = self._d(mha.in_proj_weight, "v", lambda w: w[2 * D:].t())
-                src = ops.conv_forward(fmaps[hl].F, Wsq, kml, bias=sq.bias, mode=mode, out_dtype=torch.float32)
-                kin = src + pe[hl]
-                kp = ops.conv_forward(kin, Wk, kml, bias=mha.in_proj_bias[D:2 * D], mode=mode, out_dtype=act)
-                vp = ops.conv_forward(src, Wv, kml, bias=mha.in_proj_bias[2 * D:], mode=mode, out_dtype=act)
+                kp, vp = kv[i]
                 qp = F.linear(queries + query_pos, mha.in_proj_weight[:D], mha.in_proj_bias[:D])
                 ctx = ops.masked_cross_attention(qp, kp, vp, blocked, offs[hl], H)
                 out = ca.norm(queries + F.linear(ctx, mha.out_proj.weight, mha.out_proj.bias))
-                # self-attention over the Q queries of each scene + FFN: [B, Q, D]-sized, stock torch
-                qk = (out + query_pos).transpose(0, 1)
-                t2, _ = sa.self_attn(qk, qk, out.transpose(0, 1), need_weights=False)
-                out = sa.norm(out + t2.transpose(0, 1))
+                # self-attention over the Q queries of each scene (SelfAttentionLayer.forward_post, mask3d.py:624-636):
+                # q = k = out + query_pos, v = out; packed in-projection, softmax(QK^T / sqrt(hd)) V, out-projection
+                sam = sa.self_attn
+                qk = out + query_pos
+                wq, wk_, wv = sam.in_proj_weight[:D], sam.in_proj_weight[D:2 * D], sam.in_proj_weight[2 * D:]
+                bq, bk_, bv = sam.in_proj_bias[:D], sam.in_proj_bias[D:2 * D], sam.in_proj_bias[2 * D:]
+                q_ = F.linear(qk, wq, bq).view(B, Q, H, hd).transpose(1, 2)
+                k_ = F.linear(qk, wk_, bk_).view(B, Q, H, hd).transpose(1, 2)
+                v_ = F.linear(out, wv, bv).view(B, Q, H, hd).transpose(1, 2)
+                t2 = F.scaled_dot_product_attention(q_, k_, v_).transpose(1, 2).reshape(B, Q, D)
+                out = sa.norm(out + F.linear(t2, sam.out_proj.weight, sam.out_proj.bias))
                 queries = ff.norm(out + ff.linear2(F.relu(ff.linear1(out))))
                 pred_class.append(cls)
                 pred_masks.append(logits)

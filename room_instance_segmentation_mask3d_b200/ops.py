@@ -54,6 +54,16 @@ def weight_image(W: torch.Tensor, transpose: bool = False) -> torch.Tensor:
     return img
 
 
+def _flat32(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """fp32 1-D view of a (small) parameter; no copy when it already is contiguous fp32."""
+    if t is None:
+        return None
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.reshape(-1) if t.is_contiguous() else t.contiguous().reshape(-1)
+
+
 def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     if x.dtype == dtype:
         return x
@@ -75,7 +85,7 @@ def conv_forward(x: torch.Tensor, W: torch.Tensor, km: KernelMap, bias: Optional
     if transpose_w:
         cin, cout = cout, cin
     assert K == km.K and x.shape[1] == cin, f"shape mismatch: W {tuple(W3.shape)}, x {tuple(x.shape)}, K {km.K}"
-    bias_flat = bias.detach().reshape(-1).float().contiguous() if bias is not None else None
+    bias_flat = _flat32(bias)
     if cin == 1 and not transpose_w and km.out_rows is None:
         out_dtype = out_dtype or (torch.float32 if mode == "fp32" else torch.bfloat16)
         out = torch.empty((km.n_out, cout), dtype=out_dtype, device=x.device)
@@ -103,6 +113,33 @@ def conv_forward(x: torch.Tensor, W: torch.Tensor, km: KernelMap, bias: Optional
     return out
 
 
+def conv_instnorm_bf16(x: torch.Tensor, W: torch.Tensor, km: KernelMap, scene_offsets: torch.Tensor, B: int, gamma, beta, bias=None,
+                       residual: Optional[torch.Tensor] = None, relu: bool = True, eps: float = 1e-8,
+                       out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """conv (tcgen05) -> instance norm -> (+ residual) -> (ReLU) through ONE C-ABI call (mk_conv_instnorm_bf16)."""
+    W3 = W if W.dim() == 3 else W.unsqueeze(0)
+    K, cin, cout = W3.shape
+    assert K == km.K and x.shape[1] == cin and x.dtype == torch.bfloat16 and x.is_contiguous()
+    img = weight_image(W)
+    plan = km.sorted_plan() if SORT_TILES else km
+    n = km.n_out
+    out = torch.empty((n, cout), dtype=out_dtype, device=x.device)
+    stats = torch.empty((2, B, cout), dtype=torch.float32, device=x.device)
+    wsb = lib.query("mk_instnorm_workspace_bytes", n, cout, B)
+    tmp_bytes = (n * cout * 2 + 255) // 256 * 256
+    ws = lib.scratch(tmp_bytes + wsb, x.device)
+    if residual is not None:
+        assert residual.dtype == out_dtype and residual.is_contiguous()
+    if lib._timed is not None:
+        lib.set_tag((2 * km.num_pairs * cin * cout, K, cin, cout, n))
+    base = ws.data_ptr()
+    lib.call("mk_conv_instnorm_bf16", x.data_ptr(), x.shape[0], cin, img.data_ptr(), cout, plan.nbr.data_ptr(), K, plan.n_slots,
+             lib.p(plan.out_rows), plan.tile_kmask.data_ptr(), None, n, lib.p(_flat32(bias)), scene_offsets.data_ptr(), B, eps,
+             lib.p(_flat32(gamma)), lib.p(_flat32(beta)), lib.p(residual), int(relu), base, stats.data_ptr(), out.data_ptr(), lib.dt(out),
+             base + tmp_bytes, ws.numel() - tmp_bytes, lib.stream())
+    return out
+
+
 def conv_transpose_forward_fp32(x: torch.Tensor, W: torch.Tensor, plan: KernelMap, bias=None) -> torch.Tensor:
     """fp32 parity path of the transposed conv: out[f] = x[parent[f]] @ W[koff[f]], expressed through the generic
     output-stationary kernel with the plan's table restricted to real rows (slot -> row permutation undone)."""
@@ -123,11 +160,12 @@ def conv_transpose_forward_fp32(x: torch.Tensor, W: torch.Tensor, plan: KernelMa
 # ----------------------------------------------------------------------------------------------------
 def instance_norm_stats(x: torch.Tensor, scene_offsets: torch.Tensor, B: int, eps: float = 1e-8):
     n, C = x.shape
-    mean = torch.empty((B, C), dtype=torch.float32, device=x.device)
-    rstd = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    stats = torch.empty((2, B, C), dtype=torch.float32, device=x.device)
+    mean, rstd = stats[0], stats[1]
     wsb = lib.query("mk_instnorm_workspace_bytes", n, C, B)
-    ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
-    lib.call("mk_instnorm_stats", lib.p(x), lib.dt(x), n, C, lib.p(scene_offsets), B, eps, lib.p(mean), lib.p(rstd), lib.p(ws), wsb, lib.stream())
+    ws = lib.scratch(wsb, x.device)
+    lib.call("mk_instnorm_stats", lib.p(x), lib.dt(x), n, C, lib.p(scene_offsets), B, eps, stats.data_ptr(), stats.data_ptr() + 4 * B * C,
+             lib.p(ws), ws.numel(), lib.stream())
     return mean, rstd
 
 
@@ -137,8 +175,7 @@ def norm_apply(x, scene_offsets, B, mean, rstd, gamma, beta, residual=None, relu
     out = torch.empty((n, C), dtype=out_dtype, device=x.device)
     if residual is not None:
         residual = cast(residual.contiguous(), out_dtype)
-    g = gamma.detach().reshape(-1).float().contiguous() if gamma is not None else None
-    b = beta.detach().reshape(-1).float().contiguous() if beta is not None else None
+    g, b = _flat32(gamma), _flat32(beta)
     lib.call("mk_norm_apply", lib.p(x), lib.dt(x), n, C, lib.p(scene_offsets), B, lib.p(mean), lib.p(rstd), lib.p(g), lib.p(b), lib.p(residual),
              int(relu), lib.p(out), lib.dt(out), lib.stream())
     return out
