@@ -116,7 +116,7 @@ class Res16UNet34C(nn.Module):
         offs = [mgr.scene_offsets(k) for k in keys]
 
         def cn(f, conv, norm, km, lvl, relu=True, residual=None, kind=0):
-            if mode == "bf16" and f.dtype == torch.bfloat16 and f.shape[1] % 16 == 0:
+            if ops.USE_COMPOSITE and mode == "bf16" and f.dtype == torch.bfloat16 and f.shape[1] % 16 == 0:
                 return ops.conv_instnorm_bf16(f, conv.kernel, km, offs[lvl], B, norm.weight, norm.bias, bias=conv.bias,
                                               residual=residual, relu=relu, out_dtype=act)
             if kind == 2 and mode == "fp32":

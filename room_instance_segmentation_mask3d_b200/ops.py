@@ -16,6 +16,7 @@ from .engine import KernelMap
 
 _MODE = "bf16"
 SORT_TILES = True  # mask-sorted tile plans for the tensor-core conv (engine.KernelMap.sorted_plan)
+USE_COMPOSITE = True  # conv -> instance norm -> act through one C-ABI call; bench.py turns it off to time conv launches alone
 
 
 def set_compute_mode(mode: str) -> None:
