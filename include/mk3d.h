@@ -113,6 +113,20 @@ int mk_conv_dgrad_f32(const float* dout, int cout, const float* W, int cin, cons
                       const int32_t* kidx, float* din, void* stream);
 int mk_conv_wgrad_f32(const float* in, int cin, const float* dout, int cout, const int32_t* nbr, int K, int64_t n_out,
                       float* dW, void* stream);
+/* Backward of the tensor-core path (ME ConvolutionBackwardGPU: K x (gather, gather, GEMM) launches, reached through the
+ * autograd Function of MinkowskiConvolution / MinkowskiConvolutionTranspose).
+ *   dgrad = mk_conv_fwd_bf16 over the transposed table with weight images built with transpose=1 (and `kidx` mirroring the
+ *           offsets for same-map convs), no separate entry point;
+ *   wgrad = dW[k] = sum over slots o of x[nbr[k,o]]^T dy[row(o)], one persistent tcgen05 kernel over the forward's tile plan:
+ *           both operands MN-major, fp32 accumulation in TMEM across a run of tiles of one offset, fp32 atomic flush.
+ * mk_conv_wgrad_plan turns a plan's tile_kmask into the (offset, tile) unit list the kernel partitions over its CTAs:
+ * plan int32 [mk_conv_wgrad_plan_elems(num_tiles, K)] = {n_units, count per offset [K], units (k << 26 | tile) by (k, tile)}.
+ * x bf16 [n_in,cin] (cin % 8 == 0), dy bf16 [n_out,cout] (cout % 16 == 0, <= 256), nbr / out_rows as mk_conv_fwd_bf16,
+ * dW fp32 [K,cin,cout] (zeroed inside). */
+int64_t mk_conv_wgrad_plan_elems(int64_t num_tiles, int K);
+int mk_conv_wgrad_plan(const uint32_t* tile_kmask, int64_t num_tiles, int K, int32_t* plan, void* stream);
+int mk_conv_wgrad_bf16(const void* x, int64_t n_in, int cin, const void* dy, int cout, const int32_t* nbr, int K, int64_t n_slots,
+                       const int32_t* out_rows, const int32_t* plan, int64_t n_out, float* dW, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (4) Normalisation / activation.  Replaces MinkowskiInstanceNorm (global avg-pool + broadcast kernels,

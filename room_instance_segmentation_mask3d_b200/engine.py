@@ -94,6 +94,7 @@ class KernelMap:
         self._pairs_dev: Optional[torch.Tensor] = None
         self._pairs: Optional[int] = None
         self._sorted: Optional["KernelMap"] = None
+        self._wgrad_plan: Optional[torch.Tensor] = None
 
     def _build_kmask(self):
         ntiles = (self.n_slots + lib.TILE - 1) // lib.TILE
@@ -128,6 +129,15 @@ class KernelMap:
         if self._kmask is None:
             self._build_kmask()
         return self._kmask
+
+    @property
+    def wgrad_plan(self) -> torch.Tensor:
+        """(offset, tile) unit list of this plan for the tensor-core weight gradient (mk_conv_wgrad_plan); K <= 32."""
+        if self._wgrad_plan is None:
+            ntiles = (self.n_slots + lib.TILE - 1) // lib.TILE
+            self._wgrad_plan = torch.empty(lib.query("mk_conv_wgrad_plan_elems", ntiles, self.K), dtype=I32, device=self.nbr.device)
+            lib.call("mk_conv_wgrad_plan", lib.p(self.tile_kmask), ntiles, self.K, lib.p(self._wgrad_plan), lib.stream())
+        return self._wgrad_plan
 
     @property
     def num_pairs(self) -> int:

@@ -202,9 +202,21 @@ class _ConvFn(torch.autograd.Function):
         km, kind, n_in = ctx.km, ctx.kind, ctx.n_in
         W3 = (W if W.dim() == 3 else W.unsqueeze(0)).detach().float().contiguous()
         K, cin, cout = W3.shape
+        dx = dW = None
+        if ops.get_compute_mode() == "bf16" and K <= 32 and cin % 16 == 0 and cout % 16 == 0 and cout <= 256:
+            # tensor-core backward: dgrad = the forward kernel over the transposed table with W^T, wgrad = tcgen05 kernel over
+            # the forward's own table (x rows gathered through nbr, dy rows through the plan's slot -> row map)
+            db = ops.cast(dout.contiguous(), torch.bfloat16)
+            if ctx.needs_input_grad[0]:
+                if kind == 0:
+                    dx = ops.conv_dgrad_bf16(db, W3, km, kidx=torch.arange(K - 1, -1, -1, device=x.device, dtype=torch.int32))
+                else:
+                    dx = ops.conv_dgrad_bf16(db, W3, ctx.aux)  # kind 1: transpose plan; kind 2: fine -> coarse table
+            if ctx.needs_input_grad[1]:
+                dW = ops.conv_wgrad_bf16(x.detach(), db, km, K, cin, cout).reshape(W.shape)
+            return dx, dW, None, None, None, None
         dout = dout.contiguous().float()
         xf = x.detach().float().contiguous()
-        dx = dW = None
         if kind == 0:
             nbr_t, kidx, nbr_w = km.nbr, torch.arange(K - 1, -1, -1, device=x.device, dtype=torch.int32), km.nbr
         elif kind == 1:

@@ -114,6 +114,39 @@ def conv_forward(x: torch.Tensor, W: torch.Tensor, km: KernelMap, bias: Optional
     return out
 
 
+def conv_dgrad_bf16(dout: torch.Tensor, W: torch.Tensor, km_t: KernelMap, kidx: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """din[i] = sum_k dout[nbr_t[k, i]] @ W[kidx[k]]^T on the tensor-core kernel (fp32 out).  W fp32 [K, cin, cout]; the
+    kernel's accumulator holds at most 256 columns, so wider inputs (block5's 384-channel concat) go in column slices."""
+    W3 = W if W.dim() == 3 else W.unsqueeze(0)
+    K, cin, cout = W3.shape
+    if cin <= 256:
+        return conv_forward(dout, W3, km_t, mode="bf16", out_dtype=torch.float32, kidx=kidx, transpose_w=True)
+    db = cast(dout.contiguous(), torch.bfloat16)
+    din = torch.empty((km_t.n_out, cin), dtype=torch.float32, device=dout.device)
+    plan = km_t.sorted_plan() if SORT_TILES else km_t
+    nsplit = (cin + 255) // 256
+    step = ((cin + nsplit - 1) // nsplit + 15) // 16 * 16
+    for c0 in range(0, cin, step):
+        c1 = min(cin, c0 + step)
+        img = weight_image(W3[:, c0:c1, :], transpose=True)
+        lib.call("mk_conv_fwd_bf16", lib.p(db), db.shape[0], cout, lib.p(img), c1 - c0, lib.p(plan.nbr), K, plan.n_slots, lib.p(plan.out_rows),
+                 lib.p(plan.tile_kmask), lib.p(kidx), km_t.n_out, None, din.data_ptr() + 4 * c0, lib.F32, c1 - c0, cin, lib.stream())
+    return din
+
+
+def conv_wgrad_bf16(x: torch.Tensor, dout: torch.Tensor, km: KernelMap, K: int, cin: int, cout: int) -> torch.Tensor:
+    """dW[k] = sum_o x[nbr[k, o]]^T dout[o] on tcgen05 (mk_conv_wgrad_bf16) over the forward's tile plan.  fp32 [K, cin, cout]."""
+    xb = cast(x.contiguous(), torch.bfloat16)
+    db = cast(dout.contiguous(), torch.bfloat16)
+    plan = km.sorted_plan() if SORT_TILES else km
+    dW = torch.empty((K, cin, cout), dtype=torch.float32, device=x.device)
+    if lib._timed is not None:
+        lib.set_tag((2 * km.num_pairs * cin * cout, K, cin, cout, km.n_out))
+    lib.call("mk_conv_wgrad_bf16", lib.p(xb), xb.shape[0], cin, lib.p(db), cout, lib.p(plan.nbr), K, plan.n_slots, lib.p(plan.out_rows),
+             lib.p(plan.wgrad_plan), km.n_out, lib.p(dW), lib.stream())
+    return dW
+
+
 def conv_instnorm_bf16(x: torch.Tensor, W: torch.Tensor, km: KernelMap, scene_offsets: torch.Tensor, B: int, gamma, beta, bias=None,
                        residual: Optional[torch.Tensor] = None, relu: bool = True, eps: float = 1e-8,
                        out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:

@@ -67,6 +67,14 @@ for C in widths:
         fl = 2 * km3.num_pairs * C * C
         print(f"conv 3^3 {C:3d}->{C:3d} N={n0} sorted={int(sort)}: {t:.3f} ms  {fl / t / 1e9:8.1f} TFLOP/s")
     ops.SORT_TILES = True
+    if os.environ.get("MK3D_BENCH_BWD", "1") != "0":
+        dy = torch.randn(n0, C, device="cuda").bfloat16()
+        kidx = torch.arange(26, -1, -1, device="cuda", dtype=torch.int32)
+        fl = 2 * km3.num_pairs * C * C
+        t = timeit(lambda: ops.conv_dgrad_bf16(dy, W, km3, kidx=kidx))
+        print(f"dgrad 3^3 {C:3d}->{C:3d} N={n0}: {t:.3f} ms  {fl / t / 1e9:8.1f} TFLOP/s")
+        t = timeit(lambda: ops.conv_wgrad_bf16(x, dy, km3, 27, C, C))
+        print(f"wgrad 3^3 {C:3d}->{C:3d} N={n0}: {t:.3f} ms  {fl / t / 1e9:8.1f} TFLOP/s")
     W2 = torch.randn(8, C, C, device="cuda") / (8 * C) ** 0.5
     t = timeit(lambda: ops.conv_forward(x, W2, km2, mode="bf16", out_dtype=torch.bfloat16))
     print(f"conv 2^3 s2 {C:3d}->{C:3d} N={n0}->{n1}: {t:.3f} ms  {2 * km2.num_pairs * C * C / t / 1e9:8.1f} TFLOP/s")

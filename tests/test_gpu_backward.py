@@ -1,5 +1,5 @@
-"""GPU parity of the BACKWARD of the module path (me_api autograd Functions -> mk_conv_dgrad/wgrad, mk_instnorm_bwd,
-mk_pool_bwd) against torch autograd through the CPU oracle's modules on the same seeded inputs.
+"""GPU parity of the BACKWARD of the module path (me_api autograd Functions -> fp32 mode: mk_conv_dgrad/wgrad_f32; bf16 mode:
+tcgen05 dgrad (mk_conv_fwd_bf16 over the transposed table) + mk_conv_wgrad_bf16; mk_instnorm_bwd, mk_pool_bwd) against torch autograd through the CPU oracle's modules on the same seeded inputs.
 
 The oracle's modules are built from index_select / mm / index_add, so torch differentiates them exactly; the reference's
 own backward is ME's ConvolutionBackward + its custom instance-norm backward.
@@ -66,7 +66,8 @@ def _check(ME, m_gpu, m_ref, xg, xr, mode, tol):
 
 
 @pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("bf16", 3e-2)])
-@pytest.mark.parametrize("cin,cout,ks,stride", [(16, 32, 3, 1), (32, 32, 2, 2), (48, 16, 1, 1)])
+@pytest.mark.parametrize("cin,cout,ks,stride", [(16, 32, 3, 1), (32, 32, 2, 2), (48, 16, 1, 1), (96, 96, 3, 1), (288, 48, 3, 1),
+                                                (64, 256, 3, 1)])
 def test_conv_backward(ME, cin, cout, ks, stride, mode, tol):
     coords = _batch(3)
     mk = lambda M: M.MinkowskiConvolution(cin, cout, kernel_size=ks, stride=stride, dilation=1, bias=True, dimension=3)

@@ -175,6 +175,75 @@ def test_conv_bf16_tensor_core_parity(R, cin, cout, ksize, stride):
     assert rel_err(out_b.float(), ref_same_operands) < 1e-2
 
 
+def _wgrad_ref(x, dy, nbr, K):
+    """dW[k] = sum_o x[nbr[k, o]]^T dy[o] in fp64 (the oracle's per-offset gather-mm, me_oracle.conv_from_table differentiated)."""
+    out = torch.zeros(K, x.shape[1], dy.shape[1], dtype=torch.float64)
+    for k in range(K):
+        o = np.nonzero(nbr[k] >= 0)[0]
+        if len(o):
+            out[k] = x[nbr[k, o]].double().t() @ dy[o].double()
+    return out
+
+
+@pytest.mark.parametrize("cin,cout,ksize,stride", [(32, 32, 3, 1), (96, 96, 3, 1), (128, 96, 3, 1), (288, 48, 3, 1), (64, 256, 3, 1),
+                                                  (256, 256, 3, 1), (96, 96, 2, 2), (48, 16, 1, 1), (24, 16, 3, 1)])
+def test_conv_wgrad_tensor_core(R, cin, cout, ksize, stride):
+    """tcgen05 weight gradient (MN-major operands) against the fp64 per-offset product on the SAME bf16-rounded operands."""
+    mgr, k_in, k_out, km, x, W, bias = _conv_setup(R, cin, cout, ksize, stride, seed=cin + cout + 1)
+    g = torch.Generator().manual_seed(5)
+    dy = torch.randn(km.n_out, cout, generator=g)
+    xb, dyb = x.bfloat16(), dy.bfloat16()
+    K = ksize ** 3
+    ref = _wgrad_ref(xb.float(), dyb.float(), km.nbr.cpu().numpy(), K)
+    got = R.ops.conv_wgrad_bf16(xb.cuda(), dyb.cuda(), km, K, cin, cout)
+    torch.cuda.synchronize()
+    assert rel_err(got, ref) < 1e-4
+    # per offset too: a wrong offset -> weight slot mapping could hide in the global maximum
+    for k in range(K):
+        if float(ref[k].abs().max()) > 0:
+            assert rel_err(got[k], ref[k]) < 1e-3, f"offset {k}"
+        else:
+            assert float(got[k].abs().max()) == 0.0
+
+
+def test_conv_wgrad_tensor_core_transposed_plan(R):
+    """weight gradient of the transposed conv: same kernel over the per-offset padded transpose plan (one offset per tile)."""
+    coords = make_batch(4)
+    mgr = R.engine.CoordinateManager(D=3)
+    k0, _ = mgr.insert_and_map(torch.from_numpy(coords).cuda())
+    k1 = mgr.stride(k0, 2)
+    plan = mgr.transpose_plan(k1, k0, 2, 1)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(mgr.size(k1), 64, generator=g).bfloat16()
+    dy = torch.randn(len(coords), 96, generator=g).bfloat16()
+    parent, koff = plan.parent.cpu().numpy(), plan.koff.cpu().numpy()
+    ref = torch.zeros(8, 64, 96, dtype=torch.float64)
+    for k in range(8):
+        f = np.nonzero(koff == k)[0]
+        ref[k] = x.float()[parent[f]].double().t() @ dy.float()[f].double()
+    got = R.ops.conv_wgrad_bf16(x.cuda(), dy.cuda(), plan, 8, 64, 96)
+    assert rel_err(got, ref) < 1e-4
+
+
+@pytest.mark.parametrize("cin,cout,ksize", [(96, 96, 3), (288, 64, 3), (64, 128, 1)])
+def test_conv_dgrad_tensor_core(R, cin, cout, ksize):
+    """dgrad = the forward kernel over the same-map table with mirrored offsets and W^T (column slices when cin > 256)."""
+    mgr, k_in, k_out, km, x, W, bias = _conv_setup(R, cin, cout, ksize, 1, seed=cin + cout + 2)
+    g = torch.Generator().manual_seed(6)
+    dy = torch.randn(km.n_out, cout, generator=g).bfloat16()
+    K = ksize ** 3
+    nbr = km.nbr.cpu().numpy()
+    Wb = W.bfloat16().float()
+    ref = torch.zeros(len(nbr[0]), cin, dtype=torch.float64)
+    for k in range(K):
+        o = np.nonzero(nbr[k] >= 0)[0]
+        if len(o):
+            ref.index_add_(0, torch.from_numpy(nbr[k, o]).long(), dy.float()[o].double() @ Wb[k].double().t())
+    kidx = torch.arange(K - 1, -1, -1, dtype=torch.int32, device="cuda")
+    got = R.ops.conv_dgrad_bf16(dy.cuda(), W.cuda(), km, kidx=kidx)
+    assert rel_err(got, ref) < 2e-3
+
+
 def test_conv_stem_5x5x5(R):
     mgr, k_in, k_out, km, x, W, bias = _conv_setup(R, 1, 32, 5, 1)
     ref = O.conv_from_table(x, W, km.nbr.cpu().numpy(), km.n_out)
