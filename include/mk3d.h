@@ -108,6 +108,11 @@ int mk_set_gather_mode(int mode);
 /* Stem: Cin == 1, K up to 125 (5^3): pure lookup, CUDA cores.  in fp32 [n_in], W fp32 [K,1,cout]. */
 int mk_conv_stem_f32(const float* in, const float* W, int cout, const int32_t* nbr, int K, int64_t n_out, void* out,
                      int out_dtype, void* stream);
+/* Stem weight gradient (cin == 1, cout <= 32, K <= 128): dW[k,c] = sum_o in[nbr[k,o]] * dout[o,c]; register accumulators per
+ * warp, per-block partials in `workspace`, fixed-order merge (deterministic). */
+int64_t mk_conv_stem_wgrad_workspace_bytes(int64_t n_out, int K, int cout);
+int mk_conv_stem_wgrad_f32(const float* in, const float* dout, int cout, const int32_t* nbr, int K, int64_t n_out, float* dW,
+                           void* workspace, int64_t workspace_bytes, void* stream);
 /* Backward of the fp32 path (dgrad + wgrad); CUDA cores, deterministic (no atomics on dgrad). */
 int mk_conv_dgrad_f32(const float* dout, int cout, const float* W, int cin, const int32_t* nbr_t, int K, int64_t n_in,
                       const int32_t* kidx, float* din, void* stream);

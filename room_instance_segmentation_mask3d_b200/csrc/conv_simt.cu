@@ -100,6 +100,123 @@ __global__ void __launch_bounds__(256) k_conv_stem(const float* __restrict__ in,
   }
 }
 
+// Stem, row-per-thread form (cout <= CO): thread = output row, so the K table reads of a warp are 128-byte coalesced
+// (nbr is [K, n_out]) and the weights are shared-memory broadcasts; the one-warp-per-row form above reads 32 different
+// table lines per load.  Same summation order (k ascending) => same bits.
+template <typename TOut, int CO>
+__global__ void __launch_bounds__(256) k_conv_stem_rows(const float* __restrict__ in, const float* __restrict__ W, int cout,
+                                                        const int32_t* __restrict__ nbr, int K, int64_t n_out,
+                                                        TOut* __restrict__ out) {
+  extern __shared__ __align__(16) float sW[];  // [K, CO], zero padded
+  for (int i = threadIdx.x; i < K * CO; i += blockDim.x) {
+    const int k = i / CO, c = i - k * CO;
+    sW[i] = c < cout ? W[k * cout + c] : 0.f;
+  }
+  __syncthreads();
+  for (int64_t o0 = (int64_t)blockIdx.x * blockDim.x; o0 < n_out; o0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t o = o0 + threadIdx.x;
+    const bool valid = o < n_out;
+    float acc[CO];
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+    int idx_next = valid ? nbr[o] : -1;
+    for (int k = 0; k < K; ++k) {
+      const int idx = idx_next;
+      idx_next = (valid && k + 1 < K) ? nbr[(int64_t)(k + 1) * n_out + o] : -1;
+      if (idx >= 0) {
+        const float xv = in[idx];
+        const float4* w = reinterpret_cast<const float4*>(sW + k * CO);
+#pragma unroll
+        for (int c4 = 0; c4 < CO / 4; ++c4) {
+          const float4 wv = w[c4];
+          acc[4 * c4 + 0] = fmaf(xv, wv.x, acc[4 * c4 + 0]);
+          acc[4 * c4 + 1] = fmaf(xv, wv.y, acc[4 * c4 + 1]);
+          acc[4 * c4 + 2] = fmaf(xv, wv.z, acc[4 * c4 + 2]);
+          acc[4 * c4 + 3] = fmaf(xv, wv.w, acc[4 * c4 + 3]);
+        }
+      }
+    }
+    if (valid) {
+      TOut* dst = out + o * cout;
+      if ((cout & 15) == 0) {
+#pragma unroll
+        for (int c0 = 0; c0 < CO; c0 += 16) {
+          if (c0 < cout) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = acc[c0 + j];
+            store16(dst + c0, v);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < CO; ++c)
+          if (c < cout) dst[c] = from_f32<TOut>(acc[c]);
+      }
+    }
+  }
+}
+
+// Stem weight gradient (cin == 1, cout <= 32, K <= 128): dW[k, c] = sum_o in[nbr[k,o]] * dout[o, c].
+// Block = 8 warps = 2 row tiles (32 rows each) x 4 offset groups (32 offsets each).  A warp keeps 32 accumulators
+// (its offsets x lane = channel) in registers over all its row tiles; the dout tile sits in shared memory; table reads
+// are coalesced (lane = row).  Partials per (block, row-tile slot) go to a workspace and are merged in fixed order by
+// k_conv_stem_wgrad_merge => deterministic.
+__global__ void __launch_bounds__(256) k_conv_stem_wgrad(const float* __restrict__ in, const float* __restrict__ dout, int cout,
+                                                         const int32_t* __restrict__ nbr, int K, int64_t n_out,
+                                                         float* __restrict__ partial) {
+  __shared__ float dys[2][32][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int kg = warp & 3, rt = warp >> 2;
+  float acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+  const int64_t ntiles = (n_out + 31) >> 5;
+  for (int64_t t0 = (int64_t)blockIdx.x * 2; t0 < ntiles; t0 += (int64_t)gridDim.x * 2) {
+    const int64_t tile = t0 + rt;
+    const int64_t o0 = tile * 32;
+    __syncthreads();
+    // the 4 warps of a row tile load 8 rows each
+    for (int r = kg * 8; r < kg * 8 + 8; ++r) {
+      const int64_t o = o0 + r;
+      dys[rt][r][lane] = (tile < ntiles && o < n_out && lane < cout) ? dout[o * cout + lane] : 0.f;
+    }
+    __syncthreads();
+    if (tile < ntiles) {
+      const int64_t o = o0 + lane;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int k = kg * 32 + j;
+        if (k < K) {  // warp-uniform
+          const int idx = o < n_out ? nbr[(int64_t)k * n_out + o] : -1;
+          const float xv = idx >= 0 ? in[idx] : 0.f;
+          unsigned present = __ballot_sync(0xffffffffu, idx >= 0);
+          while (present) {
+            const int t = __ffs(present) - 1;
+            present &= present - 1;
+            acc[j] = fmaf(__shfl_sync(0xffffffffu, xv, t), dys[rt][t][lane], acc[j]);
+          }
+        }
+      }
+    }
+  }
+  // partial[(block * 2 + rt), k, c]
+  float* dst = partial + ((int64_t)blockIdx.x * 2 + rt) * K * cout;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int k = kg * 32 + j;
+    if (k < K && lane < cout) dst[k * cout + lane] = acc[j];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_conv_stem_wgrad_merge(const float* __restrict__ partial, int nparts, int n, float* __restrict__ dW) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += partial[(int64_t)p * n + i];
+  dW[i] = s;
+}
+
 // wgrad: dW[k, ci, c] = sum_o in[nbr[k,o], ci] * dout[o, c].  One block per (k, ci-tile of 8); threads over c;
 // sequential over o => fixed order, deterministic.  Parity/backward-correctness path, not a throughput path.
 __global__ void __launch_bounds__(256) k_conv_wgrad_f32(const float* __restrict__ in, int cin, const float* __restrict__ dout,
@@ -178,11 +295,48 @@ int mk_conv_wgrad_f32(const float* in, int cin, const float* dout, int cout, con
   return check_launch(__func__);
 }
 
+static int stem_wgrad_grid(int64_t n_out) {
+  int64_t g = ceil_div(ceil_div(n_out, 32), 2);
+  if (g > 4 * num_sms()) g = 4 * num_sms();
+  return (int)(g < 1 ? 1 : g);
+}
+
+int64_t mk_conv_stem_wgrad_workspace_bytes(int64_t n_out, int K, int cout) {
+  return (int64_t)stem_wgrad_grid(n_out) * 2 * K * cout * (int64_t)sizeof(float);
+}
+
+int mk_conv_stem_wgrad_f32(const float* in, const float* dout, int cout, const int32_t* nbr, int K, int64_t n_out, float* dW,
+                           void* workspace, int64_t workspace_bytes, void* stream_) {
+  MK_REQUIRE(cout >= 1 && cout <= 32 && K >= 1 && K <= 128, "stem wgrad: cout <= 32 and K <= 128 required");
+  MK_REQUIRE(workspace_bytes >= mk_conv_stem_wgrad_workspace_bytes(n_out, K, cout), "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (n_out == 0) {
+    cudaMemsetAsync(dW, 0, (size_t)K * cout * sizeof(float), st);
+    return check_launch(__func__);
+  }
+  const int grid = stem_wgrad_grid(n_out);
+  k_conv_stem_wgrad<<<grid, 256, 0, st>>>(in, dout, cout, nbr, K, n_out, (float*)workspace);
+  k_conv_stem_wgrad_merge<<<(unsigned)ceil_div((int64_t)K * cout, 256), 256, 0, st>>>((const float*)workspace, grid * 2, K * cout, dW);
+  return check_launch(__func__);
+}
+
 int mk_conv_stem_f32(const float* in, const float* W, int cout, const int32_t* nbr, int K, int64_t n_out, void* out,
                      int out_dtype, void* stream_) {
   MK_REQUIRE(cout <= 256, "cout must be <= 256");
   MK_REQUIRE((size_t)K * cout * sizeof(float) <= 48 * 1024, "stem weights must fit 48 KB of shared memory");
   if (n_out == 0) return 0;
+  if (cout <= 32) {
+    // row-per-thread form: coalesced table reads (see k_conv_stem_rows)
+    int64_t blocks = ceil_div(n_out, 256);
+    if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+    const size_t smem32 = (size_t)K * 32 * sizeof(float);
+    if (out_dtype == MK_F32)
+      k_conv_stem_rows<float, 32><<<(unsigned)blocks, 256, smem32, (cudaStream_t)stream_>>>(in, W, cout, nbr, K, n_out, (float*)out);
+    else
+      k_conv_stem_rows<__nv_bfloat16, 32><<<(unsigned)blocks, 256, smem32, (cudaStream_t)stream_>>>(in, W, cout, nbr, K, n_out,
+                                                                                                (__nv_bfloat16*)out);
+    return check_launch(__func__);
+  }
   int64_t blocks = ceil_div(n_out, 8);
   if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
   size_t smem = (size_t)K * cout * sizeof(float);

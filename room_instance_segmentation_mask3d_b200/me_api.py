@@ -228,7 +228,14 @@ class _ConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty((n_in, cin), dtype=torch.float32, device=x.device)
             lib.call("mk_conv_dgrad_f32", lib.p(dout), cout, lib.p(W3), cin, lib.p(nbr_t), K, n_in, lib.p(kidx), lib.p(dx), lib.stream())
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and cin == 1 and cout <= 32 and K <= 128 and kind == 0:
+            dW = torch.empty_like(W3)
+            wsb = lib.query("mk_conv_stem_wgrad_workspace_bytes", dout.shape[0], K, cout)
+            ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
+            lib.call("mk_conv_stem_wgrad_f32", lib.p(xf), lib.p(dout), cout, lib.p(nbr_w), K, dout.shape[0], lib.p(dW), lib.p(ws), wsb,
+                     lib.stream())
+            dW = dW.reshape(W.shape)
+        elif ctx.needs_input_grad[1]:
             dW = torch.empty_like(W3)
             lib.call("mk_conv_wgrad_f32", lib.p(xf), cin, lib.p(dout), cout, lib.p(nbr_w), K, dout.shape[0], lib.p(dW), lib.stream())
             dW = dW.reshape(W.shape)

@@ -67,7 +67,7 @@ def _check(ME, m_gpu, m_ref, xg, xr, mode, tol):
 
 @pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("bf16", 3e-2)])
 @pytest.mark.parametrize("cin,cout,ks,stride", [(16, 32, 3, 1), (32, 32, 2, 2), (48, 16, 1, 1), (96, 96, 3, 1), (288, 48, 3, 1),
-                                                (64, 256, 3, 1)])
+                                                (64, 256, 3, 1), (1, 32, 5, 1), (1, 24, 3, 1)])
 def test_conv_backward(ME, cin, cout, ks, stride, mode, tol):
     coords = _batch(3)
     mk = lambda M: M.MinkowskiConvolution(cin, cout, kernel_size=ks, stride=stride, dilation=1, bias=True, dimension=3)
