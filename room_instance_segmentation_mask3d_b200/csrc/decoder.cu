@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(1024) k_xattn_partial(const float* __restrict_
                                                         const uint8_t* __restrict__ blocked, const int32_t* __restrict__ any_open,
                                                         const int32_t* __restrict__ scene_offsets, int Q, int D, int H, float scale,
                                                         int keys_per_split, float* __restrict__ partial) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int hd = D / H;
   float* sK = sm;                                   // [tile][D]
   float* sV = sm + (size_t)kXaKeysPerTile * D;      // [tile][D]
@@ -211,19 +211,33 @@ __global__ void __launch_bounds__(1024) k_xattn_partial(const float* __restrict_
     if (active) {
       for (int r = 0; r < nk; ++r) {
         if (use_mask && sM[r * Q + q]) continue;
-        const float* kr = sK + r * D + h * hd;
+        const float4* kr = reinterpret_cast<const float4*>(sK + r * D + h * hd);  // hd % 4 == 0 (checked by the entry point)
         float s = 0.f;
 #pragma unroll
-        for (int j = 0; j < HD; ++j)
-          if (j < hd) s = fmaf(qv[j], kr[j], s);
+        for (int j = 0; j < HD; j += 4) {
+          if (j < hd) {
+            const float4 kk = kr[j >> 2];
+            s = fmaf(qv[j], kk.x, s);
+            s = fmaf(qv[j + 1], kk.y, s);
+            s = fmaf(qv[j + 2], kk.z, s);
+            s = fmaf(qv[j + 3], kk.w, s);
+          }
+        }
         const float mn = fmaxf(m, s);
         const float corr = expf(m - mn);  // m = -inf on the first key: exp(-inf) = 0
         const float pw = expf(s - mn);
         l = l * corr + pw;
-        const float* vr = sV + r * D + h * hd;
+        const float4* vr = reinterpret_cast<const float4*>(sV + r * D + h * hd);
 #pragma unroll
-        for (int j = 0; j < HD; ++j)
-          if (j < hd) acc[j] = fmaf(acc[j], corr, pw * vr[j]);
+        for (int j = 0; j < HD; j += 4) {
+          if (j < hd) {
+            const float4 vv = vr[j >> 2];
+            acc[j] = fmaf(acc[j], corr, pw * vv.x);
+            acc[j + 1] = fmaf(acc[j + 1], corr, pw * vv.y);
+            acc[j + 2] = fmaf(acc[j + 2], corr, pw * vv.z);
+            acc[j + 3] = fmaf(acc[j + 3], corr, pw * vv.w);
+          }
+        }
         m = mn;
       }
     }
@@ -283,9 +297,10 @@ __global__ void __launch_bounds__(256) k_xattn_combine(const float* __restrict__
 }
 
 inline int xattn_splits(int64_t n, int B) {
-  // ~2 blocks per SM over the batch, at least 256 keys per split
-  int64_t s = ceil_div(2 * (int64_t)num_sms(), B > 0 ? B : 1);
-  int64_t by_keys = ceil_div(n > 0 ? n : 1, 256);
+  // ~6 resident blocks (7 warps each, 34 KB of shared memory) per SM over the batch so that one block's tile load /
+  // barrier hides behind the others' arithmetic; at least 128 keys per split
+  int64_t s = ceil_div(6 * (int64_t)num_sms(), B > 0 ? B : 1);
+  int64_t by_keys = ceil_div(n > 0 ? n : 1, 128);
   if (s > by_keys) s = by_keys;
   if (s < 1) s = 1;
   return (int)s;
@@ -355,7 +370,7 @@ int mk_masked_xattn_fwd(const float* qp, const void* kp, const void* vp, int kv_
                         const int32_t* scene_offsets, int B, int Q, int D, int H, float scale, float* ctx, void* workspace,
                         int64_t workspace_bytes, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  MK_REQUIRE(D % H == 0 && D / H <= kXaMaxHd && D % 4 == 0, "head dim must be <= 32 and D a multiple of 4");
+  MK_REQUIRE(D % H == 0 && D / H <= kXaMaxHd && (D / H) % 4 == 0, "head dim must be a multiple of 4, <= 32");
   MK_REQUIRE(Q * H <= 1024, "Q*H must be <= 1024");
   MK_REQUIRE(workspace_bytes >= mk_xattn_workspace_bytes(B, Q, H, n), "workspace too small");
   const int splits = xattn_splits(n, B);

@@ -92,6 +92,125 @@ __global__ void __launch_bounds__(256) k_in_stats_final(const float* __restrict_
   }
 }
 
+// Single-launch statistics: the chunk pass above with 16-byte loads, four rows in flight per thread, and the merge done
+// by the LAST block of each scene to finish (ticket counter), in the same fixed order as k_in_stats_final => same bits,
+// one launch and no second kernel whose ~10 us of latency was pure overhead on the small levels.
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads) k_in_stats(const T* __restrict__ x, int C, const int32_t* __restrict__ scene_offsets,
+                                                           int rows_per_chunk, int chunks_per_scene, float eps,
+                                                           float* __restrict__ partial, unsigned* __restrict__ counters,
+                                                           float* __restrict__ mean, float* __restrict__ rstd) {
+  constexpr int V = 16 / (int)sizeof(T);  // channels per 16-byte load
+  const int b = blockIdx.y;
+  const int chunk = blockIdx.x;
+  const int64_t start = (int64_t)scene_offsets[b] + (int64_t)chunk * rows_per_chunk;
+  const int64_t end = min((int64_t)scene_offsets[b + 1], start + rows_per_chunk);
+  const int CV = C / V;
+  const int RL = kNormThreads / CV;
+  const int cv = threadIdx.x % CV, rl = threadIdx.x / CV;
+  float* out = partial + ((int64_t)(b * chunks_per_scene + chunk)) * 4 * C;
+  extern __shared__ float sm[];  // [RL][2][C]
+  __shared__ int s_last;
+  float s1[V], s2[V], shift[V];
+  auto ld = [&](int64_t r, float (&v)[V]) {
+    if constexpr (sizeof(T) == 2) {
+      const uint4 q = *reinterpret_cast<const uint4*>(x + r * C + V * cv);
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+        v[2 * j] = f.x;
+        v[2 * j + 1] = f.y;
+      }
+    } else {
+      const float4 q = *reinterpret_cast<const float4*>(x + r * C + V * cv);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    }
+  };
+#pragma unroll
+  for (int j = 0; j < V; ++j) s1[j] = s2[j] = shift[j] = 0.f;
+  if (rl < RL) {
+    if (start < end) ld(start, shift);
+    int64_t r = start + rl;
+    for (; r + 3 * (int64_t)RL < end; r += 4 * (int64_t)RL) {
+      float v[4][V];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) ld(r + u * (int64_t)RL, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const float d = v[u][j] - shift[j];
+          s1[j] += d;
+          s2[j] = fmaf(d, d, s2[j]);
+        }
+      }
+    }
+    for (; r < end; r += RL) {
+      float v[V];
+      ld(r, v);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const float d = v[j] - shift[j];
+        s1[j] += d;
+        s2[j] = fmaf(d, d, s2[j]);
+      }
+    }
+    float* p = sm + (int64_t)rl * 2 * C + V * cv;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      p[j] = s1[j];
+      p[C + j] = s2[j];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kNormThreads) {
+    float a = 0.f, q = 0.f;
+    for (int l = 0; l < RL; ++l) {  // fixed order
+      a += sm[l * 2 * C + c];
+      q += sm[l * 2 * C + C + c];
+    }
+    out[c] = (float)(end > start ? end - start : 0);
+    out[C + c] = a;
+    out[2 * C + c] = q;
+  }
+  if (rl == 0) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) out[3 * C + V * cv + j] = shift[j];
+  }
+  // ---- last block of the scene merges the chunk statistics (Chan, fp64, fixed order)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&counters[b], 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int lane = threadIdx.x & 31;
+  for (int c = threadIdx.x >> 5; c < C; c += kNormThreads / 32) {
+    double n = 0, mu = 0, m2 = 0;
+    for (int ch = lane; ch < chunks_per_scene; ch += 32) {
+      const float* p = partial + ((int64_t)(b * chunks_per_scene + ch)) * 4 * C;
+      const double nb = __ldcg(p + c);
+      if (nb <= 0) continue;
+      const double a1 = __ldcg(p + C + c), a2 = __ldcg(p + 2 * C + c), sh = __ldcg(p + 3 * C + c);
+      double m2b = a2 - a1 * a1 / nb;
+      if (m2b < 0) m2b = 0;
+      chan_merge(n, mu, m2, nb, sh + a1 / nb, m2b);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const double nb = __shfl_down_sync(0xffffffffu, n, d), mub = __shfl_down_sync(0xffffffffu, mu, d),
+                   m2b = __shfl_down_sync(0xffffffffu, m2, d);
+      chan_merge(n, mu, m2, nb, mub, m2b);
+    }
+    if (lane == 0) {
+      const double var = n > 0 ? m2 / n : 0.0;
+      mean[b * C + c] = (float)mu;
+      rstd[b * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+  }
+}
+
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256) k_norm_apply(const TIn* __restrict__ x, int64_t n, int C,
                                                     const int32_t* __restrict__ scene_offsets, int B,
@@ -210,7 +329,7 @@ extern "C" {
 int64_t mk_instnorm_workspace_bytes(int64_t n, int C, int B) {
   int rpc, cps;
   norm_chunking(n, B, &rpc, &cps);
-  return ((int64_t)B * cps * 4 * C + 2 * (int64_t)B * C + 64) * (int64_t)sizeof(float);
+  return ((int64_t)B * cps * 4 * C + 2 * (int64_t)B * C + 64 + (int64_t)B) * (int64_t)sizeof(float);
 }
 
 int mk_instnorm_stats(const void* x, int x_dtype, int64_t n, int C, const int32_t* scene_offsets, int B, float eps,
@@ -222,9 +341,22 @@ int mk_instnorm_stats(const void* x, int x_dtype, int64_t n, int C, const int32_
   int rpc, cps;
   norm_chunking(n, B, &rpc, &cps);
   float* partial = (float*)workspace;
+  unsigned* counters = (unsigned*)(partial + (int64_t)B * cps * 4 * C + 2 * (int64_t)B * C + 64);
+  cudaMemsetAsync(counters, 0, (size_t)B * sizeof(unsigned), st);
+  dim3 grid((unsigned)cps, (unsigned)B);
+  const int V = x_dtype == MK_F32 ? 4 : 8;
+  if (C % V == 0 && C / V <= kNormThreads && ((uintptr_t)x & 15) == 0) {
+    const int RL = kNormThreads / (C / V);
+    const size_t smem = (size_t)RL * 2 * C * sizeof(float);
+    if (x_dtype == MK_F32)
+      k_in_stats<float><<<grid, kNormThreads, smem, st>>>((const float*)x, C, scene_offsets, rpc, cps, eps, partial, counters, mean, rstd);
+    else
+      k_in_stats<__nv_bfloat16><<<grid, kNormThreads, smem, st>>>((const __nv_bfloat16*)x, C, scene_offsets, rpc, cps, eps, partial,
+                                                                  counters, mean, rstd);
+    return check_launch(__func__);
+  }
   const int CV = C / 4, RL = kNormThreads / CV;
   size_t smem = (size_t)RL * 2 * C * sizeof(float);
-  dim3 grid((unsigned)cps, (unsigned)B);
   if (x_dtype == MK_F32)
     k_in_stats_partial<float><<<grid, kNormThreads, smem, st>>>((const float*)x, C, scene_offsets, rpc, cps, partial);
   else

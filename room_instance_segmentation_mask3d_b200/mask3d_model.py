@@ -202,6 +202,73 @@ class FFNLayer(nn.Module):
                 nn.init.xavier_uniform_(p)
 
 
+class _QueryGraphs:
+    """CUDA graphs of the query-side work of the decoder (everything that touches only the [B, Q, D] query tensors).
+
+    Between two of the big varlen kernels (mask-logit product / pooling / masked cross-attention over all voxels) the
+    reference runs ~45 tiny ops on 25 x 128 tensors per layer (mask3d.py:384-495: out-proj, 3 LayerNorms, self-attention,
+    FFN, mask-embed MLP, class head, query projection).  Their shapes depend only on (B, Q, D), never on the scene, so they
+    are captured ONCE per batch size into one graph per decoder level and replayed: the host pays one cudaGraphLaunch per
+    layer instead of ~45 launches, and the GPU runs them back to back.  Static buffers: queries, query_pos, ctx (written by
+    mk_masked_xattn_fwd), qp, embed / its bf16 weight image (read by the mask-logit kernel), cls."""
+
+    def __init__(self, model: "Mask3D", B: int, mode: str, device):
+        Q, D = model.num_queries, model.mask_dim
+        f32 = dict(dtype=torch.float32, device=device)
+        self.queries, self.query_pos = torch.zeros((B, Q, D), **f32), torch.zeros((B, Q, D), **f32)
+        self.ctx, self.qp = torch.zeros((B, Q, D), **f32), torch.zeros((B, Q, D), **f32)
+        self.emb = torch.zeros((B, Q, D), **f32)
+        self.cls = torch.zeros((B, Q, model.num_classes + 1), **f32)
+        self.mode = mode
+        Qp = ((Q + 15) // 16) * 16
+        self.W = torch.zeros((B, D, Qp), **f32)
+        self.img = torch.empty(lib.query("mk_conv_weight_image_elems", B, D, Qp, 0), dtype=torch.bfloat16, device=device)
+        L = len(model.hlevels)
+        fns = [lambda: self._head(model, 0)] + [(lambda i=i: (self._post(model, i), self._head(model, (i + 1) % L))) for i in range(L)]
+        saved = lib._stream_cache
+        lib._stream_cache = None  # capture runs on torch's capture stream, not on the stream pinned by stream_scope
+        try:
+            side = torch.cuda.Stream(device=device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):  # eager warm-up (cuBLAS handles / workspaces) before capture
+                for f in fns:
+                    f()
+            torch.cuda.current_stream(device).wait_stream(side)
+            torch.cuda.synchronize(device)
+            self.graphs = []
+            pool = None
+            for f in fns:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    f()
+                pool = g.pool()
+                self.graphs.append(g)
+        finally:
+            lib._stream_cache = saved
+        self.queries.zero_()
+
+    def _head(self, m: "Mask3D", i_next: int):
+        """mask_module head (mask3d.py:520-533) + query projection of the next cross-attention (:686-697)."""
+        D = m.mask_dim
+        qn = m.decoder_norm(self.queries)
+        self.emb.copy_(m.mask_embed_head(qn))
+        self.cls.copy_(m.class_embed_head(qn))
+        if self.mode == "bf16":
+            ops.mask_embed_image(self.emb, img=self.img, W=self.W)
+        mha = m.cross_attention[0][i_next].multihead_attn
+        self.qp.copy_(F.linear(self.queries + self.query_pos, mha.in_proj_weight[:D], mha.in_proj_bias[:D]))
+
+    def _post(self, m: "Mask3D", i: int):
+        """out-proj + LN of the cross-attention, self-attention, FFN (mask3d.py:478-495)."""
+        self.queries.copy_(m._query_update(i, self.queries, self.query_pos, self.ctx))
+
+    def first(self):
+        self.graphs[0].replay()
+
+    def layer(self, i: int):
+        self.graphs[1 + i].replay()
+
+
 class Mask3D(nn.Module):
     """Default reference configuration (mask3d/conf/model/mask3d.yaml): non-parametric queries (FPS + fourier PE), shared
     decoder, post-norm, dropout 0, no level embedding, is_eval=True (keys never subsampled, trainer.py:274)."""
@@ -227,6 +294,8 @@ class Mask3D(nn.Module):
         self.lin_squeeze = mk(lambda i: nn.Linear(sizes[self.hlevels[i]], d))
         self.decoder_norm = nn.LayerNorm(d)
         self._derived: Dict[Tuple[int, str], Tuple[int, torch.Tensor]] = {}
+        self.use_cuda_graphs = True   # query-side work of the decoder as CUDA graphs (_QueryGraphs)
+        self._qgraphs: Dict[tuple, _QueryGraphs] = {}
 
     def _d(self, p: torch.Tensor, tag: str, fn):
         """cache of derived weight layouts (transposes / slices), invalidated by the parameter's version counter"""
@@ -236,6 +305,33 @@ class Mask3D(nn.Module):
             e = (p._version, fn(p.detach()).contiguous())
             self._derived[k] = e
         return e[1]
+
+    def _query_update(self, i: int, queries, query_pos, ctx):
+        """Everything of decoder layer i after the attention core: cross-attention out-proj + LN (CrossAttentionLayer.forward_post,
+        mask3d.py:686-705), self-attention over the Q queries of each scene (SelfAttentionLayer.forward_post, :624-636: q = k =
+        out + query_pos, v = out), FFN (:776-783)."""
+        B, Q, D = queries.shape
+        H = self.num_heads
+        hd = D // H
+        ca, sa, ff = self.cross_attention[0][i], self.self_attention[0][i], self.ffn_attention[0][i]
+        mha, sam = ca.multihead_attn, sa.self_attn
+        out = ca.norm(queries + F.linear(ctx, mha.out_proj.weight, mha.out_proj.bias))
+        qk = out + query_pos
+        wq, wk_, wv = sam.in_proj_weight[:D], sam.in_proj_weight[D:2 * D], sam.in_proj_weight[2 * D:]
+        bq, bk_, bv = sam.in_proj_bias[:D], sam.in_proj_bias[D:2 * D], sam.in_proj_bias[2 * D:]
+        q_ = F.linear(qk, wq, bq).view(B, Q, H, hd).transpose(1, 2)
+        k_ = F.linear(qk, wk_, bk_).view(B, Q, H, hd).transpose(1, 2)
+        v_ = F.linear(out, wv, bv).view(B, Q, H, hd).transpose(1, 2)
+        t2 = F.scaled_dot_product_attention(q_, k_, v_).transpose(1, 2).reshape(B, Q, D)
+        out = sa.norm(out + F.linear(t2, sam.out_proj.weight, sam.out_proj.bias))
+        return ff.norm(out + ff.linear2(F.relu(ff.linear1(out))))
+
+    def _query_graphs(self, B: int, mode: str, device) -> _QueryGraphs:
+        key = (B, mode, str(device), self.decoder_norm.weight.data_ptr())
+        g = self._qgraphs.get(key)
+        if g is None:
+            g = self._qgraphs[key] = _QueryGraphs(self, B, mode, device)
+        return g
 
     @torch.no_grad()
     def forward(self, x: ME.SparseTensor, is_eval: bool = True) -> dict:
@@ -314,31 +410,49 @@ class Mask3D(nn.Module):
             kv[i] = (ops.conv_forward(kin, Wk, kml, bias=mha.in_proj_bias[D:2 * D], mode=mode, out_dtype=act),
                      ops.conv_forward(src, Wv, kml, bias=mha.in_proj_bias[2 * D:], mode=mode, out_dtype=act))
 
-        hd = D // H
-        for _ in range(self.num_decoders):
-            for i, hl in enumerate(self.hlevels):
-                cls, logits, blocked = mask_module(queries, nl - hl - 1, True)
-                ca, sa, ff = self.cross_attention[0][i], self.self_attention[0][i], self.ffn_attention[0][i]
-                mha = ca.multihead_attn
-                kp, vp = kv[i]
-                qp = F.linear(queries + query_pos, mha.in_proj_weight[:D], mha.in_proj_bias[:D])
-                ctx = ops.masked_cross_attention(qp, kp, vp, blocked, offs[hl], H)
-                out = ca.norm(queries + F.linear(ctx, mha.out_proj.weight, mha.out_proj.bias))
-                # self-attention over the Q queries of each scene (SelfAttentionLayer.forward_post, mask3d.py:624-636):
-                # q = k = out + query_pos, v = out; packed in-projection, softmax(QK^T / sqrt(hd)) V, out-projection
-                sam = sa.self_attn
-                qk = out + query_pos
-                wq, wk_, wv = sam.in_proj_weight[:D], sam.in_proj_weight[D:2 * D], sam.in_proj_weight[2 * D:]
-                bq, bk_, bv = sam.in_proj_bias[:D], sam.in_proj_bias[D:2 * D], sam.in_proj_bias[2 * D:]
-                q_ = F.linear(qk, wq, bq).view(B, Q, H, hd).transpose(1, 2)
-                k_ = F.linear(qk, wk_, bk_).view(B, Q, H, hd).transpose(1, 2)
-                v_ = F.linear(out, wv, bv).view(B, Q, H, hd).transpose(1, 2)
-                t2 = F.scaled_dot_product_attention(q_, k_, v_).transpose(1, 2).reshape(B, Q, D)
-                out = sa.norm(out + F.linear(t2, sam.out_proj.weight, sam.out_proj.bias))
-                queries = ff.norm(out + ff.linear2(F.relu(ff.linear1(out))))
-                pred_class.append(cls)
-                pred_masks.append(logits)
-        cls, logits, _ = mask_module(queries, 0, False)
+        if self.use_cuda_graphs:
+            # query-side work replayed from CUDA graphs; the varlen voxel kernels in between run eagerly
+            qg = self._query_graphs(B, mode, query_pos.device)
+            qg.query_pos.copy_(query_pos)
+            qg.queries.zero_()
+            qg.first()
+
+            def masks_from_graph(n_pool, want_mask):
+                cls = qg.cls.clone()
+                if mode == "bf16":
+                    logits = ops.mask_logits_from_image(mask_features, qg.img, sel0, Q)
+                else:
+                    logits = ops.mask_logits(mask_features, offs[-1], B, qg.emb, select=None)
+                blocked = None
+                if want_mask:
+                    pooled = logits
+                    for s_ in range(n_pool):
+                        pooled = ops.pool_forward(pooled, pool_km[nl - 2 - s_], average=True)
+                    blocked = ops.threshold_blocked(pooled)
+                return cls, logits, blocked
+
+            for _ in range(self.num_decoders):
+                for i, hl in enumerate(self.hlevels):
+                    cls, logits, blocked = masks_from_graph(nl - hl - 1, True)
+                    kp, vp = kv[i]
+                    ops.masked_cross_attention(qg.qp, kp, vp, blocked, offs[hl], H, out=qg.ctx)
+                    qg.layer(i)
+                    pred_class.append(cls)
+                    pred_masks.append(logits)
+            cls, logits, _ = masks_from_graph(0, False)
+            queries = qg.queries.clone()
+        else:
+            for _ in range(self.num_decoders):
+                for i, hl in enumerate(self.hlevels):
+                    cls, logits, blocked = mask_module(queries, nl - hl - 1, True)
+                    mha = self.cross_attention[0][i].multihead_attn
+                    kp, vp = kv[i]
+                    qp = F.linear(queries + query_pos, mha.in_proj_weight[:D], mha.in_proj_bias[:D])
+                    ctx = ops.masked_cross_attention(qp, kp, vp, blocked, offs[hl], H)
+                    queries = self._query_update(i, queries, query_pos, ctx)
+                    pred_class.append(cls)
+                    pred_masks.append(logits)
+            cls, logits, _ = mask_module(queries, 0, False)
         pred_class.append(cls)
         pred_masks.append(logits)
         off0 = mgr.scene_offsets_host(keys[-1])

@@ -257,6 +257,33 @@ def mask_logits(feat: torch.Tensor, scene_offsets: torch.Tensor, B: int, embed: 
     return out
 
 
+def mask_embed_image(embed: torch.Tensor, img: Optional[torch.Tensor] = None, W: Optional[torch.Tensor] = None):
+    """Weight image of the mask-logit product for the tensor-core path: W[b] = embed[b]^T zero-padded to a multiple of 16
+    queries.  Optional preallocated `W` / `img` (CUDA-graph capture: static buffers, no caching by parameter version)."""
+    B, Q, C = embed.shape
+    Qp = ((Q + 15) // 16) * 16
+    if W is None:
+        W = torch.zeros((B, C, Qp), dtype=torch.float32, device=embed.device)
+    W[:, :, :Q] = embed.detach().float().transpose(1, 2)
+    if img is None:
+        img = torch.empty(lib.query("mk_conv_weight_image_elems", B, C, Qp, 0), dtype=torch.bfloat16, device=embed.device)
+    lib.call("mk_conv_weight_image_bf16", lib.p(W), B, C, Qp, 0, lib.p(img), lib.stream())
+    return img, W
+
+
+def mask_logits_from_image(feat: torch.Tensor, img: torch.Tensor, select: KernelMap, Q: int) -> torch.Tensor:
+    """logits [n, Q] fp32 = feat (bf16) x the per-scene embedding image built by `mask_embed_image`."""
+    n, C = feat.shape
+    Qp = ((Q + 15) // 16) * 16
+    assert feat.dtype == torch.bfloat16 and feat.is_contiguous()
+    out = torch.empty((n, Q), dtype=torch.float32, device=feat.device)
+    if lib._timed is not None:
+        lib.set_tag((2 * n * C * Q, select.K, C, Qp, n))
+    lib.call("mk_conv_fwd_bf16", lib.p(feat), n, C, lib.p(img), Qp, lib.p(select.nbr), select.K, select.n_slots, lib.p(select.out_rows),
+             lib.p(select.tile_kmask), None, n, None, lib.p(out), lib.F32, Q, Q, lib.stream())
+    return out
+
+
 def threshold_blocked(pooled: torch.Tensor) -> torch.Tensor:
     """uint8 [n, Q]: sigmoid(pooled) < 0.5   (mask3d.py:550)."""
     out = torch.empty(pooled.shape, dtype=torch.uint8, device=pooled.device)
@@ -282,14 +309,15 @@ def fourier_pe(xyz, scene_offsets, B, cmin, cmax, gauss_B, base: Optional[torch.
 
 
 def masked_cross_attention(qp: torch.Tensor, kp: torch.Tensor, vp: torch.Tensor, blocked: torch.Tensor, scene_offsets: torch.Tensor,
-                           num_heads: int) -> torch.Tensor:
+                           num_heads: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """ctx [B, Q, D] (heads concatenated, before out_proj)."""
     B, Q, D = qp.shape
     n = kp.shape[0]
     assert kp.dtype == vp.dtype
     wsb = lib.query("mk_xattn_workspace_bytes", B, Q, num_heads, n)
-    ws = torch.empty(wsb, dtype=torch.uint8, device=qp.device)
-    ctx = torch.empty((B, Q, D), dtype=torch.float32, device=qp.device)
+    ws = lib.scratch(wsb, qp.device)
+    ctx = out if out is not None else torch.empty((B, Q, D), dtype=torch.float32, device=qp.device)
+    assert ctx.is_contiguous() and ctx.dtype == torch.float32
     scale = float((D // num_heads) ** -0.5)
     lib.call("mk_masked_xattn_fwd", lib.p(qp.detach().float().contiguous()), lib.p(kp.contiguous()), lib.p(vp.contiguous()), lib.dt(kp), n,
              lib.p(blocked.contiguous()), lib.p(scene_offsets), B, Q, D, num_heads, scale, lib.p(ctx), lib.p(ws), wsb, lib.stream())
