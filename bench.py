@@ -26,6 +26,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_conv_umma launch from an `ncu --set full` capture (profiles/), next to the
+# algorithmic bytes of that launch; filled in from the capture named in `note` (None until a capture of the current kernel exists)
+NCU_TRAFFIC = {"bytes_per_launch": None, "note": None}
+
 METRIC = "Mask3D inference throughput (Res16UNet34C sparse-conv backbone + 12-layer masked-attention decoder)"
 UNIT = "voxels/s"
 
@@ -217,7 +221,7 @@ def main_ours(args):
     for i in range(max(args.warmup, 3)):
         step_resident(i)
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not args.no_clocks:
         sampler.start()
     launches0 = lib.kernel_launches
     ms = timed(step_resident, args.steps)
@@ -256,20 +260,46 @@ def main_ours(args):
         lib.instrument(None)
         ops.USE_COMPOSITE = True
         recs = ev["mk_conv_fwd_bf16"]
-        tot_ms = sum(s.elapsed_time(e) for s, e, _ in recs)
-        tot_flops = sum(t[0] for _, _, t in recs)
-        n_launch = len(recs)
+        step_ms = t0.elapsed_time(t1)
+
+        def summarize(sel):
+            ms_ = sum(s.elapsed_time(e) for s, e, t in recs if sel(t))
+            fl_ = sum(t[0] for s, e, t in recs if sel(t))
+            n_ = sum(1 for s, e, t in recs if sel(t))
+            return ms_, fl_, n_
+
+        tot_ms, tot_flops, n_launch = summarize(lambda t: True)
         by_shape = {}
         for s, e, t in recs:
             k = f"K{t[1]}_{t[2]}x{t[3]}"
             a = by_shape.setdefault(k, [0.0, 0.0, 0])
             a[0] += t[0]; a[1] += s.elapsed_time(e); a[2] += 1
-        top = sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:6]
+        top = sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:8]
         achieved = tot_flops / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
-        roofline = {"kernel": "k_conv_umma (tcgen05 gather-GEMM sparse conv)", "bound": "tensor", "achieved": achieved, "peak": peak,
-                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        # launch classes of the same kernel: the gather-GEMM proper (K = 27 / 8 offsets, tensor-bound by design) and the
+        # K = 1 launches (1x1 convs, K/V projections, mask-logit product: one pass over [N, C], HBM-bound)
+        g_ms, g_fl, g_n = summarize(lambda t: t[1] > 1)
+        big_ms, big_fl, big_n = summarize(lambda t: t[1] > 1 and t[4] >= 128 * 148 * 4)   # enough tiles to fill 148 SMs
+        o_ms, o_fl, o_n = summarize(lambda t: t[1] == 1)
+        hbm_peak = float(peaks.get("hbm_gbs", 6455.0))
+        # algorithmic bytes of a K = 1 launch: read [N, Cin] bf16, write [N, Cout_stored] (bf16 activations; fp32 for the
+        # 25-column mask logits and the fp32 `src` of the key projection) -- taken as 2 B in, 2 or 4 B out per element
+        o_bytes = sum(t[4] * (2 * t[2] + (4 if (t[3] <= 32 or t[2] != t[3]) else 2) * min(t[3], 128)) for s, e, t in recs if t[1] == 1)
+        tf = lambda fl, ms_: fl / (ms_ * 1e-3) / 1e12 if ms_ > 0 else 0.0
+        roofline = {"kernel": "k_conv_umma (tcgen05 gather-GEMM sparse conv), all launches of the step", "bound": "tensor", "achieved": achieved,
+                    "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC.get("bytes_per_launch"),
+                    "traffic_note": NCU_TRAFFIC.get("note"), "peak_source": peak_src,
                     "launches_per_step": n_launch / isteps, "flops_per_launch_avg": tot_flops / max(n_launch, 1),
-                    "ms_per_launch_avg": tot_ms / max(n_launch, 1), "share_of_step": tot_ms / t0.elapsed_time(t1),
+                    "ms_per_launch_avg": tot_ms / max(n_launch, 1), "share_of_step": tot_ms / step_ms,
+                    "classes": {
+                        "gather_gemm_K>1": {"launches_per_step": g_n / isteps, "ms_per_step": g_ms / isteps, "achieved_tflops": tf(g_fl, g_ms),
+                                            "frac_of_tensor_peak": tf(g_fl, g_ms) / peak},
+                        "gather_gemm_K>1_levels_with_>=4_tiles_per_SM": {"launches_per_step": big_n / isteps, "ms_per_step": big_ms / isteps,
+                                                                        "achieved_tflops": tf(big_fl, big_ms),
+                                                                        "frac_of_tensor_peak": tf(big_fl, big_ms) / peak},
+                        "K=1_hbm_bound": {"launches_per_step": o_n / isteps, "ms_per_step": o_ms / isteps, "achieved_tflops": tf(o_fl, o_ms),
+                                          "achieved_gbs": o_bytes / (o_ms * 1e-3) / 1e9 if o_ms > 0 else 0.0, "hbm_peak_gbs": hbm_peak,
+                                          "frac_of_hbm_peak": (o_bytes / (o_ms * 1e-3) / 1e9) / hbm_peak if o_ms > 0 else 0.0}},
                     "by_shape_tflops": {k: round(v[0] / (v[1] * 1e-3) / 1e12, 1) for k, v in top},
                     "by_shape_ms_per_step": {k: round(v[1] / isteps, 3) for k, v in top}}
 
@@ -301,6 +331,7 @@ if __name__ == "__main__":
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--voxel-cm", type=float, default=2.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi during the timed region (debugging)")
     a = ap.parse_args()
     if a.impl == "reference":
         main_reference(a)

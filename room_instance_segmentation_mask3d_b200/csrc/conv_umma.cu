@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
   uint64_t* tmem_full = bars + 2 * kMaxStages;     // [2]  one tcgen05.commit
   uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;  // [2]  128 epilogue threads
   uint32_t* tmem_base_slot = (uint32_t*)(bars + 2 * kMaxStages + 4);
+  float* out_stage = (float*)(bars + 2 * kMaxStages + 6);  // [4 epilogue warps][32 rows x out_cols] when p.stage_out
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dbg = kDbg ? p.debug : 0;
@@ -351,6 +352,35 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
         if (g >= G || st * G + g >= p.num_tiles) continue;
         TOut* optr = orow[g] >= 0 ? (TOut*)p.out + orow[g] * p.out_stride : nullptr;
         const uint32_t tcol = (uint32_t)((acc_buf * G + g) * acc_cols);
+        if (p.stage_out) {
+          // Row pitch of e.g. 25 fp32 (mask logits): per-thread row stores would touch 32 sectors per instruction.  The
+          // warp's 32 rows are one contiguous run of 32 * out_cols elements in global memory, so transpose through shared
+          // memory (odd pitch => conflict free) and store the run with fully coalesced 128-byte instructions.
+          float* stg = out_stage + (size_t)q * 32 * p.out_cols;
+          for (int c0 = 0; c0 < p.out_cols; c0 += 16) {
+            uint32_t r[16];
+            if (km[g] != 0u) {
+              tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + tcol + (uint32_t)c0, r);
+              tmem_ld_wait();
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) r[j] = 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < p.out_cols) stg[lane * p.out_cols + c0 + j] = __uint_as_float(r[j]) + (p.bias ? p.bias[c0 + j] : 0.f);
+          }
+          __syncwarp();
+          const int64_t row0 = ((int64_t)(st * G + g)) * kTileM + q * 32;
+          const int64_t nrows = min((int64_t)32, p.n_out - row0);
+          if (nrows > 0 && !(dbg & 8)) {
+            TOut* dst = (TOut*)p.out + row0 * p.out_cols;
+            const int total = (int)nrows * p.out_cols;
+            for (int i = lane; i < total; i += 32) dst[i] = from_f32<TOut>(stg[i]);
+          }
+          __syncwarp();
+          continue;
+        }
         for (int c0 = 0; c0 < p.out_cols; c0 += 16) {
           float v[16];
           if (km[g] != 0u) {
@@ -427,8 +457,9 @@ __global__ void __launch_bounds__(256) k_weight_image(const float* __restrict__ 
   }
 }
 
-inline size_t conv_smem_bytes(int cout, int stages, int group = 1) {
-  return 1024 + (size_t)stages * ((size_t)group * kABytes + (size_t)cout * 128) + (2 * kMaxStages + 4) * sizeof(uint64_t) + 16;
+inline size_t conv_smem_bytes(int cout, int stages, int group = 1, int stage_out_cols = 0) {
+  return 1024 + (size_t)stages * ((size_t)group * kABytes + (size_t)cout * 128) + (2 * kMaxStages + 6) * sizeof(uint64_t) + 16 +
+         (size_t)4 * 32 * stage_out_cols * sizeof(float);
 }
 
 int conv_tma_launch(const ConvParams& p, int64_t n_in, int out_dtype, cudaStream_t st);  // conv_tma.cu
@@ -498,6 +529,9 @@ int mk_conv_fwd_bf16(const void* in, int64_t n_in, int cin, const void* wimg, in
   p.nchunks = (cin + kChunkElems - 1) / kChunkElems;
   p.out_cols = out_cols;
   p.out_stride = out_stride;
+  const int elem = out_dtype == MK_F32 ? 4 : 2;
+  p.stage_out = (out_rows == nullptr && out_stride == out_cols && ((out_stride * elem) & 15) != 0 && out_cols <= 64) ? 1 : 0;
+  const int soc = p.stage_out ? out_cols : 0;
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("MK3D_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -513,13 +547,13 @@ int mk_conv_fwd_bf16(const void* in, int64_t n_in, int cin, const void* wimg, in
   if (grp_env == 1 || (grp_env == 2 && cout <= 128)) group = grp_env;
   p.group = group;
   int stages = kMaxStages;
-  while (stages > 2 && conv_smem_bytes(cout, stages, group) > 222 * 1024) --stages;
+  while (stages > 2 && conv_smem_bytes(cout, stages, group, soc) > 222 * 1024) --stages;
   // Super-tiles: 4 stages (<= 176 KB) instead of the 5 that fit.  The kernel is bound by shared-memory bandwidth (LDGSTS
   // writes + tcgen05 operand reads, ncu: l1tex data-pipe wavefronts ~59 %, tensor pipe ~22 % at 96 channels), not by
   // latency, so the fifth stage buys nothing, while the smaller carve-out leaves ~60 KB of L1 for the neighbour rows a
   // compact tile re-gathers across offsets (L1 sector hit rate 13 % -> 50+ %, 96->96: 486 -> 541 TFLOP/s; 128 unchanged).
   if (group == 2 && stages > 4) stages = 4;
-  MK_REQUIRE(conv_smem_bytes(cout, stages, group) <= 227 * 1024, "shared memory budget exceeded");
+  MK_REQUIRE(conv_smem_bytes(cout, stages, group, soc) <= 227 * 1024, "shared memory budget exceeded");
   {
     static int st_env = -1, np_env = -1;
     if (st_env < 0) { const char* e = getenv("MK3D_STAGES"); st_env = e ? atoi(e) : 0; }
@@ -529,7 +563,7 @@ int mk_conv_fwd_bf16(const void* in, int64_t n_in, int cin, const void* wimg, in
     if (np_env >= 1 && np_env < p.num_producers) p.num_producers = np_env;
   }
   p.num_stages = stages;
-  const size_t smem = conv_smem_bytes(cout, stages, group);
+  const size_t smem = conv_smem_bytes(cout, stages, group, soc);
   int grid = num_sms();
   const int num_super = (p.num_tiles + group - 1) / group;
   if (grid > num_super) grid = num_super;

@@ -69,32 +69,42 @@ __global__ void __launch_bounds__(256) k_in_stats_final(const float* __restrict_
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (c >= C) return;  // whole warp
-  double n = 0, mu = 0, m2 = 0;
+  // Sums about ONE reference value (the first chunk's shift, a sample of the channel): per chunk
+  //   sum(x - ref) = s1 + n d,  sum((x - ref)^2) = s2 + 2 d s1 + n d^2,  d = shift_chunk - ref
+  // in fp64 with multiply-adds only (the pairwise Chan merge needed an fp64 division per chunk on the critical path of a
+  // kernel that is pure latency: ~10 us per call, 62 calls per forward).  Fixed order: lane l folds chunks l, l+32, ...,
+  // then a fixed shuffle tree => bit-reproducible run to run.
+  const float* p0 = partial + ((int64_t)(b * chunks_per_scene)) * 4 * C;
+  const double ref = p0[3 * C + c];
+  double n = 0, S = 0, SS = 0;
   for (int ch = lane; ch < chunks_per_scene; ch += 32) {
     const float* p = partial + ((int64_t)(b * chunks_per_scene + ch)) * 4 * C;
     const double nb = p[c];
     if (nb <= 0) continue;
-    const double s1 = p[C + c], s2 = p[2 * C + c], sh = p[3 * C + c];
-    double m2b = s2 - s1 * s1 / nb;
-    if (m2b < 0) m2b = 0;
-    chan_merge(n, mu, m2, nb, sh + s1 / nb, m2b);
+    const double s1 = p[C + c], s2 = p[2 * C + c], d = (double)p[3 * C + c] - ref;
+    n += nb;
+    S += fma(nb, d, s1);
+    SS += fma(d, fma(nb, d, 2.0 * s1), s2);
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
-    const double nb = __shfl_down_sync(0xffffffffu, n, d), mub = __shfl_down_sync(0xffffffffu, mu, d),
-                 m2b = __shfl_down_sync(0xffffffffu, m2, d);
-    chan_merge(n, mu, m2, nb, mub, m2b);
+    n += __shfl_down_sync(0xffffffffu, n, d);
+    S += __shfl_down_sync(0xffffffffu, S, d);
+    SS += __shfl_down_sync(0xffffffffu, SS, d);
   }
   if (lane == 0) {
-    const double var = n > 0 ? m2 / n : 0.0;
+    double mu = ref, var = 0.0;
+    if (n > 0) {
+      const double m = S / n;
+      mu = ref + m;
+      var = SS / n - m * m;
+      if (var < 0) var = 0;
+    }
     mean[b * C + c] = (float)mu;
     rstd[b * C + c] = (float)(1.0 / sqrt(var + (double)eps));
   }
 }
 
-// Single-launch statistics: the chunk pass above with 16-byte loads, four rows in flight per thread, and the merge done
-// by the LAST block of each scene to finish (ticket counter), in the same fixed order as k_in_stats_final => same bits,
-// one launch and no second kernel whose ~10 us of latency was pure overhead on the small levels.
 template <typename T>
 __global__ void __launch_bounds__(kNormThreads) k_in_stats(const T* __restrict__ x, int C, const int32_t* __restrict__ scene_offsets,
                                                            int rows_per_chunk, int chunks_per_scene, float eps,
@@ -178,6 +188,7 @@ __global__ void __launch_bounds__(kNormThreads) k_in_stats(const T* __restrict__
 #pragma unroll
     for (int j = 0; j < V; ++j) out[3 * C + V * cv + j] = shift[j];
   }
+  if (counters == nullptr) return;  // statistics merged by k_in_stats_final (separate launch)
   // ---- last block of the scene merges the chunk statistics (Chan, fp64, fixed order)
   __threadfence();
   __syncthreads();
@@ -341,8 +352,9 @@ int mk_instnorm_stats(const void* x, int x_dtype, int64_t n, int C, const int32_
   int rpc, cps;
   norm_chunking(n, B, &rpc, &cps);
   float* partial = (float*)workspace;
-  unsigned* counters = (unsigned*)(partial + (int64_t)B * cps * 4 * C + 2 * (int64_t)B * C + 64);
-  cudaMemsetAsync(counters, 0, (size_t)B * sizeof(unsigned), st);
+  // The in-kernel merge by the last block (pass `counters`) saves a launch but serialises C channels x chunks of fp64 merge
+  // on ONE SM (measured 0.115 ms per call on B200 vs ~0.01 ms for the 12-block k_in_stats_final), so it is off.
+  unsigned* counters = nullptr;
   dim3 grid((unsigned)cps, (unsigned)B);
   const int V = x_dtype == MK_F32 ? 4 : 8;
   if (C % V == 0 && C / V <= kNormThreads && ((uintptr_t)x & 15) == 0) {
@@ -353,6 +365,7 @@ int mk_instnorm_stats(const void* x, int x_dtype, int64_t n, int C, const int32_
     else
       k_in_stats<__nv_bfloat16><<<grid, kNormThreads, smem, st>>>((const __nv_bfloat16*)x, C, scene_offsets, rpc, cps, eps, partial,
                                                                   counters, mean, rstd);
+    k_in_stats_final<<<dim3((unsigned)ceil_div(C, 8), (unsigned)B), 256, 0, st>>>(partial, C, cps, eps, mean, rstd);
     return check_launch(__func__);
   }
   const int CV = C / 4, RL = kNormThreads / CV;

@@ -14,6 +14,7 @@ The architecture is written from the layer table, not fro
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -294,7 +295,7 @@ class Mask3D(nn.Module):
         self.lin_squeeze = mk(lambda i: nn.Linear(sizes[self.hlevels[i]], d))
         self.decoder_norm = nn.LayerNorm(d)
         self._derived: Dict[Tuple[int, str], Tuple[int, torch.Tensor]] = {}
-        self.use_cuda_graphs = True   # query-side work of the decoder as CUDA graphs (_QueryGraphs)
+        self.use_cuda_graphs = os.environ.get("MK3D_NO_GRAPHS", "0") != "1"   # query-side work of the decoder as CUDA graphs (_QueryGraphs)
         self._qgraphs: Dict[tuple, _QueryGraphs] = {}
 
     def _d(self, p: torch.Tensor, tag: str, fn):
