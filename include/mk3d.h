@@ -124,8 +124,9 @@ int mk_conv_wgrad_f32(const float* in, int cin, const float* dout, int cout, con
  *           offsets for same-map convs), no separate entry point;
  *   wgrad = dW[k] = sum over slots o of x[nbr[k,o]]^T dy[row(o)], one persistent tcgen05 kernel over the forward's tile plan:
  *           both operands MN-major, fp32 accumulation in TMEM across a run of tiles of one offset, fp32 atomic flush.
- * mk_conv_wgrad_plan turns a plan's tile_kmask into the (offset, tile) unit list the kernel partitions over its CTAs:
- * plan int32 [mk_conv_wgrad_plan_elems(num_tiles, K)] = {n_units, count per offset [K], units (k << 26 | tile) by (k, tile)}.
+ * mk_conv_wgrad_plan turns a plan's tile_kmask into the work items the kernel deals to its CTAs: item = (tile block, offset) ->
+ * the tiles of the block that have the offset; plan int32 [mk_conv_wgrad_plan_elems(num_tiles, K)] =
+ * {n_items, n_units, tiles per block, 0 | items [start, k << 26 | count] ordered by (block, k) | unit tile ids | scratch}.
  * x bf16 [n_in,cin] (cin % 8 == 0), dy bf16 [n_out,cout] (cout % 16 == 0, <= 256), nbr / out_rows as mk_conv_fwd_bf16,
  * dW fp32 [K,cin,cout] (zeroed inside). */
 int64_t mk_conv_wgrad_plan_elems(int64_t num_tiles, int K);
