@@ -52,6 +52,12 @@ int64_t mk_coordmap_workspace_bytes(int64_t n);
 int mk_coordmap_build(const int32_t* in_coords, int64_t n, const int32_t* stride3_host, uint64_t* keys, int32_t* vals,
                       int64_t cap, int32_t* out_coords, int32_t* unique_index, int32_t* inverse, int32_t* n_out,
                       int32_t* status, void* workspace, int64_t workspace_bytes, void* stream);
+/* Voxel dedup in the reference's own order (np.unique(coords, axis=0, return_index=True) per scene followed by
+ * ME.utils.sparse_collate, mask3d/datasets/utils.py:96-126): keys[i] = packed (batch,x,y,z) of row i, whose unsigned order is the
+ * lexicographic order of the signed rows; the caller sorts (key, row) pairs stably and feeds the sorted rows to
+ * mk_coordmap_build, whose first-occurrence order then IS the lexicographic order and whose unique_index picks the
+ * lowest original row of every voxel.  status (device int32): non-zero = a coordinate outside the packable range. */
+int mk_pack_keys(const int32_t* coords, int64_t n, uint64_t* keys, int32_t* status, void* stream);
 /* rows[i] = row of query coordinate i in the map, or -1. */
 int mk_hash_query(const uint64_t* keys, const int32_t* vals, int64_t cap, const int32_t* query_coords, int64_t n,
                   int32_t* rows, void* stream);

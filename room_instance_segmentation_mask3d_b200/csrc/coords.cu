@@ -259,6 +259,20 @@ __global__ void k_row_sort_keys(const int32_t* __restrict__ nbr, int K, int64_t 
 }
 
 // nbr_sorted[k, s] = nbr[k, order[s]]
+// Lexicographic sort keys of (batch, x, y, z) rows: the packed 64-bit coordinate key (biased, so unsigned key order ==
+// signed lexicographic row order, what np.unique(axis=0) sorts by).  status |= 1 for rows outside the packable range.
+__global__ void k_pack_keys(const int4* __restrict__ coords, int64_t n, unsigned long long* __restrict__ keys, int32_t* __restrict__ status) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int4 c = coords[i];
+    if (!coord_in_range(c.x, c.y, c.z, c.w)) {
+      *status = 1;
+      keys[i] = kEmptyKey;
+    } else {
+      keys[i] = pack_key(c.x, c.y, c.z, c.w);
+    }
+  }
+}
+
 __global__ void k_permute_table(const int32_t* __restrict__ nbr, int64_t n, const int32_t* __restrict__ order, int64_t n_slots,
                                 int32_t* __restrict__ out) {
   const int k = blockIdx.y;
@@ -382,6 +396,16 @@ int mk_row_sort_keys(const int32_t* nbr, int K, int64_t n, const int32_t* coords
   const int sx = stride3_host ? stride3_host[0] : 1, sy = stride3_host ? stride3_host[1] : 1, sz = stride3_host ? stride3_host[2] : 1;
   k_row_sort_keys<<<(unsigned)bx, 256, 0, (cudaStream_t)stream_>>>(nbr, K, n, (const int4*)coords, sx, sy, sz,
                                                                   (unsigned long long*)keys);
+  return check_launch(__func__);
+}
+
+int mk_pack_keys(const int32_t* coords, int64_t n, uint64_t* keys, int32_t* status, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  cudaMemsetAsync(status, 0, sizeof(int32_t), st);
+  if (n == 0) return check_launch(__func__);
+  int64_t bx = ceil_div(n, 256);
+  if (bx > 8 * num_sms()) bx = 8 * num_sms();
+  k_pack_keys<<<(unsigned)bx, 256, 0, st>>>((const int4*)coords, n, (unsigned long long*)keys, status);
   return check_launch(__func__);
 }
 

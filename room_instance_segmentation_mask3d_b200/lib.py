@@ -27,6 +27,7 @@ _SIGS = {
     "mk_coordmap_workspace_bytes": (c_int64, [c_int64]),
     "mk_coordmap_build": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_int64, c_void_p]),
+    "mk_pack_keys": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "mk_hash_query": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "mk_kernel_map": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "mk_tile_kmask": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),

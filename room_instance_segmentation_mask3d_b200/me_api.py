@@ -508,6 +508,52 @@ def sparse_collate(coords, feats, labels=None, dtype=torch.int32, device=None):
     return bcoords, f, (l.to(device) if device is not None else l)
 
 
+def voxelize_collate(coords, feats=None, labels=None, device="cuda"):
+    """GPU form of the reference's per-scene dedup + collate (mask3d/datasets/utils.py:96-126):
+
+        for every scene:  coords, unique_indices = np.unique(coords.int(), axis=0, return_index=True);  feats = feats[unique_indices] ...
+        ME.utils.sparse_collate(coords, feats, labels)
+
+    `coords`: list of per-scene [N_b, 3] arrays / tensors (floats are truncated like `.int()` does).  Returns
+    (bcoords int32 [sum N', 4] batch-first, rows of a scene lexicographically sorted exactly as np.unique orders them,
+    feats, labels, unique_indices: list of int64 tensors = np.unique's first-occurrence indices, and the SparseTensor-ready
+    (coordinate_manager, coordinate_map_key) whose hash map was built on the way, so SparseTensor(...) needs no second insert)."""
+    lib.require_cuda()
+    dev = torch.device(device)
+    cs = [torch.as_tensor(c).to(dev).to(torch.int32) for c in coords]
+    counts = [int(c.shape[0]) for c in cs]
+    bc = torch.cat([torch.cat([torch.full((c.shape[0], 1), b, dtype=torch.int32, device=dev), c], 1) for b, c in enumerate(cs)], 0).contiguous() \
+        if cs else torch.zeros((0, 4), dtype=torch.int32, device=dev)
+    n = bc.shape[0]
+    keys = torch.empty(n, dtype=torch.int64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    lib.call("mk_pack_keys", lib.p(bc), n, lib.p(keys), lib.p(status), lib.stream())
+    # unsigned key order: the packed key uses 64 bits only through bit 63 = 0 (10 + 3 * 18 = 64 bits, batch < 512 keeps the sign
+    # bit clear), so the signed int64 sort below is the unsigned order for every batch index the collate can produce here
+    assert len(cs) < 512, "voxelize_collate: at most 511 scenes per batch"
+    order = torch.sort(keys, stable=True).indices
+    sorted_rows = bc[order].contiguous()
+    mgr = CoordinateManager(D=3, device=dev)
+    key, (uniq, _) = mgr.insert_and_map(sorted_rows)  # raises on out-of-range coordinates
+    if int(status.item()) != 0:
+        raise RuntimeError("coordinate out of the packable range [-2^17, 2^17)")
+    bcoords = mgr.get_coordinates(key)
+    src = order[uniq]  # original (concatenated) row of every voxel = lowest index among its duplicates (stable sort)
+    starts = [0]
+    for c in counts:
+        starts.append(starts[-1] + c)
+    off = mgr.coord_map(key).scene_offsets_host(len(cs)) if len(cs) else [0]
+    unique_indices = [src[off[b]:off[b + 1]] - starts[b] for b in range(len(cs))]
+
+    def gather(parts):
+        if parts is None:
+            return None
+        cat = torch.cat([torch.as_tensor(p).to(dev) for p in parts], 0)
+        return cat[src]
+
+    return bcoords, gather(feats), gather(labels), unique_indices, (mgr, key)
+
+
 def sparse_quantize(coordinates, features=None, labels=None, ignore_label=-100, return_index=False, return_inverse=False,
                     return_maps_only=False, quantization_size=None, device="cuda"):
     """ME.utils.sparse_quantize on the GPU hash: floor(coords / quantization_size), first-occurrence

@@ -73,6 +73,36 @@ def test_out_of_range_coordinate_raises(R):
         mgr.insert_and_map(torch.tensor([[0, 1 << 17, 0, 0]], dtype=torch.int32).cuda())
 
 
+def test_voxelize_collate_matches_numpy_unique(R):
+    """GPU dedup + collate == the reference's np.unique(axis=0, return_index=True) per scene + sparse_collate
+    (mask3d/datasets/utils.py:96-126): same rows, same lexicographic order, same first-occurrence indices; negative
+    coordinates, duplicates (augmentation rounding), float inputs truncated like `.int()`, an empty scene in the middle."""
+    rng = np.random.default_rng(3)
+    scenes_in, feats_in, labels_in = [], [], []
+    for b, n in enumerate([5000, 0, 1237, 20000]):
+        c = rng.integers(-40, 40, size=(n, 3)).astype(np.float32) + rng.uniform(-0.4, 0.4, size=(n, 3)).astype(np.float32) * (b % 2)
+        if n:
+            c = np.concatenate([c, c[rng.integers(0, n, size=n // 4)]], 0)  # exact duplicates
+        scenes_in.append(c)
+        feats_in.append(rng.standard_normal((len(c), 3)).astype(np.float32))
+        labels_in.append(rng.integers(0, 7, size=(len(c), 2)))
+    bcoords, feats, labels, uidx, (mgr, key) = R.me.voxelize_collate(scenes_in, feats_in, labels_in)
+    want_c, want_f, want_l = [], [], []
+    for b, (c, f, l) in enumerate(zip(scenes_in, feats_in, labels_in)):
+        ci = torch.from_numpy(c).int().numpy()
+        u, idx = np.unique(ci, axis=0, return_index=True)
+        assert np.array_equal(uidx[b].cpu().numpy(), idx), f"scene {b}: first-occurrence indices"
+        want_c.append(np.concatenate([np.full((len(u), 1), b, dtype=np.int32), u.astype(np.int32)], 1))
+        want_f.append(f[idx])
+        want_l.append(l[idx])
+    assert np.array_equal(bcoords.cpu().numpy(), np.concatenate(want_c, 0))
+    assert np.array_equal(feats.cpu().numpy(), np.concatenate(want_f, 0))
+    assert np.array_equal(labels.cpu().numpy(), np.concatenate(want_l, 0))
+    # the coordinate map built on the way is the SparseTensor's map
+    x = R.me.SparseTensor(feats, coordinate_map_key=key, coordinate_manager=mgr)
+    assert x.C.shape[0] == feats.shape[0] and np.array_equal(x.C.cpu().numpy(), bcoords.cpu().numpy())
+
+
 def test_stride_maps_bit_exact(R):
     coords = make_batch(5)
     mgr = R.engine.CoordinateManager(D=3)
