@@ -77,14 +77,28 @@ __global__ void __launch_bounds__(256) k_in_stats_final(const float* __restrict_
   const float* p0 = partial + ((int64_t)(b * chunks_per_scene)) * 4 * C;
   const double ref = p0[3 * C + c];
   double n = 0, S = 0, SS = 0;
-  for (int ch = lane; ch < chunks_per_scene; ch += 32) {
-    const float* p = partial + ((int64_t)(b * chunks_per_scene + ch)) * 4 * C;
-    const double nb = p[c];
-    if (nb <= 0) continue;
-    const double s1 = p[C + c], s2 = p[2 * C + c], d = (double)p[3 * C + c] - ref;
-    n += nb;
-    S += fma(nb, d, s1);
-    SS += fma(d, fma(nb, d, 2.0 * s1), s2);
+  // four chunks per lane per round, all 16 loads issued before the first use (the kernel is a chain of L2 latencies)
+  for (int ch0 = lane; ch0 < chunks_per_scene; ch0 += 128) {
+    float v[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int ch = ch0 + 32 * u;
+      const float* p = partial + ((int64_t)(b * chunks_per_scene + (ch < chunks_per_scene ? ch : 0))) * 4 * C;
+      const bool ok = ch < chunks_per_scene;
+      v[u][0] = ok ? p[c] : 0.f;
+      v[u][1] = ok ? p[C + c] : 0.f;
+      v[u][2] = ok ? p[2 * C + c] : 0.f;
+      v[u][3] = ok ? p[3 * C + c] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {  // ascending chunk order per lane, as before
+      const double nb = v[u][0];
+      if (nb <= 0) continue;
+      const double s1 = v[u][1], s2 = v[u][2], d = (double)v[u][3] - ref;
+      n += nb;
+      S += fma(nb, d, s1);
+      SS += fma(d, fma(nb, d, 2.0 * s1), s2);
+    }
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {

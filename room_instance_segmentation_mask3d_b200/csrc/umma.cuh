@@ -191,6 +191,7 @@ struct ConvParams {
   int out_stride;  // elements between consecutive output rows
   int stage_out;   // 1: epilogue transposes each warp's 32 x out_cols block through shared memory and stores it as one
                    // contiguous run (rows are contiguous: out_rows == nullptr, out_stride == out_cols, row pitch not 16-byte aligned)
+  int chunk_major; // iteration order inside a super-tile (see SuperCursor)
   int debug;       // timing ablation flags (MK3D_DEBUG), 0 in production
   unsigned long long* trace;  // MK3D_TRACE: per-CTA role timers [grid][8], nullptr in production
 };
