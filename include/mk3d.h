@@ -158,6 +158,15 @@ int mk_instnorm_bwd(const float* x, const float* dy, int64_t n, int C, const int
                     const float* mean, const float* rstd, const float* gamma, float* dx, float* dgamma, float* dbeta,
                     void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Fused backward of (instance norm -> [+ residual] -> [ReLU]) for fp32 or bf16 tensors: dy = gradient w.r.t. the unit's output,
+ * out = that output (NULL: no ReLU), x = the un-normalised input of the norm (the conv output).  Writes dx (gradient w.r.t. x;
+ * dtype `dx_dtype`, fp32 allowed for bf16 inputs), dres (NULL or the gradient of the residual branch = masked dy), dgamma /
+ * dbeta fp32 [C].  One statistics pass (16-byte loads, deterministic merge) + one apply pass; replaces ME's five broadcast /
+ * pooling launches of MinkowskiInstanceNormFunction.backward plus the ReLU backward.  workspace as mk_instnorm_workspace_bytes. */
+int mk_instnorm_relu_bwd(const void* dy, const void* out, const void* x, int dtype, int64_t n, int C, const int32_t* scene_offsets,
+                         int B, const float* mean, const float* rstd, const float* gamma, void* dx, int dx_dtype, void* dres,
+                         float* dgamma, float* dbeta, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Composite: conv (tensor cores) -> instance norm -> (+ residual) -> (ReLU) in one call, the unit Res16UNet34C repeats per
  * layer (mask3d/models/res16unet.py:244-307, mask3d/models/modules/resnet_block.py:52-68).  Conv arguments as
  * mk_conv_fwd_bf16; tmp = bf16 [n_out,cout] scratch holding the un-normalised conv output; stats = fp32 [2,B,cout]

@@ -335,6 +335,191 @@ __global__ void __launch_bounds__(256) k_in_bwd_dx(const float* __restrict__ x, 
   }
 }
 
+// ---- fused backward of (instance norm -> [+ residual] -> [ReLU]): one statistics pass + one apply pass, any dtype ----------
+// g = dy where the unit's output was positive (or dy when there is no ReLU); x_hat = (x - mean) * rstd with x the conv output.
+//   sums per (scene, channel):  A = sum g,  Q = sum g * x_hat            (also dbeta = sum_b A, dgamma = sum_b Q)
+//   dx = gamma * rstd * (g - A / n_b - x_hat * Q / n_b),   dres = g
+template <typename T, int V>
+__device__ __forceinline__ void ld_vec(const T* p, float (&v)[V]) {
+  if constexpr (sizeof(T) == 2) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+      v[2 * j] = f.x;
+      v[2 * j + 1] = f.y;
+    }
+  } else {
+    const float4 q = *reinterpret_cast<const float4*>(p);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  }
+}
+template <typename T, int V>
+__device__ __forceinline__ void st_vec(T* p, const float (&v)[V]) {
+  if constexpr (sizeof(T) == 2) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      w[j] = *reinterpret_cast<uint32_t*>(&t);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  } else {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// partial [chunk][2][C] = {A, Q}; grid (chunks, B)
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads) k_inr_bwd_partial(const T* __restrict__ dy, const T* __restrict__ out,
+                                                                  const T* __restrict__ x, int C,
+                                                                  const int32_t* __restrict__ scene_offsets, int rows_per_chunk,
+                                                                  int chunks_per_scene, const float* __restrict__ mean,
+                                                                  const float* __restrict__ rstd, float* __restrict__ partial) {
+  constexpr int V = 16 / (int)sizeof(T);
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int64_t start = (int64_t)scene_offsets[b] + (int64_t)chunk * rows_per_chunk;
+  const int64_t end = min((int64_t)scene_offsets[b + 1], start + rows_per_chunk);
+  const int CV = C / V;
+  const int RL = kNormThreads / CV;
+  const int cv = threadIdx.x % CV, rl = threadIdx.x / CV;
+  float* po = partial + ((int64_t)(b * chunks_per_scene + chunk)) * 2 * C;
+  extern __shared__ float sm[];  // [RL][2][C]
+  float a[V], q[V], mu[V], rs[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) a[j] = q[j] = 0.f;
+  if (rl < RL) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      mu[j] = mean[b * C + V * cv + j];
+      rs[j] = rstd[b * C + V * cv + j];
+    }
+    auto acc = [&](int64_t r) {
+      float g[V], xv[V];
+      ld_vec<T, V>(dy + r * C + V * cv, g);
+      ld_vec<T, V>(x + r * C + V * cv, xv);
+      if (out) {
+        float o[V];
+        ld_vec<T, V>(out + r * C + V * cv, o);
+#pragma unroll
+        for (int j = 0; j < V; ++j) g[j] = o[j] > 0.f ? g[j] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        a[j] += g[j];
+        q[j] = fmaf(g[j], (xv[j] - mu[j]) * rs[j], q[j]);
+      }
+    };
+    int64_t r = start + rl;
+    for (; r + (int64_t)RL < end; r += 2 * (int64_t)RL) {  // two rows (six loads) in flight
+      acc(r);
+      acc(r + RL);
+    }
+    if (r < end) acc(r);
+    float* p = sm + (int64_t)rl * 2 * C + V * cv;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      p[j] = a[j];
+      p[C + j] = q[j];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kNormThreads) {
+    float sa = 0.f, sq = 0.f;
+    for (int l = 0; l < RL; ++l) {  // fixed order
+      sa += sm[l * 2 * C + c];
+      sq += sm[l * 2 * C + C + c];
+    }
+    po[c] = sa;
+    po[C + c] = sq;
+  }
+}
+
+// grid ceil(C / 8), block 256: one warp per channel, scenes in sequence (B is small), lanes over chunks, fixed merge order.
+__global__ void __launch_bounds__(256) k_inr_bwd_final(const float* __restrict__ partial, int C, int chunks_per_scene, int B,
+                                                       float* __restrict__ sum_a, float* __restrict__ sum_q,
+                                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double ta = 0, tq = 0;
+  for (int b = 0; b < B; ++b) {
+    double sa = 0, sq = 0;
+    for (int ch0 = lane; ch0 < chunks_per_scene; ch0 += 128) {
+      float va[4], vq[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int ch = ch0 + 32 * u;
+        const bool ok = ch < chunks_per_scene;
+        const float* p = partial + ((int64_t)(b * chunks_per_scene + (ok ? ch : 0))) * 2 * C;
+        va[u] = ok ? p[c] : 0.f;
+        vq[u] = ok ? p[C + c] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        sa += va[u];
+        sq += vq[u];
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      sa += __shfl_down_sync(0xffffffffu, sa, d);
+      sq += __shfl_down_sync(0xffffffffu, sq, d);
+    }
+    if (lane == 0) {
+      sum_a[b * C + c] = (float)sa;
+      sum_q[b * C + c] = (float)sq;
+    }
+    ta += sa;
+    tq += sq;
+  }
+  if (lane == 0) {
+    if (dbeta) dbeta[c] = (float)ta;
+    if (dgamma) dgamma[c] = (float)tq;
+  }
+}
+
+template <typename T, typename TD>
+__global__ void __launch_bounds__(256) k_inr_bwd_apply(const T* __restrict__ dy, const T* __restrict__ out, const T* __restrict__ x,
+                                                       int64_t n, int C, const int32_t* __restrict__ scene_offsets, int B,
+                                                       const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                       const float* __restrict__ gamma, const float* __restrict__ sum_a,
+                                                       const float* __restrict__ sum_q, TD* __restrict__ dx, T* __restrict__ dres) {
+  constexpr int V = 16 / (int)sizeof(T);
+  const int CV = C / V;
+  const int64_t total = n * CV;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / CV;
+    const int c = (int)(i - r * CV) * V;
+    const int b = scene_of_row(scene_offsets, B, r);
+    const float inv_n = 1.f / (float)(scene_offsets[b + 1] - scene_offsets[b]);
+    float g[V], xv[V], d[V];
+    ld_vec<T, V>(dy + r * C + c, g);
+    ld_vec<T, V>(x + r * C + c, xv);
+    if (out) {
+      float o[V];
+      ld_vec<T, V>(out + r * C + c, o);
+#pragma unroll
+      for (int j = 0; j < V; ++j) g[j] = o[j] > 0.f ? g[j] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float rs = rstd[b * C + c + j];
+      const float xh = (xv[j] - mean[b * C + c + j]) * rs;
+      const float gm = gamma ? gamma[c + j] : 1.f;
+      d[j] = gm * rs * (g[j] - sum_a[b * C + c + j] * inv_n - xh * sum_q[b * C + c + j] * inv_n);
+    }
+    if constexpr (sizeof(TD) == sizeof(T)) {
+      st_vec<TD, V>(dx + r * C + c, d);
+    } else {
+#pragma unroll
+      for (int j = 0; j < V; ++j) dx[r * C + c + j] = from_f32<TD>(d[j]);
+    }
+    if (dres) st_vec<T, V>(dres + r * C + c, g);
+  }
+}
+
 inline void norm_chunking(int64_t n, int B, int* rows_per_chunk, int* chunks_per_scene) {
   // target ~4 chunks per SM over the whole batch; chunks are per scene, sized for the largest possible scene (n)
   int64_t target = 2 * (int64_t)num_sms();
@@ -410,6 +595,51 @@ int mk_norm_apply(const void* x, int x_dtype, int64_t n, int C, const int32_t* s
   else if (x_dtype == MK_BF16 && out_dtype == MK_F32) MK_APPLY(__nv_bfloat16, float);
   else MK_APPLY(__nv_bfloat16, __nv_bfloat16);
 #undef MK_APPLY
+  return check_launch(__func__);
+}
+
+int mk_instnorm_relu_bwd(const void* dy, const void* out, const void* x, int dtype, int64_t n, int C, const int32_t* scene_offsets,
+                         int B, const float* mean, const float* rstd, const float* gamma, void* dx, int dx_dtype, void* dres,
+                         float* dgamma, float* dbeta, void* workspace, int64_t workspace_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  const int V = dtype == MK_F32 ? 4 : 8;
+  MK_REQUIRE(C % V == 0 && C / V <= kNormThreads, "C must be a multiple of 4 (fp32) / 8 (bf16)");
+  MK_REQUIRE(dx_dtype == dtype || (dtype == MK_BF16 && dx_dtype == MK_F32), "dx must have the input dtype (or fp32 for bf16 inputs)");
+  MK_REQUIRE(workspace_bytes >= mk_instnorm_workspace_bytes(n, C, B), "workspace too small");
+  MK_REQUIRE((((uintptr_t)dy | (uintptr_t)x | (uintptr_t)out | (uintptr_t)dx | (uintptr_t)dres) & 15) == 0, "16-byte alignment");
+  int rpc, cps;
+  norm_chunking(n, B, &rpc, &cps);
+  float* partial = (float*)workspace;
+  float* sum_a = partial + (int64_t)B * cps * 4 * C;
+  float* sum_q = sum_a + (int64_t)B * C;
+  dim3 grid((unsigned)cps, (unsigned)B);
+  const int RL = kNormThreads / (C / V);
+  const size_t smem = (size_t)RL * 2 * C * sizeof(float);
+  if (dtype == MK_F32)
+    k_inr_bwd_partial<float><<<grid, kNormThreads, smem, st>>>((const float*)dy, (const float*)out, (const float*)x, C, scene_offsets, rpc,
+                                                              cps, mean, rstd, partial);
+  else
+    k_inr_bwd_partial<__nv_bfloat16><<<grid, kNormThreads, smem, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)out,
+                                                                      (const __nv_bfloat16*)x, C, scene_offsets, rpc, cps, mean, rstd,
+                                                                      partial);
+  k_inr_bwd_final<<<(unsigned)ceil_div(C, 8), 256, 0, st>>>(partial, C, cps, B, sum_a, sum_q, dgamma, dbeta);
+  if (n > 0) {
+    int64_t blocks = ceil_div(n * (C / V), 256);
+    const int64_t cap = 8 * (int64_t)num_sms();
+    if (blocks > cap) blocks = cap;
+    if (dtype == MK_F32)
+      k_inr_bwd_apply<float, float><<<(unsigned)blocks, 256, 0, st>>>((const float*)dy, (const float*)out, (const float*)x, n, C,
+                                                                      scene_offsets, B, mean, rstd, gamma, sum_a, sum_q, (float*)dx,
+                                                                      (float*)dres);
+    else if (dx_dtype == MK_BF16)
+      k_inr_bwd_apply<__nv_bfloat16, __nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(
+          (const __nv_bfloat16*)dy, (const __nv_bfloat16*)out, (const __nv_bfloat16*)x, n, C, scene_offsets, B, mean, rstd, gamma, sum_a,
+          sum_q, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres);
+    else
+      k_inr_bwd_apply<__nv_bfloat16, float><<<(unsigned)blocks, 256, 0, st>>>(
+          (const __nv_bfloat16*)dy, (const __nv_bfloat16*)out, (const __nv_bfloat16*)x, n, C, scene_offsets, B, mean, rstd, gamma, sum_a,
+          sum_q, (float*)dx, (__nv_bfloat16*)dres);
+  }
   return check_launch(__func__);
 }
 

@@ -60,6 +60,41 @@ def _stage(cin, cout, n):
     return nn.Sequential(*[BasicBlock(cin if i == 0 else cout, cout) for i in range(n)])
 
 
+class _ConvNormActFn(torch.autograd.Function):
+    """conv (tcgen05) -> instance norm -> (+ residual) -> (ReLU) as ONE autograd node on bf16 activations: the training unit of
+    the backbone (reference: the MinkowskiConvolution / MinkowskiInstanceNorm / `+=` / MinkowskiReLU sequence of
+    res16unet.py:244-307 and resnet_block.py:52-68, four autograd nodes and fp32 tensors there).  Forward = one C call
+    (mk_conv_instnorm_bf16), backward = mk_instnorm_relu_bwd + tcgen05 dgrad + tcgen05 wgrad.  Saved for backward: the bf16
+    input, the bf16 un-normalised conv output, the statistics, and the bf16 output (ReLU mask)."""
+
+    @staticmethod
+    def forward(ctx, x, W, gamma, beta, residual, km, kind, aux, offs, B, relu):
+        x = x.contiguous()
+        out, tmp, stats = ops.conv_instnorm_bf16(x, W, km, offs, B, gamma, beta, residual=residual, relu=relu, keep=True)
+        ctx.km, ctx.kind, ctx.aux, ctx.B, ctx.relu, ctx.has_res = km, kind, aux, B, relu, residual is not None
+        ctx.save_for_backward(x, W, gamma, tmp, stats, out if relu else None, offs)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, gamma, tmp, stats, out, offs = ctx.saved_tensors
+        km, kind, B = ctx.km, ctx.kind, ctx.B
+        W3 = W if W.dim() == 3 else W.unsqueeze(0)
+        K, cin, cout = W3.shape
+        dy = dy.contiguous()
+        dtmp, dres, dgamma, dbeta = ops.instnorm_relu_bwd(dy, out, tmp, offs, B, stats[0], stats[1], gamma, want_dres=ctx.has_res)
+        dx = dW = None
+        if ctx.needs_input_grad[0]:
+            if kind == 0:
+                dx = ops.conv_dgrad_bf16(dtmp, W3, km, kidx=torch.arange(K - 1, -1, -1, device=x.device, dtype=torch.int32),
+                                         out_dtype=torch.bfloat16)
+            else:
+                dx = ops.conv_dgrad_bf16(dtmp, W3, ctx.aux, out_dtype=torch.bfloat16)
+        if ctx.needs_input_grad[1]:
+            dW = ops.conv_wgrad_bf16(x, dtmp, km, K, cin, cout).reshape(W.shape)
+        return dx, dW, dgamma.view_as(gamma), dbeta.view_as(gamma), dres, None, None, None, None, None, None
+
+
 class Res16UNet34C(nn.Module):
     """Sparse U-Net: 4 stride-2 encoder levels, 4 transposed-conv decoder levels with skip concatenation."""
 
@@ -101,6 +136,52 @@ class Res16UNet34C(nn.Module):
             out = getattr(self, f"block{5 + j}")(out)
             fmaps.append(out)
         return (out, fmaps) if self.out_fpn else out
+
+    # ---- fused training path: same composition, every conv + norm + activation one autograd node on bf16 activations
+    def forward_train(self, x: ME.SparseTensor):
+        """Autograd-capable fused forward (bf16 tensor-core mode).  Returns what `forward` returns; `.F` of the results is
+        bf16.  The stem (Cin = 1) runs through the fp32 modules."""
+        assert ops.get_compute_mode() == "bf16", "forward_train is the bf16 tensor-core path"
+        with lib.stream_scope():
+            mgr = x.coordinate_manager
+            B = mgr.number_of_unique_batch_indices()
+            keys = mgr.prebuild(x.coordinate_map_key, 5, self.conv0p1s1.kernel_generator.kernel_size[0])
+            offs = [mgr.scene_offsets(k) for k in keys]
+
+            def unit(f, conv, norm, km, lvl, kind=0, aux=None, relu=True, residual=None):
+                assert conv.bias is None
+                return _ConvNormActFn.apply(f, conv.kernel, norm.weight, norm.bias, residual, km, kind, aux, offs[lvl], B, relu)
+
+            def block(f, blk, lvl):
+                km3 = mgr.neighbor_table(keys[lvl], keys[lvl], 3, 1)
+                h = unit(f, blk.conv1, blk.norm1, km3, lvl)
+                res = f
+                if blk.downsample is not None:
+                    res = unit(f, blk.downsample[0], blk.downsample[1], mgr.neighbor_table(keys[lvl], keys[lvl], 1, 1), lvl, relu=False)
+                return unit(h, blk.conv2, blk.norm2, km3, lvl, residual=res)
+
+            f = self.relu(self.bn0(self.conv0p1s1(x))).F.to(torch.bfloat16)
+            skips = [f]
+            for lvl in range(1, 5):
+                km = mgr.neighbor_table(keys[lvl - 1], keys[lvl], 2, 1)
+                tplan = mgr.transpose_plan(keys[lvl], keys[lvl - 1], 2, 1)
+                f = unit(f, getattr(self, f"conv{lvl}p{2 ** (lvl - 1)}s2"), getattr(self, f"bn{lvl}"), km, lvl, kind=1, aux=tplan)
+                for blk in getattr(self, f"block{lvl}"):
+                    f = block(f, blk, lvl)
+                skips.append(f)
+            fmaps = [f]
+            for j, lvl in enumerate(range(4, 0, -1)):
+                plan = mgr.transpose_plan(keys[lvl], keys[lvl - 1], 2, 1)
+                down = mgr.neighbor_table(keys[lvl - 1], keys[lvl], 2, 1)
+                f = unit(f, getattr(self, f"convtr{4 + j}p{2 ** lvl}s2"), getattr(self, f"bntr{4 + j}"), plan, lvl - 1, kind=2, aux=down)
+                f = torch.cat([f, skips[lvl - 1]], dim=1)
+                for blk in getattr(self, f"block{5 + j}"):
+                    f = block(f, blk, lvl - 1)
+                fmaps.append(f)
+            wrap = lambda t, k: ME.SparseTensor(t, coordinate_map_key=k, coordinate_manager=mgr)
+            out = wrap(f, keys[0])
+            fm = [wrap(t, keys[4 - i]) for i, t in enumerate(fmaps)]
+            return (out, fm) if self.out_fpn else out
 
     # ---- fused inference path
     @torch.no_grad()

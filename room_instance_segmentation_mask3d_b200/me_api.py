@@ -256,13 +256,16 @@ class _InstanceNormFn(torch.autograd.Function):
         x, weight, mean, rstd, offsets = ctx.saved_tensors
         n, C = x.shape
         xf, dy = x.float().contiguous(), dy.contiguous().float()
-        dx = torch.empty_like(xf)
-        dg = torch.empty(C, dtype=torch.float32, device=x.device)
-        db = torch.empty(C, dtype=torch.float32, device=x.device)
-        wsb = lib.query("mk_instnorm_workspace_bytes", n, C, ctx.B)
-        ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
-        lib.call("mk_instnorm_bwd", lib.p(xf), lib.p(dy), n, C, lib.p(offsets), ctx.B, lib.p(mean), lib.p(rstd),
-                 lib.p(weight.detach().reshape(-1).float().contiguous()), lib.p(dx), lib.p(dg), lib.p(db), lib.p(ws), wsb, lib.stream())
+        if C % 4 == 0:
+            dx, _, dg, db = ops.instnorm_relu_bwd(dy, None, xf, offsets, ctx.B, mean, rstd, weight)
+        else:  # odd widths: scalar kernels
+            dx = torch.empty_like(xf)
+            dg = torch.empty(C, dtype=torch.float32, device=x.device)
+            db = torch.empty(C, dtype=torch.float32, device=x.device)
+            wsb = lib.query("mk_instnorm_workspace_bytes", n, C, ctx.B)
+            ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
+            lib.call("mk_instnorm_bwd", lib.p(xf), lib.p(dy), n, C, lib.p(offsets), ctx.B, lib.p(mean), lib.p(rstd),
+                     lib.p(weight.detach().reshape(-1).float().contiguous()), lib.p(dx), lib.p(dg), lib.p(db), lib.p(ws), wsb, lib.stream())
         return dx, dg.reshape(weight.shape), db.reshape(weight.shape), None, None, None
 
 

@@ -114,15 +114,16 @@ def conv_forward(x: torch.Tensor, W: torch.Tensor, km: KernelMap, bias: Optional
     return out
 
 
-def conv_dgrad_bf16(dout: torch.Tensor, W: torch.Tensor, km_t: KernelMap, kidx: Optional[torch.Tensor] = None) -> torch.Tensor:
+def conv_dgrad_bf16(dout: torch.Tensor, W: torch.Tensor, km_t: KernelMap, kidx: Optional[torch.Tensor] = None,
+                    out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """din[i] = sum_k dout[nbr_t[k, i]] @ W[kidx[k]]^T on the tensor-core kernel (fp32 out).  W fp32 [K, cin, cout]; the
     kernel's accumulator holds at most 256 columns, so wider inputs (block5's 384-channel concat) go in column slices."""
     W3 = W if W.dim() == 3 else W.unsqueeze(0)
     K, cin, cout = W3.shape
     if cin <= 256:
-        return conv_forward(dout, W3, km_t, mode="bf16", out_dtype=torch.float32, kidx=kidx, transpose_w=True)
+        return conv_forward(dout, W3, km_t, mode="bf16", out_dtype=out_dtype, kidx=kidx, transpose_w=True)
     db = cast(dout.contiguous(), torch.bfloat16)
-    din = torch.empty((km_t.n_out, cin), dtype=torch.float32, device=dout.device)
+    din = torch.empty((km_t.n_out, cin), dtype=out_dtype, device=dout.device)
     plan = km_t.sorted_plan() if SORT_TILES else km_t
     nsplit = (cin + 255) // 256
     step = ((cin + nsplit - 1) // nsplit + 15) // 16 * 16
@@ -130,7 +131,8 @@ def conv_dgrad_bf16(dout: torch.Tensor, W: torch.Tensor, km_t: KernelMap, kidx: 
         c1 = min(cin, c0 + step)
         img = weight_image(W3[:, c0:c1, :], transpose=True)
         lib.call("mk_conv_fwd_bf16", lib.p(db), db.shape[0], cout, lib.p(img), c1 - c0, lib.p(plan.nbr), K, plan.n_slots, lib.p(plan.out_rows),
-                 lib.p(plan.tile_kmask), lib.p(kidx), km_t.n_out, None, din.data_ptr() + 4 * c0, lib.F32, c1 - c0, cin, lib.stream())
+                 lib.p(plan.tile_kmask), lib.p(kidx), km_t.n_out, None, din.data_ptr() + din.element_size() * c0, lib.dt(din), c1 - c0, cin,
+                 lib.stream())
     return din
 
 
@@ -149,7 +151,7 @@ def conv_wgrad_bf16(x: torch.Tensor, dout: torch.Tensor, km: KernelMap, K: int, 
 
 def conv_instnorm_bf16(x: torch.Tensor, W: torch.Tensor, km: KernelMap, scene_offsets: torch.Tensor, B: int, gamma, beta, bias=None,
                        residual: Optional[torch.Tensor] = None, relu: bool = True, eps: float = 1e-8,
-                       out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+                       out_dtype: torch.dtype = torch.bfloat16, keep: bool = False):
     """conv (tcgen05) -> instance norm -> (+ residual) -> (ReLU) through ONE C-ABI call (mk_conv_instnorm_bf16)."""
     W3 = W if W.dim() == 3 else W.unsqueeze(0)
     K, cin, cout = W3.shape
@@ -160,7 +162,9 @@ def conv_instnorm_bf16(x: torch.Tensor, W: torch.Tensor, km: KernelMap, scene_of
     out = torch.empty((n, cout), dtype=out_dtype, device=x.device)
     stats = torch.empty((2, B, cout), dtype=torch.float32, device=x.device)
     wsb = lib.query("mk_instnorm_workspace_bytes", n, cout, B)
-    tmp_bytes = (n * cout * 2 + 255) // 256 * 256
+    # keep=True (training): the un-normalised conv output is a tensor of its own, returned with the statistics for the backward
+    tmp = torch.empty((n, cout), dtype=torch.bfloat16, device=x.device) if keep else None
+    tmp_bytes = 0 if keep else (n * cout * 2 + 255) // 256 * 256
     ws = lib.scratch(tmp_bytes + wsb, x.device)
     if residual is not None:
         assert residual.dtype == out_dtype and residual.is_contiguous()
@@ -169,9 +173,9 @@ def conv_instnorm_bf16(x: torch.Tensor, W: torch.Tensor, km: KernelMap, scene_of
     base = ws.data_ptr()
     lib.call("mk_conv_instnorm_bf16", x.data_ptr(), x.shape[0], cin, img.data_ptr(), cout, plan.nbr.data_ptr(), K, plan.n_slots,
              lib.p(plan.out_rows), plan.tile_kmask.data_ptr(), None, n, lib.p(_flat32(bias)), scene_offsets.data_ptr(), B, eps,
-             lib.p(_flat32(gamma)), lib.p(_flat32(beta)), lib.p(residual), int(relu), base, stats.data_ptr(), out.data_ptr(), lib.dt(out),
-             base + tmp_bytes, ws.numel() - tmp_bytes, lib.stream())
-    return out
+             lib.p(_flat32(gamma)), lib.p(_flat32(beta)), lib.p(residual), int(relu), tmp.data_ptr() if keep else base, stats.data_ptr(),
+             out.data_ptr(), lib.dt(out), base + tmp_bytes, ws.numel() - tmp_bytes, lib.stream())
+    return (out, tmp, stats) if keep else out
 
 
 def conv_transpose_forward_fp32(x: torch.Tensor, W: torch.Tensor, plan: KernelMap, bias=None) -> torch.Tensor:
@@ -219,6 +223,24 @@ def instance_norm(x, scene_offsets, B, gamma, beta, residual=None, relu=False, o
     x = x.contiguous()
     mean, rstd = instance_norm_stats(x, scene_offsets, B, eps)
     return norm_apply(x, scene_offsets, B, mean, rstd, gamma, beta, residual, relu, out_dtype)
+
+
+def instnorm_relu_bwd(dy: torch.Tensor, out: Optional[torch.Tensor], x: torch.Tensor, scene_offsets: torch.Tensor, B: int, mean, rstd,
+                      gamma, want_dres: bool = False, dx_dtype: Optional[torch.dtype] = None):
+    """Backward of (instance norm -> [+ residual] -> [ReLU]) in one statistics + one apply pass (mk_instnorm_relu_bwd).
+    dy / out / x share a dtype (fp32 or bf16); `out` = the unit's output when it ends in a ReLU, else None.
+    Returns (dx, dres or None, dgamma fp32 [C], dbeta fp32 [C])."""
+    n, C = x.shape
+    assert dy.dtype == x.dtype and dy.is_contiguous() and x.is_contiguous() and (out is None or (out.dtype == x.dtype and out.is_contiguous()))
+    dx = torch.empty((n, C), dtype=dx_dtype or x.dtype, device=x.device)
+    dres = torch.empty((n, C), dtype=x.dtype, device=x.device) if want_dres else None
+    dgb = torch.empty((2, C), dtype=torch.float32, device=x.device)
+    wsb = lib.query("mk_instnorm_workspace_bytes", n, C, B)
+    ws = lib.scratch(wsb, x.device)
+    lib.call("mk_instnorm_relu_bwd", dy.data_ptr(), lib.p(out), x.data_ptr(), lib.dt(x), n, C, scene_offsets.data_ptr(), B, mean.data_ptr(),
+             rstd.data_ptr(), lib.p(_flat32(gamma)), dx.data_ptr(), lib.dt(dx), lib.p(dres), dgb.data_ptr(), dgb.data_ptr() + 4 * C,
+             ws.data_ptr(), ws.numel(), lib.stream())
+    return dx, dres, dgb[0], dgb[1]
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -10,6 +10,7 @@ from room_instance_segmentation_mask3d_b200 import lib, mask3d_model, me_api, op
 
 scene = sys.argv[1] if len(sys.argv) > 1 else "s200k"
 mode = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+path = sys.argv[3] if len(sys.argv) > 3 else "module"
 ops.set_compute_mode(mode)
 s = scenes.box_room() if scene == "s200k" else scenes.floor_plan(1000, voxel_m=0.02)
 c, f = scenes.collate([s])
@@ -22,7 +23,8 @@ model = model.cuda().train()
 def step():
     for p in model.parameters():
         p.grad = None
-    out, fm = model(me_api.SparseTensor(features=f, coordinates=c))
+    x = me_api.SparseTensor(features=f, coordinates=c)
+    out, fm = model.forward_train(x) if path == "fused" else model(x)
     (out.F.float().square().mean() + sum(t.F.float().square().mean() for t in fm[:-1])).backward()
 
 
@@ -41,7 +43,7 @@ for e in prof.key_averages():
 rows.sort(reverse=True)
 tot = sum(r[0] for r in rows)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-with open(os.path.join(ROOT, "gpurun_out", f"profile_train_{scene}_{mode}.txt"), "w") as fh:
+with open(os.path.join(ROOT, "gpurun_out", f"profile_train_{scene}_{mode}_{path}.txt"), "w") as fh:
     hdr = f"scene {scene} voxels {c.shape[0]} mode {mode}: sum of GPU kernel time {tot/1e3:.1f} ms\n"
     fh.write(hdr)
     print(hdr)

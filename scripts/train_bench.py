@@ -3,7 +3,7 @@
 BASELINE.json metric, first clause: "voxels/sec Res16UNet34C fwd+bwd".  bf16 mode = tcgen05 forward, dgrad and wgrad with fp32
 accumulation; activations at module boundaries stay fp32 as in the reference (MinkowskiEngine modules exchange fp32 .F).
 
-usage: python scripts/train_bench.py [scene=s200k|floor2|floor4] [reps] [mode=bf16|fp32]"""
+usage: python scripts/train_bench.py [scene=s200k|floor2|floor4] [reps] [mode=bf16|fp32] [path=module|fused]"""
 import json
 import os
 import sys
@@ -53,7 +53,7 @@ def tag_levels(model):
     model.final._bench_level = 0
 
 
-def run(scene="s200k", reps=5, mode="bf16", quiet=False):
+def run(scene="s200k", reps=5, mode="bf16", quiet=False, path="module"):
     s = {"s200k": lambda: scenes.box_room(), "floor2": lambda: scenes.floor_plan(1000, voxel_m=0.02),
          "floor4": lambda: scenes.floor_plan(1000, voxel_m=0.04)}[scene]()
     c, f = scenes.collate([s])
@@ -70,13 +70,14 @@ def run(scene="s200k", reps=5, mode="bf16", quiet=False):
         for p in params:
             p.grad = None
         x = me_api.SparseTensor(features=f, coordinates=c)
-        out, fm = model(x)
+        out, fm = model.forward_train(x) if path == "fused" else model(x)
         loss = out.F.float().square().mean() + sum(t.F.float().square().mean() for t in fm[:-1])
         loss.backward()
         return x
 
     x = step()
-    step()
+    for _ in range(7):  # the caching allocator keeps growing (cudaMalloc) for the first handful of training steps
+        step()
     torch.cuda.synchronize()
     mgr = x.coordinate_manager
     keys = [x.coordinate_map_key]
@@ -91,7 +92,7 @@ def run(scene="s200k", reps=5, mode="bf16", quiet=False):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     n0 = c.shape[0]
-    res = {"scene": scene, "voxels": n0, "mode": mode, "ms_fwd_bwd": ms, "voxels_per_s": n0 / (ms * 1e-3), "fwd_gflop": fl / 1e9,
+    res = {"scene": scene, "voxels": n0, "mode": mode, "path": path, "ms_fwd_bwd": ms, "voxels_per_s": n0 / (ms * 1e-3), "fwd_gflop": fl / 1e9,
            "fwd_bwd_tflops_algorithmic": 3 * fl / (ms * 1e-3) / 1e12,
            "includes": "coordinate maps + kernel maps + tile plans + forward + backward (all parameters), one scene per step"}
     if not quiet:
@@ -100,4 +101,5 @@ def run(scene="s200k", reps=5, mode="bf16", quiet=False):
 
 
 if __name__ == "__main__":
-    run(sys.argv[1] if len(sys.argv) > 1 else "s200k", int(sys.argv[2]) if len(sys.argv) > 2 else 5, sys.argv[3] if len(sys.argv) > 3 else "bf16")
+    run(sys.argv[1] if len(sys.argv) > 1 else "s200k", int(sys.argv[2]) if len(sys.argv) > 2 else 5, sys.argv[3] if len(sys.argv) > 3 else "bf16",
+        path=sys.argv[4] if len(sys.argv) > 4 else "module")
