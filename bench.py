@@ -28,7 +28,10 @@ sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_conv_umma launch from an `ncu --set full` capture (profiles/), next to the
 # algorithmic bytes of that launch; filled in from the capture named in `note` (None until a capture of the current kernel exists)
-NCU_TRAFFIC = {"bytes_per_launch": None, "note": None}
+NCU_TRAFFIC = {"bytes_per_launch": 228184064 + 132803584,
+               "note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE k_conv_umma launch of the dominant shape (3^3 96->96 on the "
+                       "889057-voxel level-0 map: 155.2 GFLOP, algorithmic minimum 437.9 MB incl. the 96 MB neighbour table, part of which "
+                       "is L2-resident), ncu --set full, profiles/r01_ncu_conv96_summary.txt"}
 
 METRIC = "Mask3D inference throughput (Res16UNet34C sparse-conv backbone + 12-layer masked-attention decoder)"
 UNIT = "voxels/s"
@@ -173,6 +176,7 @@ def main_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib.load()
+    lib.reserve_device_pool(32.0, dev)  # one splittable 32 GB segment instead of cudaMalloc stalls while the allocator grows
     ops.set_compute_mode(args.mode)
     voxel = args.voxel_cm / 100.0
     n_scenes = 3
@@ -218,7 +222,8 @@ def main_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for i in range(max(args.warmup, 3)):
+    n_warm = max(args.warmup, 2 * n_scenes)  # every scene twice: CUDA-graph capture, allocator growth, weight images
+    for i in range(n_warm):
         step_resident(i)
     sampler = ClockSampler(local)
     if rank == 0 and not args.no_clocks:
@@ -230,7 +235,7 @@ def main_ours(args):
     vox_per_step = float(np.mean([nvox[i % n_scenes] for i in range(args.steps)]))
     value = world * vox_per_step * args.steps / (ms * 1e-3)
 
-    for i in range(2):
+    for i in range(n_scenes):
         step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps)
     e2e_value = world * vox_per_step * args.steps / (ms_e2e * 1e-3)
@@ -309,14 +314,41 @@ def main_ours(args):
         cpu_baseline = {"value": val, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                         "sample": f"floor_plan(seed=1000) at {v * 100:.0f} cm voxels = {n} voxels, one full Mask3D forward ({t:.1f} s)"}
 
+    # first clause of BASELINE.json's metric: Res16UNet34C forward + backward voxels/s (fused training path, bf16 tensor cores),
+    # on the same scene generator; reported beside the headline, not part of the timed regions above
+    train = None
+    if rank == 0 and world == 1 and not args.no_train:
+        try:
+            bb = mask3d_model.Res16UNet34C()
+            weights.load_synth(bb, seed=0)
+            bb = bb.to(dev).train()
+            c_t, f_t = resident[0]
+
+            def tstep():
+                for prm in bb.parameters():
+                    prm.grad = None
+                out, fm = bb.forward_train(me_api.SparseTensor(features=f_t, coordinates=c_t))
+                (out.F.float().square().mean() + sum(t.F.float().square().mean() for t in fm[:-1])).backward()
+
+            for _ in range(8):
+                tstep()
+            tsteps = 5
+            t_ms = timed(lambda i: tstep(), tsteps) / tsteps
+            train = {"what": "Res16UNet34C forward + backward, fused training path (bf16 activations, tcgen05 fwd/dgrad/wgrad), maps and "
+                             "plans rebuilt every step, one scene per step", "voxels": nvox[0], "ms_fwd_bwd": t_ms,
+                     "voxels_per_s": nvox[0] / (t_ms * 1e-3)}
+            del bb
+        except Exception as exc:  # the headline line must survive a failure here
+            train = {"error": repr(exc)[:200]}
+
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic", "config": workload_config(voxel, n_scenes),
                 "scenes_per_sec": world * args.steps / (ms * 1e-3), "voxels_per_scene": vox_per_step,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "train_fwd_bwd": train}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -331,6 +363,7 @@ if __name__ == "__main__":
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--voxel-cm", type=float, default=2.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the backbone forward+backward measurement")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi during the timed region (debugging)")
     a = ap.parse_args()
     if a.impl == "reference":

@@ -94,6 +94,7 @@ class KernelMap:
         self._pairs_dev: Optional[torch.Tensor] = None
         self._pairs: Optional[int] = None
         self._sorted: Optional["KernelMap"] = None
+        self._sorted_is_self = False
         self._wgrad_plan: Optional[torch.Tensor] = None
 
     def _build_kmask(self):
@@ -108,9 +109,15 @@ class KernelMap:
         tensor-core tiles (a lexicographic tile of a surface scene touches ~23 of 27 offsets, a mask-sorted one ~10, i.e.
         2.3x less gather + MMA work) and, inside a mask group, follow a Z-curve so that a tile is a compact spatial patch
         whose neighbour gathers overlap.  Slots map back to rows through `out_rows`."""
+        # NB: no `self._sorted = self`: a self-reference is a cycle, and cyclic garbage is only freed by Python's generational
+        # collector — every kernel map (up to 444 MB for the 5^3 table of a 0.9 M-voxel scene) then outlives its step, the
+        # caching allocator keeps growing by cudaMalloc, and the eventual collection is a 100-300 ms pause.
+        if self._sorted_is_self:
+            return self
         if self._sorted is None:
             if self.K == 1 or self.K > 32 or self.out_rows is not None or self.n_out == 0 or self.out_coords is None:
-                self._sorted = self
+                self._sorted_is_self = True
+                return self
             else:
                 n, dev = self.n_out, self.nbr.device
                 keys = torch.empty(n, dtype=torch.int64, device=dev)
@@ -121,7 +128,7 @@ class KernelMap:
                 nbr_s = torch.empty_like(self.nbr)
                 lib.call("mk_permute_table", lib.p(self.nbr), self.K, n, lib.p(order), n, lib.p(nbr_s), lib.stream())
                 self._sorted = KernelMap(nbr_s, self.K, n, order)
-                self._sorted._sorted = self._sorted
+                self._sorted._sorted_is_self = True
         return self._sorted
 
     @property

@@ -59,6 +59,7 @@ def run(scene="s200k", reps=5, mode="bf16", quiet=False, path="module"):
     c, f = scenes.collate([s])
     c, f = torch.from_numpy(c).cuda(), torch.from_numpy(f).cuda()
     lib.load()
+    lib.reserve_device_pool(48.0)
     ops.set_compute_mode(mode)
     model = mask3d_model.Res16UNet34C()
     weights.load_synth(model, seed=0)
