@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
   uint64_t* tmem_full = bars + 2 * kMaxStages;     // [2]  one tcgen05.commit
   uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;  // [2]  128 epilogue threads
   uint32_t* tmem_base_slot = (uint32_t*)(bars + 2 * kMaxStages + 4);
-  float* out_stage = (float*)(bars + 2 * kMaxStages + 6);  // [4 epilogue warps][32 rows x out_cols] when p.stage_out
+  float* out_stage = (float*)(bars + 2 * kMaxStages + 6);  // [4 epilogue warps][32 rows x out_cols] when p.stage_out (16-byte aligned)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dbg = kDbg ? p.debug : 0;
@@ -389,7 +389,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
           // Row pitch of e.g. 25 fp32 (mask logits): per-thread row stores would touch 32 sectors per instruction.  The
           // warp's 32 rows are one contiguous run of 32 * out_cols elements in global memory, so transpose through shared
           // memory (odd pitch => conflict free) and store the run with fully coalesced 128-byte instructions.
-          float* stg = out_stage + (size_t)q * 32 * p.out_cols;
+          const uint32_t stg = smem_u32(out_stage) + (uint32_t)(q * 32 * p.out_cols) * 4u;  // this warp's staging block
+          const uint32_t my_row = stg + (uint32_t)(lane * p.out_cols) * 4u;
           for (int c0 = 0; c0 < p.out_cols; c0 += 16) {
             uint32_t r[16];
             if (km[g] != 0u) {
@@ -399,9 +400,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
 #pragma unroll
               for (int j = 0; j < 16; ++j) r[j] = 0u;
             }
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < p.out_cols) r[j] = __float_as_uint(__uint_as_float(r[j]) + p.bias[c0 + j]);
+            }
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (c0 + j < p.out_cols) stg[lane * p.out_cols + c0 + j] = __uint_as_float(r[j]) + (p.bias ? p.bias[c0 + j] : 0.f);
+              if (c0 + j < p.out_cols) sts_f32(my_row + (uint32_t)(c0 + j) * 4u, __uint_as_float(r[j]));
           }
           __syncwarp();
           const int64_t row0 = ((int64_t)(st * G + g)) * kTileM + q * 32;
@@ -409,7 +415,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
           if (nrows > 0 && !(dbg & 8)) {
             TOut* dst = (TOut*)p.out + row0 * p.out_cols;
             const int total = (int)nrows * p.out_cols;
-            for (int i = lane; i < total; i += 32) dst[i] = from_f32<TOut>(stg[i]);
+            if constexpr (sizeof(TOut) == 4) {
+              // the run starts 16-byte aligned (row0 is a multiple of 32 rows): 16-byte shared-memory reads and global stores,
+              // ~7 of each per lane for a 32 x 25 block instead of 25 + 25 scalar ones (the epilogue, not the MMAs or the
+              // gathers, bounded the 25-column mask-logit product: ~780 instructions per tile and warp)
+              const int nvec = total >> 2;
+              for (int i = lane; i < nvec; i += 32) reinterpret_cast<float4*>(dst)[i] = lds_v4(stg + (uint32_t)i * 16u);
+              for (int i = (nvec << 2) + lane; i < total; i += 32) dst[i] = from_f32<TOut>(lds_f32(stg + (uint32_t)i * 4u));
+            } else {
+              for (int i = lane; i < total; i += 32) dst[i] = from_f32<TOut>(lds_f32(stg + (uint32_t)i * 4u));
+            }
           }
           __syncwarp();
           continue;

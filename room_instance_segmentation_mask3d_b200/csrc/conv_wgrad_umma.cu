@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_wgrad_umma(const WgradP
   } else {
     // ===================== flush (4 warps): TMEM -> shared-memory transpose -> coalesced fp32 RED into dW =====================
     const int q = warp & 3;
-    float* stg = flush_stage + (size_t)q * 32 * kWgFlushPitch;
+    const uint32_t stg = smem_u32(flush_stage) + (uint32_t)(q * 32 * kWgFlushPitch) * 4u;  // explicit shared-space accesses (umma.cuh)
     int acc_buf = 0;
     uint32_t acc_phase = 0;
     for (int64_t j = blockIdx.x; j < J; j += gridDim.x) {
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_wgrad_umma(const WgradP
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_buf * 256 + c0), r);
         tmem_ld_wait();
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) stg[lane * kWgFlushPitch + jj] = __uint_as_float(r[jj]);
+        for (int jj = 0; jj < 16; ++jj) sts_f32(stg + (uint32_t)(lane * kWgFlushPitch + jj) * 4u, __uint_as_float(r[jj]));
         __syncwarp();
         // 32 rows x 16 columns as 16-byte vector REDs: lane = (row within a group of 8, 4-column quad) => one instruction adds
         // 8 rows x 64 contiguous bytes; 4 instructions per chunk instead of 16 scalar ones
@@ -297,9 +297,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_wgrad_umma(const WgradP
         for (int i = 0; i < 4; ++i) {
           const int rr = 8 * i + rsel;
           if (row0 + rr < p.cin) {
-            const float* sv = stg + rr * kWgFlushPitch + 4 * quad;
+            const uint32_t sv = stg + (uint32_t)(rr * kWgFlushPitch + 4 * quad) * 4u;
             float* dst = p.dw + ((int64_t)item.k * p.cin + row0 + rr) * p.cout + c0 + 4 * quad;
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(sv[0]), "f"(sv[1]), "f"(sv[2]), "f"(sv[3])
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(lds_f32(sv)), "f"(lds_f32(sv + 4u)),
+                         "f"(lds_f32(sv + 8u)), "f"(lds_f32(sv + 12u))
                          : "memory");
           }
         }

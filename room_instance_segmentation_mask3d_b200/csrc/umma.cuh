@@ -76,6 +76,20 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
+// explicit shared-state-space accesses by 32-bit address (a pointer carved out of the dynamic shared-memory block is generic to
+// the compiler, which then emits generic ST.E / LD.E with 64-bit address arithmetic per element)
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
   // .ca: allocate in L1 — a tile is a compact spatial patch (mask + Z-curve sorted), so the neighbour rows gathered for its
   // different offsets overlap heavily and are re-read from L1 instead of L2
