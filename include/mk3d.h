@@ -169,13 +169,14 @@ int mk_instnorm_relu_bwd(const void* dy, const void* out, const void* x, int dty
 
 /* Composite: conv (tensor cores) -> instance norm -> (+ residual) -> (ReLU) in one call, the unit Res16UNet34C repeats per
  * layer (mask3d/models/res16unet.py:244-307, mask3d/models/modules/resnet_block.py:52-68).  Conv arguments as
- * mk_conv_fwd_bf16; tmp = bf16 [n_out,cout] scratch holding the un-normalised conv output; stats = fp32 [2,B,cout]
+ * mk_conv_fwd_bf16; tmp = scratch of tmp_bytes >= 2 * n_out * cout holding the un-normalised conv output as bf16 — or as fp32 when
+ * tmp_bytes >= 4 * n_out * cout and the level is small enough for the conv's offset split (then several CTAs per tile); stats = fp32 [2,B,cout]
  * (mean, rstd: outputs); residual/out share out_dtype; workspace as mk_instnorm_workspace_bytes(n_out, cout, B). */
 int mk_conv_instnorm_bf16(const void* in, int64_t n_in, int cin, const void* wimg, int cout, const int32_t* nbr, int K,
                           int64_t n_slots, const int32_t* out_rows, const uint32_t* tile_kmask, const int32_t* kidx, int64_t n_out,
                           const float* bias, const int32_t* scene_offsets, int B, float eps, const float* gamma, const float* beta,
-                          const void* residual, int relu, void* tmp, float* stats, void* out, int out_dtype, void* workspace,
-                          int64_t workspace_bytes, void* stream);
+                          const void* residual, int relu, void* tmp, int64_t tmp_bytes, float* stats, void* out, int out_dtype,
+                          void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (5) Pooling.  Replaces MinkowskiAvgPooling / MinkowskiSumPooling (mask3d/models/mask3d.py:209,297,547).

@@ -40,22 +40,38 @@ constexpr int kMaxProducers = 5;  // warps 0-3 and 5
 // share every weight chunk, which halves the weight traffic and the per-stage bookkeeping of all three roles; mask-sorted
 // plans give neighbouring tiles the same offset set, so the union costs nothing).  Items are the set bits of the union of the
 // member tiles' offset masks, ascending; an iteration is (item, 64-channel chunk).
+// keep the set bits of m whose ordinal is congruent to `part` modulo `ksplit` (offset split of small problems)
+__device__ __forceinline__ uint32_t split_bits(uint32_t m, int part, int ksplit) {
+  if (ksplit <= 1) return m;
+  uint32_t r = 0;
+  for (int i = 0; m; ++i) {
+    const uint32_t b = m & (0u - m);
+    if (i % ksplit == part) r |= b;
+    m ^= b;
+  }
+  return r;
+}
+
 struct SuperCursor {
   const uint32_t* kmask;
   int G, st, stride, num_st, num_tiles;
+  int part, ksplit;
   uint32_t m0, m1, mu;      // member masks of the current super-tile, remaining union bits (of the current chunk pass)
   uint32_t n0, n1;          // masks of the next super-tile (prefetched)
   int ch, nchunks;
   int chunk_major;          // 1: all offsets of chunk 0, then all offsets of chunk 1, ... ; 0: (offset, chunk) with chunk inner
   __device__ uint32_t mask_of(int t) const { return t < num_tiles ? kmask[t] : 0u; }
-  __device__ SuperCursor(const uint32_t* kmask_, int G_, int first, int stride_, int num_tiles_, int nchunks_, int chunk_major_)
-      : kmask(kmask_), G(G_), st(first), stride(stride_), num_tiles(num_tiles_), ch(0), nchunks(nchunks_), chunk_major(chunk_major_) {
+  __device__ SuperCursor(const uint32_t* kmask_, int G_, int first, int stride_, int num_tiles_, int nchunks_, int chunk_major_,
+                         int part_ = 0, int ksplit_ = 1)
+      : kmask(kmask_), G(G_), st(first), stride(stride_), num_tiles(num_tiles_), part(part_), ksplit(ksplit_), ch(0), nchunks(nchunks_),
+        chunk_major(chunk_major_) {
     num_st = (num_tiles + G - 1) / G;
     load(st, m0, m1);
     load(st + stride, n0, n1);
-    mu = m0 | m1;
+    mu = split_bits(m0 | m1, part, ksplit);
     skip_empty();
   }
+  __device__ uint32_t all_bits() const { return split_bits(m0 | m1, part, ksplit); }
   __device__ void load(int s, uint32_t& a, uint32_t& b) const {
     a = s < num_st ? mask_of(G * s) : 0u;
     b = (s < num_st && G == 2) ? mask_of(2 * s + 1) : 0u;
@@ -64,7 +80,7 @@ struct SuperCursor {
     st += stride;
     m0 = n0;
     m1 = n1;
-    mu = m0 | m1;
+    mu = all_bits();
     ch = 0;
     load(st + stride, n0, n1);
   }
@@ -80,7 +96,7 @@ struct SuperCursor {
     if (chunk_major) {
       mu &= mu - 1;
       if (mu == 0u) {
-        if (++ch < nchunks) mu = m0 | m1;
+        if (++ch < nchunks) mu = all_bits();
         else {
           next_super();
           skip_empty();
@@ -146,6 +162,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
   const uint32_t tmem_base = *tmem_base_slot;
 
   const int nchunks = p.nchunks;
+  const int ksplit = p.ksplit;
+  const int cta_first = (int)blockIdx.x / ksplit, cta_stride = (int)gridDim.x / ksplit, cta_part = (int)blockIdx.x % ksplit;
 
   if (warp < kNumProducerWarps || warp == kLoadWarp) {
     // ===================== producers (up to 5 warps, one stage each, round-robin) =====================
@@ -240,7 +258,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
     // Three index sets rotate WITHOUT register copies (the loop is unrolled by three): a `ci = ni; ni = nni;` rotation makes
     // the compiler move the just-loaded index registers at the end of the same iteration, i.e. wait for the table loads it
     // was meant to hide for two stages (1x1 and 2^3 convs, whose stages are short, gained ~25 %).
-    SuperCursor la(p.tile_kmask, G, blockIdx.x, gridDim.x, p.num_tiles, nchunks, p.chunk_major);  // lookahead cursor
+    SuperCursor la(p.tile_kmask, G, cta_first, cta_stride, p.num_tiles, nchunks, p.chunk_major, cta_part, ksplit);  // lookahead cursor
     if (active) la.advance(pi);
     Idx i0 = load_idx(la);
     la.advance(NP);
@@ -277,7 +295,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
     bool tile_open = false;
     uint32_t started = 0;  // bit g: accumulator of member tile g holds a partial sum
     long long tw_full = 0, tw_tmem = 0, t_start = kDbg ? clock64() : 0, n_it = 0;
-    for (SuperCursor cur(p.tile_kmask, G, blockIdx.x, gridDim.x, p.num_tiles, nchunks, p.chunk_major); cur.valid(); cur.step()) {
+    for (SuperCursor cur(p.tile_kmask, G, cta_first, cta_stride, p.num_tiles, nchunks, p.chunk_major, cta_part, ksplit); cur.valid(); cur.step()) {
       if (!tile_open) {
         const long long t0 = kDbg ? clock64() : 0;
         mbar_wait(smem_u32(&tmem_empty[acc_buf]), acc_phase ^ 1);
@@ -355,23 +373,30 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
     int64_t orow_next[2];
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
-      const int t = g < G ? (int)blockIdx.x * G + g : p.num_tiles;
-      km_next[g] = (int)blockIdx.x < num_st ? load_mask(t) : 0u;
-      orow_next[g] = (int)blockIdx.x < num_st ? load_row(t) : -1;
+      const int t = g < G ? cta_first * G + g : p.num_tiles;
+      km_next[g] = cta_first < num_st ? load_mask(t) : 0u;
+      orow_next[g] = cta_first < num_st ? load_row(t) : -1;
     }
     const bool vec_ok = ((p.out_stride * (int)sizeof(TOut)) & 15) == 0;
     long long te_wait = 0, te_start = kDbg ? clock64() : 0;
-    for (int st = blockIdx.x; st < num_st; st += gridDim.x) {
+    for (int st = cta_first; st < num_st; st += cta_stride) {
       uint32_t km[2];
       int64_t orow[2];
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
         km[g] = km_next[g];
         orow[g] = orow_next[g];
-        const int tn = g < G ? (st + (int)gridDim.x) * G + g : p.num_tiles;
-        const bool vn = st + (int)gridDim.x < num_st;
+        const int tn = g < G ? (st + cta_stride) * G + g : p.num_tiles;
+        const bool vn = st + cta_stride < num_st;
         km_next[g] = vn ? load_mask(tn) : 0u;
         orow_next[g] = vn ? load_row(tn) : -1;
+      }
+      if (ksplit > 1) {
+        // this CTA's share of the super-tile's offsets (same filter as the cursor of the other roles): a member tile takes
+        // part iff one of ITS offsets is in the share; an empty share means no accumulator and nothing to add
+        const uint32_t share = split_bits(km[0] | km[1], cta_part, ksplit);
+        km[0] &= share;
+        km[1] &= share;
       }
       const bool any = (km[0] | km[1]) != 0u;
       if (any) {
@@ -441,11 +466,25 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = 0.f;
           }
-          if (p.bias) {
+          if (p.bias && (ksplit == 1 || cta_part == 0)) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] += (c0 + j < p.out_cols) ? p.bias[c0 + j] : 0.f;
           }
-          if (optr && !(dbg & 8)) {
+          if (ksplit > 1) {
+            // offset split: add this CTA's partial sums (the bias comes from part 0 alone, also for tiles part 0 has no offset of;
+            // rows a part did not touch add nothing)
+            if constexpr (sizeof(TOut) == 4) {
+              if (optr && (km[g] != 0u || (cta_part == 0 && p.bias))) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                  if (c0 + j + 4 <= p.out_cols)
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"((float*)optr + c0 + j), "f"(v[j]), "f"(v[j + 1]),
+                                 "f"(v[j + 2]), "f"(v[j + 3])
+                                 : "memory");
+                }
+              }
+            }
+          } else if (optr && !(dbg & 8)) {
             if (vec_ok && c0 + 16 <= p.out_cols) {
               store16(optr + c0, v);
             } else {
@@ -603,6 +642,23 @@ int mk_conv_fwd_bf16(const void* in, int64_t n_in, int cin, const void* wimg, in
   int group = (cout <= 128 && p.num_tiles >= 4 * num_sms()) ? 2 : 1;
   if (grp_env == 1 || (grp_env == 2 && cout <= 128)) group = grp_env;
   p.group = group;
+  // Offset split for the coarse levels: a level with fewer super-tiles than SMs (L3 / L4 of a single scene: 7-27 tiles for 148
+  // SMs) ran as 7-27 CTAs walking all 27 offsets each, pure latency.  With an fp32 output the offsets of a super-tile are dealt
+  // to `ksplit` CTAs that add their partial sums with vector REDs (the output is zeroed here first).
+  p.ksplit = 1;
+  {
+    static int ks_env = -1;
+    if (ks_env < 0) { const char* e = getenv("MK3D_KSPLIT"); ks_env = e ? atoi(e) : 0; }
+    const int num_super0 = (p.num_tiles + group - 1) / group;
+    if (out_dtype == MK_F32 && K > 1 && !p.stage_out && (out_cols & 3) == 0 && ((out_stride * 4) & 15) == 0 && ks_env != 1 &&
+        2 * num_super0 <= num_sms()) {
+      int ks = num_sms() / num_super0;
+      if (ks > K) ks = K;
+      if (ks > 9) ks = 9;
+      if (ks_env > 1 && ks > ks_env) ks = ks_env;
+      p.ksplit = ks;
+    }
+  }
   int stages = kMaxStages;
   while (stages > 2 && conv_smem_bytes(cout, stages, group, soc) > 222 * 1024) --stages;
   // Super-tiles: 4 stages (<= 176 KB) instead of the 5 that fit.  The kernel is bound by shared-memory bandwidth (LDGSTS
@@ -624,6 +680,11 @@ int mk_conv_fwd_bf16(const void* in, int64_t n_in, int cin, const void* wimg, in
   int grid = num_sms();
   const int num_super = (p.num_tiles + group - 1) / group;
   if (grid > num_super) grid = num_super;
+  if (p.ksplit > 1) {
+    grid = num_super * p.ksplit;
+    // only the columns this call owns (the output may be a column slice of a wider row, e.g. the sliced dgrad of 384 channels)
+    cudaMemset2DAsync(out, (size_t)out_stride * sizeof(float), 0, (size_t)out_cols * sizeof(float), (size_t)n_out, (cudaStream_t)stream_);
+  }
   cudaStream_t st = (cudaStream_t)stream_;
   static int carve_env = -2;
   if (carve_env == -2) { const char* e = getenv("MK3D_CARVEOUT"); carve_env = e ? atoi(e) : -1; }

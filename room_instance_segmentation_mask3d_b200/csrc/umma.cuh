@@ -206,6 +206,8 @@ struct ConvParams {
   int stage_out;   // 1: epilogue transposes each warp's 32 x out_cols block through shared memory and stores it as one
                    // contiguous run (rows are contiguous: out_rows == nullptr, out_stride == out_cols, row pitch not 16-byte aligned)
   int chunk_major; // iteration order inside a super-tile (see SuperCursor)
+  int ksplit;      // > 1: gridDim.x = super-tiles x ksplit; CTA (st, part) takes every ksplit-th active offset of its super-tile
+                   // and ADDS its partial result into the (zeroed, fp32) output with vector REDs
   int debug;       // timing ablation flags (MK3D_DEBUG), 0 in production
   unsigned long long* trace;  // MK3D_TRACE: per-CTA role timers [grid][8], nullptr in production
 };

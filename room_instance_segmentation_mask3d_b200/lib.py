@@ -58,8 +58,8 @@ _SIGS = {
     "mk_instnorm_relu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "mk_conv_instnorm_bf16": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
-                                      c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
-                                      c_int, c_void_p, c_int64, c_void_p]),
+                                      c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p,
+                                      c_void_p, c_int, c_void_p, c_int64, c_void_p]),
     "mk_pool_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
     "mk_pool_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_int64, c_void_p, c_void_p]),
     "mk_mask_logits": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),

@@ -204,7 +204,9 @@ class Res16UNet34C(nn.Module):
             if kind == 2 and mode == "fp32":
                 y = ops.conv_transpose_forward_fp32(f, conv.kernel, km)
             else:
-                y = ops.conv_forward(f, conv.kernel, km, bias=conv.bias, mode=mode, out_dtype=act)
+                # small levels: fp32 conv output, as the composite call uses (lets the kernel split a tile's offsets over CTAs)
+                small = mode == "bf16" and km.K > 1 and 2 * ((km.n_slots + lib.TILE - 1) // lib.TILE) <= 148
+                y = ops.conv_forward(f, conv.kernel, km, bias=conv.bias, mode=mode, out_dtype=torch.float32 if small else act)
             return ops.instance_norm(y, offs[lvl], B, norm.weight, norm.bias, residual=residual, relu=relu, out_dtype=act)
 
         def block(f, blk, lvl):

@@ -164,7 +164,9 @@ def conv_instnorm_bf16(x: torch.Tensor, W: torch.Tensor, km: KernelMap, scene_of
     wsb = lib.query("mk_instnorm_workspace_bytes", n, cout, B)
     # keep=True (training): the un-normalised conv output is a tensor of its own, returned with the statistics for the backward
     tmp = torch.empty((n, cout), dtype=torch.bfloat16, device=x.device) if keep else None
-    tmp_bytes = 0 if keep else (n * cout * 2 + 255) // 256 * 256
+    # scratch tmp: 4 bytes per element on small levels so that the composite may use an fp32 intermediate (offset split)
+    small = K > 1 and 2 * ((plan.n_slots + lib.TILE - 1) // lib.TILE) <= 148
+    tmp_bytes = 0 if keep else (n * cout * (4 if small else 2) + 255) // 256 * 256
     ws = lib.scratch(tmp_bytes + wsb, x.device)
     if residual is not None:
         assert residual.dtype == out_dtype and residual.is_contiguous()
@@ -173,8 +175,9 @@ def conv_instnorm_bf16(x: torch.Tensor, W: torch.Tensor, km: KernelMap, scene_of
     base = ws.data_ptr()
     lib.call("mk_conv_instnorm_bf16", x.data_ptr(), x.shape[0], cin, img.data_ptr(), cout, plan.nbr.data_ptr(), K, plan.n_slots,
              lib.p(plan.out_rows), plan.tile_kmask.data_ptr(), None, n, lib.p(_flat32(bias)), scene_offsets.data_ptr(), B, eps,
-             lib.p(_flat32(gamma)), lib.p(_flat32(beta)), lib.p(residual), int(relu), tmp.data_ptr() if keep else base, stats.data_ptr(),
-             out.data_ptr(), lib.dt(out), base + tmp_bytes, ws.numel() - tmp_bytes, lib.stream())
+             lib.p(_flat32(gamma)), lib.p(_flat32(beta)), lib.p(residual), int(relu), tmp.data_ptr() if keep else base,
+             n * cout * 2 if keep else tmp_bytes, stats.data_ptr(), out.data_ptr(), lib.dt(out), base + tmp_bytes, ws.numel() - tmp_bytes,
+             lib.stream())
     return (out, tmp, stats) if keep else out
 
 
