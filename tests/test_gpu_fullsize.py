@@ -1,0 +1,138 @@
+"""Size-independent properties at the benchmark's FULL size (BASELINE.json configs[1]: the 889 k-voxel single-floor scene at 2 cm),
+where the CPU oracle would take minutes: idempotence of the coordinate map, parent/child consistency of the strided maps,
+symmetry of the kernel map, bit-exact agreement of the tensor-core convolution with the exact-fp32 kernel on integer-valued
+operands (every product and partial sum is exactly representable, so ANY summation order gives the same bits), adjointness of
+forward / dgrad / wgrad, the instance-norm moments, and the furthest-point-sampling invariants."""
+import numpy as np
+import pytest
+import torch
+
+from room_instance_segmentation_mask3d_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def S():
+    from room_instance_segmentation_mask3d_b200 import engine, lib, ops
+
+    lib.load()
+    coords, _ = scenes.collate([scenes.floor_plan(1000, voxel_m=0.02)])
+    c = torch.from_numpy(coords).cuda()
+    mgr = engine.CoordinateManager(D=3)
+    k0, (uniq, inv) = mgr.insert_and_map(c)
+
+    class NS:
+        pass
+
+    ns = NS()
+    ns.engine, ns.lib, ns.ops, ns.mgr, ns.k0, ns.c, ns.uniq, ns.inv = engine, lib, ops, mgr, k0, c, uniq, inv
+    return ns
+
+
+def test_fullsize_coordinate_map_idempotent_and_strided_maps_consistent(S):
+    n = S.c.shape[0]
+    assert n > 800_000
+    # unique, lexicographically sorted input -> the map is the identity
+    assert S.mgr.size(S.k0) == n
+    assert torch.equal(S.uniq, torch.arange(n, device="cuda")) and torch.equal(S.inv, torch.arange(n, device="cuda"))
+    assert torch.equal(S.mgr.get_coordinates(S.k0), S.c)
+    prev = S.k0
+    for lvl in range(1, 5):
+        k = S.mgr.stride(prev, 2)
+        cc, fc = S.mgr.get_coordinates(k), S.mgr.get_coordinates(prev)
+        s = 2 ** lvl
+        assert bool((cc[:, 1:] % s == 0).all())
+        # coarse rows are unique
+        key = lambda t: ((t[:, 0].long() << 54) | ((t[:, 1].long() + 131072) << 36) | ((t[:, 2].long() + 131072) << 18) | (t[:, 3].long() + 131072))
+        assert torch.unique(key(cc)).numel() == cc.shape[0]
+        # every fine row has exactly one (offset, parent) pair in the 2^3 stride-2 map, and the parent is floor(c / s) * s
+        down = S.mgr.neighbor_table(prev, k, 2, 1).nbr  # [8, n_coarse] -> fine row
+        present = down >= 0
+        assert int(present.sum()) == fc.shape[0]
+        hit = torch.zeros(fc.shape[0], dtype=torch.int32, device="cuda")
+        hit.index_add_(0, down[present].long(), torch.ones(int(present.sum()), dtype=torch.int32, device="cuda"))
+        assert bool((hit == 1).all())
+        parent_of = torch.empty(fc.shape[0], dtype=torch.long, device="cuda")
+        parent_of[down[present].long()] = torch.nonzero(present)[:, 1]
+        want = torch.div(fc[:, 1:], s, rounding_mode="floor") * s
+        assert torch.equal(cc[parent_of][:, 1:], want) and torch.equal(cc[parent_of][:, 0], fc[:, 0])
+        prev = k
+
+
+def test_fullsize_kernel_map_symmetry(S):
+    """nbr[k, o] = i  <=>  nbr[K-1-k, i] = o for the centred odd kernel on one map (what makes dgrad a forward conv)."""
+    km = S.mgr.neighbor_table(S.k0, S.k0, 3, 1)
+    nbr, n = km.nbr, km.n_out
+    rows = torch.arange(n, device="cuda", dtype=torch.int32)
+    assert torch.equal(nbr[13], rows)  # centre offset
+    for k in (0, 5, 12):
+        i = nbr[k]
+        m = i >= 0
+        assert torch.equal(nbr[26 - k][i[m].long()], rows[m])
+    assert km.num_pairs == int((nbr >= 0).sum())
+
+
+def test_fullsize_tensor_core_conv_bit_exact_on_integer_operands(S):
+    """Integer-valued bf16 operands: products and all partial sums are exact in fp32, so the tcgen05 kernel (any tile order, any
+    offset split) must equal the exact-fp32 CUDA-core kernel BIT FOR BIT on all 889 k rows."""
+    km = S.mgr.neighbor_table(S.k0, S.k0, 3, 1)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    cin, cout = 32, 48
+    x = torch.randint(-3, 4, (km.n_out, cin), device="cuda", generator=g).float()
+    W = torch.randint(-2, 3, (27, cin, cout), device="cuda", generator=g).float()
+    ref = S.ops.conv_forward(x, W, km, mode="fp32")
+    got = S.ops.conv_forward(x.bfloat16(), W, km, mode="bf16", out_dtype=torch.float32)
+    assert torch.equal(got, ref)
+    # the strided conv and its transpose on the same operands
+    k1 = S.mgr.stride(S.k0, 2)
+    km2 = S.mgr.neighbor_table(S.k0, k1, 2, 1)
+    W2 = torch.randint(-2, 3, (8, cin, cout), device="cuda", generator=g).float()
+    assert torch.equal(S.ops.conv_forward(x.bfloat16(), W2, km2, mode="bf16", out_dtype=torch.float32), S.ops.conv_forward(x, W2, km2, mode="fp32"))
+    # weight gradient: exact integers as well (|sum| < 2^24 per entry is not guaranteed over 0.9 M rows, so compare in fp64 with
+    # the bound of fp32 accumulation instead of bit-exactly)
+    dy = torch.randint(-2, 3, (km.n_out, cout), device="cuda", generator=g).float()
+    dW = S.ops.conv_wgrad_bf16(x.bfloat16(), dy.bfloat16(), km, 27, cin, cout)
+    nb = km.nbr
+    k = 7
+    m = nb[k] >= 0
+    want = x[nb[k][m].long()].double().t() @ dy[m].double()
+    assert float((dW[k].double() - want).abs().max()) <= 1e-6 * float(want.abs().max()) + 64.0
+
+
+def test_fullsize_forward_dgrad_wgrad_are_adjoint(S):
+    """<conv(x; W), dy> = <x, dgrad(dy; W)> = <W, wgrad(x, dy)> on the full scene (fp32 accumulation, bf16 operands)."""
+    km = S.mgr.neighbor_table(S.k0, S.k0, 3, 1)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    cin, cout = 96, 96
+    x = torch.randn(km.n_out, cin, device="cuda", generator=g).bfloat16()
+    dy = torch.randn(km.n_out, cout, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(27, cin, cout, device="cuda", generator=g) / 50).bfloat16().float()
+    y = S.ops.conv_forward(x, W, km, mode="bf16", out_dtype=torch.float32)
+    kidx = torch.arange(26, -1, -1, device="cuda", dtype=torch.int32)
+    dx = S.ops.conv_dgrad_bf16(dy, W, km, kidx=kidx)
+    dW = S.ops.conv_wgrad_bf16(x, dy, km, 27, cin, cout)
+    a = float((y.double() * dy.double()).sum())
+    b = float((x.double() * dx.double()).sum())
+    c = float((W.double() * dW.double()).sum())
+    scale = float(y.double().abs().mean() * dy.double().abs().mean() * y.numel()) ** 0.5 + abs(a)
+    assert abs(a - b) < 1e-4 * scale and abs(a - c) < 1e-4 * scale, (a, b, c)
+
+
+def test_fullsize_instance_norm_moments_and_fps_invariants(S):
+    n = S.c.shape[0]
+    off = S.mgr.scene_offsets(S.k0)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = (torch.randn(n, 96, device="cuda", generator=g) * torch.linspace(0.1, 30, 96, device="cuda") + torch.linspace(-50, 50, 96, device="cuda"))
+    y = S.ops.instance_norm(x, off, 1, torch.ones(1, 96, device="cuda"), torch.zeros(1, 96, device="cuda"))
+    assert float(y.mean(0).abs().max()) < 1e-3 and float((y.var(0, unbiased=False) - 1).abs().max()) < 1e-3
+    xyz = S.c[:, 1:].float().contiguous()
+    idx = S.ops.furthest_point_sample(xyz, off, 1, 25)[0].long()
+    assert int(idx[0]) == 0 and torch.unique(idx).numel() == 25
+    # the distance of every new sample to the set chosen before it never increases (greedy max-min), and is the max over all points
+    pts = xyz[idx]
+    d = torch.cdist(pts, pts)
+    mind = torch.stack([d[j, :j].min() for j in range(1, 25)])
+    assert bool((mind[1:] <= mind[:-1] + 1e-3).all())
+    cover = torch.cdist(xyz[::7], pts[:24]).min(1).values.max()
+    assert float(mind[-1]) >= float(cover) - 1e-3
