@@ -181,9 +181,12 @@ __global__ void __launch_bounds__(1024) k_xattn_partial(const float* __restrict_
                                                         int keys_per_split, float* __restrict__ partial) {
   extern __shared__ __align__(16) float sm[];
   const int hd = D / H;
-  float* sK = sm;                                   // [tile][D]
-  float* sV = sm + (size_t)kXaKeysPerTile * D;      // [tile][D]
-  uint8_t* sM = (uint8_t*)(sV + (size_t)kXaKeysPerTile * D);  // [tile][Q]
+  // [tile][H][hd + 4]: the 4-float pad per head spreads the 8 heads a quarter-warp reads (16 bytes each, stride hd floats = 64 B
+  // => heads 0,2,4,6 on the same banks: 4-way conflicts) over distinct bank groups (stride 80 B)
+  const int HP = hd + 4, RS = H * HP;
+  float* sK = sm;
+  float* sV = sm + (size_t)kXaKeysPerTile * RS;
+  uint8_t* sM = (uint8_t*)(sV + (size_t)kXaKeysPerTile * RS);  // [tile][Q]
   const int b = blockIdx.y, split = blockIdx.x, nsplit = gridDim.x;
   const int64_t s0 = (int64_t)scene_offsets[b] + (int64_t)split * keys_per_split;
   const int64_t s1 = min((int64_t)scene_offsets[b + 1], s0 + keys_per_split);
@@ -193,7 +196,8 @@ __global__ void __launch_bounds__(1024) k_xattn_partial(const float* __restrict_
   float qv[HD], acc[HD];
 #pragma unroll
   for (int j = 0; j < HD; ++j) {
-    qv[j] = (active && j < hd) ? qp[((int64_t)b * Q + q) * D + h * hd + j] * scale : 0.f;
+    // scores are kept in log2 units (scale * log2(e) folded into q): exp2f is one MUFU.EX2, expf a ~10-instruction sequence
+    qv[j] = (active && j < hd) ? qp[((int64_t)b * Q + q) * D + h * hd + j] * (scale * 1.4426950408889634f) : 0.f;
     acc[j] = 0.f;
   }
   const bool use_mask = active && any_open[b * Q + q] != 0;
@@ -203,15 +207,16 @@ __global__ void __launch_bounds__(1024) k_xattn_partial(const float* __restrict_
     __syncthreads();
     for (int i = t; i < nk * (D >> 2); i += blockDim.x) {
       const int r = i / (D >> 2), c = (i - r * (D >> 2)) * 4;
-      store4(sK + r * D + c, load4(kp + (k0 + r) * D + c));
-      store4(sV + r * D + c, load4(vp + (k0 + r) * D + c));
+      const int hh = c / hd, jj = c - hh * hd;
+      store4(sK + r * RS + hh * HP + jj, load4(kp + (k0 + r) * D + c));
+      store4(sV + r * RS + hh * HP + jj, load4(vp + (k0 + r) * D + c));
     }
     for (int i = t; i < nk * Q; i += blockDim.x) sM[i] = blocked[k0 * Q + i];
     __syncthreads();
     if (active) {
       for (int r = 0; r < nk; ++r) {
         if (use_mask && sM[r * Q + q]) continue;
-        const float4* kr = reinterpret_cast<const float4*>(sK + r * D + h * hd);  // hd % 4 == 0 (checked by the entry point)
+        const float4* kr = reinterpret_cast<const float4*>(sK + r * RS + h * HP);  // hd % 4 == 0 (checked by the entry point)
         float s = 0.f;
 #pragma unroll
         for (int j = 0; j < HD; j += 4) {
@@ -224,10 +229,10 @@ __global__ void __launch_bounds__(1024) k_xattn_partial(const float* __restrict_
           }
         }
         const float mn = fmaxf(m, s);
-        const float corr = expf(m - mn);  // m = -inf on the first key: exp(-inf) = 0
-        const float pw = expf(s - mn);
+        const float corr = exp2f(m - mn);  // m = -inf on the first key: exp2(-inf) = 0
+        const float pw = exp2f(s - mn);
         l = l * corr + pw;
-        const float4* vr = reinterpret_cast<const float4*>(sV + r * D + h * hd);
+        const float4* vr = reinterpret_cast<const float4*>(sV + r * RS + h * HP);
 #pragma unroll
         for (int j = 0; j < HD; j += 4) {
           if (j < hd) {
@@ -268,7 +273,7 @@ __global__ void __launch_bounds__(256) k_xattn_combine(const float* __restrict__
     const float pm = p[0], pl = p[1];
     if (pl == 0.f) continue;
     const float mn = fmaxf(m, pm);
-    const float c0 = expf(m - mn), c1 = expf(pm - mn);
+    const float c0 = exp2f(m - mn), c1 = exp2f(pm - mn);
     l = l * c0 + pl * c1;
 #pragma unroll
     for (int j = 0; j < kXaMaxHd; ++j)
@@ -279,7 +284,7 @@ __global__ void __launch_bounds__(256) k_xattn_combine(const float* __restrict__
   for (int d = 16; d > 0; d >>= 1) {
     const float om = __shfl_down_sync(0xffffffffu, m, d), ol = __shfl_down_sync(0xffffffffu, l, d);
     const float mn = fmaxf(m, om);
-    const float c0 = (m == -INFINITY) ? 0.f : expf(m - mn), c1 = (om == -INFINITY) ? 0.f : expf(om - mn);
+    const float c0 = (m == -INFINITY) ? 0.f : exp2f(m - mn), c1 = (om == -INFINITY) ? 0.f : exp2f(om - mn);
     l = l * c0 + ol * c1;
 #pragma unroll
     for (int j = 0; j < kXaMaxHd; ++j) {
@@ -384,7 +389,7 @@ int mk_masked_xattn_fwd(const float* qp, const void* kp, const void* vp, int kv_
   }
   const int keys_per_split = (int)ceil_div(n > 0 ? n : 1, splits);  // upper bound on any scene's size / splits
   const int threads = ((Q * H + 31) / 32) * 32;
-  const size_t smem = (size_t)2 * kXaKeysPerTile * D * sizeof(float) + (size_t)kXaKeysPerTile * Q;
+  const size_t smem = (size_t)2 * kXaKeysPerTile * (D + 4 * H) * sizeof(float) + (size_t)kXaKeysPerTile * Q;
   dim3 grid((unsigned)splits, (unsigned)B);
 #define MK_XA(T, HD)                                                                                                        \
   k_xattn_partial<T, HD><<<grid, threads, smem, st>>>(qp, (const T*)kp, (const T*)vp, blocked, any_open, scene_offsets, Q, D, H, \
