@@ -16,15 +16,21 @@ h_mask = [torch.empty((n, 25), dtype=torch.float32).pin_memory() for n in nvox]
 mode = sys.argv[1] if len(sys.argv) > 1 else "async"
 
 
+state = {"x": None}
+
+
 def step(i):
-    c, f = pinned[i % 3]
-    cd, fd = c.to(dev, non_blocking=True), f.to(dev, non_blocking=True)
-    o = model(me_api.SparseTensor(features=fd, coordinates=cd))
+    x = state["x"] if state["x"] is not None else model.prepare(*pinned[i % 3])
+    o = model(x, prefetch=pinned[(i + 1) % 3])
+    state["x"] = o.pop("prefetched")
     h_cls.copy_(torch.stack(o["pred_class_all_decoders"]), non_blocking=True)
     h_mask[i % 3].copy_(o["pred_mask_all_decoders"][-1], non_blocking=True)
 
 
-ts, allocs = [], []
+import gc
+if os.environ.get("NOGC"):
+    gc.collect(); gc.freeze(); gc.disable()
+ts, allocs, mem = [], [], []
 torch.cuda.synchronize(); t_prev = time.perf_counter()
 for i in range(30):
     step(i)
@@ -32,6 +38,8 @@ for i in range(30):
         torch.cuda.synchronize()
     t = time.perf_counter(); ts.append((t - t_prev) * 1e3); t_prev = t
     allocs.append(torch.cuda.memory_stats().get("num_device_alloc"))
+    mem.append(torch.cuda.memory_allocated() >> 20)
 torch.cuda.synchronize()
 print(mode, " ".join(f"{t:.1f}" for t in ts))
 print("cudaMalloc count per step:", allocs)
+print("allocated MiB per step:", mem, "gc counts", gc.get_count())

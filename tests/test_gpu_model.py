@@ -99,3 +99,30 @@ def test_mask3d_bf16_tensor_core_mode(setup):
         assert e_mask < 0.5
     finally:
         ops.set_compute_mode("bf16")
+
+
+def test_prefetch_on_side_stream_gives_identical_results(setup):
+    """Mask3D.forward(x, prefetch=next): the coordinate phase of the next scene runs on a side stream behind the current
+    scene's backbone.  Outputs must equal the plain sequential calls bit for bit (fp32 mode), over several alternating scenes."""
+    import numpy as np
+    from room_instance_segmentation_mask3d_b200 import mask3d_model, me_api, ops, scenes, weights
+
+    ops.set_compute_mode("fp32")
+    try:
+        model = mask3d_model.Mask3D().eval()
+        weights.load_synth(model, seed=0)
+        model = model.cuda()
+        batches = [scenes.collate([scenes.tiny_scene(3 + j), scenes.tiny_scene(7 + j, (20, 16, 10))]) for j in range(3)]
+        dev = [(torch.from_numpy(c).cuda(), torch.from_numpy(f).cuda()) for c, f in batches]
+        plain = [model(me_api.SparseTensor(features=f, coordinates=c)) for c, f in dev]
+        x = model.prepare(*dev[0])
+        for i in range(6):
+            o = model(x, prefetch=dev[(i + 1) % 3])
+            x = o.pop("prefetched")
+            ref = plain[i % 3]
+            assert torch.equal(o["fps_idx"], ref["fps_idx"])
+            assert torch.equal(o["pred_mask_all_decoders"][-1], ref["pred_mask_all_decoders"][-1])
+            assert torch.equal(o["pred_class"], ref["pred_class"])
+        torch.cuda.synchronize()
+    finally:
+        ops.set_compute_mode("bf16")
