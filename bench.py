@@ -381,6 +381,29 @@ def main_ours(args):
         dist.destroy_process_group()
 
 
+class _StdoutToStderr:
+    """Everything other than the final JSON line goes to stderr, also what native libraries write to file descriptor 1 (NCCL
+    prints its version banner there at the first collective): the contract is ONE JSON line on stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def restore(self):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+
+    def __exit__(self, *exc):
+        self.restore()
+        os.close(self.saved)
+        return False
+
+
+_real_print = print
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -393,7 +416,15 @@ if __name__ == "__main__":
     ap.add_argument("--no-train", action="store_true", help="skip the backbone forward+backward measurement")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi during the timed region (debugging)")
     a = ap.parse_args()
-    if a.impl == "reference":
-        main_reference(a)
-    else:
-        main_ours(a)
+    with _StdoutToStderr() as guard:
+        lines = []
+        print = lambda *args, **kw: lines.append(" ".join(str(x) for x in args))  # noqa: A001  (collect the JSON line)
+        globals()["print"] = print
+        if a.impl == "reference":
+            main_reference(a)
+        else:
+            main_ours(a)
+        guard.restore()
+        for ln in lines:
+            _real_print(ln, flush=True)
+        os.dup2(2, 1)
