@@ -690,7 +690,11 @@ int mk_conv_fwd_bf16(const void* in, int64_t n_in, int cin, const void* wimg, in
   if (carve_env == -2) { const char* e = getenv("MK3D_CARVEOUT"); carve_env = e ? atoi(e) : -1; }
 #define MK_LAUNCH(T, D)                                                                                     \
   do {                                                                                                      \
-    cudaFuncSetAttribute(k_conv_umma<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+    static size_t smem_set_##D = 0; /* per instantiation: raise the limit only when a launch needs more */  \
+    if (smem > smem_set_##D) {                                                                              \
+      cudaFuncSetAttribute(k_conv_umma<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+      smem_set_##D = smem;                                                                                  \
+    }                                                                                                       \
     if (carve_env >= 0) cudaFuncSetAttribute(k_conv_umma<T, D>, cudaFuncAttributePreferredSharedMemoryCarveout, carve_env); \
     k_conv_umma<T, D><<<grid, kNumThreads, smem, st>>>(p);                                                  \
   } while (0)

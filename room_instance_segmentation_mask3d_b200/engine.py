@@ -332,6 +332,31 @@ class CoordinateManager:
             self._tplans[ck] = plan
         return plan
 
+    def record_stream(self, stream) -> None:
+        """Tell the caching allocator that every tensor of this manager is (also) used on `stream` — needed when the maps were
+        built on one stream (Mask3D.prepare's side stream) and are consumed on another: their blocks must not be handed out again
+        before the consumer's work that was enqueued up to the moment they are freed has finished."""
+        def rec(t):
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                t.record_stream(stream)
+
+        for m in self._maps.values():
+            for t in (m.coords, m.keys, m.vals, m._offsets):
+                rec(t)
+        seen = set()
+
+        def walk(km):
+            if km is None or id(km) in seen:
+                return
+            seen.add(id(km))
+            for t in (km.nbr, km.out_rows, km._kmask, km._pairs_dev, km._wgrad_plan, km.out_coords, getattr(km, "parent", None),
+                      getattr(km, "koff", None)):
+                rec(t)
+            walk(km._sorted)
+
+        for km in list(self._kmaps.values()) + list(self._tplans.values()):
+            walk(km)
+
     def prebuild(self, in_key, levels: int = 5, first_kernel: int = 5) -> List[CoordinateMapKey]:
         """Build every coordinate map, kernel map and tile plan a Res16UNet-style network needs, up front: the host syncs
         of the data-dependent map sizes then happen while the GPU queue is still empty instead of draining it mid-network."""

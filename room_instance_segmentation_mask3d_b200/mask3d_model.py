@@ -198,9 +198,8 @@ class Res16UNet34C(nn.Module):
         offs = [mgr.scene_offsets(k) for k in keys]
 
         def cn(f, conv, norm, km, lvl, relu=True, residual=None, kind=0):
-            if ops.USE_COMPOSITE and mode == "bf16" and f.dtype == torch.bfloat16 and f.shape[1] % 16 == 0:
-                return ops.conv_instnorm_bf16(f, conv.kernel, km, offs[lvl], B, norm.weight, norm.bias, bias=conv.bias,
-                                              residual=residual, relu=relu, out_dtype=act)
+            if ops.USE_COMPOSITE and mode == "bf16" and f.dtype == torch.bfloat16 and f.shape[1] % 16 == 0 and conv.bias is None:
+                return ops.conv_instnorm_fast(f, ops.layer_plan(conv.kernel, norm.weight, norm.bias), km, offs[lvl], B, residual, relu, act)
             if kind == 2 and mode == "fp32":
                 y = ops.conv_transpose_forward_fp32(f, conv.kernel, km)
             else:
@@ -413,7 +412,7 @@ class Mask3D(nn.Module):
         return ff.norm(out + ff.linear2(F.relu(ff.linear1(out))))
 
     def _query_graphs(self, B: int, mode: str, device) -> _QueryGraphs:
-        key = (B, mode, str(device), self.decoder_norm.weight.data_ptr())
+        key = (B, mode, str(device), self.decoder_norm.weight.data_ptr(), torch.cuda.current_stream(device).cuda_stream)
         g = self._qgraphs.get(key)
         if g is None:
             g = self._qgraphs[key] = _QueryGraphs(self, B, mode, device)
@@ -456,10 +455,20 @@ class Mask3D(nn.Module):
 
         `prefetch = (coordinates, features)` of the NEXT scene (host pinned or device tensors): its coordinate phase is
         enqueued on a side stream behind this scene's backbone and the prepared SparseTensor is returned under
-        "prefetched" — pass it as `x` of the next call."""
+        "prefetched" — pass it as `x` of the next call.
+
+        The forward runs on the CURRENT torch stream and keeps its static CUDA-graph buffers per stream, so consecutive scenes may
+        alternate between two streams (`with torch.cuda.stream(lane[i % 2]): model(x, prefetch=...)`): the latency-bound
+        decoder chain of one scene then overlaps the bandwidth- and tensor-bound backbone of the next (bench.py does this)."""
         ev = getattr(x, "_ready_event", None)
         if ev is not None:
-            torch.cuda.current_stream().wait_event(ev)
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ev)
+            # built on the side stream, consumed here: keep the allocator from recycling the maps under this stream's feet
+            # (matters once scenes alternate between two streams, see `forward` docstring)
+            x.coordinate_manager.record_stream(cur)
+            x.F.record_stream(cur)
+            x.C.record_stream(cur)
         with lib.stream_scope():
             out = self._forward(x)
         if prefetch is not None:

@@ -181,6 +181,56 @@ def conv_instnorm_bf16(x: torch.Tensor, W: torch.Tensor, km: KernelMap, scene_of
     return (out, tmp, stats) if keep else out
 
 
+# ---- lean inference path of the composite call: per-layer constants resolved once, per-call work = two allocations + one C call
+_layer_plans: Dict[int, tuple] = {}
+_wsb_cache: Dict[tuple, int] = {}
+
+
+def layer_plan(W: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor):
+    """(weight image, gamma fp32 [C], beta fp32 [C], K, cin, cout) of one conv + instance-norm layer, cached until a parameter changes."""
+    key = id(W)
+    ver = (W._version, gamma._version, beta._version, W.data_ptr(), gamma.data_ptr())
+    ent = _layer_plans.get(key)
+    if ent is not None and ent[0] == ver:
+        return ent[1]
+    W3 = W if W.dim() == 3 else W.unsqueeze(0)
+    K, cin, cout = W3.shape
+    lp = (weight_image(W), _flat32(gamma), _flat32(beta), K, cin, cout)
+    if len(_layer_plans) > 4096:
+        _layer_plans.clear()
+    _layer_plans[key] = (ver, lp)
+    return lp
+
+
+def conv_instnorm_fast(x: torch.Tensor, lp: tuple, km: KernelMap, scene_offsets: torch.Tensor, B: int, residual: Optional[torch.Tensor],
+                       relu: bool, out_dtype: torch.dtype, eps: float = 1e-8) -> torch.Tensor:
+    """conv_instnorm_bf16 for inference with the per-layer constants of `layer_plan` (no bias, no kept intermediates)."""
+    img, g, b, K, cin, cout = lp
+    plan = km.sorted_plan() if SORT_TILES else km
+    n = km.n_out
+    out = torch.empty((n, cout), dtype=out_dtype, device=x.device)
+    wk = (n, cout, B)
+    wsb = _wsb_cache.get(wk)
+    if wsb is None:
+        if len(_wsb_cache) > 4096:
+            _wsb_cache.clear()
+        wsb = _wsb_cache[wk] = lib.query("mk_instnorm_workspace_bytes", n, cout, B)
+    small = K > 1 and 2 * ((plan.n_slots + lib.TILE - 1) // lib.TILE) <= 148
+    tmp_bytes = (n * cout * (4 if small else 2) + 255) // 256 * 256
+    stats_bytes = (2 * B * cout * 4 + 255) // 256 * 256
+    ws = lib.scratch(tmp_bytes + stats_bytes + wsb, x.device)
+    base = ws.data_ptr()
+    if lib._timed is not None:
+        lib.set_tag((2 * km.num_pairs * cin * cout, K, cin, cout, n))
+    out_rows = plan.out_rows
+    lib.call("mk_conv_instnorm_bf16", x.data_ptr(), x.shape[0], cin, img.data_ptr(), cout, plan.nbr.data_ptr(), K, plan.n_slots,
+             out_rows.data_ptr() if out_rows is not None else None, plan.tile_kmask.data_ptr(), None, n, None, scene_offsets.data_ptr(), B, eps,
+             g.data_ptr(), b.data_ptr(), residual.data_ptr() if residual is not None else None, int(relu), base, tmp_bytes,
+             base + tmp_bytes, out.data_ptr(), lib.BF16 if out_dtype == torch.bfloat16 else lib.F32, base + tmp_bytes + stats_bytes,
+             ws.numel() - tmp_bytes - stats_bytes, lib.stream())
+    return out
+
+
 def conv_transpose_forward_fp32(x: torch.Tensor, W: torch.Tensor, plan: KernelMap, bias=None) -> torch.Tensor:
     """fp32 parity path of the transposed conv: out[f] = x[parent[f]] @ W[koff[f]], expressed through the generic
     output-stationary kernel with the plan's table restricted to real rows (slot -> row permutation undone)."""
