@@ -140,6 +140,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dbg = kDbg ? p.debug : 0;
   const int acc_cols = G == 2 ? 128 : 256;  // TMEM columns per accumulator: [buffer][member tile] x acc_cols = 512
+  // bias staged once per CTA: the epilogue adds it per element, and reading it from global memory there cost one load
+  // instruction per output element and thread (the 1x1 convs with bias ran at a quarter of the HBM rate)
+  __shared__ float s_bias[256];
+  if (p.bias) {
+    for (int i = threadIdx.x; i < p.out_cols; i += blockDim.x) s_bias[i] = p.bias[i];
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
@@ -428,7 +434,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
             if (p.bias) {
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (c0 + j < p.out_cols) r[j] = __float_as_uint(__uint_as_float(r[j]) + p.bias[c0 + j]);
+                if (c0 + j < p.out_cols) r[j] = __float_as_uint(__uint_as_float(r[j]) + s_bias[c0 + j]);
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j)
@@ -468,7 +474,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
           }
           if (p.bias && (ksplit == 1 || cta_part == 0)) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += (c0 + j < p.out_cols) ? p.bias[c0 + j] : 0.f;
+            for (int j = 0; j < 16; ++j) v[j] += (c0 + j < p.out_cols) ? s_bias[c0 + j] : 0.f;
           }
           if (ksplit > 1) {
             // offset split: add this CTA's partial sums (the bias comes from part 0 alone, also for tiles part 0 has no offset of;
