@@ -52,14 +52,14 @@ def workload_config(voxel_m: float, n_scenes: int):
 # ----------------------------------------------------------------------------------------------------
 class ClockSampler:
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.first = index, [], None, 0
 
     def start(self):
         import subprocess
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -70,6 +70,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def mark(self):
+        """Rows from here on belong to the timed region."""
+        self.first = len(self.rows)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -77,7 +81,8 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows[self.first:] or self.rows  # inside the timed region (all rows if the region was shorter than a period)
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for n, v in zip(names, r[3:7]):
@@ -255,12 +260,16 @@ def main_ours(args):
     gc.collect()
     gc.freeze()
     gc.disable()
-    n_warm = max(args.warmup, 2 * n_scenes)  # every scene twice: CUDA-graph capture, allocator growth, weight images
-    for i in range(n_warm):
-        step_resident(i)
+    # nvidia-smi is started BEFORE the warm-up: its start-up (NVML initialisation, first query) takes driver locks for tens of
+    # milliseconds, which used to land inside the first timed region; the rows that fall inside the timed region are the ones
+    # reported (ClockSampler.window)
     sampler = ClockSampler(local)
     if rank == 0 and not args.no_clocks:
         sampler.start()
+    n_warm = max(args.warmup, 2 * n_scenes)  # every scene twice: CUDA-graph capture, allocator growth, weight images
+    for i in range(n_warm):
+        step_resident(i)
+    sampler.mark()
     launches0 = lib.kernel_launches
     state["vox"] = 0
     ms = timed(step_resident, args.steps)
