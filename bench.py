@@ -51,20 +51,68 @@ def workload_config(voxel_m: float, n_scenes: int):
 # clocks sampler (nvidia-smi, as the profiling recipe prescribes)
 # ----------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region.  In-process NVML (a thread polling every 50 ms: two cheap
+    driver queries) — an `nvidia-smi -lms` subprocess re-initialises NVML and takes driver locks that showed up as occasional
+    slow first timed regions; nvidia-smi remains the fallback when pynvml is unavailable."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
     def __init__(self, index: int):
-        self.index, self.rows, self.proc, self.first = index, [], None, 0
+        self.index, self.rows, self.proc, self.first, self.h, self._stop = index, [], None, 0, None, False
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            uuid = None
+            try:
+                import torch
+
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            except Exception:
+                pass
+            h = None
+            if uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+                except Exception:
+                    h = None
+            self.h = h if h is not None else pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nv = pynvml
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.h = None
         import subprocess
+
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "50"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        nv = self.nv
+        bits = [nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown, nv.nvmlClocksEventReasonSwThermalSlowdown,
+                nv.nvmlClocksEventReasonSwPowerCap]
+        while not self._stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append([str(sm), str(self.mx), "0"] + ["Active" if (r & b) else "Not Active" for b in bits])
+            except Exception:
+                pass
+            time.sleep(0.05)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -75,23 +123,24 @@ class ClockSampler:
         self.first = len(self.rows)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.h is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        time.sleep(0.12)
+        self._stop = True
+        if self.proc is not None:
+            self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         rows = self.rows[self.first:] or self.rows  # inside the timed region (all rows if the region was shorter than a period)
         for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
-                for n, v in zip(names, r[3:7]):
+                for n, v in zip(self.NAMES, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if self.h is not None else "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -183,7 +232,7 @@ def main_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib.load()
-    lib.reserve_device_pool(32.0, dev)  # one splittable 32 GB segment instead of cudaMalloc stalls while the allocator grows
+    lib.reserve_device_pool(8.0, dev)  # one splittable segment instead of cudaMalloc stalls while the allocator grows
     ops.set_compute_mode(args.mode)
     voxel = args.voxel_cm / 100.0
     n_scenes = 3
@@ -205,6 +254,9 @@ def main_ours(args):
     # buffers; the timed region ends when BOTH lanes have drained (see `timed`).
     n_lanes = 1 if args.lanes < 2 else 2
     lanes = [torch.cuda.Stream(device=dev) for _ in range(n_lanes)]
+    for st_ in lanes:  # the caching allocator keeps blocks per stream: one up-front segment for every stream a forward runs on
+        lib.reserve_device_pool(12.0, dev, stream=st_)
+    lib.reserve_device_pool(6.0, dev, stream=model.side_stream(dev))
     h_cls = [torch.empty((13, 1, 25, 2), dtype=torch.float32).pin_memory() for _ in range(n_lanes)]
     h_mask = [[torch.empty((n, 25), dtype=torch.float32).pin_memory() for n in nvox] for _ in range(n_lanes)]
     state = {"res": None, "e2e": None, "g_res": 0, "g_e2e": 0, "vox": 0}

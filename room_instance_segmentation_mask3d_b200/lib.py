@@ -190,20 +190,25 @@ def scratch(nbytes: int, device) -> torch.Tensor:
     return buf
 
 
-def reserve_device_pool(gigabytes: float = 32.0, device=None) -> None:
+def reserve_device_pool(gigabytes: float = 32.0, device=None, stream=None) -> None:
     """Make torch's caching allocator hold ONE large splittable segment up front.
 
     Scenes differ in size, so a step's allocation pattern never repeats exactly; with the default growth policy the allocator
     keeps finding no fit every few steps and calls cudaMalloc for another segment (measured: 91 -> 145 segments over 30
     inference steps), each a 10-100 ms stall with an implicit device synchronisation — the source of occasional 2x slower
     benchmark phases.  A B200 has 180 GB: reserving a few tens of GB once and releasing them to the cache turns every later
-    request into a split of that segment."""
+    request into a split of that segment.  The allocator caches blocks PER STREAM: pass `stream` to reserve for a side stream
+    (every stream a forward pass runs on needs its own reservation)."""
     require_cuda()
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     free, _ = torch.cuda.mem_get_info(dev)
-    nbytes = int(min(gigabytes * (1 << 30), 0.5 * free))
+    nbytes = int(min(gigabytes * (1 << 30), 0.25 * free))
     if nbytes > 0:
-        t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        if stream is None:
+            t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        else:
+            with torch.cuda.stream(stream):
+                t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         del t
 
 

@@ -431,9 +431,7 @@ class Mask3D(nn.Module):
         the current scene), i.e. after every main-stream kernel that may still read map tensors of EARLIER scenes whose blocks
         the side stream's pool is about to recycle."""
         dev = next(self.parameters()).device
-        side = self._side_streams.get(dev)
-        if side is None:
-            side = self._side_streams[dev] = torch.cuda.Stream(device=dev)
+        side = self.side_stream(dev)
         if wait_event is not None:
             side.wait_event(wait_event)
         with torch.cuda.stream(side):
@@ -448,6 +446,14 @@ class Mask3D(nn.Module):
             ev.record(side)
         x._ready_event = ev
         return x
+
+    def side_stream(self, device=None) -> torch.cuda.Stream:
+        """The stream `prepare` runs on (created on first use)."""
+        dev = torch.device(device) if device is not None else next(self.parameters()).device
+        side = self._side_streams.get(dev)
+        if side is None:
+            side = self._side_streams[dev] = torch.cuda.Stream(device=dev)
+        return side
 
     @torch.no_grad()
     def forward(self, x: ME.SparseTensor, is_eval: bool = True, prefetch=None) -> dict:
