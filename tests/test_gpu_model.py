@@ -126,3 +126,35 @@ def test_prefetch_on_side_stream_gives_identical_results(setup):
         torch.cuda.synchronize()
     finally:
         ops.set_compute_mode("bf16")
+
+
+def test_two_lane_alternation_gives_identical_results(setup):
+    """Consecutive scenes alternating between two CUDA streams with the next scene prepared on the side stream (what bench.py
+    does): every scene's outputs must equal the plain single-stream call bit for bit (fp32 mode), also under memory reuse
+    across many steps."""
+    from room_instance_segmentation_mask3d_b200 import mask3d_model, me_api, ops, scenes, weights
+
+    ops.set_compute_mode("fp32")
+    try:
+        model = mask3d_model.Mask3D().eval()
+        weights.load_synth(model, seed=0)
+        model = model.cuda()
+        batches = [scenes.collate([scenes.tiny_scene(11 + j), scenes.tiny_scene(17 + j, (20, 16, 10))]) for j in range(3)]
+        dev = [(torch.from_numpy(c).cuda(), torch.from_numpy(f).cuda()) for c, f in batches]
+        plain = [model(me_api.SparseTensor(features=f, coordinates=c)) for c, f in dev]
+        want = [(p["fps_idx"].clone(), p["pred_mask_all_decoders"][-1].clone(), p["pred_class"].clone()) for p in plain]
+        del plain
+        lanes = [torch.cuda.Stream(), torch.cuda.Stream()]
+        x = model.prepare(*dev[0])
+        got = []
+        for i in range(12):
+            with torch.cuda.stream(lanes[i % 2]):
+                o = model(x, prefetch=dev[(i + 1) % 3])
+                x = o.pop("prefetched")
+                got.append((i % 3, o["fps_idx"], o["pred_mask_all_decoders"][-1], o["pred_class"]))
+            del o
+        torch.cuda.synchronize()
+        for j, a, b, c in got:
+            assert torch.equal(a, want[j][0]) and torch.equal(b, want[j][1]) and torch.equal(c, want[j][2])
+    finally:
+        ops.set_compute_mode("bf16")
