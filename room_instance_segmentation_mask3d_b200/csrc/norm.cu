@@ -236,6 +236,73 @@ __global__ void __launch_bounds__(kNormThreads) k_in_stats(const T* __restrict__
   }
 }
 
+template <typename T, int V>
+__device__ __forceinline__ void ld_vec(const T* p, float (&v)[V]) {
+  if constexpr (sizeof(T) == 2) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+      v[2 * j] = f.x;
+      v[2 * j + 1] = f.y;
+    }
+  } else {
+    const float4 q = *reinterpret_cast<const float4*>(p);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  }
+}
+template <typename T, int V>
+__device__ __forceinline__ void st_vec(T* p, const float (&v)[V]) {
+  if constexpr (sizeof(T) == 2) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      w[j] = *reinterpret_cast<uint32_t*>(&t);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  } else {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// bf16 -> bf16 apply, 8 channels (16 bytes) per thread and 32-bit index arithmetic: the generic kernel below moves 8 bytes per
+// thread and pays a 64-bit division per element group, which made this HBM-bound pass instruction-bound.
+__global__ void __launch_bounds__(256) k_norm_apply_bf16x8(const __nv_bfloat16* __restrict__ x, unsigned total, unsigned CV,
+                                                          const int32_t* __restrict__ scene_offsets, int B,
+                                                          const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          const __nv_bfloat16* __restrict__ residual, int relu,
+                                                          __nv_bfloat16* __restrict__ out) {
+  const unsigned C = CV * 8u;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned r = i / CV;
+    const unsigned c = (i - r * CV) * 8u;
+    float v[8];
+    ld_vec<__nv_bfloat16, 8>(x + (size_t)r * C + c, v);
+    const int b = scene_of_row(scene_offsets, B, (int64_t)r);
+    const float4 m0 = load4(mean + b * C + c), m1 = load4(mean + b * C + c + 4);
+    const float4 s0 = load4(rstd + b * C + c), s1 = load4(rstd + b * C + c + 4);
+    const float4 g0 = load4(gamma + c), g1 = load4(gamma + c + 4), e0 = load4(beta + c), e1 = load4(beta + c + 4);
+    const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w}, ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf((v[j] - mm[j]) * ss[j], gg[j], ee[j]);
+    if (residual) {
+      float q[8];
+      ld_vec<__nv_bfloat16, 8>(residual + (size_t)r * C + c, q);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += q[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    st_vec<__nv_bfloat16, 8>(out + (size_t)r * C + c, v);
+  }
+}
+
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256) k_norm_apply(const TIn* __restrict__ x, int64_t n, int C,
                                                     const int32_t* __restrict__ scene_offsets, int B,
@@ -339,37 +406,6 @@ __global__ void __launch_bounds__(256) k_in_bwd_dx(const float* __restrict__ x, 
 // g = dy where the unit's output was positive (or dy when there is no ReLU); x_hat = (x - mean) * rstd with x the conv output.
 //   sums per (scene, channel):  A = sum g,  Q = sum g * x_hat            (also dbeta = sum_b A, dgamma = sum_b Q)
 //   dx = gamma * rstd * (g - A / n_b - x_hat * Q / n_b),   dres = g
-template <typename T, int V>
-__device__ __forceinline__ void ld_vec(const T* p, float (&v)[V]) {
-  if constexpr (sizeof(T) == 2) {
-    const uint4 q = *reinterpret_cast<const uint4*>(p);
-    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
-      v[2 * j] = f.x;
-      v[2 * j + 1] = f.y;
-    }
-  } else {
-    const float4 q = *reinterpret_cast<const float4*>(p);
-    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-  }
-}
-template <typename T, int V>
-__device__ __forceinline__ void st_vec(T* p, const float (&v)[V]) {
-  if constexpr (sizeof(T) == 2) {
-    uint32_t w[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-      w[j] = *reinterpret_cast<uint32_t*>(&t);
-    }
-    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
-  } else {
-    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-  }
-}
-
 // partial [chunk][2][C] = {A, Q}; grid (chunks, B)
 template <typename T>
 __global__ void __launch_bounds__(kNormThreads) k_inr_bwd_partial(const T* __restrict__ dy, const T* __restrict__ out,
@@ -587,6 +623,15 @@ int mk_norm_apply(const void* x, int x_dtype, int64_t n, int C, const int32_t* s
   int64_t blocks = ceil_div(total, 256);
   int64_t cap = 8 * (int64_t)num_sms();
   if (blocks > cap) blocks = cap;
+  if (x_dtype == MK_BF16 && out_dtype == MK_BF16 && C % 8 == 0 && mean && gamma && n * (int64_t)(C / 8) < ((int64_t)1 << 31) &&
+      (((uintptr_t)x | (uintptr_t)out | (uintptr_t)residual) & 15) == 0) {
+    const int64_t tot8 = n * (C / 8);
+    int64_t b8 = ceil_div(tot8, 256);
+    if (b8 > 16 * (int64_t)num_sms()) b8 = 16 * (int64_t)num_sms();
+    k_norm_apply_bf16x8<<<(unsigned)b8, 256, 0, st>>>((const __nv_bfloat16*)x, (unsigned)tot8, (unsigned)(C / 8), scene_offsets, B, mean, rstd,
+                                                      gamma, beta, (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)out);
+    return check_launch(__func__);
+  }
 #define MK_APPLY(TI, TO)                                                                                              \
   k_norm_apply<TI, TO><<<(unsigned)blocks, 256, 0, st>>>((const TI*)x, n, C, scene_offsets, B, mean, rstd, gamma, beta, \
                                                          (const TO*)residual, relu, (TO*)out)
