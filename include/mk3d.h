@@ -224,6 +224,34 @@ int mk_fps(const float* xyz, const int32_t* scene_offsets, int B, int m, int64_t
            void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * (8) Loss side of the mask logits.  Replaces, per decoder output and scene,
+ *   batch_sigmoid_ce_loss / batch_dice_loss         mask3d/models/matcher.py:17-56 (cost matrices, called at :143-146)
+ *   sigmoid_ce_loss / dice_loss of matched pairs     mask3d/models/criterion.py:27-72 (called at :195-196)
+ *   mask score of the post-processing                mask3d/trainer/trainer.py:389-392
+ * with one pass over the fp32 logits [n,Q] (all scenes of the batch, rows of a scene contiguous).
+ * Targets are per-voxel bit words: bits uint32 [n,W], bit (t & 31) of word (t >> 5) = voxel belongs to instance t of ITS
+ * scene (ItemTargets.instances_masks[t, voxel], mask3d/datasets/utils.py:149-160).
+ * ------------------------------------------------------------------------------------------- */
+/* masks uint8 [T, n_scene] (the bool instance masks of ONE scene) -> bits [n_scene, W] (pass bits + row0 * W). */
+int mk_target_bits(const uint8_t* masks, int T, int64_t n_scene, int W, uint32_t* bits, void* stream);
+int64_t mk_mask_costs_workspace_bytes(int B, int64_t max_scene_rows, int Q, int W);
+/* Outputs, all fp32, Tp = 32 W (columns t >= T of a scene are those of an empty target):
+ *   cost_mask [B,Q,Tp]  mean_n BCEWithLogits(x[n,q], tgt[t,n])                        (matcher.py:39-56)
+ *   cost_dice [B,Q,Tp]  1 - (2 sum_n sig(x) tgt + 1) / (sum_n sig(x) + sum_n tgt + 1)  (matcher.py:17-33)
+ *   dice_den  [B,Q,Tp]  the dice denominator (backward needs it)
+ *   mask_score [B,Q]    sum_n sig(x) [x > 0] / (sum_n [x > 0] + 1e-6)                  (trainer.py:389-392)
+ *   n_rows [B]          rows that took part (scene size, or the selected rows)
+ * row_select uint8 [n] or NULL: rows with 0 are left out (the matcher's / criterion's `point_idx` subset when
+ * num_points != -1, matcher.py:125-127, criterion.py:181-182).  max_scene_rows (host) = largest scene of the batch. */
+int mk_mask_costs(const float* logits, int64_t n, int Q, const uint32_t* bits, int W, const uint8_t* row_select,
+                  const int32_t* scene_offsets, int B, int64_t max_scene_rows, float* cost_mask, float* cost_dice, float* dice_den,
+                  float* mask_score, float* n_rows, void* workspace, int64_t workspace_bytes, void* stream);
+/* Gradient of the matched mask losses w.r.t. the logits: match int32 [B,Q] = target matched to the query or -1,
+ * coef fp32 [B,Q,3] = (a, c1, c2):  grad[n,q] = a (sig - tgt) + sig (1 - sig) (c1 - tgt c2);  unmatched / unselected = 0. */
+int mk_mask_loss_bwd(const float* logits, int64_t n, int Q, const uint32_t* bits, int W, const uint8_t* row_select,
+                     const int32_t* scene_offsets, int B, const int32_t* match, const float* coef, float* grad, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Casts (plumbing between fp32 module boundaries and the bf16 tensor-core path).
  * ------------------------------------------------------------------------------------------- */
 int mk_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n_elems, void* stream);

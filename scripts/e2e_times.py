@@ -17,14 +17,22 @@ mode = sys.argv[1] if len(sys.argv) > 1 else "async"
 
 
 state = {"x": None}
+lanes = [torch.cuda.Stream(), torch.cuda.Stream()]
+for st_ in lanes:
+    lib.reserve_device_pool(12.0, dev, stream=st_)
+lib.reserve_device_pool(6.0, dev, stream=model.side_stream(dev))
+h_cls2 = [torch.empty((13, 1, 25, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
+h_mask2 = [[torch.empty((n, 25), dtype=torch.float32).pin_memory() for n in nvox] for _ in range(2)]
 
 
 def step(i):
     x = state["x"] if state["x"] is not None else model.prepare(*pinned[i % 3])
-    o = model(x, prefetch=pinned[(i + 1) % 3])
+    ln = i % 2
+    with torch.cuda.stream(lanes[ln]):
+        o = model(x, prefetch=pinned[(i + 1) % 3])
+        h_cls2[ln].copy_(torch.stack(o["pred_class_all_decoders"]), non_blocking=True)
+        h_mask2[ln][i % 3].copy_(o["pred_mask_all_decoders"][-1], non_blocking=True)
     state["x"] = o.pop("prefetched")
-    h_cls.copy_(torch.stack(o["pred_class_all_decoders"]), non_blocking=True)
-    h_mask[i % 3].copy_(o["pred_mask_all_decoders"][-1], non_blocking=True)
 
 
 import gc
@@ -32,7 +40,7 @@ if os.environ.get("NOGC"):
     gc.collect(); gc.freeze(); gc.disable()
 ts, allocs, mem = [], [], []
 torch.cuda.synchronize(); t_prev = time.perf_counter()
-for i in range(30):
+for i in range(60):
     step(i)
     if mode == "sync":
         torch.cuda.synchronize()
