@@ -249,7 +249,8 @@ int mk_mask_costs(const float* logits, int64_t n, int Q, const uint32_t* bits, i
 /* Gradient of the matched mask losses w.r.t. the logits: match int32 [B,Q] = target matched to the query or -1,
  * coef fp32 [B,Q,3] = (a, c1, c2):  grad[n,q] = a (sig - tgt) + sig (1 - sig) (c1 - tgt c2);  unmatched / unselected = 0. */
 int mk_mask_loss_bwd(const float* logits, int64_t n, int Q, const uint32_t* bits, int W, const uint8_t* row_select,
-                     const int32_t* scene_offsets, int B, const int32_t* match, const float* coef, float* grad, void* stream);
+                     const int32_t* scene_offsets, int B, int64_t max_scene_rows, const int32_t* match, const float* coef, float* grad,
+                     void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Casts (plumbing between fp32 module boundaries and the bf16 tensor-core path).

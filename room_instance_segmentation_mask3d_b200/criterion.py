@@ -239,7 +239,7 @@ class _MaskLossFn(torch.autograd.Function):
         grad = torch.empty_like(x)
         n, Q = x.shape
         lib.call("mk_mask_loss_bwd", lib.p(x), n, Q, lib.p(tg.bits), tg.W, lib.p(ctx.row_select), lib.p(tg.scene_offsets), tg.B,
-                 lib.p(match), lib.p(coef), lib.p(grad), lib.stream())
+                 tg.max_rows, lib.p(match), lib.p(coef), lib.p(grad), lib.stream())
         return grad.to(logits.dtype), None, None, None, None
 
 

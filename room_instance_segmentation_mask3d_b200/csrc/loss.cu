@@ -22,9 +22,9 @@
 
 namespace mk {
 
-constexpr int kLossRows = 2048;  // rows of one scene handled by one block
-constexpr int kLossWarps = 4;
-constexpr int kLossRowsPerWarp = kLossRows / kLossWarps;
+constexpr int kLossWarps = 8;     // warps per block up to 64 queries; 4 above (the warp-private accumulators must fit in shared memory)
+constexpr int kLossRows = 1024;   // rows of one scene handled by one block
+constexpr int kLossU = 8;                                 // rows per load group (two groups in flight per warp)
 
 // bits[n, w] bit j = masks[(32 w + j), n]   (masks = ItemTargets.instances_masks as bytes, [T, n_scene])
 __global__ void __launch_bounds__(256) k_target_bits(const uint8_t* __restrict__ masks, int T, int64_t n_scene, int W,
@@ -73,20 +73,55 @@ __device__ __forceinline__ void flush_run(float2* acc_w, uint32_t cur, const flo
   }
 }
 
-// grid (ranges, scenes, words).  Block = 4 warps, each walking a contiguous run of rows with lane = query (QC chunks of 32).
-// A lane keeps the sums of the current RUN of rows with identical target word in registers and adds them to the warp's
-// private [32 targets][Q] shared-memory accumulator only when the word changes (rows are in lexicographic voxel order, so
-// runs are long).
+// A group of kLossU consecutive rows held by a warp, lane = query (QC chunks of 32): logits, target word, row flag.
 template <int QC>
-__global__ void __launch_bounds__(kLossWarps * 32)
+struct RowGroup {
+  float x[kLossU][QC];
+  uint32_t word[kLossU];
+  uint32_t keep;  // bit u: row exists and is selected
+};
+
+template <int QC>
+__device__ __forceinline__ void load_group(RowGroup<QC>& g, const float* __restrict__ logits, int Q, const uint32_t* __restrict__ bits,
+                                           int W, int w, const uint8_t* __restrict__ sel, int64_t base, int64_t end, int lane) {
+  g.keep = 0;
+#pragma unroll
+  for (int u = 0; u < kLossU; ++u) {
+    const int64_t row = base + u;
+    const bool in = row < end;
+    g.word[u] = in ? bits[row * W + w] : 0u;
+    if (in && (sel == nullptr || sel[row] != 0)) g.keep |= 1u << u;
+#pragma unroll
+    for (int j = 0; j < QC; ++j) {
+      const int q = j * 32 + lane;
+      g.x[u][j] = (in && q < Q) ? logits[row * Q + q] : 0.f;
+    }
+  }
+}
+
+// Row layout of the per-(scene, range) partial sums, all fp32 (counts <= 1024 are exact):
+//   [0, 64 W Q)                (sum_{n in t} x, sum_{n in t} sig) per (word, bit, query)
+//   [64 W Q, +4 Q)             (softplus sum, sig sum, sum sig [x>0], sum [x>0]) per query        (written by word 0)
+//   [.., +32 W)                |t| per (word, bit)
+//   [.., +1)                   rows that took part                                                 (written by word 0)
+__host__ __device__ inline int loss_off_q(int Q, int W) { return 64 * W * Q; }
+__host__ __device__ inline int loss_off_t(int Q, int W) { return 64 * W * Q + 4 * Q; }
+__host__ __device__ inline int loss_off_n(int Q, int W) { return 64 * W * Q + 4 * Q + 32 * W; }
+__host__ __device__ inline int loss_row_len(int Q, int W) { return (loss_off_n(Q, W) + 1 + 3) & ~3; }
+
+// grid (ranges, scenes, words).  Block = 8 warps, each walking 128 consecutive rows with lane = query.  A lane keeps the sums
+// of the current RUN of rows with identical target word in registers and adds them to the warp's private [32 targets][Q]
+// shared-memory accumulator only when the word changes (rows are in lexicographic voxel order, so runs are long).  Two groups
+// of 8 rows are in flight per warp (the next group is loaded before the current one is processed).
+template <int QC, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
     k_mask_stats(const float* __restrict__ logits, int Q, const uint32_t* __restrict__ bits, int W, const uint8_t* __restrict__ sel,
-                 const int32_t* __restrict__ scene_offsets, float2* __restrict__ part_qt, float4* __restrict__ part_q,
-                 int32_t* __restrict__ part_t, int32_t* __restrict__ part_n, int R_max) {
+                 const int32_t* __restrict__ scene_offsets, float* __restrict__ part, int R_max) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int QP = QC * 32;
   float2* acc = reinterpret_cast<float2*>(smem_raw);                       // [warps][32][QP]
-  float4* stat = reinterpret_cast<float4*>(acc + kLossWarps * 32 * QP);    // [warps][QP]
-  int32_t* scnt = reinterpret_cast<int32_t*>(stat + kLossWarps * QP);      // [warps][32] + [warps]
+  float4* stat = reinterpret_cast<float4*>(acc + WARPS * 32 * QP);    // [warps][QP]
+  int32_t* scnt = reinterpret_cast<int32_t*>(stat + WARPS * QP);      // [warps][32] + [warps]
 
   const int r = blockIdx.x, b = blockIdx.y, w = blockIdx.z;
   const int64_t s0 = scene_offsets[b], s1 = scene_offsets[b + 1];
@@ -102,29 +137,16 @@ __global__ void __launch_bounds__(kLossWarps * 32)
   for (int j = 0; j < QC; ++j) ax[j] = as[j] = G[j] = S[j] = HS[j] = HC[j] = 0.f;
   uint32_t cur = 0;
   int cnt = 0, nsel = 0;
-  const int64_t a0 = row0 + (int64_t)wi * kLossRowsPerWarp, a1 = min(row1, a0 + kLossRowsPerWarp);
-  constexpr int U = 4;
-  for (int64_t base = a0; base < a1; base += U) {
-    float x[U][QC];
-    uint32_t word[U];
-    bool keep[U];
+  const int64_t a0 = row0 + (int64_t)wi * (kLossRows / WARPS), a1 = min(row1, a0 + (kLossRows / WARPS));
+  RowGroup<QC> g, nx;
+  if (a0 < a1) load_group<QC>(g, logits, Q, bits, W, w, sel, a0, a1, lane);
+  for (int64_t base = a0; base < a1; base += kLossU) {
+    if (base + kLossU < a1) load_group<QC>(nx, logits, Q, bits, W, w, sel, base + kLossU, a1, lane);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t row = base + u;
-      const bool in = row < a1;
-      word[u] = in ? bits[row * W + w] : 0u;
-      keep[u] = in && (sel == nullptr || sel[row] != 0);
-#pragma unroll
-      for (int j = 0; j < QC; ++j) {
-        const int q = j * 32 + lane;
-        x[u][j] = (in && q < Q) ? logits[row * Q + q] : 0.f;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (!keep[u]) continue;  // warp-uniform
+    for (int u = 0; u < kLossU; ++u) {
+      if (!((g.keep >> u) & 1u)) continue;  // warp-uniform
       ++nsel;
-      const uint32_t wd = word[u];
+      const uint32_t wd = g.word[u];
       cnt += (wd >> lane) & 1u;
       if (wd != cur) {
         flush_run<QC>(acc_w, cur, ax, as, lane);
@@ -134,31 +156,33 @@ __global__ void __launch_bounds__(kLossWarps * 32)
       }
 #pragma unroll
       for (int j = 0; j < QC; ++j) {
-        const SigSp v = sig_softplus(x[u][j]);
+        const float xv = g.x[u][j];
+        const SigSp v = sig_softplus(xv);
         G[j] += v.sp;
         S[j] += v.s;
-        const bool pos = x[u][j] > 0.f;
+        const bool pos = xv > 0.f;
         HS[j] += pos ? v.s : 0.f;
         HC[j] += pos ? 1.f : 0.f;
-        ax[j] += x[u][j];
+        ax[j] += xv;
         as[j] += v.s;
       }
     }
+    g = nx;
   }
   flush_run<QC>(acc_w, cur, ax, as, lane);
 #pragma unroll
   for (int j = 0; j < QC; ++j) stat[wi * QP + j * 32 + lane] = make_float4(G[j], S[j], HS[j], HC[j]);
   scnt[wi * 32 + lane] = cnt;
-  if (lane == 0) scnt[kLossWarps * 32 + wi] = nsel;
+  if (lane == 0) scnt[WARPS * 32 + wi] = nsel;
   __syncthreads();
 
-  const int64_t slot = ((int64_t)b * R_max + r) * W + w;
-  float2* pq = part_qt + slot * 32 * Q;
+  float* prow = part + ((int64_t)b * R_max + r) * loss_row_len(Q, W);
+  float2* pq = reinterpret_cast<float2*>(prow) + (int64_t)w * 32 * Q;
   for (int i = threadIdx.x; i < 32 * Q; i += blockDim.x) {
     const int t = i / Q, q = i - t * Q;
     float2 v = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < kLossWarps; ++k) {
+    for (int k = 0; k < WARPS; ++k) {
       const float2 a = acc[(k * 32 + t) * QP + q];
       v.x += a.x;
       v.y += a.y;
@@ -168,35 +192,56 @@ __global__ void __launch_bounds__(kLossWarps * 32)
   if (threadIdx.x < 32) {
     int c = 0;
 #pragma unroll
-    for (int k = 0; k < kLossWarps; ++k) c += scnt[k * 32 + threadIdx.x];
-    part_t[slot * 32 + threadIdx.x] = c;
+    for (int k = 0; k < WARPS; ++k) c += scnt[k * 32 + threadIdx.x];
+    prow[loss_off_t(Q, W) + w * 32 + threadIdx.x] = (float)c;
   }
   if (w == 0) {
+    float4* p4 = reinterpret_cast<float4*>(prow + loss_off_q(Q, W));
     for (int q = threadIdx.x; q < Q; q += blockDim.x) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int k = 0; k < kLossWarps; ++k) {
+      for (int k = 0; k < WARPS; ++k) {
         const float4 a = stat[k * QP + q];
         v.x += a.x, v.y += a.y, v.z += a.z, v.w += a.w;
       }
-      part_q[((int64_t)b * R_max + r) * Q + q] = v;
+      p4[q] = v;
     }
     if (threadIdx.x == 0) {
       int c = 0;
-      for (int k = 0; k < kLossWarps; ++k) c += scnt[kLossWarps * 32 + k];
-      part_n[(int64_t)b * R_max + r] = c;
+      for (int k = 0; k < WARPS; ++k) c += scnt[WARPS * 32 + k];
+      prow[loss_off_n(Q, W)] = (float)c;
     }
   }
 }
 
-// One thread per (scene, query, target): fixed-order fp64 merge of the range partials, then
+// sums[b, c] = sum over the scene's ranges of part[b, r, c] in fp64: block = 32 columns x 32 range lanes, every lane adds its
+// ranges in ascending order, then a fixed-order tree over the lanes (deterministic).
+__global__ void __launch_bounds__(1024) k_loss_merge(const float* __restrict__ part, const int32_t* __restrict__ scene_offsets, int L,
+                                                     int R_max, double* __restrict__ sums) {
+  __shared__ double sm[32][33];
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int64_t nb = scene_offsets[b + 1] - scene_offsets[b];
+  const int R = (int)((nb + kLossRows - 1) / kLossRows);
+  double a = 0.0;
+  if (c < L)
+    for (int r = threadIdx.y; r < R; r += 32) a += (double)part[((int64_t)b * R_max + r) * L + c];
+  sm[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  for (int h = 16; h > 0; h >>= 1) {
+    if (threadIdx.y < h) sm[threadIdx.y][threadIdx.x] += sm[threadIdx.y + h][threadIdx.x];
+    __syncthreads();
+  }
+  if (threadIdx.y == 0 && c < L) sums[(int64_t)b * L + c] = sm[0][threadIdx.x];
+}
+
+// One thread per (scene, query, target):
 //   cost_mask = (sum_n softplus(x) - sum_{n in t} x) / n            matcher.py:39-56 (== sigmoid_ce_loss of the pair)
 //   cost_dice = 1 - (2 sum_{n in t} sig + 1) / (sum_n sig + |t| + 1)  matcher.py:17-33 (== dice_loss of the pair)
+// rows written by word w > 0 blocks only hold their own columns; the word-0 columns (per-query sums, n) come from word 0.
 __global__ void __launch_bounds__(128)
-    k_mask_costs_final(const float2* __restrict__ part_qt, const float4* __restrict__ part_q, const int32_t* __restrict__ part_t,
-                       const int32_t* __restrict__ part_n, const int32_t* __restrict__ scene_offsets, int B, int Q, int W, int R_max,
-                       float* __restrict__ cost_mask, float* __restrict__ cost_dice, float* __restrict__ dice_den,
-                       float* __restrict__ mask_score, float* __restrict__ n_rows) {
+    k_mask_costs_final(const double* __restrict__ sums, int B, int Q, int W, float* __restrict__ cost_mask, float* __restrict__ cost_dice,
+                       float* __restrict__ dice_den, float* __restrict__ mask_score, float* __restrict__ n_rows) {
   const int Tp = 32 * W;
   const int64_t total = (int64_t)B * Q * Tp;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -204,19 +249,11 @@ __global__ void __launch_bounds__(128)
   const int t = (int)(i % Tp);
   const int q = (int)((i / Tp) % Q);
   const int b = (int)(i / ((int64_t)Tp * Q));
-  const int64_t nb = scene_offsets[b + 1] - scene_offsets[b];
-  const int R = (int)((nb + kLossRows - 1) / kLossRows);
-  const int w = t >> 5, tb = t & 31;
-  double sx = 0, ss = 0, G = 0, S = 0, HS = 0, HC = 0, cnt = 0, n = 0;
-  for (int r = 0; r < R; ++r) {
-    const int64_t rr = (int64_t)b * R_max + r;
-    const float2 p = part_qt[((rr * W + w) * 32 + tb) * Q + q];
-    sx += p.x, ss += p.y;
-    const float4 g = part_q[rr * Q + q];
-    G += g.x, S += g.y, HS += g.z, HC += g.w;
-    cnt += part_t[(rr * W + w) * 32 + tb];
-    n += part_n[rr];
-  }
+  const double* s = sums + (int64_t)b * loss_row_len(Q, W);
+  const double sx = s[2 * (t * Q + q)], ss = s[2 * (t * Q + q) + 1];
+  const double* sq = s + loss_off_q(Q, W) + 4 * q;
+  const double G = sq[0], S = sq[1], HS = sq[2], HC = sq[3];
+  const double cnt = s[loss_off_t(Q, W) + t], n = s[loss_off_n(Q, W)];
   const double den = S + cnt + 1.0;
   cost_mask[i] = n > 0 ? (float)((G - sx) / n) : 0.f;
   cost_dice[i] = (float)(1.0 - (2.0 * ss + 1.0) / den);
@@ -230,27 +267,64 @@ __global__ void __launch_bounds__(128)
 // d(sum_i coef-weighted losses)/dx: for the query's matched target t (match[b,q], -1 = unmatched)
 //   grad = a (sig - tgt) + sig (1 - sig) (c1 - tgt c2),   (a, c1, c2) = coef[b,q,:]
 // with a = g_mask / (M n), c1 = g_dice num / (M den^2), c2 = 2 g_dice / (M den)   (criterion.py:27-72 differentiated).
-template <typename I>
-__global__ void __launch_bounds__(256)
-    k_mask_loss_bwd(const float* __restrict__ logits, I total, int Q, const uint32_t* __restrict__ bits, int W,
-                    const uint8_t* __restrict__ sel, const int32_t* __restrict__ scene_offsets, int B, const int32_t* __restrict__ match,
-                    const float* __restrict__ coef, float* __restrict__ grad) {
-  for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
-    const I row = i / (I)Q;
-    const int q = (int)(i - row * (I)Q);
-    const int b = scene_of_row(scene_offsets, B, (int64_t)row);
-    const int t = match[b * Q + q];
-    float g = 0.f;
-    if (t >= 0 && (sel == nullptr || sel[row] != 0)) {
-      const float x = logits[i];
-      const float e = __expf(-fabsf(x));
-      const float inv = __fdividef(1.f, 1.f + e);
-      const float s = x >= 0.f ? inv : e * inv;
-      const float tgt = (float)((bits[(int64_t)row * W + (t >> 5)] >> (t & 31)) & 1u);
-      const float* c = coef + (b * Q + q) * 3;
-      g = c[0] * (s - tgt) + s * (1.f - s) * (c[1] - tgt * c[2]);
+// Same shape as k_mask_stats: lane = query, so the query's target and coefficients live in registers for the whole scene and
+// the target word of a row is one broadcast load.
+template <int QC>
+__global__ void __launch_bounds__(kLossWarps * 32)
+    k_mask_loss_bwd(const float* __restrict__ logits, int Q, const uint32_t* __restrict__ bits, int W, const uint8_t* __restrict__ sel,
+                    const int32_t* __restrict__ scene_offsets, const int32_t* __restrict__ match, const float* __restrict__ coef,
+                    float* __restrict__ grad) {
+  const int r = blockIdx.x, b = blockIdx.y;
+  const int64_t s0 = scene_offsets[b], s1 = scene_offsets[b + 1];
+  const int64_t row0 = s0 + (int64_t)r * kLossRows;
+  if (row0 >= s1) return;
+  const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t a0 = row0 + (int64_t)wi * (kLossRows / kLossWarps), a1 = min(min(s1, row0 + kLossRows), a0 + (kLossRows / kLossWarps));
+  int tw[QC], tb[QC];
+  float ca[QC], c1[QC], c2[QC];
+#pragma unroll
+  for (int j = 0; j < QC; ++j) {
+    const int q = j * 32 + lane;
+    const int t = q < Q ? match[b * Q + q] : -1;
+    tw[j] = t >= 0 ? (t >> 5) : -1;
+    tb[j] = t & 31;
+    const float* c = coef + (int64_t)(b * Q + (q < Q ? q : 0)) * 3;
+    ca[j] = c[0], c1[j] = c[1], c2[j] = c[2];
+  }
+  for (int64_t base = a0; base < a1; base += kLossU) {
+    float x[kLossU][QC];
+    uint32_t wd[kLossU][QC];
+    bool keep[kLossU];
+#pragma unroll
+    for (int u = 0; u < kLossU; ++u) {
+      const int64_t row = base + u;
+      const bool in = row < a1;
+      keep[u] = in && (sel == nullptr || sel[row] != 0);
+#pragma unroll
+      for (int j = 0; j < QC; ++j) {
+        const int q = j * 32 + lane;
+        x[u][j] = (in && q < Q) ? logits[row * Q + q] : 0.f;
+        wd[u][j] = (in && tw[j] >= 0) ? bits[row * W + tw[j]] : 0u;
+      }
     }
-    grad[i] = g;
+#pragma unroll
+    for (int u = 0; u < kLossU; ++u) {
+      const int64_t row = base + u;
+      if (row >= a1) break;
+#pragma unroll
+      for (int j = 0; j < QC; ++j) {
+        const int q = j * 32 + lane;
+        float gv = 0.f;
+        if (keep[u] && tw[j] >= 0) {
+          const float e = __expf(-fabsf(x[u][j]));
+          const float inv = __fdividef(1.f, 1.f + e);
+          const float s = x[u][j] >= 0.f ? inv : e * inv;
+          const float tgt = (float)((wd[u][j] >> tb[j]) & 1u);
+          gv = ca[j] * (s - tgt) + s * (1.f - s) * (c1[j] - tgt * c2[j]);
+        }
+        if (q < Q) grad[row * Q + q] = gv;
+      }
+    }
   }
 }
 
@@ -258,17 +332,18 @@ inline int64_t loss_ranges(int64_t max_scene_rows) { return max_scene_rows > 0 ?
 
 template <int QC>
 int launch_mask_stats(dim3 grid, cudaStream_t st, const float* logits, int Q, const uint32_t* bits, int W, const uint8_t* sel,
-                      const int32_t* scene_offsets, float2* part_qt, float4* part_q, int32_t* part_t, int32_t* part_n, int R_max) {
+                      const int32_t* scene_offsets, float* part, int R_max) {
   constexpr int QP = QC * 32;
-  const size_t smem = (size_t)kLossWarps * 32 * QP * sizeof(float2) + (size_t)kLossWarps * QP * sizeof(float4) +
-                      (size_t)(kLossWarps * 32 + kLossWarps) * sizeof(int32_t);
+  constexpr int WARPS = QC <= 2 ? kLossWarps : 4;
+  const size_t smem = (size_t)WARPS * 32 * QP * sizeof(float2) + (size_t)WARPS * QP * sizeof(float4) +
+                      (size_t)(WARPS * 32 + WARPS) * sizeof(int32_t);
   static bool attr_set = false;
   if (smem > 48 * 1024 && !attr_set) {
-    if (cudaFuncSetAttribute(k_mask_stats<QC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(k_mask_stats<QC, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return fail("mk_mask_costs", "cannot reserve shared memory");
     attr_set = true;
   }
-  k_mask_stats<QC><<<grid, kLossWarps * 32, smem, st>>>(logits, Q, bits, W, sel, scene_offsets, part_qt, part_q, part_t, part_n, R_max);
+  k_mask_stats<QC, WARPS><<<grid, WARPS * 32, smem, st>>>(logits, Q, bits, W, sel, scene_offsets, part, R_max);
   return 0;
 }
 
@@ -288,8 +363,8 @@ int mk_target_bits(const uint8_t* masks, int T, int64_t n_scene, int W, uint32_t
 }
 
 int64_t mk_mask_costs_workspace_bytes(int B, int64_t max_scene_rows, int Q, int W) {
-  const int64_t slots = (int64_t)B * loss_ranges(max_scene_rows);
-  return slots * ((int64_t)W * 32 * Q * 8 + (int64_t)Q * 16 + (int64_t)W * 32 * 4 + 4) + 64;
+  const int64_t L = loss_row_len(Q, W);
+  return (int64_t)B * loss_ranges(max_scene_rows) * L * 4 + (int64_t)B * L * 8 + 64;
 }
 
 int mk_mask_costs(const float* logits, int64_t n, int Q, const uint32_t* bits, int W, const uint8_t* row_select,
@@ -302,46 +377,41 @@ int mk_mask_costs(const float* logits, int64_t n, int Q, const uint32_t* bits, i
   MK_REQUIRE(max_scene_rows >= 0 && max_scene_rows <= n, "max_scene_rows out of range");
   MK_REQUIRE(workspace_bytes >= mk_mask_costs_workspace_bytes(B, max_scene_rows, Q, W), "workspace too small");
   const int R_max = (int)loss_ranges(max_scene_rows);
-  const int64_t slots = (int64_t)B * R_max;
-  unsigned char* ws = (unsigned char*)workspace;
-  float4* part_q = (float4*)ws;  // 16-byte aligned first
-  ws += slots * Q * 16;
-  float2* part_qt = (float2*)ws;
-  ws += slots * W * 32 * Q * 8;
-  int32_t* part_t = (int32_t*)ws;
-  ws += slots * W * 32 * 4;
-  int32_t* part_n = (int32_t*)ws;
+  const int L = loss_row_len(Q, W);
+  double* sums = (double*)workspace;  // [B, L]
+  float* part = (float*)((unsigned char*)workspace + (((int64_t)B * L * 8 + 15) & ~15ll));  // [B, R_max, L]
   if (n > 0 && max_scene_rows > 0) {
     dim3 grid((unsigned)R_max, (unsigned)B, (unsigned)W);
     int rc = 0;
     switch ((Q + 31) / 32) {
-      case 1: rc = launch_mask_stats<1>(grid, st, logits, Q, bits, W, row_select, scene_offsets, part_qt, part_q, part_t, part_n, R_max); break;
-      case 2: rc = launch_mask_stats<2>(grid, st, logits, Q, bits, W, row_select, scene_offsets, part_qt, part_q, part_t, part_n, R_max); break;
-      case 3: rc = launch_mask_stats<3>(grid, st, logits, Q, bits, W, row_select, scene_offsets, part_qt, part_q, part_t, part_n, R_max); break;
-      default: rc = launch_mask_stats<4>(grid, st, logits, Q, bits, W, row_select, scene_offsets, part_qt, part_q, part_t, part_n, R_max); break;
+      case 1: rc = launch_mask_stats<1>(grid, st, logits, Q, bits, W, row_select, scene_offsets, part, R_max); break;
+      case 2: rc = launch_mask_stats<2>(grid, st, logits, Q, bits, W, row_select, scene_offsets, part, R_max); break;
+      case 3: rc = launch_mask_stats<3>(grid, st, logits, Q, bits, W, row_select, scene_offsets, part, R_max); break;
+      default: rc = launch_mask_stats<4>(grid, st, logits, Q, bits, W, row_select, scene_offsets, part, R_max); break;
     }
     if (rc) return rc;
     if (check_launch(__func__)) return 1;
   }
+  k_loss_merge<<<dim3((unsigned)ceil_div(L, 32), (unsigned)B), dim3(32, 32), 0, st>>>(part, scene_offsets, L, R_max, sums);
   const int64_t total = (int64_t)B * Q * 32 * W;
-  k_mask_costs_final<<<(unsigned)ceil_div(total, 128), 128, 0, st>>>(part_qt, part_q, part_t, part_n, scene_offsets, B, Q, W, R_max,
-                                                                    cost_mask, cost_dice, dice_den, mask_score, n_rows);
+  k_mask_costs_final<<<(unsigned)ceil_div(total, 128), 128, 0, st>>>(sums, B, Q, W, cost_mask, cost_dice, dice_den, mask_score, n_rows);
   return check_launch(__func__);
 }
 
 int mk_mask_loss_bwd(const float* logits, int64_t n, int Q, const uint32_t* bits, int W, const uint8_t* row_select,
-                     const int32_t* scene_offsets, int B, const int32_t* match, const float* coef, float* grad, void* stream_) {
+                     const int32_t* scene_offsets, int B, int64_t max_scene_rows, const int32_t* match, const float* coef, float* grad,
+                     void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  MK_REQUIRE(Q >= 1 && W >= 1 && B >= 1, "bad sizes");
-  const int64_t total = n * Q;
-  if (total == 0) return 0;
-  int64_t blocks = ceil_div(total, 256);
-  const int64_t cap = 16 * (int64_t)num_sms();
-  const unsigned g = (unsigned)(blocks > cap ? cap : blocks);
-  if (total < (1ll << 31) - (int64_t)g * 256)
-    k_mask_loss_bwd<int32_t><<<g, 256, 0, st>>>(logits, (int32_t)total, Q, bits, W, row_select, scene_offsets, B, match, coef, grad);
-  else
-    k_mask_loss_bwd<int64_t><<<g, 256, 0, st>>>(logits, total, Q, bits, W, row_select, scene_offsets, B, match, coef, grad);
+  MK_REQUIRE(Q >= 1 && Q <= 128 && W >= 1 && B >= 1 && B <= 65535, "bad sizes");
+  MK_REQUIRE(max_scene_rows >= 0 && max_scene_rows <= n, "max_scene_rows out of range");
+  if (n == 0 || max_scene_rows == 0) return 0;
+  dim3 grid((unsigned)loss_ranges(max_scene_rows), (unsigned)B);
+  switch ((Q + 31) / 32) {
+    case 1: k_mask_loss_bwd<1><<<grid, kLossWarps * 32, 0, st>>>(logits, Q, bits, W, row_select, scene_offsets, match, coef, grad); break;
+    case 2: k_mask_loss_bwd<2><<<grid, kLossWarps * 32, 0, st>>>(logits, Q, bits, W, row_select, scene_offsets, match, coef, grad); break;
+    case 3: k_mask_loss_bwd<3><<<grid, kLossWarps * 32, 0, st>>>(logits, Q, bits, W, row_select, scene_offsets, match, coef, grad); break;
+    default: k_mask_loss_bwd<4><<<grid, kLossWarps * 32, 0, st>>>(logits, Q, bits, W, row_select, scene_offsets, match, coef, grad); break;
+  }
   return check_launch(__func__);
 }
 

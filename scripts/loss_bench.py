@@ -77,7 +77,7 @@ grads = [torch.empty(n, Q, device=dev) for _ in range(D)]
 def bwd():
     i[0] += 1
     k = i[0] % D
-    lib.call("mk_mask_loss_bwd", lib.p(pm[k].detach()), n, Q, lib.p(tg.bits), tg.W, None, lib.p(tg.scene_offsets), 1, lib.p(m), lib.p(coef),
+    lib.call("mk_mask_loss_bwd", lib.p(pm[k].detach()), n, Q, lib.p(tg.bits), tg.W, None, lib.p(tg.scene_offsets), 1, n, lib.p(m), lib.p(coef),
              lib.p(grads[k]), lib.stream())
 
 
