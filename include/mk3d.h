@@ -239,7 +239,7 @@ int64_t mk_mask_costs_workspace_bytes(int B, int64_t max_scene_rows, int Q, int 
  *   cost_mask [B,Q,Tp]  mean_n BCEWithLogits(x[n,q], tgt[t,n])                        (matcher.py:39-56)
  *   cost_dice [B,Q,Tp]  1 - (2 sum_n sig(x) tgt + 1) / (sum_n sig(x) + sum_n tgt + 1)  (matcher.py:17-33)
  *   dice_den  [B,Q,Tp]  the dice denominator (backward needs it)
- *   mask_score [B,Q]    sum_n sig(x) [x > 0] / (sum_n [x > 0] + 1e-6)                  (trainer.py:389-392)
+ *   mask_score [B,Q]    sum_n sig(x) [x > 0] / (sum_n [x > 0] + 1e-6)                  (trainer.py:389-392); NULL = not wanted
  *   n_rows [B]          rows that took part (scene size, or the selected rows)
  * row_select uint8 [n] or NULL: rows with 0 are left out (the matcher's / criterion's `point_idx` subset when
  * num_points != -1, matcher.py:125-127, criterion.py:181-182).  max_scene_rows (host) = largest scene of the batch. */

@@ -111,30 +111,40 @@ def _sizes_of(pm, targets) -> List[int]:
 
 
 class MaskStats:
+    """cost_mask / cost_dice / dice_den [..., B, Q, 32 W], n_rows [..., B] (leading dim = decoder outputs when stacked),
+    mask_score [B, Q] or None, row_select = the uint8 row mask(s) the sums were taken over (None = all rows)."""
     __slots__ = ("cost_mask", "cost_dice", "dice_den", "mask_score", "n_rows", "row_select")
 
+    def __init__(self, buf, n_rows, mask_score=None, row_select=None):
+        self.cost_mask, self.cost_dice, self.dice_den = buf.unbind(-4)
+        self.n_rows, self.mask_score, self.row_select = n_rows, mask_score, row_select
 
-def mask_costs(logits: torch.Tensor, tg: PackedTargets, row_select: Optional[torch.Tensor] = None) -> MaskStats:
-    """One pass over fp32 logits [sum N, Q] -> cost_mask / cost_dice / dice_den [B, Q, 32 W], mask_score [B, Q], n_rows [B]."""
-    lib.require_cuda()
+
+def _f32c(logits: torch.Tensor) -> torch.Tensor:
     x = logits.detach()
-    if x.dtype != torch.float32:
-        x = x.float()
-    x = x.contiguous()
+    return (x if x.dtype == torch.float32 else x.float()).contiguous()
+
+
+def mask_costs(logits: torch.Tensor, tg: PackedTargets, row_select: Optional[torch.Tensor] = None, want_score: bool = False,
+               out: Optional[torch.Tensor] = None, n_rows: Optional[torch.Tensor] = None) -> MaskStats:
+    """One pass over fp32 logits [sum N, Q] -> cost_mask / cost_dice / dice_den [B, Q, 32 W], n_rows [B] (+ mask_score [B, Q]).
+    `out` [3, B, Q, 32 W] / `n_rows` [B]: write into slices of a caller's stacked buffers."""
+    lib.require_cuda()
+    x = _f32c(logits)
     n, Q = x.shape
     assert n == tg.bits.shape[0], f"logits have {n} rows, targets were packed for {tg.bits.shape[0]}"
     B, W = tg.B, tg.W
     dev = x.device
-    out = torch.empty((3, B, Q, 32 * W), dtype=torch.float32, device=dev)
-    score = torch.empty((B, Q), dtype=torch.float32, device=dev)
-    n_rows = torch.empty((B,), dtype=torch.float32, device=dev)
-    wsb = lib.query("mk_mask_costs_workspace_bytes", B, tg.max_rows, Q, W)
-    ws = lib.scratch(wsb, dev)
+    if out is None:
+        out = torch.empty((3, B, Q, 32 * W), dtype=torch.float32, device=dev)
+    if n_rows is None:
+        n_rows = torch.empty((B,), dtype=torch.float32, device=dev)
+    assert out.is_contiguous() and tuple(out.shape) == (3, B, Q, 32 * W) and n_rows.is_contiguous()
+    score = torch.empty((B, Q), dtype=torch.float32, device=dev) if want_score else None
+    ws = lib.scratch(lib.query("mk_mask_costs_workspace_bytes", B, tg.max_rows, Q, W), dev)
     lib.call("mk_mask_costs", lib.p(x), n, Q, lib.p(tg.bits), W, lib.p(row_select), lib.p(tg.scene_offsets), B, tg.max_rows,
-             out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), lib.p(score), lib.p(n_rows), lib.p(ws), ws.numel(), lib.stream())
-    s = MaskStats()
-    s.cost_mask, s.cost_dice, s.dice_den, s.mask_score, s.n_rows, s.row_select = out[0], out[1], out[2], score, n_rows, row_select
-    return s
+             out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), lib.p(score), n_rows.data_ptr(), lib.p(ws), ws.numel(), lib.stream())
+    return MaskStats(out, n_rows, score, row_select)
 
 
 def mask_scores(pred_mask: torch.Tensor) -> torch.Tensor:
@@ -145,7 +155,7 @@ def mask_scores(pred_mask: torch.Tensor) -> torch.Tensor:
     dev = pred_mask.device
     tg = PackedTargets(torch.zeros((n, 1), dtype=torch.int32, device=dev), torch.tensor([0, n], dtype=torch.int32, device=dev), [n], [0],
                        [], None, None)
-    return mask_costs(pred_mask, tg).mask_score[0]
+    return mask_costs(pred_mask, tg, want_score=True).mask_score[0]
 
 
 def _row_subset(tg: PackedTargets, num_points: float, device) -> torch.Tensor:
@@ -170,11 +180,13 @@ class HungarianMatcher(nn.Module):
         self.num_points = num_points
 
     def cost_matrix(self, pred_class: torch.Tensor, stats: MaskStats, tg: PackedTargets) -> torch.Tensor:
-        """C [B, Q, 32 W] on the device (matcher.py:103-160); columns >= T of a scene are padding."""
-        prob = pred_class.detach().float().softmax(-1)  # [B, Q, C+1]
-        Q = prob.shape[1]
-        cc = -prob.gather(2, tg.labels_dev[:, None, :].expand(-1, Q, -1))
-        cc = torch.where(tg.ignore_dev[:, None, :], torch.full_like(cc, -1.0), cc)  # matcher.py:117
+        """C [..., B, Q, 32 W] on the device (matcher.py:103-160) for pred_class [..., B, Q, C+1]; columns >= T of a scene are
+        padding."""
+        prob = pred_class.detach().float().softmax(-1)
+        lead = (1,) * (prob.dim() - 3)
+        shape = (*prob.shape[:-1], tg.labels_dev.shape[1])
+        cc = -prob.gather(-1, tg.labels_dev.view(*lead, tg.B, 1, -1).expand(shape))
+        cc = torch.where(tg.ignore_dev.view(*lead, tg.B, 1, -1), torch.full_like(cc, -1.0), cc)  # matcher.py:117
         return self.cost_mask * stats.cost_mask + self.cost_class * cc + self.cost_dice * stats.cost_dice
 
     @staticmethod
@@ -210,37 +222,47 @@ class HungarianMatcher(nn.Module):
 
 
 class _MaskLossFn(torch.autograd.Function):
-    """(loss_mask, loss_dice) of the matched pairs of one decoder output, summed over the scenes of the batch
-    (criterion.py:168-213).  Forward = gathers from the cost matrices; backward = mk_mask_loss_bwd."""
+    """(loss_mask, loss_dice) of the matched pairs of D decoder outputs at once, each summed over the scenes of the batch
+    (criterion.py:168-213) -> [D, 2].  Forward = gathers from the stacked cost matrices; backward = one mk_mask_loss_bwd per
+    output.  `stats` fields carry a leading D dimension, match int32 [D, B, Q], inv_m fp32 [D, B] = 1 / matched pairs."""
 
     @staticmethod
-    def forward(ctx, logits, tg: PackedTargets, stats: MaskStats, match: torch.Tensor, inv_m: torch.Tensor):
-        valid = match >= 0
+    def forward(ctx, tg: PackedTargets, stats: MaskStats, match: torch.Tensor, inv_m: torch.Tensor, *logits):
         m = match.long().clamp(min=0).unsqueeze(-1)
-        live = (valid & (stats.n_rows > 0)[:, None]).float()  # no points, no loss (criterion.py:197-203)
-        cm = stats.cost_mask.gather(2, m).squeeze(-1) * live
-        cd = stats.cost_dice.gather(2, m).squeeze(-1) * live
-        den = stats.dice_den.gather(2, m).squeeze(-1)
-        ctx.tg, ctx.row_select = tg, stats.row_select
-        ctx.save_for_backward(logits, match, inv_m, cd, den, stats.n_rows, live)
-        return torch.stack([(cm.sum(1) * inv_m).sum(), (cd.sum(1) * inv_m).sum()])
+        live = ((match >= 0) & (stats.n_rows > 0).unsqueeze(-1)).float()  # no points, no loss (criterion.py:197-203)
+        cm = stats.cost_mask.gather(-1, m).squeeze(-1) * live
+        cd = stats.cost_dice.gather(-1, m).squeeze(-1) * live
+        den = stats.dice_den.gather(-1, m).squeeze(-1)
+        ctx.tg = tg
+        ctx.row_select = stats.row_select if isinstance(stats.row_select, (list, tuple)) else [stats.row_select] * len(logits)
+        ctx.logits = logits
+        ctx.save_for_backward(match, inv_m, cd, den, stats.n_rows, live)
+        return torch.stack([(cm.sum(-1) * inv_m).sum(-1), (cd.sum(-1) * inv_m).sum(-1)], dim=-1)
 
     @staticmethod
     def backward(ctx, g):
-        logits, match, inv_m, cd, den, n_rows, live = ctx.saved_tensors
+        match, inv_m, cd, den, n_rows, live = ctx.saved_tensors
         tg = ctx.tg
         g = g.float()
-        a = g[0] * inv_m[:, None] / n_rows.clamp(min=1.0)[:, None] * live
-        c1 = g[1] * inv_m[:, None] * (1.0 - cd) / den * live  # num / den^2 = (1 - cost_dice) / den
-        c2 = 2.0 * g[1] * inv_m[:, None] / den * live
-        coef = torch.stack([a, c1, c2], dim=-1).contiguous()
-        x = logits.detach()
-        x = (x if x.dtype == torch.float32 else x.float()).contiguous()
-        grad = torch.empty_like(x)
-        n, Q = x.shape
-        lib.call("mk_mask_loss_bwd", lib.p(x), n, Q, lib.p(tg.bits), tg.W, lib.p(ctx.row_select), lib.p(tg.scene_offsets), tg.B,
-                 tg.max_rows, lib.p(match), lib.p(coef), lib.p(grad), lib.stream())
-        return grad.to(logits.dtype), None, None, None, None
+        gm, gd, im = g[:, 0, None, None], g[:, 1, None, None], inv_m.unsqueeze(-1)
+        a = gm * im / n_rows.clamp(min=1.0).unsqueeze(-1) * live
+        c1 = gd * im * (1.0 - cd) / den * live  # num / den^2 = (1 - cost_dice) / den
+        c2 = 2.0 * gd * im / den * live
+        coef = torch.stack([a, c1, c2], dim=-1).contiguous()  # [D, B, Q, 3]
+        match = match.contiguous()
+        grads = []
+        st = lib.stream()
+        for d, lg in enumerate(ctx.logits):
+            if not ctx.needs_input_grad[4 + d]:
+                grads.append(None)
+                continue
+            x = _f32c(lg)
+            grad = torch.empty_like(x)
+            n, Q = x.shape
+            lib.call("mk_mask_loss_bwd", lib.p(x), n, Q, lib.p(tg.bits), tg.W, lib.p(ctx.row_select[d]), lib.p(tg.scene_offsets), tg.B,
+                     tg.max_rows, match[d].data_ptr(), coef[d].data_ptr(), lib.p(grad), st)
+            grads.append(grad if lg.dtype == torch.float32 else grad.to(lg.dtype))
+        return (None, None, None, None, *grads)
 
 
 class SetCriterion(nn.Module):
@@ -260,44 +282,63 @@ class SetCriterion(nn.Module):
         self.register_buffer("empty_weight", empty_weight)
         self.num_points, self.oversample_ratio, self.importance_sample_ratio = num_points, oversample_ratio, importance_sample_ratio
 
-    # -- per-output pieces -------------------------------------------------------------------------------------------
-    def _target_classes(self, matches, tg: PackedTargets, Q: int) -> torch.Tensor:
-        tc = torch.full((tg.B, Q), self.num_classes, dtype=torch.int64)  # criterion.py:152-158
-        for b, (iq, it) in enumerate(matches):
-            tc[b, iq] = tg.labels_host[b][it]
-        return tc
+    # -- pieces, each for D decoder outputs at once (host work per step, not per output) -------------------------------------
+    def _tables(self, matches_all, tg: PackedTargets, Q: int):
+        """matches_all[d][b] = (query idx, target idx) -> target classes int64 [D, B, Q] (criterion.py:152-158), matched target
+        int32 [D, B, Q] (-1 = none), 1 / matched pairs fp32 [D, B] (num_masks = target_mask.shape[0], criterion.py:190)."""
+        D = len(matches_all)
+        tc = torch.full((D, tg.B, Q), self.num_classes, dtype=torch.int64)
+        m = torch.full((D, tg.B, Q), -1, dtype=torch.int32)
+        inv = torch.zeros((D, tg.B), dtype=torch.float32)
+        for d, matches in enumerate(matches_all):
+            for b, (iq, it) in enumerate(matches):
+                tc[d, b, iq] = tg.labels_host[b][it]
+                m[d, b, iq] = it.to(torch.int32)
+                inv[d, b] = 1.0 / len(it) if len(it) > 0 else 0.0
+        return tc, m, inv
 
     @staticmethod
     def _match_table(matches, tg: PackedTargets, Q: int):
+        """One decoder output: matched target int32 [B, Q] and 1 / matched pairs [B]."""
         m = torch.full((tg.B, Q), -1, dtype=torch.int32)
         inv = torch.zeros(tg.B, dtype=torch.float32)
         for b, (iq, it) in enumerate(matches):
             m[b, iq] = it.to(torch.int32)
-            inv[b] = 1.0 / len(it) if len(it) > 0 else 0.0  # num_masks = target_mask.shape[0], criterion.py:190
+            inv[b] = 1.0 / len(it) if len(it) > 0 else 0.0
         return m, inv
 
-    def loss_labels(self, pred_class, target_classes):
-        """criterion.py:141-166"""
-        return {"loss_ce": F.cross_entropy(pred_class.float().transpose(1, 2), target_classes, weight=self.empty_weight)}
+    def loss_labels(self, pred_class: torch.Tensor, target_classes: torch.Tensor) -> torch.Tensor:
+        """criterion.py:141-166 for pred_class [D, B, Q, C+1], target_classes [D, B, Q] -> [D]: F.cross_entropy with class
+        weights and mean reduction = sum(w[target] nll) / sum(w[target]), per decoder output."""
+        D = pred_class.shape[0]
+        ce = F.cross_entropy(pred_class.float().flatten(0, 1).transpose(1, 2), target_classes.flatten(0, 1), weight=self.empty_weight,
+                             reduction="none")
+        return ce.view(D, -1).sum(1) / self.empty_weight[target_classes].view(D, -1).sum(1)
 
-    def loss_masks(self, logits, tg, stats, match, inv_m):
-        """criterion.py:168-213"""
-        if self.num_points != -1:  # a fresh random subset for the loss (criterion.py:181-182)
-            stats = mask_costs(logits, tg, _row_subset(tg, self.num_points, logits.device))
-        lm = _MaskLossFn.apply(logits, tg, stats, match, inv_m)
-        return {"loss_mask": lm[0], "loss_dice": lm[1]}
+    def loss_masks(self, logits: Sequence[torch.Tensor], tg, stats: MaskStats, match, inv_m) -> torch.Tensor:
+        """criterion.py:168-213 for D decoder outputs -> [D, 2] = (loss_mask, loss_dice)."""
+        if self.num_points != -1:  # a fresh random subset for the loss (criterion.py:181-182), drawn per output in order
+            D, dev = len(logits), logits[0].device
+            buf = torch.empty((D, 3, tg.B, logits[0].shape[1], 32 * tg.W), dtype=torch.float32, device=dev)
+            nr = torch.empty((D, tg.B), dtype=torch.float32, device=dev)
+            sels = [_row_subset(tg, self.num_points, dev) for _ in range(D)]
+            for d in range(D):
+                mask_costs(logits[d], tg, sels[d], out=buf[d], n_rows=nr[d])
+            stats = MaskStats(buf, nr, None, sels)
+        return _MaskLossFn.apply(tg, stats, match, inv_m, *logits)
 
-    def _losses_of(self, pred_class, logits, tg, stats, matches):
-        Q = pred_class.shape[1]
-        dev = pred_class.device
+    def _losses(self, cls_stack, logits, tg, stats, matches_all):
+        Q = cls_stack.shape[2]
+        dev = cls_stack.device
+        tc, m, inv = self._tables(matches_all, tg, Q)
         out = {}
         for name in self.loss_names:
             assert name in ("labels", "masks"), f"Invalid loss '{name}'"
             if name == "labels":
-                out.update(self.loss_labels(pred_class, self._target_classes(matches, tg, Q).to(dev, non_blocking=True)))
+                out["loss_ce"] = self.loss_labels(cls_stack, tc.to(dev, non_blocking=True))
             else:
-                m, inv = self._match_table(matches, tg, Q)
-                out.update(self.loss_masks(logits, tg, stats, m.to(dev, non_blocking=True), inv.to(dev, non_blocking=True)))
+                lm = self.loss_masks(logits, tg, stats, m.to(dev, non_blocking=True), inv.to(dev, non_blocking=True))
+                out["loss_mask"], out["loss_dice"] = lm[:, 0], lm[:, 1]
         return out
 
     # -- forward -----------------------------------------------------------------------------------------------------
@@ -310,7 +351,9 @@ class SetCriterion(nn.Module):
         sizes = _sizes_of(pm_all[-1], targets)
         dev = cls_all[-1].device
         tg = pack_targets(targets, sizes, dev)
-        logits = [_batched_logits(pm, sizes) for pm in pm_all]
+        logits = [_batched_logits(pm_all[d], sizes) for d in order]
+        cls = [cls_all[d] for d in order]
+        D, Q = len(order), cls[0].shape[1]
 
         # num_masks (criterion.py:243-252) only feeds arguments the loss functions overwrite or ignore; keep its collective so
         # that ranks running this class and ranks running the reference's stay in step
@@ -318,21 +361,33 @@ class SetCriterion(nn.Module):
             nm = torch.as_tensor([float(sum(tg.n_targets))], dtype=torch.float, device=dev)
             torch.distributed.all_reduce(nm)
 
-        losses = {}
+        per_output = {}
         with lib.stream_scope():
             if self.matcher.num_points == -1:
                 with torch.no_grad():
-                    stats = {d: mask_costs(logits[d], tg) for d in order}
-                    C = torch.stack([self.matcher.cost_matrix(cls_all[d], stats[d], tg) for d in order]).cpu()  # the one sync
-                matches = {d: self.matcher.assign(C[i], tg) for i, d in enumerate(order)}
-            for i, d in enumerate(order):
-                if self.matcher.num_points != -1:  # keep the reference's order of random draws: matcher, then loss, per output
-                    m, st = self.matcher.memory_efficient_forward({"pred_class": cls_all[d], "pred_mask": logits[d]}, targets, tg, True)
-                    matches, stats = {d: m}, {d: st}
-                l_dict = self._losses_of(cls_all[d], logits[d], tg, stats[d], matches[d])
-                suffix = "" if i == 0 else f"_mask_module_{d}"
-                losses.update({k + suffix: v for k, v in l_dict.items()})
-        self.last_matches = matches if self.matcher.num_points == -1 else None
+                    buf = torch.empty((D, 3, tg.B, Q, 32 * tg.W), dtype=torch.float32, device=dev)
+                    nr = torch.empty((D, tg.B), dtype=torch.float32, device=dev)
+                    for i in range(D):
+                        mask_costs(logits[i], tg, out=buf[i], n_rows=nr[i])
+                    stats = MaskStats(buf, nr)
+                    C = self.matcher.cost_matrix(torch.stack(cls), stats, tg).cpu()  # the one device -> host copy of the step
+                matches_all = [self.matcher.assign(C[i], tg) for i in range(D)]
+                per_output = self._losses(torch.stack(cls), logits, tg, stats, matches_all)
+            else:  # keep the reference's order of random draws: matcher subset, then loss subset, output by output
+                matches_all, rows = [], []
+                for i in range(D):
+                    m, st = self.matcher.memory_efficient_forward({"pred_class": cls[i], "pred_mask": logits[i]}, targets, tg, True)
+                    matches_all.append(m)
+                    one = self._losses(cls[i][None], [logits[i]], tg, MaskStats(torch.stack([st.cost_mask, st.cost_dice, st.dice_den])[None],
+                                                                             st.n_rows[None], None, [st.row_select]), [m])
+                    rows.append(one)
+                per_output = {k: torch.cat([r[k] for r in rows]) for k in rows[0]}
+        losses = {}
+        for i, d in enumerate(order):
+            suffix = "" if i == 0 else f"_mask_module_{d}"
+            for k, v in per_output.items():
+                losses[k + suffix] = v[i]
+        self.last_matches = {d: matches_all[i] for i, d in enumerate(order)}
         return losses
 
     def __repr__(self):

@@ -41,13 +41,19 @@ __global__ void __launch_bounds__(256) k_target_bits(const uint8_t* __restrict__
   }
 }
 
+__device__ __forceinline__ float fast_rcp(float v) {  // MUFU.RCP, 1 ulp; v in [1, 2]
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+
 struct SigSp {
   float s, sp;
 };
 // sigmoid(x) and softplus(x) = max(x,0) + log1p(exp(-|x|)) from one exponential
 __device__ __forceinline__ SigSp sig_softplus(float x) {
   const float e = __expf(-fabsf(x));
-  const float inv = __fdividef(1.f, 1.f + e);
+  const float inv = fast_rcp(1.f + e);
   // log1p(e), e in (0, 1]: three series terms below 2^-6 (relative error < 1e-6), MUFU log above (absolute error < 4e-7 on
   // values > 0.0155)
   const float l = e < 0.015625f ? e * (1.f - e * (0.5f - e * (1.f / 3.f))) : __logf(1.f + e);
@@ -73,7 +79,7 @@ __device__ __forceinline__ void flush_run(float2* acc_w, uint32_t cur, const flo
   }
 }
 
-// A group of kLossU consecutive rows held by a warp, lane = query (QC chunks of 32): logits, target word, row flag.
+// A group of kLossU consecutive rows held by a warp, lane = query (QC chunks of 32): logits, target word, row flags.
 template <int QC>
 struct RowGroup {
   float x[kLossU][QC];
@@ -81,20 +87,33 @@ struct RowGroup {
   uint32_t keep;  // bit u: row exists and is selected
 };
 
+// px = logits + row * Q + lane, pb = bits + row * W + w, ps = row_select + row (or null) of the group's first row; `rows` of the
+// group exist (kLossU for every group but the last).  The full-group path carries no per-row predicates or 64-bit multiplies.
 template <int QC>
-__device__ __forceinline__ void load_group(RowGroup<QC>& g, const float* __restrict__ logits, int Q, const uint32_t* __restrict__ bits,
-                                           int W, int w, const uint8_t* __restrict__ sel, int64_t base, int64_t end, int lane) {
-  g.keep = 0;
+__device__ __forceinline__ void load_group(RowGroup<QC>& g, const float* __restrict__ px, int Q, const uint32_t* __restrict__ pb, int W,
+                                           const uint8_t* __restrict__ ps, int rows, const bool (&qv)[QC]) {
+  if (rows == kLossU) {
+    g.keep = (1u << kLossU) - 1;
 #pragma unroll
-  for (int u = 0; u < kLossU; ++u) {
-    const int64_t row = base + u;
-    const bool in = row < end;
-    g.word[u] = in ? bits[row * W + w] : 0u;
-    if (in && (sel == nullptr || sel[row] != 0)) g.keep |= 1u << u;
+    for (int u = 0; u < kLossU; ++u) {
+      g.word[u] = pb[u * W];
 #pragma unroll
-    for (int j = 0; j < QC; ++j) {
-      const int q = j * 32 + lane;
-      g.x[u][j] = (in && q < Q) ? logits[row * Q + q] : 0.f;
+      for (int j = 0; j < QC; ++j) g.x[u][j] = qv[j] ? px[u * Q + j * 32] : 0.f;
+    }
+    if (ps != nullptr) {
+      g.keep = 0;
+#pragma unroll
+      for (int u = 0; u < kLossU; ++u) g.keep |= (ps[u] != 0 ? 1u : 0u) << u;
+    }
+  } else {
+    g.keep = 0;
+#pragma unroll
+    for (int u = 0; u < kLossU; ++u) {
+      const bool in = u < rows;
+      g.word[u] = in ? pb[u * W] : 0u;
+      if (in && (ps == nullptr || ps[u] != 0)) g.keep |= 1u << u;
+#pragma unroll
+      for (int j = 0; j < QC; ++j) g.x[u][j] = (in && qv[j]) ? px[u * Q + j * 32] : 0.f;
     }
   }
 }
@@ -113,7 +132,7 @@ __host__ __device__ inline int loss_row_len(int Q, int W) { return (loss_off_n(Q
 // of the current RUN of rows with identical target word in registers and adds them to the warp's private [32 targets][Q]
 // shared-memory accumulator only when the word changes (rows are in lexicographic voxel order, so runs are long).  Two groups
 // of 8 rows are in flight per warp (the next group is loaded before the current one is processed).
-template <int QC, int WARPS>
+template <int QC, int WARPS, bool SCORE>
 __global__ void __launch_bounds__(WARPS * 32)
     k_mask_stats(const float* __restrict__ logits, int Q, const uint32_t* __restrict__ bits, int W, const uint8_t* __restrict__ sel,
                  const int32_t* __restrict__ scene_offsets, float* __restrict__ part, int R_max) {
@@ -133,38 +152,77 @@ __global__ void __launch_bounds__(WARPS * 32)
   for (int i = lane; i < 32 * QP; i += 32) acc_w[i] = make_float2(0.f, 0.f);
 
   float ax[QC], as[QC], G[QC], S[QC], HS[QC], HC[QC];
+  bool qv[QC];
 #pragma unroll
-  for (int j = 0; j < QC; ++j) ax[j] = as[j] = G[j] = S[j] = HS[j] = HC[j] = 0.f;
+  for (int j = 0; j < QC; ++j) {
+    ax[j] = as[j] = G[j] = S[j] = HS[j] = HC[j] = 0.f;
+    qv[j] = j * 32 + lane < Q;
+  }
   uint32_t cur = 0;
   int cnt = 0, nsel = 0;
-  const int64_t a0 = row0 + (int64_t)wi * (kLossRows / WARPS), a1 = min(row1, a0 + (kLossRows / WARPS));
+  const int64_t a0 = row0 + (int64_t)wi * (kLossRows / WARPS);
+  const int nrows = (int)max((int64_t)0, min(row1 - a0, (int64_t)(kLossRows / WARPS)));
+  const float* px = logits + a0 * Q + lane;
+  const uint32_t* pb = bits + a0 * W + w;
+  const uint8_t* ps = sel != nullptr ? sel + a0 : nullptr;
+  const int stepx = kLossU * Q, stepb = kLossU * W;
   RowGroup<QC> g, nx;
-  if (a0 < a1) load_group<QC>(g, logits, Q, bits, W, w, sel, a0, a1, lane);
-  for (int64_t base = a0; base < a1; base += kLossU) {
-    if (base + kLossU < a1) load_group<QC>(nx, logits, Q, bits, W, w, sel, base + kLossU, a1, lane);
+  if (nrows > 0) load_group<QC>(g, px, Q, pb, W, ps, min(nrows, kLossU), qv);
+  for (int done = 0; done < nrows; done += kLossU) {
+    px += stepx, pb += stepb;
+    if (ps != nullptr) ps += kLossU;
+    const int left = nrows - done - kLossU;
+    if (left > 0) load_group<QC>(nx, px, Q, pb, W, ps, min(left, kLossU), qv);
+    uint32_t diff = g.keep ^ ((1u << kLossU) - 1);
 #pragma unroll
-    for (int u = 0; u < kLossU; ++u) {
-      if (!((g.keep >> u) & 1u)) continue;  // warp-uniform
-      ++nsel;
-      const uint32_t wd = g.word[u];
-      cnt += (wd >> lane) & 1u;
-      if (wd != cur) {
-        flush_run<QC>(acc_w, cur, ax, as, lane);
-        cur = wd;
+    for (int u = 0; u < kLossU; ++u) diff |= g.word[u] ^ cur;
+    if (diff == 0) {  // the whole group continues the current run (warp-uniform): straight-line accumulation
+      nsel += kLossU;
+      cnt += kLossU * ((cur >> lane) & 1u);
 #pragma unroll
-        for (int j = 0; j < QC; ++j) ax[j] = as[j] = 0.f;
+      for (int u = 0; u < kLossU; ++u) {
+#pragma unroll
+        for (int j = 0; j < QC; ++j) {
+          const float xv = g.x[u][j];
+          const SigSp v = sig_softplus(xv);
+          G[j] += v.sp;
+          S[j] += v.s;
+          if (SCORE) {
+            const bool pos = xv > 0.f;
+            HS[j] += pos ? v.s : 0.f;
+            HC[j] += pos ? 1.f : 0.f;
+          }
+          ax[j] += xv;
+          as[j] += v.s;
+        }
       }
+    } else {
 #pragma unroll
-      for (int j = 0; j < QC; ++j) {
-        const float xv = g.x[u][j];
-        const SigSp v = sig_softplus(xv);
-        G[j] += v.sp;
-        S[j] += v.s;
-        const bool pos = xv > 0.f;
-        HS[j] += pos ? v.s : 0.f;
-        HC[j] += pos ? 1.f : 0.f;
-        ax[j] += xv;
-        as[j] += v.s;
+      for (int u = 0; u < kLossU; ++u) {
+        if (!((g.keep >> u) & 1u)) continue;  // warp-uniform
+        ++nsel;
+        const uint32_t wd = g.word[u];
+        cnt += (wd >> lane) & 1u;
+        if (wd != cur) {
+          flush_run<QC>(acc_w, cur, ax, as, lane);
+          cur = wd;
+#pragma unroll
+          for (int j = 0; j < QC; ++j) ax[j] = as[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < QC; ++j) {
+          const float xv = g.x[u][j];
+          const SigSp v = sig_softplus(xv);
+          G[j] += v.sp;
+          S[j] += v.s;
+          if (SCORE) {
+            const bool pos = xv > 0.f;
+            HS[j] += pos ? v.s : 0.f;
+            HC[j] += pos ? 1.f : 0.f;
+          }
+          ax[j] += xv;
+          as[j] += v.s;
+        }
       }
     }
     g = nx;
@@ -259,7 +317,7 @@ __global__ void __launch_bounds__(128)
   cost_dice[i] = (float)(1.0 - (2.0 * ss + 1.0) / den);
   dice_den[i] = (float)den;
   if (t == 0) {
-    mask_score[b * Q + q] = (float)(HS / (HC + 1e-6));
+    if (mask_score != nullptr) mask_score[b * Q + q] = (float)(HS / (HC + 1e-6));
     if (q == 0) n_rows[b] = (float)n;
   }
 }
@@ -279,58 +337,80 @@ __global__ void __launch_bounds__(kLossWarps * 32)
   const int64_t row0 = s0 + (int64_t)r * kLossRows;
   if (row0 >= s1) return;
   const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t a0 = row0 + (int64_t)wi * (kLossRows / kLossWarps), a1 = min(min(s1, row0 + kLossRows), a0 + (kLossRows / kLossWarps));
+  const int64_t a0 = row0 + (int64_t)wi * (kLossRows / kLossWarps);
+  const int nrows = (int)max((int64_t)0, min(min(s1, row0 + kLossRows) - a0, (int64_t)(kLossRows / kLossWarps)));
   int tw[QC], tb[QC];
   float ca[QC], c1[QC], c2[QC];
+  bool qv[QC];
 #pragma unroll
   for (int j = 0; j < QC; ++j) {
     const int q = j * 32 + lane;
-    const int t = q < Q ? match[b * Q + q] : -1;
-    tw[j] = t >= 0 ? (t >> 5) : -1;
+    qv[j] = q < Q;
+    const int t = qv[j] ? match[b * Q + q] : -1;
+    tw[j] = t >= 0 ? (t >> 5) : 0;
     tb[j] = t & 31;
-    const float* c = coef + (int64_t)(b * Q + (q < Q ? q : 0)) * 3;
-    ca[j] = c[0], c1[j] = c[1], c2[j] = c[2];
+    const float* c = coef + (int64_t)(b * Q + (qv[j] ? q : 0)) * 3;
+    const bool live = t >= 0;  // unmatched query: all coefficients 0 -> gradient 0
+    ca[j] = live ? c[0] : 0.f, c1[j] = live ? c[1] : 0.f, c2[j] = live ? c[2] : 0.f;
   }
-  for (int64_t base = a0; base < a1; base += kLossU) {
+  const float* px = logits + a0 * Q + lane;
+  float* pg = grad + a0 * Q + lane;
+  const uint32_t* pb = bits + a0 * W;
+  const uint8_t* ps = sel != nullptr ? sel + a0 : nullptr;
+  for (int done = 0; done < nrows; done += kLossU) {
+    const int rows = min(kLossU, nrows - done);
     float x[kLossU][QC];
     uint32_t wd[kLossU][QC];
-    bool keep[kLossU];
+    uint32_t keep = 0;
+    if (rows == kLossU) {
 #pragma unroll
-    for (int u = 0; u < kLossU; ++u) {
-      const int64_t row = base + u;
-      const bool in = row < a1;
-      keep[u] = in && (sel == nullptr || sel[row] != 0);
+      for (int u = 0; u < kLossU; ++u) {
 #pragma unroll
-      for (int j = 0; j < QC; ++j) {
-        const int q = j * 32 + lane;
-        x[u][j] = (in && q < Q) ? logits[row * Q + q] : 0.f;
-        wd[u][j] = (in && tw[j] >= 0) ? bits[row * W + tw[j]] : 0u;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kLossU; ++u) {
-      const int64_t row = base + u;
-      if (row >= a1) break;
-#pragma unroll
-      for (int j = 0; j < QC; ++j) {
-        const int q = j * 32 + lane;
-        float gv = 0.f;
-        if (keep[u] && tw[j] >= 0) {
-          const float e = __expf(-fabsf(x[u][j]));
-          const float inv = __fdividef(1.f, 1.f + e);
-          const float s = x[u][j] >= 0.f ? inv : e * inv;
-          const float tgt = (float)((wd[u][j] >> tb[j]) & 1u);
-          gv = ca[j] * (s - tgt) + s * (1.f - s) * (c1[j] - tgt * c2[j]);
+        for (int j = 0; j < QC; ++j) {
+          x[u][j] = qv[j] ? px[u * Q + j * 32] : 0.f;
+          wd[u][j] = pb[u * W + tw[j]];
         }
-        if (q < Q) grad[row * Q + q] = gv;
+      }
+      keep = (1u << kLossU) - 1;
+      if (ps != nullptr) {
+        keep = 0;
+#pragma unroll
+        for (int u = 0; u < kLossU; ++u) keep |= (ps[u] != 0 ? 1u : 0u) << u;
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < kLossU; ++u) {
+        const bool in = u < rows;
+        if (in && (ps == nullptr || ps[u] != 0)) keep |= 1u << u;
+#pragma unroll
+        for (int j = 0; j < QC; ++j) {
+          x[u][j] = (in && qv[j]) ? px[u * Q + j * 32] : 0.f;
+          wd[u][j] = in ? pb[u * W + tw[j]] : 0u;
+        }
       }
     }
+#pragma unroll
+    for (int u = 0; u < kLossU; ++u) {
+      if (u >= rows) break;
+      const float k = (keep >> u) & 1u ? 1.f : 0.f;
+#pragma unroll
+      for (int j = 0; j < QC; ++j) {
+        const float e = __expf(-fabsf(x[u][j]));
+        const float inv = fast_rcp(1.f + e);
+        const float s = x[u][j] >= 0.f ? inv : e * inv;
+        const float tgt = (float)((wd[u][j] >> tb[j]) & 1u);
+        const float gv = k * (ca[j] * (s - tgt) + s * (1.f - s) * (c1[j] - tgt * c2[j]));
+        if (qv[j]) pg[u * Q + j * 32] = gv;
+      }
+    }
+    px += kLossU * Q, pg += kLossU * Q, pb += kLossU * W;
+    if (ps != nullptr) ps += kLossU;
   }
 }
 
 inline int64_t loss_ranges(int64_t max_scene_rows) { return max_scene_rows > 0 ? ceil_div(max_scene_rows, kLossRows) : 1; }
 
-template <int QC>
+template <int QC, bool SCORE>
 int launch_mask_stats(dim3 grid, cudaStream_t st, const float* logits, int Q, const uint32_t* bits, int W, const uint8_t* sel,
                       const int32_t* scene_offsets, float* part, int R_max) {
   constexpr int QP = QC * 32;
@@ -339,11 +419,11 @@ int launch_mask_stats(dim3 grid, cudaStream_t st, const float* logits, int Q, co
                       (size_t)(WARPS * 32 + WARPS) * sizeof(int32_t);
   static bool attr_set = false;
   if (smem > 48 * 1024 && !attr_set) {
-    if (cudaFuncSetAttribute(k_mask_stats<QC, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(k_mask_stats<QC, WARPS, SCORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return fail("mk_mask_costs", "cannot reserve shared memory");
     attr_set = true;
   }
-  k_mask_stats<QC, WARPS><<<grid, WARPS * 32, smem, st>>>(logits, Q, bits, W, sel, scene_offsets, part, R_max);
+  k_mask_stats<QC, WARPS, SCORE><<<grid, WARPS * 32, smem, st>>>(logits, Q, bits, W, sel, scene_offsets, part, R_max);
   return 0;
 }
 
@@ -383,12 +463,16 @@ int mk_mask_costs(const float* logits, int64_t n, int Q, const uint32_t* bits, i
   if (n > 0 && max_scene_rows > 0) {
     dim3 grid((unsigned)R_max, (unsigned)B, (unsigned)W);
     int rc = 0;
+#define MK_STATS(QC)                                                                                                       \
+  (mask_score != nullptr ? launch_mask_stats<QC, true>(grid, st, logits, Q, bits, W, row_select, scene_offsets, part, R_max) \
+                         : launch_mask_stats<QC, false>(grid, st, logits, Q, bits, W, row_select, scene_offsets, part, R_max))
     switch ((Q + 31) / 32) {
-      case 1: rc = launch_mask_stats<1>(grid, st, logits, Q, bits, W, row_select, scene_offsets, part, R_max); break;
-      case 2: rc = launch_mask_stats<2>(grid, st, logits, Q, bits, W, row_select, scene_offsets, part, R_max); break;
-      case 3: rc = launch_mask_stats<3>(grid, st, logits, Q, bits, W, row_select, scene_offsets, part, R_max); break;
-      default: rc = launch_mask_stats<4>(grid, st, logits, Q, bits, W, row_select, scene_offsets, part, R_max); break;
+      case 1: rc = MK_STATS(1); break;
+      case 2: rc = MK_STATS(2); break;
+      case 3: rc = MK_STATS(3); break;
+      default: rc = MK_STATS(4); break;
     }
+#undef MK_STATS
     if (rc) return rc;
     if (check_launch(__func__)) return 1;
   }

@@ -155,6 +155,11 @@ def test_matcher_ignore_label_and_scene_without_targets():
         assert np.array_equal(got[b][0].numpy(), fx[f"case2_match_q_{b}"]) and np.array_equal(got[b][1].numpy(), fx[f"case2_match_t_{b}"])
 
 
+def _stack1(CR, st):
+    """MaskStats of one decoder output -> the stacked (D = 1) form _MaskLossFn takes."""
+    return CR.MaskStats(torch.stack([st.cost_mask, st.cost_dice, st.dice_den])[None], st.n_rows[None], None, [st.row_select])
+
+
 def _random_case(seed, sizes, n_targets, Q, overlap=True):
     g = torch.Generator().manual_seed(seed)
     masks, pm = [], []
@@ -184,7 +189,7 @@ def test_mask_costs_and_scores_vs_oracle(sizes, n_targets, Q):
     masks, pm = _random_case(3, sizes, n_targets, Q)
     tg = CR.pack_targets([SimpleNamespace(instances_labels=torch.zeros(T, dtype=torch.long), instances_masks=m) for m, T in zip(masks, n_targets)],
                          sizes, "cuda")
-    st = CR.mask_costs(torch.cat(pm).cuda(), tg)
+    st = CR.mask_costs(torch.cat(pm).cuda(), tg, want_score=True)
     for b, (n, T) in enumerate(zip(sizes, n_targets)):
         if n == 0:
             continue
@@ -220,7 +225,7 @@ def test_mask_losses_forward_backward_vs_oracle_with_row_subset():
         x = torch.cat(pm).cuda().requires_grad_(True)
         st = CR.mask_costs(x, tg, sel)
         m, inv = CR.SetCriterion._match_table(matches, tg, Q)
-        lm = CR._MaskLossFn.apply(x, tg, st, m.cuda(), inv.cuda())
+        lm = CR._MaskLossFn.apply(tg, _stack1(CR, st), m.cuda()[None], inv.cuda()[None], x)[0]
         (3.0 * lm[0] + 0.7 * lm[1]).backward()
         ref_x = [p_.clone().requires_grad_(True) for p_ in pm]
         ref = [LO.mask_losses(ref_x[b], masks[b], *matches[b], rows=rows[b]) for b in range(len(sizes))]
@@ -282,11 +287,11 @@ def test_mask_costs_full_size_properties():
     matches = [(torch.arange(T), torch.arange(T))]
     m, inv = CR.SetCriterion._match_table(matches, tg1, Q)
     xr = x.clone().requires_grad_(True)
-    lm = CR._MaskLossFn.apply(xr, tg1, CR.mask_costs(xr, tg1), m.cuda(), inv.cuda())
+    lm = CR._MaskLossFn.apply(tg1, _stack1(CR, CR.mask_costs(xr, tg1)), m.cuda()[None], inv.cuda()[None], xr)[0]
     (lm[0] + lm[1]).backward()
     d = xr.grad.sign()  # aligned direction: the directional derivative is sum |grad| ~ 0.5, far above fp32 noise of the loss
     eps = 1e-2
-    f = lambda xx: float(CR._MaskLossFn.apply(xx, tg1, CR.mask_costs(xx, tg1), m.cuda(), inv.cuda()).double().sum())
+    f = lambda xx: float(CR._MaskLossFn.apply(tg1, _stack1(CR, CR.mask_costs(xx, tg1)), m.cuda()[None], inv.cuda()[None], xx).double().sum())
     fd = (f(x + eps * d) - f(x - eps * d)) / (2 * eps)
     an = float((xr.grad.double() * d.double()).sum())
     assert abs(fd - an) <= 2e-2 * abs(an) + 1e-5, (fd, an)
