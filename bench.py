@@ -442,6 +442,48 @@ def main_ours(args):
         except Exception as exc:  # the headline line must survive a failure here
             train = {"error": repr(exc)[:200]}
 
+    # loss side on the outputs of one inference step: matcher cost matrices of all 13 decoder outputs, the
+    # Hungarian assignments (scipy on the host, as in the reference), losses and the gradient w.r.t. all 13 logit tensors
+    loss_side = None
+    if rank == 0 and world == 1 and not args.no_train:
+        try:
+            from types import SimpleNamespace
+
+            from room_instance_segmentation_mask3d_b200 import criterion as CR
+
+            with torch.no_grad():
+                o = model(model.prepare(*resident[0]))
+            n0, T = int(o["pred_mask_all_decoders"][-1].shape[0]), 24
+            seg = torch.div(torch.arange(n0, device=dev) * T, n0, rounding_mode="floor")  # 24 instances = runs of voxel rows
+            tgt = [SimpleNamespace(instances_labels=torch.zeros(T, dtype=torch.long, device=dev),
+                                   instances_masks=torch.stack([seg == t for t in range(T)]))]
+            pm = [t.detach().clone().requires_grad_(True) for t in o["pred_mask_all_decoders"]]
+            pc = [t.detach().clone().requires_grad_(True) for t in o["pred_class_all_decoders"]]
+            D = len(pm)
+            wts = {"loss_ce": 2.0, "loss_mask": 5.0, "loss_dice": 2.0}
+            wd = dict(wts)
+            for d in range(D - 1):
+                wd.update({k + f"_mask_module_{d}": v for k, v in wts.items()})
+            crit = CR.SetCriterion(pc[0].shape[-1] - 1, CR.HungarianMatcher(2.0, 5.0, 2.0, -1), wd, 0.1, ["labels", "masks"], -1, 3.0, 0.75,
+                                   -1).to(dev)
+            mo = dict(pred_class=pc[-1], pred_class_all_decoders=pc, pred_mask=pm[-1], pred_mask_all_decoders=pm)
+
+            def lstep():
+                for t in pm + pc:
+                    t.grad = None
+                ls = crit(mo, tgt)
+                sum(ls[k] * wd[k] for k in ls).backward()
+
+            for _ in range(3):
+                lstep()
+            l_ms = timed(lambda i: lstep(), 5) / 5
+            loss_side = {"what": "SetCriterion forward + backward (matcher costs, Hungarian on the host, mask/dice/class losses, gradients of all "
+                                 "decoder outputs' mask logits) on the outputs of one inference step", "voxels": n0, "decoder_outputs": D,
+                         "instances": T, "ms_fwd_bwd": l_ms}
+            del pm, pc, mo, o
+        except Exception as exc:
+            loss_side = {"error": repr(exc)[:200]}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -449,7 +491,7 @@ def main_ours(args):
                 "scenes_per_sec": world * args.steps / (ms * 1e-3), "voxels_per_scene": vox_per_step,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "train_fwd_bwd": train}
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "train_fwd_bwd": train, "loss_side": loss_side}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -1,7 +1,9 @@
 """Sparse-conv microbenchmark (BASELINE.json configs[4]): kernel-map build and tcgen05 gather-GEMM over voxel counts and
 channel widths.  Prints one line per case: algorithmic TFLOP/s = 2 * P * Cin * Cout / t (P = actual pair count).
 
-usage: python scripts/conv_bench.py [scene=s200k|floor2|floor4] [reps] [widths...]"""
+usage: python scripts/conv_bench.py [scene=s200k|floor2|floor4|vox<cm>|blob<side>] [reps] [widths...]
+  vox<cm>    the floor-plan generator at <cm> voxels (vox15 = 15 k voxels ... vox1.2 = 2.4 M): the N sweep of SURVEY section 8d config 5
+  blob<side> a dense <side>^3 cube (26 neighbours per interior voxel): the dense-occupancy variant"""
 import os
 import sys
 import time
@@ -15,10 +17,19 @@ from room_instance_segmentation_mask3d_b200 import engine, lib, ops, scenes  # n
 scene = sys.argv[1] if len(sys.argv) > 1 else "s200k"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 widths = [int(w) for w in sys.argv[3:]] or [32, 64, 96, 128, 256]
-s = {"s200k": lambda: scenes.box_room(), "floor2": lambda: scenes.floor_plan(1000, voxel_m=0.02),
-     "floor4": lambda: scenes.floor_plan(1000, voxel_m=0.04)}[scene]()
-c, _ = scenes.collate([s])
-c = torch.from_numpy(c).cuda()
+if scene.startswith("blob"):
+    side = int(scene[4:])
+    g = torch.arange(side, dtype=torch.int32)
+    xyz = torch.stack(torch.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    c = torch.cat([torch.zeros(len(xyz), 1, dtype=torch.int32), xyz], 1).cuda()
+else:
+    if scene.startswith("vox"):
+        s = scenes.floor_plan(1000, voxel_m=float(scene[3:]) / 100.0)
+    else:
+        s = {"s200k": lambda: scenes.box_room(), "floor2": lambda: scenes.floor_plan(1000, voxel_m=0.02),
+             "floor4": lambda: scenes.floor_plan(1000, voxel_m=0.04)}[scene]()
+    c, _ = scenes.collate([s])
+    c = torch.from_numpy(c).cuda()
 lib.load()
 
 
