@@ -213,6 +213,20 @@ int mk_masked_xattn_fwd(const float* qp, const void* kp, const void* vp, int kv_
                         const int32_t* scene_offsets, int B, int Q, int D, int H, float scale, float* ctx, void* workspace,
                         int64_t workspace_bytes, void* stream);
 
+/* Same, additionally writing lse fp32 [B,Q,H] = log-sum-exp of the masked scaled scores in log2 units (what the backward
+ * recomputes the attention weights from); lse may be NULL. */
+int mk_masked_xattn_fwd_lse(const float* qp, const void* kp, const void* vp, int kv_dtype, int64_t n, const uint8_t* blocked,
+                            const int32_t* scene_offsets, int B, int Q, int D, int H, float scale, float* ctx, float* lse,
+                            void* workspace, int64_t workspace_bytes, void* stream);
+int64_t mk_xattn_bwd_workspace_bytes(int B, int Q, int H, int64_t n_keys);
+/* Backward of the core (what autograd does through nn.MultiheadAttention's softmax(QK^T)V, mask3d/models/mask3d.py:686-705):
+ * given dctx [B,Q,D] writes dqp fp32 [B,Q,D], dkp / dvp fp32 [n,D] (every row written).  ctx, lse: the forward's outputs.
+ * max_scene_rows (host): largest scene of the batch (n is always a valid bound).  No atomics, deterministic. */
+int mk_masked_xattn_bwd(const float* qp, const void* kp, const void* vp, int kv_dtype, int64_t n, const uint8_t* blocked,
+                        const int32_t* scene_offsets, int B, int Q, int D, int H, float scale, const float* ctx, const float* lse,
+                        const float* dctx, int64_t max_scene_rows, float* dqp, float* dkp, float* dvp, void* workspace,
+                        int64_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * (7) Furthest point sampling.  Replaces pointnet2._ext.furthest_point_sampling
  * (mask3d/third_party/pointnet2/_ext_src/src/sampling_gpu.cu:72-176; call site mask3d/models/mask3d.py:309-317)

@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(1024) k_xattn_partial(const float* __restrict_
 // grid (ceil(Q*H / 8), B), block 256: warp w handles (query, head) pair 8*blockIdx.x + w; its 32 lanes fold the splits
 // lane, lane+32, ... in ascending order (online-softmax merge), then the lanes are merged by a fixed shuffle tree.
 __global__ void __launch_bounds__(256) k_xattn_combine(const float* __restrict__ partial, int nsplit, int Q, int D, int H,
-                                                       float* __restrict__ ctx) {
+                                                       float* __restrict__ ctx, float* __restrict__ lse) {
   const int b = blockIdx.y, lane = threadIdx.x & 31;
   const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (t >= Q * H) return;
@@ -308,7 +308,203 @@ __global__ void __launch_bounds__(256) k_xattn_combine(const float* __restrict__
 #pragma unroll
     for (int j = 0; j < kXaMaxHd; ++j)
       if (j < hd) ctx[((int64_t)b * Q + q) * D + h * hd + j] = acc[j] * inv;
+    if (lse != nullptr) lse[(int64_t)b * Q * H + t] = m + log2f(l);  // log-sum-exp of the scaled scores in log2 units
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward of the masked cross-attention core.  With P = softmax(masked scale * q k^T) per (scene, query, head):
+//   dV = P^T dO,   dP = dO V^T,   dS = P * (dP - delta),  delta = rowsum(dO * O),   dQ = scale dS K,   dK = scale dS^T Q.
+// P is recomputed from the saved log-sum-exp.  Two kernels, neither needs atomics: a KEY-stationary one (thread = (key, head),
+// all Q queries of the scene in shared memory) for dK / dV, and a QUERY-stationary one shaped like the forward (thread =
+// (query, head), K / V tiles in shared memory, split over keys) for dQ.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_xattn_delta(const float* __restrict__ ctx, const float* __restrict__ dctx, int total, int hd,
+                                                     float* __restrict__ delta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (b, q, h) flattened; heads are contiguous hd-blocks of D
+  if (i >= total) return;
+  float a = 0.f;
+  for (int j = 0; j < hd; ++j) a = fmaf(ctx[(int64_t)i * hd + j], dctx[(int64_t)i * hd + j], a);
+  delta[i] = a;
+}
+
+constexpr int kXbKeysPerBlock = 256;
+
+template <typename T, int HD>
+__global__ void __launch_bounds__(256)
+    k_xattn_bwd_kv(const float* __restrict__ qp, const T* __restrict__ kp, const T* __restrict__ vp, const uint8_t* __restrict__ blocked,
+                   const int32_t* __restrict__ any_open, const int32_t* __restrict__ scene_offsets, const float* __restrict__ dctx,
+                   const float* __restrict__ lse, const float* __restrict__ delta, int Q, int D, int H, float scale,
+                   float* __restrict__ dk, float* __restrict__ dv) {
+  extern __shared__ __align__(16) float sm[];
+  const int hd = D / H, HP = hd + 4, RS = H * HP;
+  float* sQ = sm;                          // [Q][RS]  scale * q
+  float* sO = sQ + (size_t)Q * RS;         // [Q][RS]  dO
+  float* sL = sO + (size_t)Q * RS;         // [Q*H]
+  float* sDl = sL + Q * H;                 // [Q*H]
+  int* sOpen = (int*)(sDl + Q * H);        // [Q]
+  uint8_t* sM = (uint8_t*)(sOpen + Q);     // [32][Q]
+  const int b = blockIdx.y;
+  const int64_t s0 = (int64_t)scene_offsets[b] + (int64_t)blockIdx.x * kXbKeysPerBlock;
+  const int64_t s1 = min((int64_t)scene_offsets[b + 1], s0 + kXbKeysPerBlock);
+  if (s0 >= s1) return;
+  const int t = threadIdx.x, r = t / H, h = t - r * H;
+  for (int i = t; i < Q * (D >> 2); i += blockDim.x) {
+    const int q = i / (D >> 2), c = (i - q * (D >> 2)) * 4;
+    const int hh = c / hd, jj = c - hh * hd;
+    float4 a = load4(qp + ((int64_t)b * Q + q) * D + c);
+    a.x *= scale, a.y *= scale, a.z *= scale, a.w *= scale;
+    store4(sQ + q * RS + hh * HP + jj, a);
+    store4(sO + q * RS + hh * HP + jj, load4(dctx + ((int64_t)b * Q + q) * D + c));
+  }
+  for (int i = t; i < Q * H; i += blockDim.x) {
+    sL[i] = lse[(int64_t)b * Q * H + i];
+    sDl[i] = delta[(int64_t)b * Q * H + i];
+  }
+  for (int i = t; i < Q; i += blockDim.x) sOpen[i] = any_open[b * Q + i];
+  for (int64_t k0 = s0; k0 < s1; k0 += kXaKeysPerTile) {
+    const int nk = (int)min((int64_t)kXaKeysPerTile, s1 - k0);
+    __syncthreads();
+    for (int i = t; i < nk * Q; i += blockDim.x) sM[i] = blocked[k0 * Q + i];
+    __syncthreads();
+    if (r >= nk) continue;
+    const int64_t row = k0 + r;
+    float kk[HD], vv[HD], dkr[HD], dvr[HD];
+#pragma unroll
+    for (int j = 0; j < HD; j += 4) {
+      if (j < hd) {
+        const float4 a = load4(kp + row * D + h * hd + j), c = load4(vp + row * D + h * hd + j);
+        kk[j] = a.x, kk[j + 1] = a.y, kk[j + 2] = a.z, kk[j + 3] = a.w;
+        vv[j] = c.x, vv[j + 1] = c.y, vv[j + 2] = c.z, vv[j + 3] = c.w;
+      } else {
+        kk[j] = kk[j + 1] = kk[j + 2] = kk[j + 3] = 0.f;
+        vv[j] = vv[j + 1] = vv[j + 2] = vv[j + 3] = 0.f;
+      }
+      dkr[j] = dkr[j + 1] = dkr[j + 2] = dkr[j + 3] = 0.f;
+      dvr[j] = dvr[j + 1] = dvr[j + 2] = dvr[j + 3] = 0.f;
+    }
+    for (int q = 0; q < Q; ++q) {
+      if (sOpen[q] && sM[r * Q + q]) continue;
+      const float4* qr = reinterpret_cast<const float4*>(sQ + q * RS + h * HP);
+      const float4* orow = reinterpret_cast<const float4*>(sO + q * RS + h * HP);
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int j = 0; j < HD; j += 4) {
+        if (j < hd) {
+          const float4 a = qr[j >> 2], c = orow[j >> 2];
+          s = fmaf(a.x, kk[j], s), s = fmaf(a.y, kk[j + 1], s), s = fmaf(a.z, kk[j + 2], s), s = fmaf(a.w, kk[j + 3], s);
+          dp = fmaf(c.x, vv[j], dp), dp = fmaf(c.y, vv[j + 1], dp), dp = fmaf(c.z, vv[j + 2], dp), dp = fmaf(c.w, vv[j + 3], dp);
+        }
+      }
+      const float p = exp2f(s * 1.4426950408889634f - sL[q * H + h]);
+      const float ds = p * (dp - sDl[q * H + h]);
+#pragma unroll
+      for (int j = 0; j < HD; j += 4) {
+        if (j < hd) {
+          const float4 a = qr[j >> 2], c = orow[j >> 2];
+          dvr[j] = fmaf(p, c.x, dvr[j]), dvr[j + 1] = fmaf(p, c.y, dvr[j + 1]);
+          dvr[j + 2] = fmaf(p, c.z, dvr[j + 2]), dvr[j + 3] = fmaf(p, c.w, dvr[j + 3]);
+          dkr[j] = fmaf(ds, a.x, dkr[j]), dkr[j + 1] = fmaf(ds, a.y, dkr[j + 1]);
+          dkr[j + 2] = fmaf(ds, a.z, dkr[j + 2]), dkr[j + 3] = fmaf(ds, a.w, dkr[j + 3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < HD; j += 4) {
+      if (j < hd) {
+        store4(dk + row * D + h * hd + j, make_float4(dkr[j], dkr[j + 1], dkr[j + 2], dkr[j + 3]));
+        store4(dv + row * D + h * hd + j, make_float4(dvr[j], dvr[j + 1], dvr[j + 2], dvr[j + 3]));
+      }
+    }
+  }
+}
+
+// grid (splits, B), thread = (query, head): the forward's loop with dQ in place of the output accumulator.
+// partial[(b*splits + split)][q*H + h][hd] = sum over the split's keys of dS * k
+template <typename T, int HD>
+__global__ void __launch_bounds__(512)
+    k_xattn_bwd_q(const float* __restrict__ qp, const T* __restrict__ kp, const T* __restrict__ vp, const uint8_t* __restrict__ blocked,
+                  const int32_t* __restrict__ any_open, const int32_t* __restrict__ scene_offsets, const float* __restrict__ dctx,
+                  const float* __restrict__ lse, const float* __restrict__ delta, int Q, int D, int H, float scale, int keys_per_split,
+                  float* __restrict__ partial) {
+  extern __shared__ __align__(16) float sm[];
+  const int hd = D / H;
+  const int HP = hd + 4, RS = H * HP;
+  float* sK = sm;
+  float* sV = sm + (size_t)kXaKeysPerTile * RS;
+  uint8_t* sM = (uint8_t*)(sV + (size_t)kXaKeysPerTile * RS);  // [tile][Q]
+  const int b = blockIdx.y, split = blockIdx.x, nsplit = gridDim.x;
+  const int64_t s0 = (int64_t)scene_offsets[b] + (int64_t)split * keys_per_split;
+  const int64_t s1 = min((int64_t)scene_offsets[b + 1], s0 + keys_per_split);
+  const int t = threadIdx.x;
+  const int qb = blockDim.x / H;  // queries per block; blockIdx.z = query chunk
+  const int q = blockIdx.z * qb + t / H, h = t % H;
+  const bool active = t < qb * H && q < Q;
+  float qv[HD], ov[HD], acc[HD];
+#pragma unroll
+  for (int j = 0; j < HD; ++j) {
+    const bool in = active && j < hd;
+    qv[j] = in ? qp[((int64_t)b * Q + q) * D + h * hd + j] * (scale * 1.4426950408889634f) : 0.f;
+    ov[j] = in ? dctx[((int64_t)b * Q + q) * D + h * hd + j] : 0.f;
+    acc[j] = 0.f;
+  }
+  const bool use_mask = active && any_open[b * Q + q] != 0;
+  const float L = active ? lse[(int64_t)b * Q * H + q * H + h] : 0.f, dl = active ? delta[(int64_t)b * Q * H + q * H + h] : 0.f;
+  for (int64_t k0 = s0; k0 < s1; k0 += kXaKeysPerTile) {
+    const int nk = (int)min((int64_t)kXaKeysPerTile, s1 - k0);
+    __syncthreads();
+    for (int i = t; i < nk * (D >> 2); i += blockDim.x) {
+      const int r = i / (D >> 2), c = (i - r * (D >> 2)) * 4;
+      const int hh = c / hd, jj = c - hh * hd;
+      store4(sK + r * RS + hh * HP + jj, load4(kp + (k0 + r) * D + c));
+      store4(sV + r * RS + hh * HP + jj, load4(vp + (k0 + r) * D + c));
+    }
+    for (int i = t; i < nk * Q; i += blockDim.x) sM[i] = blocked[k0 * Q + i];
+    __syncthreads();
+    if (active) {
+      for (int r = 0; r < nk; ++r) {
+        if (use_mask && sM[r * Q + q]) continue;
+        const float4* kr = reinterpret_cast<const float4*>(sK + r * RS + h * HP);
+        const float4* vr = reinterpret_cast<const float4*>(sV + r * RS + h * HP);
+        float s = 0.f, dp = 0.f;
+#pragma unroll
+        for (int j = 0; j < HD; j += 4) {
+          if (j < hd) {
+            const float4 a = kr[j >> 2], c = vr[j >> 2];
+            s = fmaf(qv[j], a.x, s), s = fmaf(qv[j + 1], a.y, s), s = fmaf(qv[j + 2], a.z, s), s = fmaf(qv[j + 3], a.w, s);
+            dp = fmaf(ov[j], c.x, dp), dp = fmaf(ov[j + 1], c.y, dp), dp = fmaf(ov[j + 2], c.z, dp), dp = fmaf(ov[j + 3], c.w, dp);
+          }
+        }
+        const float ds = exp2f(s - L) * (dp - dl);
+#pragma unroll
+        for (int j = 0; j < HD; j += 4) {
+          if (j < hd) {
+            const float4 a = kr[j >> 2];
+            acc[j] = fmaf(ds, a.x, acc[j]), acc[j + 1] = fmaf(ds, a.y, acc[j + 1]);
+            acc[j + 2] = fmaf(ds, a.z, acc[j + 2]), acc[j + 3] = fmaf(ds, a.w, acc[j + 3]);
+          }
+        }
+      }
+    }
+  }
+  if (active) {
+    float* o = partial + (((int64_t)b * nsplit + split) * Q * H + q * H + h) * kXaMaxHd;
+#pragma unroll
+    for (int j = 0; j < HD; ++j)
+      if (j < hd) o[j] = acc[j];
+  }
+}
+
+// dq[b, q, h*hd + j] = scale * sum over splits (ascending: deterministic)
+__global__ void __launch_bounds__(256) k_xattn_bwd_q_combine(const float* __restrict__ partial, int nsplit, int B, int Q, int D, int H,
+                                                             float scale, float* __restrict__ dq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Q * D) return;
+  const int hd = D / H;
+  const int b = i / (Q * D), rem = i - b * Q * D, qq = rem / D, c = rem - qq * D, h = c / hd, j = c - h * hd;
+  float a = 0.f;
+  for (int s = 0; s < nsplit; ++s) a += partial[(((int64_t)b * nsplit + s) * Q * H + qq * H + h) * kXaMaxHd + j];
+  dq[i] = a * scale;
 }
 
 inline int xattn_splits(int64_t n, int B) {
@@ -384,6 +580,13 @@ int64_t mk_xattn_workspace_bytes(int B, int Q, int H, int64_t n_keys) {
 int mk_masked_xattn_fwd(const float* qp, const void* kp, const void* vp, int kv_dtype, int64_t n, const uint8_t* blocked,
                         const int32_t* scene_offsets, int B, int Q, int D, int H, float scale, float* ctx, void* workspace,
                         int64_t workspace_bytes, void* stream_) {
+  return mk_masked_xattn_fwd_lse(qp, kp, vp, kv_dtype, n, blocked, scene_offsets, B, Q, D, H, scale, ctx, nullptr, workspace,
+                                 workspace_bytes, stream_);
+}
+
+int mk_masked_xattn_fwd_lse(const float* qp, const void* kp, const void* vp, int kv_dtype, int64_t n, const uint8_t* blocked,
+                            const int32_t* scene_offsets, int B, int Q, int D, int H, float scale, float* ctx, float* lse,
+                            void* workspace, int64_t workspace_bytes, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   MK_REQUIRE(D % H == 0 && D / H <= kXaMaxHd && (D / H) % 4 == 0, "head dim must be a multiple of 4, <= 32");
   MK_REQUIRE(Q * H <= 1024, "Q*H must be <= 1024");
@@ -411,7 +614,73 @@ int mk_masked_xattn_fwd(const float* qp, const void* kp, const void* vp, int kv_
     if (hd16) MK_XA(__nv_bfloat16, 16); else MK_XA(__nv_bfloat16, 32);
   }
 #undef MK_XA
-  k_xattn_combine<<<dim3((unsigned)ceil_div(Q * H, 8), (unsigned)B), 256, 0, st>>>(partial, splits, Q, D, H, ctx);
+  k_xattn_combine<<<dim3((unsigned)ceil_div(Q * H, 8), (unsigned)B), 256, 0, st>>>(partial, splits, Q, D, H, ctx, lse);
+  return check_launch(__func__);
+}
+
+int64_t mk_xattn_bwd_workspace_bytes(int B, int Q, int H, int64_t n_keys) {
+  const int splits = xattn_splits(n_keys, B);
+  return ((int64_t)B * splits * Q * H * kXaMaxHd + (int64_t)B * Q * H) * (int64_t)sizeof(float) + (int64_t)B * Q * sizeof(int32_t) + 512;
+}
+
+int mk_masked_xattn_bwd(const float* qp, const void* kp, const void* vp, int kv_dtype, int64_t n, const uint8_t* blocked,
+                        const int32_t* scene_offsets, int B, int Q, int D, int H, float scale, const float* ctx, const float* lse,
+                        const float* dctx, int64_t max_scene_rows, float* dqp, float* dkp, float* dvp, void* workspace,
+                        int64_t workspace_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  MK_REQUIRE(D % H == 0 && D / H <= kXaMaxHd && (D / H) % 4 == 0, "head dim must be a multiple of 4, <= 32");
+  MK_REQUIRE(H >= 1 && H <= 8, "backward: at most 8 heads");
+  MK_REQUIRE(workspace_bytes >= mk_xattn_bwd_workspace_bytes(B, Q, H, n), "workspace too small");
+  MK_REQUIRE(max_scene_rows >= 0 && max_scene_rows <= n, "max_scene_rows out of range");
+  const int splits = xattn_splits(n, B);
+  const int hd = D / H;
+  uint8_t* w = (uint8_t*)workspace;
+  int32_t* any_open = (int32_t*)w;
+  w += (((int64_t)B * Q * sizeof(int32_t) + 255) / 256) * 256;
+  float* delta = (float*)w;
+  w += (((int64_t)B * Q * H * sizeof(float) + 255) / 256) * 256;
+  float* partial = (float*)w;
+  cudaMemsetAsync(any_open, 0, (size_t)B * Q * sizeof(int32_t), st);
+  if (n > 0) {
+    int64_t blocks = ceil_div(n * Q, 256);
+    if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+    k_any_open<<<(unsigned)blocks, 256, 0, st>>>(blocked, n, Q, scene_offsets, B, any_open);
+  }
+  k_xattn_delta<<<(unsigned)ceil_div((int64_t)B * Q * H, 256), 256, 0, st>>>(ctx, dctx, B * Q * H, hd, delta);
+  const bool hd16 = hd <= 16;
+  if (n > 0 && max_scene_rows > 0) {
+    const size_t smem = (size_t)2 * Q * (D + 4 * H) * sizeof(float) + (size_t)2 * Q * H * sizeof(float) + (size_t)Q * sizeof(int) +
+                        (size_t)kXaKeysPerTile * Q;
+    dim3 grid((unsigned)ceil_div(max_scene_rows, kXbKeysPerBlock), (unsigned)B);
+#define MK_XB(T, HD)                                                                                                             \
+  do {                                                                                                                           \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_xattn_bwd_kv<T, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    k_xattn_bwd_kv<T, HD><<<grid, 32 * H, smem, st>>>(qp, (const T*)kp, (const T*)vp, blocked, any_open, scene_offsets, dctx, lse, \
+                                                     delta, Q, D, H, scale, dkp, dvp);                                          \
+  } while (0)
+    if (kv_dtype == MK_F32) {
+      if (hd16) MK_XB(float, 16); else MK_XB(float, 32);
+    } else {
+      if (hd16) MK_XB(__nv_bfloat16, 16); else MK_XB(__nv_bfloat16, 32);
+    }
+#undef MK_XB
+    if (check_launch(__func__)) return 1;
+  }
+  const int keys_per_split = (int)ceil_div(n > 0 ? n : 1, splits);
+  const int qb = Q < 512 / H ? Q : 512 / H;  // queries per block (<= 512 threads)
+  const int threads = ((qb * H + 31) / 32) * 32;
+  const size_t smem_q = (size_t)2 * kXaKeysPerTile * (D + 4 * H) * sizeof(float) + (size_t)kXaKeysPerTile * Q;
+  dim3 gq((unsigned)splits, (unsigned)B, (unsigned)ceil_div(Q, qb));
+#define MK_XQ(T, HD)                                                                                                           \
+  k_xattn_bwd_q<T, HD><<<gq, threads, smem_q, st>>>(qp, (const T*)kp, (const T*)vp, blocked, any_open, scene_offsets, dctx, lse, \
+                                                    delta, Q, D, H, scale, keys_per_split, partial)
+  if (kv_dtype == MK_F32) {
+    if (hd16) MK_XQ(float, 16); else MK_XQ(float, 32);
+  } else {
+    if (hd16) MK_XQ(__nv_bfloat16, 16); else MK_XQ(__nv_bfloat16, 32);
+  }
+#undef MK_XQ
+  k_xattn_bwd_q_combine<<<(unsigned)ceil_div((int64_t)B * Q * D, 256), 256, 0, st>>>(partial, splits, B, Q, D, H, scale, dqp);
   return check_launch(__func__);
 }
 

@@ -383,12 +383,50 @@ def fourier_pe(xyz, scene_offsets, B, cmin, cmax, gauss_B, base: Optional[torch.
     return out
 
 
+class _MaskedXattnFn(torch.autograd.Function):
+    """Masked cross-attention core with its backward (mk_masked_xattn_fwd_lse / mk_masked_xattn_bwd): what autograd does through
+    the softmax(QK^T)V of the reference's stock nn.MultiheadAttention (mask3d/models/mask3d.py:686-705)."""
+
+    @staticmethod
+    def forward(ctx_, qp, kp, vp, blocked, scene_offsets, num_heads, max_scene_rows):
+        B, Q, D = qp.shape
+        n = kp.shape[0]
+        q32, k_, v_, bl = qp.detach().float().contiguous(), kp.detach().contiguous(), vp.detach().contiguous(), blocked.contiguous()
+        ws = lib.scratch(lib.query("mk_xattn_workspace_bytes", B, Q, num_heads, n), qp.device)
+        out = torch.empty((B, Q, D), dtype=torch.float32, device=qp.device)
+        lse = torch.empty((B, Q, num_heads), dtype=torch.float32, device=qp.device)
+        scale = float((D // num_heads) ** -0.5)
+        lib.call("mk_masked_xattn_fwd_lse", lib.p(q32), lib.p(k_), lib.p(v_), lib.dt(k_), n, lib.p(bl), lib.p(scene_offsets), B, Q, D, num_heads,
+                 scale, lib.p(out), lib.p(lse), lib.p(ws), ws.numel(), lib.stream())
+        ctx_.save_for_backward(q32, k_, v_, bl, scene_offsets, out, lse)
+        ctx_.meta = (num_heads, scale, int(max_scene_rows) if max_scene_rows is not None else n, qp.dtype, kp.dtype, vp.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx_, dout):
+        q32, k_, v_, bl, scene_offsets, out, lse = ctx_.saved_tensors
+        H, scale, max_rows, qd, kd, vd = ctx_.meta
+        B, Q, D = q32.shape
+        n = k_.shape[0]
+        dout = dout.float().contiguous()
+        dq = torch.empty_like(q32)
+        dk = torch.empty((n, D), dtype=torch.float32, device=q32.device)
+        dv = torch.empty((n, D), dtype=torch.float32, device=q32.device)
+        ws = lib.scratch(lib.query("mk_xattn_bwd_workspace_bytes", B, Q, H, n), q32.device)
+        lib.call("mk_masked_xattn_bwd", lib.p(q32), lib.p(k_), lib.p(v_), lib.dt(k_), n, lib.p(bl), lib.p(scene_offsets), B, Q, D, H, scale,
+                 lib.p(out), lib.p(lse), lib.p(dout), min(max_rows, n), lib.p(dq), lib.p(dk), lib.p(dv), lib.p(ws), ws.numel(), lib.stream())
+        return dq.to(qd), dk.to(kd), dv.to(vd), None, None, None, None
+
+
 def masked_cross_attention(qp: torch.Tensor, kp: torch.Tensor, vp: torch.Tensor, blocked: torch.Tensor, scene_offsets: torch.Tensor,
-                           num_heads: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """ctx [B, Q, D] (heads concatenated, before out_proj)."""
+                           num_heads: int, out: Optional[torch.Tensor] = None, max_scene_rows: Optional[int] = None) -> torch.Tensor:
+    """ctx [B, Q, D] (heads concatenated, before out_proj).  Differentiable w.r.t. qp, kp, vp."""
     B, Q, D = qp.shape
     n = kp.shape[0]
     assert kp.dtype == vp.dtype
+    if torch.is_grad_enabled() and (qp.requires_grad or kp.requires_grad or vp.requires_grad):
+        assert out is None, "out= is an inference-only argument"
+        return _MaskedXattnFn.apply(qp, kp, vp, blocked, scene_offsets, num_heads, max_scene_rows)
     wsb = lib.query("mk_xattn_workspace_bytes", B, Q, num_heads, n)
     ws = lib.scratch(wsb, qp.device)
     ctx = out if out is not None else torch.empty((B, Q, D), dtype=torch.float32, device=qp.device)

@@ -446,6 +446,63 @@ def test_masked_cross_attention_vs_stock_mha(R, Q):
     assert rel_err(out, ref) < 1e-4
 
 
+@pytest.mark.parametrize("Q,kv_dtype", [(25, torch.float32), (100, torch.float32), (25, torch.bfloat16)])
+def test_masked_cross_attention_backward_vs_stock_mha(R, Q, kv_dtype):
+    """Gradients through the attention core against autograd through the reference's formulation (pad to max K, dense bool mask,
+    all-blocked rule, stock nn.MultiheadAttention, mask3d.py:400-478, 686-705): d/d(query), d/d(key input), d/d(value input) and
+    the in-projection weights.  fp32 keys: <= 1e-3 relative; bf16 keys/values (the fused path's dtype): <= 2e-2."""
+    torch.manual_seed(100 + Q)
+    D, H, B = 128, 8, 3
+    sizes = [700, 37, 1300]
+    off = torch.tensor([0] + list(np.cumsum(sizes)), dtype=torch.int32)
+    n = sum(sizes)
+    mha = torch.nn.MultiheadAttention(D, H)
+    query = torch.randn(Q, B, D, requires_grad=True)
+    key_in = torch.randn(n, D, requires_grad=True)
+    val_in = torch.randn(n, D, requires_grad=True)
+    blocked = torch.rand(n, Q) < 0.6
+    blocked[off[1]:off[2], 3] = True
+    blocked[:, 5] = True
+    Kmax = max(sizes)
+    mpad = torch.ones(B, Kmax, Q, dtype=torch.bool)
+    kcols, vcols = [], []
+    for b in range(B):
+        s, e = int(off[b]), int(off[b + 1])
+        idx = torch.zeros(Kmax, dtype=torch.long)
+        idx[: e - s] = torch.arange(e - s)
+        kcols.append(key_in[s:e][idx])
+        vcols.append(val_in[s:e][idx])
+        mpad[b] = blocked[s:e][idx]
+    kpad, vpad = torch.stack(kcols, 1), torch.stack(vcols, 1)
+    mpad.permute(0, 2, 1)[mpad.sum(1) == Kmax] = False
+    pad = torch.stack([torch.arange(Kmax) >= sz for sz in sizes])
+    mpad = torch.logical_or(mpad, pad[..., None])
+    ref, _ = mha(query, kpad, vpad, attn_mask=mpad.repeat_interleave(H, dim=0).permute(0, 2, 1))
+    gout = torch.randn_like(ref)
+    (ref * gout).sum().backward()
+    want = [query.grad.clone(), key_in.grad.clone(), val_in.grad.clone(), mha.in_proj_weight.grad.clone()]
+    for t in (query, key_in, val_in, mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias):
+        t.grad = None
+
+    m2 = torch.nn.MultiheadAttention(D, H).cuda()
+    m2.load_state_dict(mha.state_dict())
+    q2, k2, v2 = (t.detach().cuda().requires_grad_(True) for t in (query, key_in, val_in))
+    Wq, Wk, Wv = m2.in_proj_weight.chunk(3)
+    bq, bk, bv = m2.in_proj_bias.chunk(3)
+    qp = q2.permute(1, 0, 2) @ Wq.T + bq
+    kp = (k2 @ Wk.T + bk).to(kv_dtype)
+    vp = (v2 @ Wv.T + bv).to(kv_dtype)
+    ctx = R.ops.masked_cross_attention(qp, kp, vp, blocked.to(torch.uint8).cuda(), off.cuda(), H, max_scene_rows=max(sizes))
+    out = (ctx @ m2.out_proj.weight.T + m2.out_proj.bias).permute(1, 0, 2)
+    tol_f = 1e-4 if kv_dtype == torch.float32 else 2e-2
+    assert rel_err(out.detach().cpu(), ref.detach()) < tol_f
+    (out * gout.cuda()).sum().backward()
+    got = [q2.grad.cpu(), k2.grad.cpu(), v2.grad.cpu(), m2.in_proj_weight.grad.cpu()]
+    tol = 1e-3 if kv_dtype == torch.float32 else 2e-2
+    for name, g, w in zip(("query", "key", "value", "in_proj_weight"), got, want):
+        assert rel_err(g, w) < tol, (name, rel_err(g, w))
+
+
 def test_fps_matches_reference_tie_breaking(R):
     sc = [scenes.tiny_scene(0), scenes.tiny_scene(1, (20, 16, 10)), scenes.box_room((1.0, 1.2, 0.6), 0.02), scenes.tiny_scene(5, (7, 5, 4), 0)]
     coords, _ = scenes.collate(sc)
