@@ -481,12 +481,29 @@ class Mask3D(nn.Module):
             out["prefetched"] = self.prepare(prefetch[0], prefetch[1], wait_event=self._ev_backbone)
         return out
 
-    def _forward(self, x: ME.SparseTensor) -> dict:
+    def forward_train(self, x: ME.SparseTensor) -> dict:
+        """Autograd-capable forward of the whole model (bf16 tensor-core mode): backbone through `Res16UNet34C.forward_train`,
+        1x1 convolutions (mask-feature head, lin_squeeze, K / V in-projections) through the tcgen05 conv forward / dgrad /
+        wgrad, mask logits and the masked cross-attention core through their own backward kernels, the [B, Q, 128] query-side
+        layers through PyTorch autograd.  Returns what `forward` returns; feed it to `criterion.SetCriterion`."""
+        assert ops.get_compute_mode() == "bf16", "forward_train is the bf16 tensor-core path"
+        with lib.stream_scope():
+            return self._forward(x, train=True)
+
+    def _forward(self, x: ME.SparseTensor, train: bool = False) -> dict:
         mgr = x.coordinate_manager
         mode = ops.get_compute_mode()
         act = torch.float32 if mode == "fp32" else torch.bfloat16
         B, Q, H, D = mgr.number_of_unique_batch_indices(), self.num_queries, self.num_heads, self.mask_dim
-        backbone_out, fmaps = self.backbone.forward_fused(x)
+        backbone_out, fmaps = self.backbone.forward_train(x) if train else self.backbone.forward_fused(x)
+
+        def lin(xf, W, km, bias, out_dtype):
+            """1x1 convolution + bias on the rows of a level; differentiable when training (W: [cin, cout] view of a parameter)"""
+            if not train:
+                return ops.conv_forward(xf, W, km, bias=bias, mode=mode, out_dtype=out_dtype)
+            y = ME._ConvFn.apply(xf, W, km, 0, xf.shape[0], None) + bias.view(1, -1)
+            return y if out_dtype == torch.float32 else y.to(out_dtype)
+
         self._ev_backbone = torch.cuda.Event()
         self._ev_backbone.record(torch.cuda.current_stream())
         keys = [fm.coordinate_map_key for fm in fmaps]  # coarse -> fine (L4 .. L0)
@@ -509,8 +526,7 @@ class Mask3D(nn.Module):
                 mins0, maxs0 = cmin, cmax
 
         km1 = mgr.neighbor_table(keys[-1], keys[-1], 1, 1)
-        mask_features = ops.conv_forward(backbone_out.F, self.mask_features_head.kernel, km1, bias=self.mask_features_head.bias,
-                                         mode=mode, out_dtype=act)
+        mask_features = lin(backbone_out.F, self.mask_features_head.kernel, km1, self.mask_features_head.bias, act)
 
         # non-parametric queries: FPS over the input voxel coordinates + fourier PE of the sampled points (:308-338)
         fps_idx = ops.furthest_point_sample(cf[nl - 1], offs[-1], B, Q).long()  # scene-local
@@ -524,15 +540,19 @@ class Mask3D(nn.Module):
 
         pred_class, pred_masks = [], []
         sel0 = mgr.scene_select_table(keys[-1])
+        off0_host = mgr.scene_offsets_host(keys[-1]) if train else None
 
         def mask_module(queries, n_pool, want_mask):
             qn = self.decoder_norm(queries)
             emb = self.mask_embed_head(qn)
             cls = self.class_embed_head(qn)
-            logits = ops.mask_logits(mask_features, offs[-1], B, emb, select=sel0)  # [N0, Q] fp32
+            if train:
+                logits = ops._MaskLogitsFn.apply(mask_features, emb, offs[-1], B, sel0, off0_host)
+            else:
+                logits = ops.mask_logits(mask_features, offs[-1], B, emb, select=sel0)  # [N0, Q] fp32
             blocked = None
             if want_mask:
-                pooled = logits
+                pooled = logits.detach()  # the attention mask carries no gradient (mask3d.py:549)
                 for s in range(n_pool):
                     pooled = ops.pool_forward(pooled, pool_km[nl - 2 - s], average=True)
                 blocked = ops.threshold_blocked(pooled)
@@ -546,15 +566,23 @@ class Mask3D(nn.Module):
             ca, sq = self.cross_attention[0][i], self.lin_squeeze[0][i]
             kml = mgr.neighbor_table(keys[hl], keys[hl], 1, 1)
             mha = ca.multihead_attn
-            Wsq = self._d(sq.weight, "T", lambda w: w.t())                                  # [C_l, D]
-            Wk = self._d(mha.in_proj_weight, "k", lambda w: w[D:2 * D].t())                   # [D, D] (in, out)
-            Wv = self._d(mha.in_proj_weight, "v", lambda w: w[2 * D:].t())
-            src = ops.conv_forward(fmaps[hl].F, Wsq, kml, bias=sq.bias, mode=mode, out_dtype=torch.float32)
+            if train:  # views of the parameters: gradients flow back through them
+                Wsq, Wk, Wv = sq.weight.t(), mha.in_proj_weight[D:2 * D].t(), mha.in_proj_weight[2 * D:].t()
+            else:
+                Wsq = self._d(sq.weight, "T", lambda w: w.t())                                  # [C_l, D]
+                Wk = self._d(mha.in_proj_weight, "k", lambda w: w[D:2 * D].t())                   # [D, D] (in, out)
+                Wv = self._d(mha.in_proj_weight, "v", lambda w: w[2 * D:].t())
+            src = lin(fmaps[hl].F, Wsq, kml, sq.bias, torch.float32)
             kin = src + pe[hl]
-            kv[i] = (ops.conv_forward(kin, Wk, kml, bias=mha.in_proj_bias[D:2 * D], mode=mode, out_dtype=act),
-                     ops.conv_forward(src, Wv, kml, bias=mha.in_proj_bias[2 * D:], mode=mode, out_dtype=act))
+            kv[i] = (lin(kin, Wk, kml, mha.in_proj_bias[D:2 * D], act), lin(src, Wv, kml, mha.in_proj_bias[2 * D:], act))
+        max_rows = None
+        if train:
+            max_rows = []
+            for hl in self.hlevels:
+                oh = mgr.scene_offsets_host(keys[hl])
+                max_rows.append(max(int(oh[b + 1]) - int(oh[b]) for b in range(B)))
 
-        if self.use_cuda_graphs:
+        if self.use_cuda_graphs and not train:
             # query-side work replayed from CUDA graphs; the varlen voxel kernels in between run eagerly
             qg = self._query_graphs(B, mode, query_pos.device)
             qg.query_pos.copy_(query_pos)
@@ -592,7 +620,7 @@ class Mask3D(nn.Module):
                     mha = self.cross_attention[0][i].multihead_attn
                     kp, vp = kv[i]
                     qp = F.linear(queries + query_pos, mha.in_proj_weight[:D], mha.in_proj_bias[:D])
-                    ctx = ops.masked_cross_attention(qp, kp, vp, blocked, offs[hl], H)
+                    ctx = ops.masked_cross_attention(qp, kp, vp, blocked, offs[hl], H, max_scene_rows=max_rows[i] if train else None)
                     queries = self._query_update(i, queries, query_pos, ctx)
                     pred_class.append(cls)
                     pred_masks.append(logits)

@@ -332,6 +332,47 @@ def mask_logits(feat: torch.Tensor, scene_offsets: torch.Tensor, B: int, embed: 
     return out
 
 
+class _MaskLogitsFn(torch.autograd.Function):
+    """Differentiable mask-logit product (mask3d.py:534-537): logits = feat . embed[b]^T.  bf16 mode: forward, d(feat) and
+    d(embed) all run on the tcgen05 conv kernels over the scene-select table (one "offset" per scene; the gradient w.r.t. the
+    logits is zero-padded to a multiple of 16 columns in bf16).  fp32 parity mode: per-scene fp32 matrix products."""
+
+    @staticmethod
+    def forward(ctx, feat, embed, scene_offsets, B, select, offs_host):
+        ctx.save_for_backward(feat, embed, scene_offsets)
+        ctx.B, ctx.select, ctx.offs_host = B, select, offs_host
+        return mask_logits(feat.detach(), scene_offsets, B, embed.detach(), select=select)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        feat, embed, scene_offsets = ctx.saved_tensors
+        B, select = ctx.B, ctx.select
+        n, C = feat.shape
+        Q = embed.shape[1]
+        dfeat = demb = None
+        if feat.dtype == torch.bfloat16 and select is not None and select.K <= 32 and C % 16 == 0:
+            Qp = ((Q + 15) // 16) * 16
+            dp = torch.zeros((n, Qp), dtype=torch.bfloat16, device=feat.device)
+            dl = dlogits.contiguous().float()
+            lib.call("mk_copy_channels", lib.p(dl), lib.F32, Q, lib.p(dp), lib.BF16, Qp, 0, n, lib.stream())
+            W = torch.zeros((embed.shape[0], C, Qp), dtype=torch.float32, device=feat.device)
+            W[:, :, :Q] = embed.detach().float().transpose(1, 2)
+            if ctx.needs_input_grad[0]:
+                dfeat = conv_forward(dp, W, select, mode="bf16", out_dtype=feat.dtype, transpose_w=True)
+            if ctx.needs_input_grad[1]:
+                dW = conv_wgrad_bf16(feat.detach(), dp, select, select.K, C, Qp)  # [B, C, Qp]
+                demb = dW[:, :, :Q].transpose(1, 2).to(embed.dtype)
+            return dfeat, demb, None, None, None, None
+        dl = dlogits.float()
+        f32 = feat.detach().float()
+        oh = ctx.offs_host
+        if ctx.needs_input_grad[0]:
+            dfeat = torch.cat([dl[oh[b]:oh[b + 1]] @ embed[b].detach().float() for b in range(B)]).to(feat.dtype)
+        if ctx.needs_input_grad[1]:
+            demb = torch.stack([dl[oh[b]:oh[b + 1]].t() @ f32[oh[b]:oh[b + 1]] for b in range(B)]).to(embed.dtype)
+        return dfeat, demb, None, None, None, None
+
+
 def mask_embed_image(embed: torch.Tensor, img: Optional[torch.Tensor] = None, W: Optional[torch.Tensor] = None):
     """Weight image of the mask-logit product for the tensor-core path: W[b] = embed[b]^T zero-padded to a multiple of 16
     queries.  Optional preallocated `W` / `img` (CUDA-graph capture: static buffers, no caching by parameter version)."""

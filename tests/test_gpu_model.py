@@ -158,3 +158,68 @@ def test_two_lane_alternation_gives_identical_results(setup):
             assert torch.equal(a, want[j][0]) and torch.equal(b, want[j][1]) and torch.equal(c, want[j][2])
     finally:
         ops.set_compute_mode("bf16")
+
+
+def test_mask3d_forward_train_gradients_vs_oracle(setup):
+    """Whole-model training forward + backward (Mask3D.forward_train: tcgen05 conv fwd/dgrad/wgrad, mask-logit and masked
+    cross-attention backward kernels, bf16 activations) against autograd through the fp32 CPU oracle of the reference model
+    (oracle/mask3d_oracle.py, pinned by the reference's golden fixture) on the same weights, input and loss.
+    Outputs: the tolerance of the bf16 inference test.  Gradients: cosine similarity per parameter — bf16 operand rounding
+    through 62 instance-normalised convolutions does not allow an element-wise bound (scripts/grad_agreement.py).  Stated bars:
+    decoder parameters (everything the new backward kernels feed directly) median >= 0.99, min >= 0.95 (measured 0.998 /
+    0.983); backbone kernels median >= 0.85, min >= 0.75 (measured 0.89 / 0.82 on this 2 x 938-voxel fixture, whose coarse
+    levels hold a handful of voxels per scene, so instance norm amplifies the bf16 rounding; the backbone's own backward is
+    bounded against the fp32 module path in test_backbone_forward_train_matches_module_path)."""
+    from oracle import mask3d_oracle, me_oracle
+    from room_instance_segmentation_mask3d_b200 import weights
+
+    g, model, ME, ops = setup
+    ops.set_compute_mode("bf16")
+    gen = torch.Generator().manual_seed(5)
+    n = g["coords"].shape[0]
+    D_out = 13
+    Rm = [torch.randn(n, 25, generator=gen) for _ in range(D_out)]
+    Rc = [torch.randn(2, 25, 2, generator=gen) for _ in range(D_out)]
+
+    def loss_of(pred_masks, pred_class, dev):
+        tot = 0
+        for d in range(D_out):
+            pm = pred_masks[d] if isinstance(pred_masks[d], torch.Tensor) else torch.cat(pred_masks[d])
+            tot = tot + (pm.float() * Rm[d].to(dev)).mean() + 0.1 * pm.float().square().mean() + (pred_class[d].float() * Rc[d].to(dev)).sum()
+        return tot
+
+    model.train()
+    for p_ in model.parameters():
+        p_.grad = None
+    o = model.forward_train(_input(g, ME))
+    assert rel(o["pred_mask_all_decoders"][0], g["pred_mask_first"]) < 5e-2
+    assert np.array_equal(o["sampled_coords"].detach().cpu().numpy(), g["sampled_coords"])
+    loss_of(o["pred_mask_all_decoders"], o["pred_class_all_decoders"], "cuda").backward()
+    got = {k: v.grad.detach().cpu() for k, v in model.named_parameters() if v.grad is not None}
+    params = {k for k, _ in model.named_parameters()}
+    model.eval()
+
+    spec = [(nm, tuple(int(d) for d in s.split(",") if d)) for nm, s in zip(g["names"], g["shapes"])]
+    sd = {k: torch.from_numpy(v) for k, v in weights.synth_state_dict(spec).items()}
+    for v in sd.values():
+        if v.is_floating_point():
+            v.requires_grad_(True)
+    x = me_oracle.SparseTensor(features=torch.from_numpy(g["feats"]), coordinates=torch.from_numpy(g["coords"]))
+    ref = mask3d_oracle.mask3d_forward(sd, x)
+    loss_of(ref["pred_masks"], ref["pred_class"], "cpu").backward()
+
+    cos = {}
+    for k, v in sd.items():
+        if v.grad is None or k.startswith("backbone.final") or k not in params:  # buffers (pos_enc.gauss_B) are not trained
+            continue
+        assert k in got, f"no gradient reached {k}"
+        a, b = got[k].double().flatten(), v.grad.double().flatten()
+        assert torch.isfinite(a).all(), k
+        cos[k] = float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
+    dec = sorted(c for k, c in cos.items() if not k.startswith("backbone."))
+    bb = sorted(c for k, c in cos.items() if k.startswith("backbone.") and k.endswith("kernel"))
+    worst = sorted(cos.items(), key=lambda kv: kv[1])[:5]
+    print(f"forward_train vs fp32 oracle: decoder cos median {dec[len(dec) // 2]:.4f} min {dec[0]:.4f} ({len(dec)} tensors); "
+          f"backbone kernels median {bb[len(bb) // 2]:.4f} min {bb[0]:.4f} ({len(bb)}); worst {worst}")
+    assert dec[len(dec) // 2] >= 0.99 and dec[0] >= 0.95
+    assert bb[len(bb) // 2] >= 0.85 and bb[0] >= 0.75
