@@ -481,8 +481,30 @@ def main_ours(args):
                                  "decoder outputs' mask logits) on the outputs of one inference step", "voxels": n0, "decoder_outputs": D,
                          "instances": T, "ms_fwd_bwd": l_ms}
             del pm, pc, mo, o
+
+            # whole training step: Mask3D.forward_train -> SetCriterion -> backward -> AdamW (lr 1e-4)
+            model.train()
+            opt = torch.optim.AdamW([p_ for n_, p_ in model.named_parameters() if not n_.startswith("backbone.final")], lr=1e-4)
+            c_t, f_t = resident[0]
+
+            def wstep():
+                opt.zero_grad(set_to_none=True)
+                out_t = model.forward_train(me_api.SparseTensor(features=f_t, coordinates=c_t))
+                ls = crit(out_t, tgt)
+                sum(ls[k] * wd[k] for k in ls).backward()
+                opt.step()
+
+            for _ in range(5):
+                wstep()
+            w_ms = timed(lambda i: wstep(), 5) / 5
+            loss_side["train_step"] = {"what": "Mask3D.forward_train + SetCriterion + backward + AdamW on the same scene (maps and plans "
+                                               "rebuilt every step)", "ms_step": w_ms, "voxels_per_s": n0 / (w_ms * 1e-3)}
+            model.eval()
+            for p_ in model.parameters():
+                p_.grad = None
+            del opt
         except Exception as exc:
-            loss_side = {"error": repr(exc)[:200]}
+            loss_side = dict(loss_side or {}, error=repr(exc)[:200])
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
