@@ -70,6 +70,11 @@ int mk_hash_query(const uint64_t* keys, const int32_t* vals, int64_t cap, const 
  * ------------------------------------------------------------------------------------------- */
 int mk_kernel_map(const uint64_t* in_keys, const int32_t* in_vals, int64_t cap, const int32_t* out_coords, int64_t n_out,
                   const int32_t* offsets, int K, int32_t* nbr, void* stream);
+/* The same table for a map onto ITSELF (stride-1 convolutions with an odd kernel: in map == out map, offsets[K-1-k] ==
+ * -offsets[k], which the caller guarantees): nbr[k,o] = i <=> nbr[K-1-k,i] = o, so half the offsets are probed and a hit writes
+ * both entries.  Bit-identical to mk_kernel_map. */
+int mk_kernel_map_same(const uint64_t* keys, const int32_t* vals, int64_t cap, const int32_t* coords, int64_t n, const int32_t* offsets,
+                       int K, int32_t* nbr, void* stream);
 /* Per 128-slot tile, bit k set iff some slot of the tile has a neighbour for offset k (K <= 32); also the
  * total pair count (device int64).  `n_slots` is the slot count of nbr (row stride of the table). */
 int mk_tile_kmask(const int32_t* nbr, int K, int64_t n_slots, uint32_t* tile_kmask, int64_t* pair_count, void* stream);

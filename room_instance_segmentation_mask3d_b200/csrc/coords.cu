@@ -208,6 +208,41 @@ __global__ void k_kernel_map(const unsigned long long* __restrict__ keys, const 
   }
 }
 
+// Same-map kernel map (in map == out map, odd kernel: offsets[K-1-k] == -offsets[k]): nbr[k, o] = i  <=>  nbr[K-1-k, i] = o, so
+// only the first K/2 offsets are probed; a hit writes both entries, the centre offset is the row itself, and the upper half is
+// pre-filled with -1 by the caller.  Each thread takes kSymK offsets of one row (one read of the row's coordinates per kSymK
+// probes).  Bit-identical to k_kernel_map; half the hash probes (the 5^3 stem map: 62 instead of 125 per voxel).
+constexpr int kSymK = 4;
+__global__ void __launch_bounds__(256) k_kernel_map_sym(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ vals,
+                                                        uint64_t mask, const int4* __restrict__ coords, int64_t n,
+                                                        const int32_t* __restrict__ offsets, int K, int32_t* __restrict__ nbr) {
+  const int half = K >> 1;
+  const int k0 = blockIdx.y * kSymK;
+  int ox[kSymK], oy[kSymK], oz[kSymK];
+#pragma unroll
+  for (int j = 0; j < kSymK; ++j) {
+    const int k = min(k0 + j, half);
+    ox[j] = offsets[3 * k], oy[j] = offsets[3 * k + 1], oz[j] = offsets[3 * k + 2];
+  }
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
+    const int4 c = coords[o];
+#pragma unroll
+    for (int j = 0; j < kSymK; ++j) {
+      const int k = k0 + j;
+      if (k > half) break;
+      if (k == half) {
+        nbr[(int64_t)k * n + o] = (int)o;
+        break;
+      }
+      const int x = c.y + ox[j], y = c.z + oy[j], z = c.w + oz[j];
+      int row = -1;
+      if (coord_in_range(c.x, x, y, z)) row = hash_lookup(keys, vals, mask, pack_key(c.x, x, y, z));
+      nbr[(int64_t)k * n + o] = row;
+      if (row >= 0) nbr[(int64_t)(K - 1 - k) * n + row] = (int)o;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(MK_TILE_ROWS) k_tile_kmask(const int32_t* __restrict__ nbr, int K, int64_t n_slots,
                                                              uint32_t* __restrict__ tile_kmask,
                                                              unsigned long long* __restrict__ pair_count) {
@@ -375,6 +410,20 @@ int mk_kernel_map(const uint64_t* in_keys, const int32_t* in_vals, int64_t cap, 
   dim3 grid((unsigned)bx, (unsigned)K);
   k_kernel_map<<<grid, 256, 0, (cudaStream_t)stream_>>>((const unsigned long long*)in_keys, in_vals, (uint64_t)(cap - 1),
                                                          (const int4*)out_coords, n_out, offsets, nbr);
+  return check_launch(__func__);
+}
+
+int mk_kernel_map_same(const uint64_t* keys, const int32_t* vals, int64_t cap, const int32_t* coords, int64_t n, const int32_t* offsets,
+                       int K, int32_t* nbr, void* stream_) {
+  MK_REQUIRE(K >= 1 && K <= 65535 && (K & 1) == 1, "same-map kernel maps have an odd number of offsets");
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream_;
+  const int half = K >> 1;
+  if (half > 0) cudaMemsetAsync(nbr + (int64_t)(half + 1) * n, 0xFF, (size_t)half * n * sizeof(int32_t), st);
+  int64_t bx = ceil_div(n, 256);
+  if (bx > 8 * num_sms()) bx = 8 * num_sms();
+  dim3 grid((unsigned)bx, (unsigned)ceil_div(half + 1, kSymK));
+  k_kernel_map_sym<<<grid, 256, 0, st>>>((const unsigned long long*)keys, vals, (uint64_t)(cap - 1), (const int4*)coords, n, offsets, K, nbr);
   return check_launch(__func__);
 }
 

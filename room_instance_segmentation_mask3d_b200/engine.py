@@ -7,6 +7,8 @@ kernel maps cached by (in_key, out_key, kernel_size, dilation).  All arithmetic 
 """
 from __future__ import annotations
 
+import os
+
 import ctypes
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -274,7 +276,9 @@ class CoordinateManager:
             K = ks[0] * ks[1] * ks[2]
             nbr = torch.empty((K, om.n), dtype=I32, device=self.device)
             offs = self._offsets_dev(ks, dl, in_key.tensor_stride)
-            lib.call("mk_kernel_map", lib.p(im.keys), lib.p(im.vals), im.cap, lib.p(om.coords), om.n, lib.p(offs), K, lib.p(nbr), lib.stream())
+            same = in_key == out_key and all(k % 2 == 1 for k in ks) and os.environ.get("MK3D_KMAP_SYM", "1") != "0"
+            lib.call("mk_kernel_map_same" if same else "mk_kernel_map", lib.p(im.keys), lib.p(im.vals), im.cap, lib.p(om.coords), om.n,
+                     lib.p(offs), K, lib.p(nbr), lib.stream())
             km = KernelMap(nbr, K, om.n, out_coords=om.coords, out_stride=out_key.tensor_stride)
             self._kmaps[ck] = km
         return km

@@ -73,6 +73,27 @@ def test_fullsize_kernel_map_symmetry(S):
     assert km.num_pairs == int((nbr >= 0).sum())
 
 
+@pytest.mark.parametrize("ks", [3, 5])
+def test_fullsize_same_map_kernel_map_equals_probe_everything(S, ks):
+    """mk_kernel_map_same (half the offsets probed, a hit writes nbr[k,o] and nbr[K-1-k,i]) against mk_kernel_map (every offset
+    probed), bit for bit, on the 3^3 and the 5^3 (stem) maps of the full scene; also a multi-scene batch with negative
+    coordinates, where hits must not cross scenes."""
+    lib, engine = S.lib, S.engine
+    for c in (S.c, torch.cat([S.c[:50000] - torch.tensor([0, 300, 7, 11], dtype=torch.int32, device="cuda"),
+                              (S.c[:70000] + torch.tensor([1, 0, 0, 0], dtype=torch.int32, device="cuda"))])):
+        mgr = engine.CoordinateManager(D=3)
+        k0, _ = mgr.insert_and_map(c)
+        cm = mgr._maps[k0]
+        K = ks ** 3
+        offs = mgr._offsets_dev((ks,) * 3, (1, 1, 1), k0.tensor_stride)
+        a = torch.empty((K, cm.n), dtype=torch.int32, device="cuda")
+        b = torch.full((K, cm.n), -7, dtype=torch.int32, device="cuda")
+        lib.call("mk_kernel_map", lib.p(cm.keys), lib.p(cm.vals), cm.cap, lib.p(cm.coords), cm.n, lib.p(offs), K, lib.p(a), lib.stream())
+        lib.call("mk_kernel_map_same", lib.p(cm.keys), lib.p(cm.vals), cm.cap, lib.p(cm.coords), cm.n, lib.p(offs), K, lib.p(b), lib.stream())
+        assert torch.equal(a, b)
+        assert torch.equal(mgr.neighbor_table(k0, k0, ks, 1).nbr, a)
+
+
 def test_fullsize_tensor_core_conv_bit_exact_on_integer_operands(S):
     """Integer-valued bf16 operands: products and all partial sums are exact in fp32, so the tcgen05 kernel (any tile order, any
     offset split) must equal the exact-fp32 CUDA-core kernel BIT FOR BIT on all 889 k rows."""
