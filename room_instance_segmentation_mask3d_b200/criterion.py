@@ -71,14 +71,18 @@ def pack_targets(targets: Sequence, sizes: Sequence[int], device) -> PackedTarge
         keep.append(m8)
         lib.call("mk_target_bits", lib.p(m8), n_targets[b], int(sizes[b]), W, bits.data_ptr() + int(offs[b]) * W * 4, st)
     Tp = 32 * W
-    labels_host = [_get(t, "instances_labels").detach().cpu().long() for t in targets]
-    lab = torch.zeros((B, Tp), dtype=torch.long)
-    ign = torch.zeros((B, Tp), dtype=torch.bool)
-    for b, l in enumerate(labels_host):
-        ign[b, : len(l)] = l == IGNORE_LABEL
-        lab[b, : len(l)] = torch.where(l == IGNORE_LABEL, torch.zeros_like(l), l)
+    labs = [_get(t, "instances_labels").detach().long() for t in targets]
+    flat = (torch.cat(labs) if B else torch.zeros(0, dtype=torch.long)).cpu().numpy()  # ONE device -> host copy for the batch
+    labels_host, lab, ign, o = [], np.zeros((B, Tp), dtype=np.int64), np.zeros((B, Tp), dtype=bool), 0
+    for b, T in enumerate(n_targets):
+        l = flat[o:o + T]
+        o += T
+        labels_host.append(l)
+        ign[b, :T] = l == IGNORE_LABEL
+        lab[b, :T] = np.where(l == IGNORE_LABEL, 0, l)
     so = torch.from_numpy(offs.astype(np.int32)).to(device)
-    return PackedTargets(bits, so, [int(s) for s in sizes], n_targets, labels_host, lab.to(device), ign.to(device))
+    return PackedTargets(bits, so, [int(s) for s in sizes], n_targets, labels_host, torch.from_numpy(lab).to(device),
+                         torch.from_numpy(ign).to(device))
 
 
 def _batched_logits(pm, sizes) -> torch.Tensor:
@@ -192,11 +196,12 @@ class HungarianMatcher(nn.Module):
     @staticmethod
     def assign(C_host: torch.Tensor, tg: PackedTargets):
         """Hungarian assignment per scene on the host copy of C [B, Q, Tp] (matcher.py:160-162)."""
-        assert not torch.isnan(C_host).any(), "out mask must not be NaN"  # matcher.py:120
+        C = C_host.numpy() if isinstance(C_host, torch.Tensor) else C_host
+        assert not np.isnan(C).any(), "out mask must not be NaN"  # matcher.py:120
         out = []
         for b in range(tg.B):
-            i, j = linear_sum_assignment(C_host[b, :, : tg.n_targets[b]].numpy())
-            out.append((torch.as_tensor(i, dtype=torch.int64), torch.as_tensor(j, dtype=torch.int64)))
+            i, j = linear_sum_assignment(C[b, :, : tg.n_targets[b]])
+            out.append((torch.from_numpy(i.astype(np.int64)), torch.from_numpy(j.astype(np.int64))))
         return out
 
     @torch.no_grad()
@@ -287,15 +292,16 @@ class SetCriterion(nn.Module):
         """matches_all[d][b] = (query idx, target idx) -> target classes int64 [D, B, Q] (criterion.py:152-158), matched target
         int32 [D, B, Q] (-1 = none), 1 / matched pairs fp32 [D, B] (num_masks = target_mask.shape[0], criterion.py:190)."""
         D = len(matches_all)
-        tc = torch.full((D, tg.B, Q), self.num_classes, dtype=torch.int64)
-        m = torch.full((D, tg.B, Q), -1, dtype=torch.int32)
-        inv = torch.zeros((D, tg.B), dtype=torch.float32)
+        tc = np.full((D, tg.B, Q), self.num_classes, dtype=np.int64)
+        m = np.full((D, tg.B, Q), -1, dtype=np.int32)
+        inv = np.zeros((D, tg.B), dtype=np.float32)
         for d, matches in enumerate(matches_all):
             for b, (iq, it) in enumerate(matches):
+                iq, it = iq.numpy(), it.numpy()
                 tc[d, b, iq] = tg.labels_host[b][it]
-                m[d, b, iq] = it.to(torch.int32)
+                m[d, b, iq] = it
                 inv[d, b] = 1.0 / len(it) if len(it) > 0 else 0.0
-        return tc, m, inv
+        return torch.from_numpy(tc), torch.from_numpy(m), torch.from_numpy(inv)
 
     @staticmethod
     def _match_table(matches, tg: PackedTargets, Q: int):
@@ -370,7 +376,7 @@ class SetCriterion(nn.Module):
                     for i in range(D):
                         mask_costs(logits[i], tg, out=buf[i], n_rows=nr[i])
                     stats = MaskStats(buf, nr)
-                    C = self.matcher.cost_matrix(torch.stack(cls), stats, tg).cpu()  # the one device -> host copy of the step
+                    C = self.matcher.cost_matrix(torch.stack(cls), stats, tg).cpu().numpy()  # the one device -> host copy of the step
                 matches_all = [self.matcher.assign(C[i], tg) for i in range(D)]
                 per_output = self._losses(torch.stack(cls), logits, tg, stats, matches_all)
             else:  # keep the reference's order of random draws: matcher subset, then loss subset, output by output
