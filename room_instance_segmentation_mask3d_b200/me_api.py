@@ -452,15 +452,40 @@ class MinkowskiInstanceNorm(nn.Module):
 
 
 class MinkowskiBatchNorm(nn.Module):
-    """BatchNorm1d over all rows (state keys bn.*).  Not instantiated by the reference's default model
-    (it uses instance norm, mask3d/models/res16unet.py:16); kept on torch for state-dict compatibility."""
+    """MinkowskiBatchNorm (mask3d/models/modules/common.py:22): batch norm over all rows of `.F`, parameters and running
+    statistics under the reference's state-dict keys (`bn.weight`, `bn.bias`, `bn.running_mean`, `bn.running_var`,
+    `bn.num_batches_tracked`).  The `nn.BatchNorm1d` child only HOLDS that state; the arithmetic is the instance-norm kernels
+    with the whole batch as one segment (mk_instnorm_stats / mk_norm_apply / mk_instnorm_relu_bwd): statistics in one read,
+    apply in one read + one write.  Not instantiated by the reference's default model (res16unet.py:16 selects instance norm)."""
 
     def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True):
         super().__init__()
         self.bn = nn.BatchNorm1d(num_features, eps=eps, momentum=momentum, affine=affine, track_running_stats=track_running_stats)
 
     def forward(self, x: SparseTensor) -> SparseTensor:
-        return x._like(self.bn(x.F.float()))
+        lib.require_cuda()
+        bn, f = self.bn, x.F
+        n, C = f.shape
+        dev = f.device
+        off = torch.tensor([0, n], dtype=torch.int32, device=dev)
+        w = bn.weight.view(1, C) if bn.affine else torch.ones(1, C, device=dev)
+        b = bn.bias.view(1, C) if bn.affine else torch.zeros(1, C, device=dev)
+        if bn.training or not bn.track_running_stats or bn.running_mean is None:
+            if bn.training and bn.track_running_stats and n > 0:
+                with torch.no_grad():
+                    mean, rstd = ops.instance_norm_stats(f.detach().contiguous(), off, 1, bn.eps)
+                    var = (1.0 / (rstd[0] * rstd[0]) - bn.eps).clamp_min(0.0) * (n / max(n - 1, 1))  # unbiased, as BatchNorm1d stores it
+                    bn.num_batches_tracked += 1
+                    mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+                    bn.running_mean.mul_(1 - mom).add_(mean[0], alpha=mom)
+                    bn.running_var.mul_(1 - mom).add_(var, alpha=mom)
+            return x._like(_InstanceNormFn.apply(f, w, b, off, 1, bn.eps))
+        rstd = torch.rsqrt(bn.running_var.float() + bn.eps)
+        if torch.is_grad_enabled() and (f.requires_grad or (bn.affine and bn.weight.requires_grad)):
+            # frozen statistics under autograd: an affine map per channel
+            return x._like((f.float() - bn.running_mean.float()) * (rstd * w) + b)
+        return x._like(ops.norm_apply(f.contiguous(), off, 1, bn.running_mean.float().view(1, C).contiguous(), rstd.view(1, C).contiguous(),
+                                      w, b, out_dtype=torch.float32))
 
 
 class _Elementwise(nn.Module):

@@ -503,6 +503,37 @@ def test_masked_cross_attention_backward_vs_stock_mha(R, Q, kv_dtype):
         assert rel_err(g, w) < tol, (name, rel_err(g, w))
 
 
+def test_batch_norm_matches_torch_batchnorm1d(R):
+    """MinkowskiBatchNorm on the instance-norm kernels vs nn.BatchNorm1d: training output, running statistics, gradients,
+    eval output (fp32, <= 1e-4 relative)."""
+    ME = R.me
+    torch.manual_seed(3)
+    n, C = 5000, 48
+    coords = torch.cat([torch.zeros(n, 1, dtype=torch.int32), torch.arange(n, dtype=torch.int32)[:, None].repeat(1, 3)], 1).cuda()
+    f = (torch.randn(n, C) * 3 + 1).cuda()
+    ref = torch.nn.BatchNorm1d(C, eps=1e-5, momentum=0.02).cuda()
+    mod = ME.MinkowskiBatchNorm(C, momentum=0.02).cuda()
+    with torch.no_grad():
+        ref.weight.uniform_(0.5, 1.5); ref.bias.uniform_(-1, 1)
+    mod.bn.load_state_dict(ref.state_dict())
+    assert sorted(mod.state_dict()) == sorted("bn." + k for k in ref.state_dict())
+    for _ in range(2):
+        fa, fb = f.clone().requires_grad_(True), f.clone().requires_grad_(True)
+        ya = ref(fa)
+        yb = mod(ME.SparseTensor(features=fb, coordinates=coords)).F
+        assert rel_err(yb, ya) < 1e-4
+        g = torch.randn_like(ya)
+        ref.zero_grad(); mod.zero_grad()
+        (ya * g).sum().backward(); (yb * g).sum().backward()
+        assert rel_err(fb.grad, fa.grad) < 1e-4
+        assert rel_err(mod.bn.weight.grad, ref.weight.grad) < 1e-4 and rel_err(mod.bn.bias.grad, ref.bias.grad) < 1e-4
+        assert rel_err(mod.bn.running_mean, ref.running_mean) < 1e-5 and rel_err(mod.bn.running_var, ref.running_var) < 1e-5
+    ref.eval(); mod.eval()
+    with torch.no_grad():
+        assert rel_err(mod(ME.SparseTensor(features=f, coordinates=coords)).F, ref(f)) < 1e-4
+    assert int(mod.bn.num_batches_tracked) == int(ref.num_batches_tracked) == 2
+
+
 def test_fps_matches_reference_tie_breaking(R):
     sc = [scenes.tiny_scene(0), scenes.tiny_scene(1, (20, 16, 10)), scenes.box_room((1.0, 1.2, 0.6), 0.02), scenes.tiny_scene(5, (7, 5, 4), 0)]
     coords, _ = scenes.collate(sc)
