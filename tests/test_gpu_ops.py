@@ -503,6 +503,29 @@ def test_masked_cross_attention_backward_vs_stock_mha(R, Q, kv_dtype):
         assert rel_err(g, w) < tol, (name, rel_err(g, w))
 
 
+def test_sparse_quantize_matches_oracle(R):
+    """ME.utils.sparse_quantize on the GPU hash vs the oracle: floats with a quantisation size, negative
+    coordinates, duplicate voxels with agreeing / conflicting labels, numpy and torch inputs, every return combination.
+    Voxel rows, first-occurrence indices and inverse maps bit-exact."""
+    rng = np.random.default_rng(4)
+    pts = rng.uniform(-3.0, 3.0, size=(4000, 3))
+    pts[::7] = pts[1::7][: len(pts[::7])]  # exact duplicates
+    lab = rng.integers(0, 3, size=len(pts))
+    feats = rng.normal(size=(len(pts), 2)).astype(np.float32)
+    want = O.sparse_quantize(pts, features=feats, labels=lab, return_index=True, return_inverse=True, quantization_size=0.25, ignore_label=-100)
+    got = R.me.sparse_quantize(pts, features=feats, labels=lab, return_index=True, return_inverse=True, quantization_size=0.25, ignore_label=-100)
+    assert len(got) == len(want) == 5
+    for g, w in zip(got, want):
+        assert np.array_equal(np.asarray(g), np.asarray(w))
+    assert (np.asarray(got[2]) == -100).any() and (np.asarray(got[2]) != -100).any()
+    # torch input, integer coordinates, maps only
+    ci = torch.from_numpy(rng.integers(-20, 20, size=(3000, 3)).astype(np.int32))
+    m_w, i_w = O.sparse_quantize(ci, return_maps_only=True, return_inverse=True)
+    m_g, i_g = R.me.sparse_quantize(ci.cuda(), return_maps_only=True, return_inverse=True)
+    assert np.array_equal(m_g.cpu().numpy(), m_w.numpy()) and np.array_equal(i_g.cpu().numpy(), i_w.numpy())
+    assert np.array_equal(R.me.sparse_quantize(ci.cuda()).cpu().numpy(), O.sparse_quantize(ci).numpy())
+
+
 def test_batch_norm_matches_torch_batchnorm1d(R):
     """MinkowskiBatchNorm on the instance-norm kernels vs nn.BatchNorm1d: training output, running statistics, gradients,
     eval output (fp32, <= 1e-4 relative)."""
