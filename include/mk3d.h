@@ -87,6 +87,9 @@ int mk_transpose_map(const int32_t* nbr_down, int K, int64_t n_coarse, int64_t n
  * a single mask and is a compact spatial patch, then permutes the table: out[k, s] = nbr[k, order[s]]  (order[s] < 0 -> -1). */
 int mk_row_sort_keys(const int32_t* nbr, int K, int64_t n, const int32_t* coords, const int32_t* stride3_host, uint64_t* keys,
                      void* stream);
+/* keys[o] = offset bitmask of slot o only (int32).  A STABLE sort by it groups equal masks and keeps each group in row order
+ * (the default plan: as fast for the gathers as the Z-curve order, half the sort). */
+int mk_row_mask_keys(const int32_t* nbr, int K, int64_t n, int32_t* keys, void* stream);
 int mk_permute_table(const int32_t* nbr, int K, int64_t n, const int32_t* order, int64_t n_slots, int32_t* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -40,6 +40,7 @@ _SIGS = {
                                  c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "mk_set_gather_mode": (c_int, [c_int]),
     "mk_row_sort_keys": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mk_row_mask_keys": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "mk_permute_table": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "mk_conv_stem_f32": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_int, c_void_p]),
     "mk_conv_stem_wgrad_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
