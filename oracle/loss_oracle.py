@@ -118,3 +118,17 @@ def mask_scores(pred_mask: torch.Tensor) -> torch.Tensor:
     x = pred_mask.double()
     hard = (x > 0).double()
     return (x.sigmoid() * hard).sum(0) / (hard.sum(0) + 1e-6)
+
+
+def get_mask_and_scores(pred_class: torch.Tensor, pred_mask: torch.Tensor, num_queries: int, num_classes: int, topk_per_image: int = -1):
+    """trainer/trainer.py:373-402, line by line (CPU)."""
+    labels = torch.arange(num_classes).unsqueeze(0).repeat(num_queries, 1).flatten(0, 1)
+    k = topk_per_image if topk_per_image != -1 else num_queries
+    scores_per_query, topk_indices = pred_class.flatten(0, 1).topk(k, sorted=True)
+    labels_per_query = labels[topk_indices]
+    topk_indices = topk_indices // num_classes
+    pm = pred_mask[:, topk_indices]
+    result_pred_mask = (pm > 0).float()
+    heatmap = pm.float().sigmoid()
+    mask_scores_per_image = (heatmap * result_pred_mask).sum(0) / (result_pred_mask.sum(0) + 1e-6)
+    return scores_per_query * mask_scores_per_image, result_pred_mask.bool(), labels_per_query, heatmap

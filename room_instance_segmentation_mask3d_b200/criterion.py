@@ -162,6 +162,29 @@ def mask_scores(pred_mask: torch.Tensor) -> torch.Tensor:
     return mask_costs(pred_mask, tg, want_score=True).mask_score[0]
 
 
+def get_mask_and_scores(pred_class: torch.Tensor, pred_mask: torch.Tensor, num_queries: int, num_classes: int, topk_per_image: int = -1):
+    """Mirror of InstanceSegmentation.get_mask_and_scores (trainer/trainer.py:373-402) for ONE scene.
+
+    pred_class [Q, num_classes] = softmax class probabilities without the no-object column (trainer.py:321-322), pred_mask
+    [N, Q] logits.  Returns (score [K], result_pred_mask bool [N, K], classes [K], heatmap fp32 [N, K]) with the reference's
+    devices: score on the CPU, the rest where the inputs live.  The per-query reduction over all N voxels — sum(sigmoid(x) *
+    (x > 0)) / (sum(x > 0) + 1e-6), the only arithmetic of the function that touches every logit more than once — is
+    `mk_mask_costs`' mask score, computed once per query column instead of once per selected (query, class) pair."""
+    lib.require_cuda()
+    dev = pred_mask.device
+    labels = torch.arange(num_classes, device=dev).unsqueeze(0).repeat(num_queries, 1).flatten(0, 1)
+    k = topk_per_image if topk_per_image != -1 else num_queries
+    scores_per_query, topk_indices = pred_class.flatten(0, 1).topk(k, sorted=True)
+    labels_per_query = labels[topk_indices]
+    topk_indices = torch.div(topk_indices, num_classes, rounding_mode="floor")
+    col_score = mask_scores(pred_mask)  # [Q], one pass over the logits
+    sel = pred_mask[:, topk_indices]
+    result_pred_mask = sel > 0
+    heatmap = sel.float().sigmoid()
+    score = scores_per_query.detach().cpu() * col_score[topk_indices].detach().cpu()
+    return score, result_pred_mask, labels_per_query, heatmap
+
+
 def _row_subset(tg: PackedTargets, num_points: float, device) -> torch.Tensor:
     """The reference's per-item random subset (matcher.py:125-127, criterion.py:181-182): torch.randperm(N)[: int(num_points N)],
     drawn per scene in scene order from the global generator of the device, as a uint8 row mask."""

@@ -202,6 +202,24 @@ def test_mask_costs_and_scores_vs_oracle(sizes, n_targets, Q):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("num_classes,topk", [(1, -1), (3, -1), (3, 40)])
+def test_get_mask_and_scores_vs_oracle(num_classes, topk):
+    """Post-processing mask scoring (trainer/trainer.py:373-402): scores, selected (query, class) pairs, binary masks, heatmap."""
+    from room_instance_segmentation_mask3d_b200 import criterion as CR
+
+    g = torch.Generator().manual_seed(21)
+    n, Q = 7001, 25
+    pm = torch.randn(n, Q, generator=g) * 3
+    pm[:, 4] = -5.0  # a query whose mask is empty: score 0 / 1e-6
+    pc = torch.rand(Q, num_classes + 1, generator=g).softmax(-1)[:, :-1]
+    ws, wm, wc, wh = LO.get_mask_and_scores(pc, pm, Q, num_classes, topk)
+    gs, gm, gc, gh = CR.get_mask_and_scores(pc.cuda(), pm.cuda(), Q, num_classes, topk)
+    assert not gs.is_cuda and torch.equal(gc.cpu(), wc) and torch.equal(gm.cpu(), wm)
+    np.testing.assert_allclose(gs.numpy(), ws.numpy(), rtol=2e-4, atol=1e-7)
+    np.testing.assert_allclose(gh.cpu().numpy(), wh.numpy(), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.gpu
 def test_mask_losses_forward_backward_vs_oracle_with_row_subset():
     """Matched losses + gradient on a ragged batch, all points and an explicit row subset (the num_points != -1 path)."""
     from room_instance_segmentation_mask3d_b200 import criterion as CR
