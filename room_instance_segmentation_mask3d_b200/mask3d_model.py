@@ -86,13 +86,41 @@ class _ConvNormActFn(torch.autograd.Function):
         dx = dW = None
         if ctx.needs_input_grad[0]:
             if kind == 0:
-                dx = ops.conv_dgrad_bf16(dtmp, W3, km, kidx=torch.arange(K - 1, -1, -1, device=x.device, dtype=torch.int32),
-                                         out_dtype=torch.bfloat16)
+                dx = ops.conv_dgrad_bf16(dtmp, W3, km, kidx=ops.reversed_offsets(K, x.device), out_dtype=torch.bfloat16)
             else:
                 dx = ops.conv_dgrad_bf16(dtmp, W3, ctx.aux, out_dtype=torch.bfloat16)
         if ctx.needs_input_grad[1]:
             dW = ops.conv_wgrad_bf16(x, dtmp, km, K, cin, cout).reshape(W.shape)
         return dx, dW, dgamma.view_as(gamma), dbeta.view_as(gamma), dres, None, None, None, None, None, None
+
+
+class _LinFn(torch.autograd.Function):
+    """1x1 convolution + bias on the rows of one level with the output in the requested dtype, as ONE autograd node (the
+    mask-feature head, lin_squeeze and the K / V in-projections of the training forward): forward = the tcgen05 conv kernel with
+    fused bias and cast, backward = tcgen05 dgrad + wgrad + a column sum for the bias."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias, km, out_dtype):
+        x = x.contiguous()
+        ctx.km = km
+        ctx.save_for_backward(x, W)
+        return ops.conv_forward(x.detach(), W, km, bias=bias, mode="bf16", out_dtype=out_dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W = ctx.saved_tensors
+        km = ctx.km
+        W3 = W.detach().unsqueeze(0) if W.dim() == 2 else W.detach()
+        _, cin, cout = W3.shape
+        db = ops.cast(dy.contiguous(), torch.bfloat16)
+        dx = dW = dbias = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.conv_dgrad_bf16(db, W3, km, kidx=ops.reversed_offsets(1, x.device), out_dtype=x.dtype)
+        if ctx.needs_input_grad[1]:
+            dW = ops.conv_wgrad_bf16(x, db, km, 1, cin, cout).reshape(W.shape)
+        if ctx.needs_input_grad[2]:
+            dbias = dy.float().sum(0)
+        return dx, dW, dbias, None, None
 
 
 class Res16UNet34C(nn.Module):
@@ -501,8 +529,7 @@ class Mask3D(nn.Module):
             """1x1 convolution + bias on the rows of a level; differentiable when training (W: [cin, cout] view of a parameter)"""
             if not train:
                 return ops.conv_forward(xf, W, km, bias=bias, mode=mode, out_dtype=out_dtype)
-            y = ME._ConvFn.apply(xf, W, km, 0, xf.shape[0], None) + bias.view(1, -1)
-            return y if out_dtype == torch.float32 else y.to(out_dtype)
+            return _LinFn.apply(xf, W, bias.view(-1), km, out_dtype)
 
         self._ev_backbone = torch.cuda.Event()
         self._ev_backbone.record(torch.cuda.current_stream())

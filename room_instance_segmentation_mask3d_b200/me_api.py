@@ -209,7 +209,7 @@ class _ConvFn(torch.autograd.Function):
             db = ops.cast(dout.contiguous(), torch.bfloat16)
             if ctx.needs_input_grad[0]:
                 if kind == 0:
-                    dx = ops.conv_dgrad_bf16(db, W3, km, kidx=torch.arange(K - 1, -1, -1, device=x.device, dtype=torch.int32))
+                    dx = ops.conv_dgrad_bf16(db, W3, km, kidx=ops.reversed_offsets(K, x.device))
                 else:
                     dx = ops.conv_dgrad_bf16(db, W3, ctx.aux)  # kind 1: transpose plan; kind 2: fine -> coarse table
             if ctx.needs_input_grad[1]:
@@ -218,7 +218,7 @@ class _ConvFn(torch.autograd.Function):
         dout = dout.contiguous().float()
         xf = x.detach().float().contiguous()
         if kind == 0:
-            nbr_t, kidx, nbr_w = km.nbr, torch.arange(K - 1, -1, -1, device=x.device, dtype=torch.int32), km.nbr
+            nbr_t, kidx, nbr_w = km.nbr, ops.reversed_offsets(K, x.device), km.nbr
         elif kind == 1:
             tplan = ctx.aux  # transpose plan of the same pair of maps (parent / koff per fine row)
             nbr_t, kidx, nbr_w = _identity_table(tplan), None, km.nbr

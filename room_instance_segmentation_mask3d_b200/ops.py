@@ -55,6 +55,19 @@ def weight_image(W: torch.Tensor, transpose: bool = False) -> torch.Tensor:
     return img
 
 
+_kidx_cache: Dict[Tuple[int, str], torch.Tensor] = {}
+
+
+def reversed_offsets(K: int, device) -> torch.Tensor:
+    """int32 [K-1, ..., 0]: the offset permutation of the same-map dgrad (offset k of the transposed table reads W[K-1-k]);
+    cached per (K, device) — one tiny kernel per backward node otherwise."""
+    key = (K, str(device))
+    t = _kidx_cache.get(key)
+    if t is None:
+        t = _kidx_cache[key] = torch.arange(K - 1, -1, -1, device=device, dtype=torch.int32)
+    return t
+
+
 def _flat32(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     """fp32 1-D view of a (small) parameter; no copy when it already is contiguous fp32."""
     if t is None:
