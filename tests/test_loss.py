@@ -96,6 +96,32 @@ def test_criterion_mirror_has_reference_signature_and_fails_without_cuda():
             CR.mask_scores(torch.zeros(4, 3))
 
 
+def test_criterion_host_logic_batched_logits_and_match_tables():
+    """Host side of the mirror (no kernel involved): per-scene logit lists that are the row blocks of one tensor are used
+    without a copy, anything else is concatenated; the match / class tables follow criterion.py:152-158,190."""
+    from room_instance_segmentation_mask3d_b200 import criterion as CR
+
+    base = torch.randn(10, 4, requires_grad=True)
+    views = list(base.split([3, 7]))
+    assert CR._batched_logits(views, [3, 7]) is base
+    assert CR._batched_logits(base, [3, 7]) is base
+    sep = [torch.randn(3, 4), torch.randn(7, 4)]
+    cat = CR._batched_logits(sep, [3, 7])
+    assert cat.shape == (10, 4) and torch.equal(cat[3:], sep[1])
+    assert CR._batched_logits(list(base[:, :2].split([3, 7])), [3, 7]).shape == (10, 2)  # column slices: not row blocks, copied
+    assert CR._sizes_of(sep, None) == [3, 7]
+
+    tg = SimpleNamespace(B=2, labels_host=[np.array([5, 6, 7]), np.array([1])])
+    crit = CR.SetCriterion(9, CR.HungarianMatcher(1, 1, 1, -1), {}, 0.1, ["labels", "masks"], -1, 3.0, 0.75, -1)
+    matches = [[(torch.tensor([4, 0, 2]), torch.tensor([0, 2, 1])), (torch.tensor([3]), torch.tensor([0]))]]
+    tc, m, inv = crit._tables(matches, tg, 5)
+    assert tc.tolist() == [[[7, 9, 6, 9, 5], [9, 9, 9, 1, 9]]]  # unmatched queries -> class num_classes
+    assert m.tolist() == [[[2, -1, 1, -1, 0], [-1, -1, -1, 0, -1]]]
+    assert torch.allclose(inv, torch.tensor([[1 / 3, 1.0]]))
+    ce = crit.loss_labels(torch.zeros(1, 2, 5, 10), tc)  # uniform logits: weighted mean of log(10)
+    assert abs(float(ce[0]) - np.log(10)) < 1e-5
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # GPU: the CUDA path
 # ------------------------------------------------------------------------------------------------------------------
