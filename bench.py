@@ -11,6 +11,9 @@ depends on the scene: coordinate hashing, 4 strided coordinate maps, 14 kernel m
           the timed region)
   e2e     voxels/s through the public API from pinned HOST buffers, H2D of coordinates/features and D2H of the class
           logits + final mask logits inside the timed region
+  train_fwd_bwd      (N = 1, beside the headline) Res16UNet34C forward + backward on the fused training path
+  loss_side          (N = 1) SetCriterion forward + backward on the outputs of one inference step, and `train_step`: the whole
+          training step Mask3D.forward_train -> SetCriterion -> backward -> AdamW on the same scene
   --impl reference   the CPU restatement of the reference's MinkowskiEngine + PyTorch path (oracle/, "port": ME 0.5.4 is
           not installable here) on all host cores, on a bounded sample of the same workload.
 """
