@@ -497,7 +497,7 @@ def main_ours(args):
                 sum(ls[k] * wd[k] for k in ls).backward()
                 opt.step()
 
-            for _ in range(5):
+            for _ in range(10):  # the caching allocator keeps growing (cudaMalloc) for the first handful of training steps
                 wstep()
             w_ms = timed(lambda i: wstep(), 5) / 5
             loss_side["train_step"] = {"what": "Mask3D.forward_train + SetCriterion + backward + AdamW on the same scene (maps and plans "
