@@ -315,6 +315,12 @@ class CoordinateManager:
         slots are the fine rows stably sorted by k and padded per k to a multiple of 128: every tile then has a single
         active offset and the tensor-core kernel does no wasted MMA work."""
         ks, dl = _tuple3(kernel_size), _tuple3(dilation)
+        ratio = tuple(c // f for c, f in zip(coarse_key.tensor_stride, fine_key.tensor_stride))
+        if ks != ratio or any(d != 1 for d in dl):
+            # one (offset, parent) pair per fine row only holds for non-overlapping kernels (kernel_size == stride, dilation 1:
+            # the 2^3 / stride-2 convs and pools of Res16UNet34C); overlapping kernels (3/2, 1/2) would race on parent[f] / koff[f]
+            raise NotImplementedError(f"transposed / strided-backward maps need kernel_size == stride and dilation 1 (got kernel "
+                                      f"{list(ks)}, stride {list(ratio)}, dilation {list(dl)}): outside the hot path (SURVEY.md section 8)")
         ck = (coarse_key, fine_key, ks, dl)
         plan = self._tplans.get(ck)
         if plan is None:

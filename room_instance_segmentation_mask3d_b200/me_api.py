@@ -352,7 +352,8 @@ class MinkowskiConvolution(_ConvBase):
                 assert all(k % 2 == 1 for k in kg.kernel_size), "even kernels need stride > 1 on this path"
                 F = _ConvFn.apply(x.F, self.kernel, km, 0, x.F.shape[0], None)
             else:
-                aux = mgr.transpose_plan(out_key, in_key, kg.kernel_size, kg.kernel_dilation) if torch.is_grad_enabled() else None
+                # backward of a strided conv needs the (offset, parent) map: raises NotImplementedError unless kernel == stride
+                aux = mgr.transpose_plan(out_key, in_key, kg.kernel_size, kg.kernel_dilation) if (torch.is_grad_enabled() and x.F.requires_grad) else None
                 F = _ConvFn.apply(x.F, self.kernel, km, 1, x.F.shape[0], aux)
         if self.bias is not None:
             F = F + self.bias
@@ -396,6 +397,9 @@ class _PoolBase(nn.Module):
         mgr, kg = x.coordinate_manager, self.kernel_generator
         out_key = mgr.stride(x.coordinate_map_key, kg.kernel_stride)
         km = mgr.neighbor_table(x.coordinate_map_key, out_key, kg.kernel_size, kg.kernel_dilation)
+        if torch.is_grad_enabled() and x.F.requires_grad and (list(kg.kernel_size) != list(kg.kernel_stride) or any(d != 1 for d in kg.kernel_dilation)):
+            # mk_pool_bwd writes each input row's gradient once: only right when every input row has one parent
+            raise NotImplementedError("pooling backward needs kernel_size == stride and dilation 1 (non-overlapping windows)")
         F = _PoolFn.apply(x.F, km, self.AVERAGE, x.F.shape[0])
         return SparseTensor(F, coordinate_map_key=out_key, coordinate_manager=mgr)
 
