@@ -116,9 +116,12 @@ int mk_conv_weight_image_bf16(const float* W, int K, int cin, int cout, int tran
 int mk_conv_fwd_bf16(const void* in, int64_t n_in, int cin, const void* wimg, int cout, const int32_t* nbr, int K, int64_t n_slots,
                      const int32_t* out_rows, const uint32_t* tile_kmask, const int32_t* kidx, int64_t n_out,
                      const float* bias, void* out, int out_dtype, int out_cols, int out_stride, void* stream);
-/* A-operand producer of mk_conv_fwd_bf16: 0 = LSU (LDG.128 -> registers -> swizzled STS.128, default), 1 = TMA gather4
- * (also env MK3D_GATHER=tma). */
+/* A-operand producer of mk_conv_fwd_bf16: 0 = LSU (16-byte cp.async into the swizzled tile, default), 1 = TMA gather4. */
 int mk_set_gather_mode(int mode);
+/* 1: results are bit-identical from run to run (the reference trains with `deterministic: true`,
+ * mask3d/conf/trainer/trainer.yaml:1): no offset split with floating-point REDs in mk_conv_fwd_bf16 (forward / dgrad), fixed-order
+ * reduction in mk_conv_wgrad_bf16.  0 (default): fastest. */
+int mk_set_deterministic(int on);
 /* Stem: Cin == 1, K up to 125 (5^3): pure lookup, CUDA cores.  in fp32 [n_in], W fp32 [K,1,cout]. */
 int mk_conv_stem_f32(const float* in, const float* W, int cout, const int32_t* nbr, int K, int64_t n_out, void* out,
                      int out_dtype, void* stream);

@@ -33,6 +33,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     objs = []
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    if os.environ.get("MK3D_BUILD_TUNING") == "1":  # measurement sweeps only: pipeline-shape overrides / ablations from the environment
+        flags.append("-DMK3D_TUNING")
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     procs = []
     for src in SOURCES:

@@ -34,15 +34,15 @@
 
 namespace mk {
 
-constexpr int kMaxProducers = 5;  // warps 0-3 and 5
+// ---- thread layout of k_conv_umma (448 threads = 14 warps) ----
+constexpr int kCvProducerWarps = 8;   // warps 0-7: gather producers (stage ownership in groups of `split` warps)
+constexpr int kCvMmaWarp = 8;         // MMA issuer
+constexpr int kCvAllocWarp = 9;       // TMEM allocation; second MMA issuer when G == 2
+constexpr int kCvEpiWarp0 = 10;       // warps 10-13: epilogue (TMEM lane quarter = warp & 3)
+constexpr int kCvThreads = 448;
 
-// Work enumeration of one CTA.  A "super-tile" is G consecutive 128-slot tiles (G = 2 when cout <= 128: the two accumulators
-// share every weight chunk, which halves the weight traffic and the per-stage bookkeeping of all three roles; mask-sorted
-// plans give neighbouring tiles the same offset set, so the union costs nothing).  Items are the set bits of the union of the
-// member tiles' offset masks, ascending; an iteration is (item, 64-channel chunk).
 // keep the set bits of m whose ordinal is congruent to `part` modulo `ksplit` (offset split of small problems)
 __device__ __forceinline__ uint32_t split_bits(uint32_t m, int part, int ksplit) {
-  if (ksplit <= 1) return m;
   uint32_t r = 0;
   for (int i = 0; m; ++i) {
     const uint32_t b = m & (0u - m);
@@ -52,74 +52,73 @@ __device__ __forceinline__ uint32_t split_bits(uint32_t m, int part, int ksplit)
   return r;
 }
 
-struct SuperCursor {
-  const uint32_t* kmask;
-  int G, st, stride, num_st, num_tiles;
-  int part, ksplit;
-  uint32_t m0, m1, mu;      // member masks of the current super-tile, remaining union bits (of the current chunk pass)
-  uint32_t n0, n1;          // masks of the next super-tile (prefetched)
-  int ch, nchunks;
-  int chunk_major;          // 1: all offsets of chunk 0, then all offsets of chunk 1, ... ; 0: (offset, chunk) with chunk inner
-  __device__ uint32_t mask_of(int t) const { return t < num_tiles ? kmask[t] : 0u; }
-  __device__ SuperCursor(const uint32_t* kmask_, int G_, int first, int stride_, int num_tiles_, int nchunks_, int chunk_major_,
-                         int part_ = 0, int ksplit_ = 1)
-      : kmask(kmask_), G(G_), st(first), stride(stride_), num_tiles(num_tiles_), part(part_), ksplit(ksplit_), ch(0), nchunks(nchunks_),
-        chunk_major(chunk_major_) {
-    num_st = (num_tiles + G - 1) / G;
-    load(st, m0, m1);
-    load(st + stride, n0, n1);
-    mu = split_bits(m0 | m1, part, ksplit);
-    skip_empty();
+// Work enumeration of one CTA, identical in every role.  A "super-tile" is G consecutive 128-slot tiles (G = 2 when cout <= 128:
+// the two accumulators share every weight chunk, and mask-sorted plans give neighbouring tiles the same offset set).  An
+// iteration is (super-tile, 64-channel chunk c, offset k in the union of the member tiles' masks), ordered super-tile, chunk,
+// offset: all offsets of chunk 0, then all offsets of chunk 1 (the rows a compact tile re-gathers across its offsets are then
+// re-touched within ~10 iterations on half the bytes, which fits the L1 left next to the pipeline stages).
+// One step is ~10 instructions; the masks of the NEXT super-tile are loaded when the current one is entered.
+struct Walk {
+  const uint32_t* __restrict__ km;
+  int st, stride, num_st, num_tiles, nch, c, part, ks;
+  uint32_t m0, m1, mall, mu, n0, n1;
+  bool two;
+  __device__ __forceinline__ void fetch(int s, uint32_t& a, uint32_t& b) const {
+    a = 0u;
+    b = 0u;
+    if (s < num_st) {
+      const int t = two ? 2 * s : s;
+      a = __ldg(km + t);
+      if (two && t + 1 < num_tiles) b = __ldg(km + t + 1);
+    }
   }
-  __device__ uint32_t all_bits() const { return split_bits(m0 | m1, part, ksplit); }
-  __device__ void load(int s, uint32_t& a, uint32_t& b) const {
-    a = s < num_st ? mask_of(G * s) : 0u;
-    b = (s < num_st && G == 2) ? mask_of(2 * s + 1) : 0u;
+  __device__ __forceinline__ void enter() {
+    mall = m0 | m1;
+    if (ks > 1) mall = split_bits(mall, part, ks);
+    mu = mall;
+    c = 0;
   }
-  __device__ void next_super() {
+  __device__ __forceinline__ void next_st() {
     st += stride;
     m0 = n0;
     m1 = n1;
-    mu = all_bits();
-    ch = 0;
-    load(st + stride, n0, n1);
+    fetch(st + stride, n0, n1);
+    enter();
   }
-  __device__ void skip_empty() {
-    while (mu == 0u && st < num_st) next_super();
+  __device__ __forceinline__ void skip() {
+    while (st < num_st && mall == 0u) next_st();
   }
-  __device__ bool valid() const { return st < num_st; }
-  __device__ int k() const { return __ffs(mu) - 1; }
-  __device__ bool has(int g) const { return (((g ? m1 : m0) >> k()) & 1u) != 0u; }
+  __device__ Walk(const uint32_t* km_, int G, int first, int stride_, int num_tiles_, int nch_, int part_, int ks_)
+      : km(km_), st(first), stride(stride_), num_tiles(num_tiles_), nch(nch_), part(part_), ks(ks_), two(G == 2) {
+    num_st = two ? (num_tiles + 1) >> 1 : num_tiles;
+    fetch(st, m0, m1);
+    fetch(st + stride, n0, n1);
+    enter();
+    skip();
+  }
+  __device__ __forceinline__ bool valid() const { return st < num_st; }
+  __device__ __forceinline__ int k() const { return __ffs(mu) - 1; }
+  __device__ __forceinline__ uint32_t has() const {
+    const int kk = __ffs(mu) - 1;
+    return ((m0 >> kk) & 1u) | (((m1 >> kk) & 1u) << 1);
+  }
   // true on the last iteration of the super-tile (its accumulators are complete after it)
-  __device__ bool last_iter() const { return (mu & (mu - 1)) == 0u && ch == nchunks - 1; }
-  __device__ void step() {  // one iteration
-    if (chunk_major) {
-      mu &= mu - 1;
-      if (mu == 0u) {
-        if (++ch < nchunks) mu = all_bits();
-        else {
-          next_super();
-          skip_empty();
-        }
-      }
-    } else {
-      if (++ch == nchunks) {
-        ch = 0;
-        mu &= mu - 1;
-        if (mu == 0u) {
-          next_super();
-          skip_empty();
-        }
+  __device__ __forceinline__ bool last() const { return (mu & (mu - 1)) == 0u && c == nch - 1; }
+  __device__ __forceinline__ void step() {
+    mu &= mu - 1;
+    if (mu == 0u) {
+      if (++c < nch) {
+        mu = mall;
+      } else {
+        next_st();
+        skip();
       }
     }
-  }
-  __device__ void advance(int n) {  // n iterations
-    for (int i = 0; i < n && valid(); ++i) step();
   }
 };
 
 template <typename TOut, bool kDbg>
-__global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p) {
+__global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x G x A 16 KB][stages x B cout*128][barriers]
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -130,9 +129,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)S * a_bytes;
   uint64_t* bars = (uint64_t*)(sB + (size_t)S * b_bytes);
-  uint64_t* full_bar = bars;                       // [S]  32 producer lanes (copy completion) + 1 expect_tx arrive
-  uint64_t* empty_bar = bars + kMaxStages;         // [S]  one tcgen05.commit
-  uint64_t* tmem_full = bars + 2 * kMaxStages;     // [2]  one tcgen05.commit
+  uint64_t* full_bar = bars;                       // [S]  32 * split producer lanes (copy completion) + 1 expect_tx arrive
+  uint64_t* empty_bar = bars + kMaxStages;         // [S]  one tcgen05.commit per MMA issuer (G of them)
+  uint64_t* tmem_full = bars + 2 * kMaxStages;     // [2]  one tcgen05.commit per MMA issuer
   uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;  // [2]  128 epilogue threads
   uint32_t* tmem_base_slot = (uint32_t*)(bars + 2 * kMaxStages + 4);
   float* out_stage = (float*)(bars + 2 * kMaxStages + 6);  // [4 epilogue warps][32 rows x out_cols] when p.stage_out (16-byte aligned)
@@ -140,6 +139,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dbg = kDbg ? p.debug : 0;
   const int acc_cols = G == 2 ? 128 : 256;  // TMEM columns per accumulator: [buffer][member tile] x acc_cols = 512
+  const int split = p.split;                // producer warps per stage (1: one warp gathers both member tiles, 2: one warp per tile)
   // bias staged once per CTA: the epilogue adds it per element, and reading it from global memory there cost one load
   // instruction per output element and thread (the 1x1 convs with bias ran at a quarter of the HBM rate)
   __shared__ float s_bias[256];
@@ -149,16 +149,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 32 + 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(smem_u32(&full_bar[s]), 32 * split + 1);
+      mbar_init(smem_u32(&empty_bar[s]), G);  // one tcgen05.commit per MMA issuer
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(smem_u32(&tmem_full[b]), 1);
+      mbar_init(smem_u32(&tmem_full[b]), G);
       mbar_init(smem_u32(&tmem_empty[b]), 4 * 32);
     }
     fence_barrier_init();
   }
-  if (warp == kLoadWarp) {
+  if (warp == kCvAllocWarp) {
     tmem_alloc(smem_u32(tmem_base_slot), kTmemCols);
     tmem_relinquish();
   }
@@ -171,198 +171,214 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
   const int ksplit = p.ksplit;
   const int cta_first = (int)blockIdx.x / ksplit, cta_stride = (int)gridDim.x / ksplit, cta_part = (int)blockIdx.x % ksplit;
 
-  if (warp < kNumProducerWarps || warp == kLoadWarp) {
-    // ===================== producers (up to 5 warps, one stage each, round-robin) =====================
-    const int pi = warp < kNumProducerWarps ? warp : kNumProducerWarps;
-    // Stage ownership: iteration i is staged by producer i mod NP into ring slot i mod S.  NP <= S is required: the
-    // parity wait on a slot's empty barrier is only unambiguous while a producer is at most ONE ring phase ahead of the
-    // consumer; having passed the wait of iteration i - NP it knows i - NP - S and everything earlier was consumed, which
-    // covers i - 2S iff S >= NP.
+  if (warp < kCvProducerWarps) {
+    // ===================== producers =====================
+    // Iteration i is staged by producer group i mod NP into ring slot i mod S (NP <= S: the parity wait on a slot's empty
+    // barrier is only unambiguous while a producer is at most ONE ring phase ahead of the consumer).  A group is `split` warps;
+    // a stage has 4 * G units of 32 rows (member tile g, row quarter q), warp `sub` of the group gathers units
+    // [sub * UW, (sub + 1) * UW), UW = 4 * G / split <= 4.
+    //
+    // Per unit a lane issues 8 LDGSTS: lane = (rsub, piece) copies the 16-byte piece `piece` of unit rows rsub * 8 + jj, jj = 0..7,
+    // i.e. one warp instruction moves 4 rows x 128 B.  The 8 row indices a lane needs are consecutive entries of the neighbour
+    // table and are read straight from it (8 lanes share each address; the unit's 32 entries are one 128-byte line, which the
+    // previous own stage prefetched into L1) -- no index shuffles: ncu's source view of the shuffle-based version showed every
+    // LDGSTS waiting ~30 cycles on its own SHFL (volatile asm is not reordered), and the 64 SHFL per iteration took a quarter
+    // of the LSU data pipe.
     const int NP = p.num_producers;
-    const int piece = lane & 7;  // 16-byte piece of the 128-byte row
-    const int rsub = lane >> 3;  // 4 rows per warp instruction
-    // swizzled piece offset inside the row: row & 7 == 4 * (jj & 1) + rsub for row = 4 * jj + rsub
-    const uint32_t sw_even = (uint32_t)((piece ^ rsub) << 4), sw_odd = (uint32_t)((piece ^ (4 + rsub)) << 4);
-    const uint32_t row_bytes = (uint32_t)p.cin * (uint32_t)sizeof(__nv_bfloat16);
-    struct Idx {
-      int r[2][4];  // per member tile: input rows gathered into tile rows lane, lane + 32, lane + 64, lane + 96
-      int kw;       // weight-image index of the item's offset
-      int ch;       // 64-channel chunk of the iteration
-      uint32_t has; // bit g: member tile g has this offset
-      bool valid;
-    };
-    auto load_idx = [&](const SuperCursor& c) -> Idx {
-      Idx x;
-      const bool v = c.valid();
-      const int k = v ? c.k() : 0;
-      x.valid = v;
-      x.ch = c.ch;
-      x.has = v ? ((c.has(0) ? 1u : 0u) | (c.has(1) ? 2u : 0u)) : 0u;
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int64_t slot = ((int64_t)c.st * G + g) * kTileM + q * 32 + lane;
-          x.r[g][q] = (((x.has >> g) & 1u) && slot < p.n_slots) ? __ldg(p.nbr + (int64_t)k * p.n_slots + slot) : -1;
+    const int gi = warp / split;
+    const int sub = warp - gi * split;
+    if (gi < NP) {
+      const int UW = 4 * G / split;  // units per warp: 4 or 2
+      const int piece = lane & 7;    // 16-byte piece of the 128-byte row
+      const int rsub = lane >> 3;    // row octet of the unit this lane copies
+      const uint32_t row_bytes = (uint32_t)p.cin * (uint32_t)sizeof(__nv_bfloat16);
+      const int cin = p.cin;
+      const int64_t n_slots = p.n_slots;
+      const int32_t* __restrict__ nbr = p.nbr;
+      const int32_t* __restrict__ kidx = p.kidx;
+      const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
+      // destination of (unit 0, jj = 0) inside a stage for this lane; row = rsub * 8 + jj => row & 7 == jj => swizzled piece = piece ^ jj
+      const uint32_t dst_lane = (uint32_t)(sub * UW * 32 * 128 + rsub * 8 * 128);
+      struct It {
+        int st, k, ch;
+        uint32_t has;
+        bool valid;
+      };
+      Walk la(p.tile_kmask, G, cta_first, cta_stride, p.num_tiles, nchunks, cta_part, ksplit);  // lookahead walker
+      for (int i = 0; i < gi && la.valid(); ++i) la.step();
+      auto next_it = [&]() -> It {
+        It x;
+        x.valid = la.valid();
+        x.st = la.st;
+        x.k = x.valid ? la.k() : 0;
+        x.ch = la.c;
+        x.has = x.valid ? la.has() : 0u;
+        if (x.valid && lane < UW) {  // pull the index lines of the stage after this one into L1 (lane u: unit u's 128-byte line)
+          const int gu = sub * UW + lane;
+          const int64_t slot = (int64_t)x.st * (G * kTileM) + gu * 32;
+          if (((x.has >> (gu >> 2)) & 1u) && slot < n_slots)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nbr + (int64_t)x.k * n_slots + slot));
         }
-      }
-      x.kw = (v && p.kidx) ? __ldg(p.kidx + k) : k;
-      return x;
-    };
-    const bool active = pi < NP;  // surplus producer warps idle
-    int stage = pi % S;
-    uint32_t phase = (uint32_t)((pi / S) & 1);
-    long long tp_wait = 0, tp_start = kDbg ? clock64() : 0;
-    auto stage_body = [&](const Idx& ci) {
-      const int ch = ci.ch;
-      const int width = min(kChunkElems, p.cin - ch * kChunkElems);  // valid elements in this chunk
-      const long long tp0 = kDbg ? clock64() : 0;
-      mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-      if (kDbg) tp_wait += clock64() - tp0;
-      const uint32_t bar = smem_u32(&full_bar[stage]);
-      // lanes whose piece lies beyond a narrow chunk (or all lanes in the gather-off ablation) still take part in the shuffles
-      const bool act = piece * 8 < width && !(dbg & 1);
-      // source address = per-lane 64-bit base + row * row_bytes as ONE 32x32+64 multiply-add (IMAD.WIDE.U32)
-      uint64_t src0 = (uint64_t)p.in + (uint64_t)(ch * kChunkElems + piece * 8) * sizeof(__nv_bfloat16);
-      asm volatile("" : "+l"(src0));  // keep the base in one register pair (otherwise it is re-derived from the constant bank per copy)
+        for (int i = 0; i < NP && la.valid(); ++i) la.step();
+        return x;
+      };
+      int stage = gi % S;
+      uint32_t phase = (uint32_t)((gi / S) & 1);
+      long long tp_wait = 0, tp_start = kDbg ? clock64() : 0;
+      It cur = next_it();
+      while (cur.valid) {
+        const It nxt = next_it();
+        const int ch = cur.ch;
+        const int width = min(kChunkElems, cin - ch * kChunkElems);  // valid elements in this chunk
+        // this lane's 8 row indices per owned unit
+        int idx[4][8];
+        const int32_t* col = nbr + (int64_t)cur.k * n_slots;
+        const int64_t slot0 = (int64_t)cur.st * (G * kTileM) + sub * UW * 32 + rsub * 8;
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        if ((ci.has >> g) & 1u) {  // warp-uniform
-          const uint32_t a_base = smem_u32(sA + (size_t)stage * a_bytes + (size_t)g * kABytes);
+        for (int u = 0; u < 4; ++u) {
+          const bool on = u < UW && ((cur.has >> ((sub * UW + u) >> 2)) & 1u);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int jj = 0; jj < 8; ++jj) {
+            const int64_t slot = slot0 + u * 32 + jj;
+            idx[u][jj] = -1;
+            if (on && slot < n_slots) idx[u][jj] = __ldg(col + slot);
+          }
+        }
+        const int kw = kidx ? __ldg(kidx + cur.k) : cur.k;
+        const long long tp0 = kDbg ? clock64() : 0;
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        if (kDbg) tp_wait += clock64() - tp0;
+        const uint32_t bar = smem_u32(&full_bar[stage]);
+        // lanes whose piece lies beyond a narrow chunk (or all lanes in the gather-off ablation) issue nothing
+        const bool act = piece * 8 < width && !(dbg & 1);
+        // source address = per-lane 64-bit base + row * row_bytes as ONE 32x32+64 multiply-add (IMAD.WIDE.U32)
+        uint64_t src0 = (uint64_t)p.in + (uint64_t)(ch * kChunkElems + piece * 8) * sizeof(__nv_bfloat16);
+        asm volatile("" : "+l"(src0));  // keep the base in one register pair (otherwise it is re-derived from the constant bank per copy)
+        const uint32_t a_lane = sA_u32 + (uint32_t)(stage * a_bytes) + dst_lane;
+        if (act) {
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-              const int idx = __shfl_sync(0xffffffffu, ci.r[g][q], 4 * jj + rsub);
-              const int row = q * 32 + 4 * jj + rsub;  // row within the tile
-              const uint32_t dst = a_base + (uint32_t)(row * 128) + ((jj & 1) ? sw_odd : sw_even);
-              const uint32_t idxc = idx < 0 ? 0u : (uint32_t)idx;
-              if (act) cp_async_16(dst, (const void*)(src0 + (uint64_t)idxc * row_bytes), idx < 0 ? 0u : 16u);
+          for (int u = 0; u < 4; ++u) {
+            if (u < UW && ((cur.has >> ((sub * UW + u) >> 2)) & 1u)) {  // warp-uniform
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                const int i = idx[u][jj];
+                const uint32_t dst = a_lane + (uint32_t)(u * 32 * 128 + jj * 128) + (uint32_t)((piece ^ jj) << 4);
+                cp_async_16(dst, (const void*)(src0 + (uint64_t)(i < 0 ? 0u : (uint32_t)i) * row_bytes), i < 0 ? 0u : 16u);
+              }
             }
           }
         }
-      }
-      // completion-triggered arrive: no wait_group / fence in the producer; the proxy hand-over is completed by the MMA
-      // thread's acquire fence after it has observed the barrier phase
-      cp_async_arrive_noinc(bar);
-      if (elect_one_sync()) {
-        if (dbg & 2) {
-          mbar_arrive(bar);
-        } else {
-          mbar_arrive_expect_tx(bar, (uint32_t)b_bytes);
-          const __nv_bfloat16* wsrc = p.wimg + ((int64_t)ci.kw * nchunks + ch) * (int64_t)p.cout * kChunkElems;
-          bulk_copy_g2s(smem_u32(sB + (size_t)stage * b_bytes), wsrc, (uint32_t)b_bytes, bar);
+        // completion-triggered arrive: no wait_group / fence in the producer; the proxy hand-over is completed by the MMA
+        // thread's acquire fence after it has observed the barrier phase
+        cp_async_arrive_noinc(bar);
+        if (sub == 0) {
+          if (elect_one_sync()) {
+            if (kDbg && (dbg & 2)) {
+              mbar_arrive(bar);
+            } else {
+              mbar_arrive_expect_tx(bar, (uint32_t)b_bytes);
+              const __nv_bfloat16* wsrc = p.wimg + ((int64_t)kw * nchunks + ch) * (int64_t)p.cout * kChunkElems;
+              bulk_copy_g2s(sB_u32 + (uint32_t)(stage * b_bytes), wsrc, (uint32_t)b_bytes, bar);
+            }
+          }
+          __syncwarp();
         }
+        stage += NP;
+        while (stage >= S) {
+          stage -= S;
+          phase ^= 1;
+        }
+        cur = nxt;
       }
-      __syncwarp();
-      stage += NP;
-      while (stage >= S) {
-        stage -= S;
-        phase ^= 1;
+      if (kDbg && p.trace && warp == 0 && lane == 0) {
+        p.trace[blockIdx.x * 16 + 0] = (unsigned long long)tp_wait;
+        p.trace[blockIdx.x * 16 + 1] = (unsigned long long)(clock64() - tp_start);
       }
-    };
-    // Three index sets rotate WITHOUT register copies (the loop is unrolled by three): a `ci = ni; ni = nni;` rotation makes
-    // the compiler move the just-loaded index registers at the end of the same iteration, i.e. wait for the table loads it
-    // was meant to hide for two stages (1x1 and 2^3 convs, whose stages are short, gained ~25 %).
-    SuperCursor la(p.tile_kmask, G, cta_first, cta_stride, p.num_tiles, nchunks, p.chunk_major, cta_part, ksplit);  // lookahead cursor
-    if (active) la.advance(pi);
-    Idx i0 = load_idx(la);
-    la.advance(NP);
-    Idx i1 = load_idx(la);
-    la.advance(NP);
-    Idx i2;
-    while (active) {
-      if (!i0.valid) break;
-      i2 = load_idx(la);
-      la.advance(NP);
-      stage_body(i0);
-      if (!i1.valid) break;
-      i0 = load_idx(la);
-      la.advance(NP);
-      stage_body(i1);
-      if (!i2.valid) break;
-      i1 = load_idx(la);
-      la.advance(NP);
-      stage_body(i2);
+      cp_async_wait<0>();
     }
-    if (kDbg && p.trace && warp == 0 && lane == 0) {
-      p.trace[blockIdx.x * 16 + 0] = (unsigned long long)tp_wait;
-      p.trace[blockIdx.x * 16 + 1] = (unsigned long long)(clock64() - tp_start);
-    }
-    cp_async_wait<0>();
-  } else if (warp == kMmaWarp) {
-    // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+  } else if (warp == kCvMmaWarp || (warp == kCvAllocWarp && G == 2)) {
+    // ===================== MMA issuers (whole warp converged, one elected lane issues) =====================
     // Every lane runs the loop so that all control flow and descriptor arithmetic stays warp-uniform; only the tcgen05
-    // instructions sit under elect_one_sync() (see umma.cuh).
-    Ring ring(S);
+    // instructions sit under elect_one_sync() (see umma.cuh).  With super-tiles (G == 2) there are TWO issuers, one per member
+    // tile (independent accumulators): the issuing warp is a serial chain of ~8-cycle instructions (barrier wait, descriptor
+    // arithmetic on the uniform datapath, 4 UTCHMMA, commit: ~500 cycles per iteration for 8 MMAs, ncu source view), above the
+    // 384 cycles the 8 MMAs of a 96-column iteration take on the tensor pipe; split over two warps both halves overlap.  Both
+    // wait on the stage's full barrier and both commit to its empty barrier (count = number of issuers).
+    const int mg = warp == kCvMmaWarp ? 0 : 1;  // member tile this warp issues for (G == 1: the only one)
     const uint32_t idesc = make_idesc(kTileM, p.cout);
+    const int cin = p.cin;
+    const uint32_t a_lo_base = smem_desc_lo(smem_u32(sA)), b_lo_base = smem_desc_lo(smem_u32(sB));
+    const uint32_t a_step = (uint32_t)(a_bytes >> 4), b_step = (uint32_t)(b_bytes >> 4);
+    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), tfull0 = smem_u32(tmem_full), tempty0 = smem_u32(tmem_empty);
+    int slot = 0;
+    uint32_t ph = 0;
     int acc_buf = 0;
     uint32_t acc_phase = 0;
-    bool tile_open = false;
-    uint32_t started = 0;  // bit g: accumulator of member tile g holds a partial sum
     long long tw_full = 0, tw_tmem = 0, t_start = kDbg ? clock64() : 0, n_it = 0;
-    for (SuperCursor cur(p.tile_kmask, G, cta_first, cta_stride, p.num_tiles, nchunks, p.chunk_major, cta_part, ksplit); cur.valid(); cur.step()) {
-      if (!tile_open) {
+    Walk w(p.tile_kmask, G, cta_first, cta_stride, p.num_tiles, nchunks, cta_part, ksplit);
+    while (w.valid()) {
+      {
         const long long t0 = kDbg ? clock64() : 0;
-        mbar_wait(smem_u32(&tmem_empty[acc_buf]), acc_phase ^ 1);
+        mbar_wait(tempty0 + 8u * acc_buf, acc_phase ^ 1);
         if (kDbg) tw_tmem += clock64() - t0;
         tc_fence_after();
-        tile_open = true;
-        started = 0;
       }
-      const uint32_t has = (cur.has(0) ? 1u : 0u) | (cur.has(1) ? 2u : 0u);
-      {
-        const int ch = cur.ch;
-        const int width = min(kChunkElems, p.cin - ch * kChunkElems);
+      uint32_t started = 0;  // 1: this warp's accumulator holds a partial sum
+      const uint32_t tmem_d = tmem_base + (uint32_t)((acc_buf * G + mg) * acc_cols);
+      bool last;
+      do {
+        const uint32_t has = w.has();
+        last = w.last();
+        const int nk = min(kChunkElems, cin - w.c * kChunkElems) >> 4;
         const long long t1 = kDbg ? clock64() : 0;
-        mbar_wait(smem_u32(&full_bar[ring.stage]), ring.phase);
+        mbar_wait(full0 + 8u * slot, ph);
         if (kDbg) {
           tw_full += clock64() - t1;
           ++n_it;
         }
-        if (dbg & 64) fence_proxy_async();  // A/B only: the bidirectional fence (MEMBAR.ALL.CTA) the acquire form replaces
-        else fence_proxy_async_acquire();   // producers' cp.async (generic proxy) writes -> visible to tcgen05.mma (async proxy)
+        fence_proxy_async_acquire();  // producers' cp.async (generic proxy) writes -> visible to tcgen05.mma (async proxy)
         tc_fence_after();
-        const uint32_t b_lo = smem_desc_lo(smem_u32(sB) + (uint32_t)(ring.stage * b_bytes));
-        const uint32_t a_lo0 = smem_desc_lo(smem_u32(sA) + (uint32_t)(ring.stage * a_bytes));
-        const int nk = width >> 4;
+        const uint32_t b_lo = b_lo_base + (uint32_t)slot * b_step;
+        const uint32_t a_lo = a_lo_base + (uint32_t)slot * a_step + (uint32_t)(mg * (kABytes >> 4));
+        const uint32_t mine = (has >> mg) & 1u;
         if (elect_one_sync()) {
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            if ((has >> g) & 1u) {
-              const uint32_t a_lo = a_lo0 + (uint32_t)(g * (kABytes >> 4));
-              const uint32_t tmem_d = tmem_base + (uint32_t)((acc_buf * G + g) * acc_cols);
-              const uint32_t first_acc = (started >> g) & 1u;
-              const int nkg = (dbg & 4) ? (first_acc ? 0 : 1) : nk;
-              for (int kk = 0; kk < nkg; ++kk) {
-                // +32 bytes along K inside the 128-byte swizzle row == +2 in the (addr >> 4) field
-                umma_bf16_lohi(tmem_d, a_lo + 2u * kk, b_lo + 2u * kk, kSmemDescHi, idesc, (kk > 0) ? 1u : first_acc);
-              }
+          if (mine) {
+            if (kDbg && (dbg & 4)) {
+              if (!started) umma_bf16_lohi(tmem_d, a_lo, b_lo, kSmemDescHi, idesc, 0u);
+            } else if (nk == 4) {
+              // +32 bytes along K inside the 128-byte swizzle row == +2 in the (addr >> 4) field
+              umma_bf16_lohi(tmem_d, a_lo, b_lo, kSmemDescHi, idesc, started);
+              umma_bf16_lohi(tmem_d, a_lo + 2u, b_lo + 2u, kSmemDescHi, idesc, 1u);
+              umma_bf16_lohi(tmem_d, a_lo + 4u, b_lo + 4u, kSmemDescHi, idesc, 1u);
+              umma_bf16_lohi(tmem_d, a_lo + 6u, b_lo + 6u, kSmemDescHi, idesc, 1u);
+            } else {
+              for (int kk = 0; kk < nk; ++kk)
+                umma_bf16_lohi(tmem_d, a_lo + 2u * kk, b_lo + 2u * kk, kSmemDescHi, idesc, (kk > 0) ? 1u : started);
             }
           }
-          umma_commit(smem_u32(&empty_bar[ring.stage]));  // frees the stage when these MMAs retire
+          umma_commit(empty0 + 8u * slot);  // frees the stage when these MMAs (and the other issuer's) retire
+          if (last) umma_commit(tfull0 + 8u * acc_buf);
         }
         __syncwarp();
-        started |= has;
-        ring.advance();
-      }
-      if (cur.last_iter()) {
-        if (elect_one_sync()) umma_commit(smem_u32(&tmem_full[acc_buf]));
-        __syncwarp();
-        tile_open = false;
-        if (++acc_buf == 2) {
-          acc_buf = 0;
-          acc_phase ^= 1;
+        started |= mine;
+        if (++slot == S) {
+          slot = 0;
+          ph ^= 1;
         }
+        w.step();
+      } while (!last);
+      if (++acc_buf == 2) {
+        acc_buf = 0;
+        acc_phase ^= 1;
       }
     }
-    if (kDbg && p.trace && lane == 0) {
+    if (kDbg && p.trace && lane == 0 && mg == 0) {
       p.trace[blockIdx.x * 16 + 2] = (unsigned long long)tw_full;
       p.trace[blockIdx.x * 16 + 3] = (unsigned long long)tw_tmem;
       p.trace[blockIdx.x * 16 + 4] = (unsigned long long)(clock64() - t_start);
       p.trace[blockIdx.x * 16 + 5] = (unsigned long long)n_it;
     }
-  } else {
+  } else if (warp >= kCvEpiWarp0) {
     // ===================== epilogue (4 warps) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     int acc_buf = 0;
@@ -510,7 +526,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
         }
       }
     }
-    if (kDbg && p.trace && warp == kFirstEpiWarp && lane == 0) {
+    if (kDbg && p.trace && warp == kCvEpiWarp0 && lane == 0) {
       p.trace[blockIdx.x * 16 + 6] = (unsigned long long)te_wait;
       p.trace[blockIdx.x * 16 + 7] = (unsigned long long)(clock64() - te_start);
     }
@@ -518,7 +534,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_umma(const ConvParams p
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kLoadWarp) {
+  if (warp == kCvAllocWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -557,22 +573,52 @@ inline size_t conv_smem_bytes(int cout, int stages, int group = 1, int stage_out
 
 int conv_tma_launch(const ConvParams& p, int64_t n_in, int out_dtype, cudaStream_t st);  // conv_tma.cu
 
-// 0 = LSU producer: LDG.128 -> registers -> swizzled STS.128 (default); 1 = TMA gather4 producer (MK3D_GATHER=tma; measured
-// ~2.5x slower on random rows, kept for A/B measurements)
-static int g_gather_mode = -1;
-inline int gather_mode() {
-  if (g_gather_mode < 0) {
-    const char* e = getenv("MK3D_GATHER");
-    g_gather_mode = (e && e[0] == 't') ? 1 : 0;
+// 0 = LSU producer: 16-byte cp.async (LDGSTS) into the swizzled A tile (default); 1 = TMA gather4 producer (mk_set_gather_mode(1);
+// measured ~2.5x slower on random rows, kept for A/B measurements)
+static int g_gather_mode = 0;
+inline int gather_mode() { return g_gather_mode; }
+
+// Pipeline-shape overrides and timing ablations for measurement sweeps.  Read from the environment ONLY in a tuning build
+// (nvcc -DMK3D_TUNING, `MK3D_BUILD_TUNING=1 python -m room_instance_segmentation_mask3d_b200.build`); the production library
+// reads no environment variable on this path.
+//   MK3D_DEBUG bit mask (results are wrong when non-zero): 1 skip gathers, 2 skip weight copies, 4 one MMA per tile, 8 skip stores
+//   MK3D_TRACE=1 per-role cycle counters; MK3D_GROUP, MK3D_KSPLIT, MK3D_STAGES, MK3D_PRODUCERS, MK3D_SPLIT, MK3D_CARVEOUT shape overrides
+struct Tuning {
+  int debug = 0, trace = 0, group = 0, ksplit = 0, stages = 0, producers = 0, split = 0, carveout = -1;
+};
+inline const Tuning& tuning() {
+  static Tuning t;
+#ifdef MK3D_TUNING
+  static bool init = false;
+  if (!init) {
+    auto geti = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
+    t.debug = geti("MK3D_DEBUG", 0);
+    t.trace = getenv("MK3D_TRACE") ? 1 : 0;
+    t.group = geti("MK3D_GROUP", 0);
+    t.ksplit = geti("MK3D_KSPLIT", 0);
+    t.stages = geti("MK3D_STAGES", 0);
+    t.producers = geti("MK3D_PRODUCERS", 0);
+    t.split = geti("MK3D_SPLIT", 0);
+    t.carveout = geti("MK3D_CARVEOUT", -1);
+    init = true;
   }
-  return g_gather_mode;
+#endif
+  return t;
 }
+
+// 1: no run-to-run variation of results (no offset split with REDs in the forward / dgrad); set by mk_set_deterministic
+int g_deterministic = 0;
 
 }  // namespace mk
 
 using namespace mk;
 
 extern "C" {
+
+int mk_set_deterministic(int on) {
+  g_deterministic = on ? 1 : 0;
+  return 0;
+}
 
 int mk_set_gather_mode(int mode) {
   g_gather_mode = mode ? 1 : 0;
@@ -625,62 +671,46 @@ int mk_conv_fwd_bf16(const void* in, int64_t n_in, int cin, const void* wimg, in
   const int elem = out_dtype == MK_F32 ? 4 : 2;
   p.stage_out = (out_rows == nullptr && out_stride == out_cols && ((out_stride * elem) & 15) != 0 && out_cols <= 64) ? 1 : 0;
   const int soc = p.stage_out ? out_cols : 0;
-  {
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("MK3D_DEBUG"); dbg = e ? atoi(e) : 0; }
-    p.debug = dbg;  // timing ablations only (results are wrong when non-zero): 1 skip gathers, 2 skip weight copies, 4 one MMA per tile, 8 skip stores
-  }
+  const Tuning& tn = tuning();
+  p.debug = tn.debug;
   p.trace = nullptr;
-  {
-    // chunk-major iteration order inside a super-tile (all offsets of channel chunk 0, then of chunk 1): the rows a compact
-    // tile re-gathers across its offsets are then re-touched within ~10 iterations on HALF the bytes, which fits the L1 left
-    // next to the pipeline stages (L1 sector hit rate 44 % -> 60 %, L2 -> L1 traffic 1.90 -> 1.57 GB at 96 channels).
-    // MK3D_CHUNK_MAJOR=0 restores (offset, chunk) order for A/B runs.
-    static int cm = -1;
-    if (cm < 0) { const char* e = getenv("MK3D_CHUNK_MAJOR"); cm = e ? atoi(e) : 1; }
-    p.chunk_major = cm;
-  }
+  p.chunk_major = 1;
   if (gather_mode() == 1) return conv_tma_launch(p, n_in, out_dtype, (cudaStream_t)stream_);
   // super-tiles of two tiles when both accumulators fit next to their double buffer (4 x 128 TMEM columns) and there are
   // enough tiles to keep every SM busy with the coarser work unit
-  static int grp_env = -1;
-  if (grp_env < 0) { const char* e = getenv("MK3D_GROUP"); grp_env = e ? atoi(e) : 0; }
   int group = (cout <= 128 && p.num_tiles >= 4 * num_sms()) ? 2 : 1;
-  if (grp_env == 1 || (grp_env == 2 && cout <= 128)) group = grp_env;
+  if (tn.group == 1 || (tn.group == 2 && cout <= 128)) group = tn.group;
   p.group = group;
   // Offset split for the coarse levels: a level with fewer super-tiles than SMs (L3 / L4 of a single scene: 7-27 tiles for 148
   // SMs) ran as 7-27 CTAs walking all 27 offsets each, pure latency.  With an fp32 output the offsets of a super-tile are dealt
-  // to `ksplit` CTAs that add their partial sums with vector REDs (the output is zeroed here first).
+  // to `ksplit` CTAs that add their partial sums with vector REDs (the output is zeroed here first).  The accumulation order of
+  // those REDs varies from run to run: mk_set_deterministic(1) turns the split off (the trainer's `deterministic: true`).
   p.ksplit = 1;
   {
-    static int ks_env = -1;
-    if (ks_env < 0) { const char* e = getenv("MK3D_KSPLIT"); ks_env = e ? atoi(e) : 0; }
     const int num_super0 = (p.num_tiles + group - 1) / group;
-    if (out_dtype == MK_F32 && K > 1 && !p.stage_out && (out_cols & 3) == 0 && ((out_stride * 4) & 15) == 0 && ks_env != 1 &&
-        2 * num_super0 <= num_sms()) {
+    if (out_dtype == MK_F32 && K > 1 && !p.stage_out && (out_cols & 3) == 0 && ((out_stride * 4) & 15) == 0 && tn.ksplit != 1 &&
+        !g_deterministic && 2 * num_super0 <= num_sms()) {
       int ks = num_sms() / num_super0;
       if (ks > K) ks = K;
       if (ks > 9) ks = 9;
-      if (ks_env > 1 && ks > ks_env) ks = ks_env;
+      if (tn.ksplit > 1 && ks > tn.ksplit) ks = tn.ksplit;
       p.ksplit = ks;
     }
   }
   int stages = kMaxStages;
   while (stages > 2 && conv_smem_bytes(cout, stages, group, soc) > 222 * 1024) --stages;
-  // Super-tiles: 4 stages (<= 176 KB) instead of the 5 that fit.  The kernel is bound by shared-memory bandwidth (LDGSTS
-  // writes + tcgen05 operand reads, ncu: l1tex data-pipe wavefronts ~59 %, tensor pipe ~22 % at 96 channels), not by
-  // latency, so the fifth stage buys nothing, while the smaller carve-out leaves ~60 KB of L1 for the neighbour rows a
-  // compact tile re-gathers across offsets (L1 sector hit rate 13 % -> 50+ %, 96->96: 486 -> 541 TFLOP/s; 128 unchanged).
+  // Super-tiles: 4 stages (<= 176 KB) instead of the 5 that fit: the smaller carve-out leaves ~50 KB of L1 for the neighbour
+  // rows a compact tile re-gathers across offsets (L1 sector hit rate 13 % -> 50+ %).
   if (group == 2 && stages > 4) stages = 4;
   MK_REQUIRE(conv_smem_bytes(cout, stages, group, soc) <= 227 * 1024, "shared memory budget exceeded");
-  {
-    static int st_env = -1, np_env = -1;
-    if (st_env < 0) { const char* e = getenv("MK3D_STAGES"); st_env = e ? atoi(e) : 0; }
-    if (np_env < 0) { const char* e = getenv("MK3D_PRODUCERS"); np_env = e ? atoi(e) : 0; }
-    if (st_env >= 2 && st_env < stages) stages = st_env;  // tuning sweeps only
-    p.num_producers = stages < kMaxProducers ? stages : kMaxProducers;
-    if (np_env >= 1 && np_env < p.num_producers) p.num_producers = np_env;
-  }
+  if (tn.stages >= 2 && tn.stages < stages) stages = tn.stages;  // tuning sweeps only
+  // producer groups: one per ring slot (a group may be at most one ring phase ahead); two warps per group (one per member
+  // tile) when there are member tiles to split and warps to spare
+  p.split = group;  // a producer warp gathers at most 4 units of 32 rows
+  while (p.split < 4 && 2 * p.split * stages <= kCvProducerWarps) p.split *= 2;  // 4 stages: 2 warps per stage
+  if (tn.split >= group && tn.split <= 4) p.split = tn.split;
+  p.num_producers = stages < kCvProducerWarps / p.split ? stages : kCvProducerWarps / p.split;
+  if (tn.producers >= 1 && tn.producers < p.num_producers) p.num_producers = tn.producers;
   p.num_stages = stages;
   const size_t smem = conv_smem_bytes(cout, stages, group, soc);
   int grid = num_sms();
@@ -692,8 +722,6 @@ int mk_conv_fwd_bf16(const void* in, int64_t n_in, int cin, const void* wimg, in
     cudaMemset2DAsync(out, (size_t)out_stride * sizeof(float), 0, (size_t)out_cols * sizeof(float), (size_t)n_out, (cudaStream_t)stream_);
   }
   cudaStream_t st = (cudaStream_t)stream_;
-  static int carve_env = -2;
-  if (carve_env == -2) { const char* e = getenv("MK3D_CARVEOUT"); carve_env = e ? atoi(e) : -1; }
 #define MK_LAUNCH(T, D)                                                                                     \
   do {                                                                                                      \
     static size_t smem_set_##D = 0; /* per instantiation: raise the limit only when a launch needs more */  \
@@ -701,16 +729,15 @@ int mk_conv_fwd_bf16(const void* in, int64_t n_in, int cin, const void* wimg, in
       cudaFuncSetAttribute(k_conv_umma<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
       smem_set_##D = smem;                                                                                  \
     }                                                                                                       \
-    if (carve_env >= 0) cudaFuncSetAttribute(k_conv_umma<T, D>, cudaFuncAttributePreferredSharedMemoryCarveout, carve_env); \
-    k_conv_umma<T, D><<<grid, kNumThreads, smem, st>>>(p);                                                  \
+    if (tn.carveout >= 0) cudaFuncSetAttribute(k_conv_umma<T, D>, cudaFuncAttributePreferredSharedMemoryCarveout, tn.carveout); \
+    k_conv_umma<T, D><<<grid, kCvThreads, smem, st>>>(p);                                                   \
   } while (0)
-  static int trace_on = -1;
-  if (trace_on < 0) trace_on = getenv("MK3D_TRACE") ? 1 : 0;
-  if (trace_on) {
+#ifdef MK3D_TUNING
+  if (tn.trace) {
     cudaMalloc(&p.trace, (size_t)grid * 16 * sizeof(unsigned long long));
     cudaMemset(p.trace, 0, (size_t)grid * 16 * sizeof(unsigned long long));
   }
-  const bool dbg_build = trace_on || p.debug != 0;
+  const bool dbg_build = tn.trace || p.debug != 0;
   if (out_dtype == MK_F32) {
     if (dbg_build) MK_LAUNCH(float, true);
     else MK_LAUNCH(float, false);
@@ -718,7 +745,7 @@ int mk_conv_fwd_bf16(const void* in, int64_t n_in, int cin, const void* wimg, in
     if (dbg_build) MK_LAUNCH(__nv_bfloat16, true);
     else MK_LAUNCH(__nv_bfloat16, false);
   }
-  if (trace_on) {
+  if (tn.trace) {
     std::vector<unsigned long long> h((size_t)grid * 16);
     cudaStreamSynchronize(st);
     cudaMemcpy(h.data(), p.trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
@@ -726,9 +753,13 @@ int mk_conv_fwd_bf16(const void* in, int64_t n_in, int cin, const void* wimg, in
     double a[16] = {0};
     for (int b = 0; b < grid; ++b)
       for (int j = 0; j < 16; ++j) a[j] += (double)h[(size_t)b * 16 + j] / grid;
-    fprintf(stderr, "[mk3d trace] cin %d cout %d K %d tiles %d stages %d | producer0: wait_empty %.0f / total %.0f | mma: wait_full %.0f wait_tmem %.0f / total %.0f, iters %.0f | epilogue: wait_full %.0f / total %.0f (cycles, CTA mean)\n",
-            cin, cout, K, p.num_tiles, stages, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+    fprintf(stderr, "[mk3d trace] cin %d cout %d K %d tiles %d stages %d producers %dx%d | producer0: wait_empty %.0f / total %.0f | mma: wait_full %.0f wait_tmem %.0f / total %.0f, iters %.0f | epilogue: wait_full %.0f / total %.0f (cycles, CTA mean)\n",
+            cin, cout, K, p.num_tiles, stages, p.num_producers, p.split, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
   }
+#else
+  if (out_dtype == MK_F32) MK_LAUNCH(float, false);
+  else MK_LAUNCH(__nv_bfloat16, false);
+#endif
 #undef MK_LAUNCH
   return check_launch(__func__);
 }

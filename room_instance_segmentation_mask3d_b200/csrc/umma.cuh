@@ -199,7 +199,8 @@ struct ConvParams {
   int num_tiles;
   int num_stages;
   int group;       // member tiles per super-tile (1 or 2)
-  int num_producers;  // active producer warps (<= 5 and < num_stages: a producer may be at most one ring phase ahead)
+  int num_producers;  // producer groups (<= num_stages: a group may be at most one ring phase ahead of the consumer)
+  int split;          // producer warps per group (2: one warp per member tile of a super-tile)
   int nchunks;
   int out_cols;    // columns actually stored (<= cout; the rest of the accumulator is padding)
   int out_stride;  // elements between consecutive output rows

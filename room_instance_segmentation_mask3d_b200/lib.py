@@ -39,6 +39,7 @@ _SIGS = {
     "mk_conv_fwd_bf16": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
                                  c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "mk_set_gather_mode": (c_int, [c_int]),
+    "mk_set_deterministic": (c_int, [c_int]),
     "mk_row_sort_keys": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mk_row_mask_keys": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "mk_permute_table": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),

@@ -40,19 +40,134 @@ def shard_scenes(voxel_counts: Sequence[int], world_size: int) -> List[List[int]
     return [sorted(o) for o in owned]
 
 
+class GradientBuckets:
+    """Bucketed gradient all-reduce overlapped with the backward pass (the one collective of the training path: data-parallel
+    replicas over scenes; the reference itself only has the 1-float all_reduce(num_masks),
+    mask3d/models/criterion.py:244-246).
+
+    * Every parameter's `.grad` is a VIEW into a persistent flat fp32 bucket, so autograd accumulates straight into the buffer the
+      collective reads and the optimizer reads the reduced values in place: no per-step flat-buffer allocation, no copy-in, no
+      copy-out.  `zero()` clears the buckets (one memset each) instead of `zero_grad(set_to_none=True)`.
+    * Buckets follow REVERSE registration order (backward produces the decoder's gradients first, the stem's last); a
+      post-accumulate hook per parameter counts its bucket down and launches `all_reduce(bucket, async_op=True)` as soon as the
+      bucket and all earlier ones are complete (same collective order on every rank), so the transfer runs on the
+      communication stream under the rest of backward.  NVSwitch reduces in the
+      switch (NVLS), so buckets are sized for launch latency and overlap (32 MB default: ~5 collectives for the 39.6 M
+      parameters), not per link.
+    * Parameters whose gradient this rank did not produce in a step (other ranks may have) still take part: their bucket slice
+      stays zero, and `finish()` launches every bucket a hook has not launched.  Parameters that NO rank ever uses are left out
+      by the caller (`backbone.final.*`, constructed and never called, res16unet.py:231-238): their `.grad` stays None, as under
+      the reference optimizer, so AdamW never touches them.
+    * world size 1: same code path without the collective (hooks only count)."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 32 << 20, average: bool = True,
+                 group: Optional[dist.ProcessGroup] = None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group, self.average = group, average
+        self.ws = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.buckets: List[torch.Tensor] = []
+        self._members: List[List[torch.nn.Parameter]] = []
+        self._bucket_of = {}
+        cur: List[torch.nn.Parameter] = []
+        size = 0
+        for p in reversed(self.params):
+            cur.append(p)
+            size += p.numel() * 4
+            if size >= bucket_bytes:
+                self._close(cur)
+                cur, size = [], 0
+        if cur:
+            self._close(cur)
+        self._pending = [len(m) for m in self._members]
+        self._handles: List = []
+        self._launched = [False] * len(self.buckets)
+        self._next = 0
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self.collectives = 0
+
+    def _close(self, members: List[torch.nn.Parameter]) -> None:
+        dev = members[0].device
+        flat = torch.zeros(sum(p.numel() for p in members), dtype=torch.float32, device=dev)
+        off = 0
+        bi = len(self.buckets)
+        for p in members:
+            assert p.dtype == torch.float32, "gradient buckets are fp32 (the model's parameters are fp32, as in the reference)"
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            self._bucket_of[id(p)] = bi
+            off += p.numel()
+        self.buckets.append(flat)
+        self._members.append(list(members))
+
+    def _launch(self, bi: int) -> None:
+        self._launched[bi] = True
+        if self.ws > 1:
+            op = dist.ReduceOp.AVG if (self.average and dist.get_backend(self.group) == "nccl") else dist.ReduceOp.SUM
+            self._handles.append((bi, dist.all_reduce(self.buckets[bi], op=op, group=self.group, async_op=True), op))
+            self.collectives += 1
+
+    def _on_grad(self, p: torch.nn.Parameter) -> None:
+        bi = self._bucket_of[id(p)]
+        flat = self.buckets[bi]
+        if p.grad is None or p.grad.data_ptr() < flat.data_ptr() or p.grad.data_ptr() >= flat.data_ptr() + flat.numel() * 4:
+            # autograd replaced the view (first accumulation after a set_to_none): copy it back into the bucket and re-attach
+            off = sum(q.numel() for q in self._members[bi][:self._members[bi].index(p)])
+            view = flat[off:off + p.numel()].view_as(p)
+            if p.grad is not None:
+                view.copy_(p.grad)
+            p.grad = view
+        self._pending[bi] -= 1
+        # collectives must be issued in the same order on every rank: buckets launch strictly in index order, each as soon as
+        # it and all earlier ones are complete
+        while self._next < len(self.buckets) and self._pending[self._next] == 0:
+            self._launch(self._next)
+            self._next += 1
+
+    def zero(self) -> None:
+        """Start of a step: clear the buckets (the gradients are views into them) and re-arm the hooks."""
+        for b in self.buckets:
+            b.zero_()
+        self._pending = [len(m) for m in self._members]
+        self._launched = [False] * len(self.buckets)
+        self._handles = []
+        self._next = 0
+
+    def finish(self) -> int:
+        """After backward: launch the buckets no hook completed (parameters without a gradient on this rank), wait for all
+        collectives (the compute stream then waits for the communication stream).  Returns the number of collectives of the step."""
+        while self._next < len(self.buckets):
+            self._launch(self._next)
+            self._next += 1
+        n = len(self._handles)
+        for bi, h, op in self._handles:
+            h.wait()
+            if self.average and op == dist.ReduceOp.SUM:
+                self.buckets[bi].div_(self.ws)
+        self._handles = []
+        return n
+
+    def remove(self) -> None:
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
 def allreduce_gradients(params: Iterable[torch.nn.Parameter], bucket_bytes: int = 64 << 20, average: bool = True,
                         group: Optional[dist.ProcessGroup] = None) -> int:
-    """Sum (or average) the gradients of `params` over all ranks through flat buckets.  Returns the number of collectives.
-
-    Parameters without a gradient on this rank (e.g. `backbone.final.*`, which the model never calls, res16unet.py:231-238)
-    contribute zeros, so the bucket layout is identical on every rank and ranks whose scenes produced no gradient for a
-    parameter still take part.  NVSwitch reduces in the switch (NVLS), so buckets are sized for launch latency
-    (64 MB default: 3 collectives for the 39.6 M-parameter model), not per link."""
+    """One-shot form (after backward, not overlapped): sum (or average) the gradients of `params` over all ranks through flat
+    buckets; returns the number of collectives.  A parameter whose gradient is None on EVERY rank keeps `grad = None` (a 1-byte
+    presence map is reduced first), so the optimizer skips it exactly as the reference's does; one that some rank produced is
+    zero-filled on the others.  world size 1: nothing to do.  For training loops use `GradientBuckets` (persistent buffers,
+    overlapped with backward)."""
     params = [p for p in params if p.requires_grad]
-    if not params:
+    ws = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    if not params or ws == 1:
         return 0
-    ws = dist.get_world_size(group) if dist.is_initialized() else 1
-    n_coll = 0
+    dev = params[0].device
+    present = torch.tensor([0 if p.grad is None else 1 for p in params], dtype=torch.int32, device=dev)
+    dist.all_reduce(present, op=dist.ReduceOp.MAX, group=group)
+    present = present.tolist()
+    params = [p for p, f in zip(params, present) if f]
+    n_coll = 1
     bucket: List[torch.nn.Parameter] = []
     size = 0
 
@@ -60,18 +175,16 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], bucket_bytes: int 
         nonlocal bucket, size, n_coll
         if not bucket:
             return
-        dev, dt = bucket[0].device, torch.float32
-        flat = torch.zeros(sum(p.numel() for p in bucket), dtype=dt, device=dev)
+        flat = torch.zeros(sum(p.numel() for p in bucket), dtype=torch.float32, device=dev)
         off = 0
         for p in bucket:
             if p.grad is not None:
                 flat[off:off + p.numel()].copy_(p.grad.reshape(-1))
             off += p.numel()
-        if ws > 1:
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-            n_coll += 1
-            if average:
-                flat.div_(ws)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        n_coll += 1
+        if average:
+            flat.div_(ws)
         off = 0
         for p in bucket:
             g = flat[off:off + p.numel()].view_as(p)

@@ -95,3 +95,25 @@ def test_s200k_scene_statistics():
         cur = O.stride_coords(cur, (2 ** lvl,) * 3)
         sizes.append(len(cur))
     assert sizes == [223_648, 55_328, 13_626, 3_360, 794]
+
+
+def test_unmodified_reference_model_imports_on_compat_without_cuda():
+    """The reference's own mask3d/models code imports and constructs on top of compat/ (the drop-in MinkowskiEngine) with no CUDA
+    device, and its state dict has the names/shapes of the golden fixture (tests/boundary_check.py --cpu, a clean subprocess)."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = None
+    for c in ("/root/reference/mask3d", os.path.join(root, "oracle", "_ref", "mask3d")):
+        if os.path.isfile(os.path.join(c, "models", "mask3d.py")):
+            ref = c
+            break
+    if ref is None:
+        pytest.skip("reference tree not staged")
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "boundary_check.py"), "--cpu", ref], capture_output=True, text=True,
+                       timeout=600, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert res["state_dict_matches_golden"] and res["n_params"] == 283
