@@ -42,12 +42,18 @@ METRIC = "Mask3D inference throughput (Res16UNet34C sparse-conv backbone + 12-la
 UNIT = "voxels/s"
 
 
-def workload_config(voxel_m: float, n_scenes: int):
-    return {"workload": "BASELINE.json configs[1]: Mask3D full inference, synthetic single-floor 6-room scene "
-                        f"(10x8x2.8 m, surfaces + furniture), {voxel_m * 100:.0f} cm voxels, 25 queries, 1 scene per step per GPU",
-            "voxel_cm": voxel_m * 100, "scenes_cycled": n_scenes, "queries": 25, "decoder_layers": 12,
-            "l2_policy": "inputs larger than L2: ~0.9 M voxels x 96..384 channels per layer (>170 MB activations per layer), "
-                         "a different scene every step"}
+def workload_config(voxel_m: float, n_scenes: int, scenes_per_step: int = 1, workload: str = "floor"):
+    if workload == "building":
+        what = ("BASELINE.json configs[3]: Mask3D full inference on synthetic multi-floor buildings (4 floors of 20x15x2.8 m, surfaces + "
+                f"furniture), {voxel_m * 100:.1f} cm voxels, 25 queries, {scenes_per_step} building(s) per step per GPU, scenes sharded over GPUs")
+    else:
+        what = ("BASELINE.json configs[1]: Mask3D full inference, synthetic single-floor 6-room scenes "
+                f"(10x8x2.8 m, surfaces + furniture), {voxel_m * 100:.1f} cm voxels, 25 queries, {scenes_per_step} scene(s) per step per GPU "
+                "(one batch, as the reference batches scenes: conf/data/indoor.yaml:21)")
+    return {"workload": what, "voxel_cm": voxel_m * 100, "scenes_per_step": scenes_per_step, "batches_cycled": n_scenes, "queries": 25,
+            "decoder_layers": 12,
+            "l2_policy": "inputs larger than L2: >= 0.9 M voxels x 96..384 channels per layer per scene (>170 MB activations per layer), "
+                         "a different batch every step"}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -208,7 +214,8 @@ def main_reference(args):
     sample = f"floor_plan(seed=1000) at {v * 100:.0f} cm voxels = {n} voxels, one full Mask3D forward per step (median of {steps})"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(0.02, 3),
+            "config": dict(workload_config(v, 1), note="the CPU arm runs the same generator at the finest voxel size that fits its time budget; "
+                                                      "voxels/s normalises the scene size (the GPU arm's own 2 cm cpu_baseline is the slower figure)"),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                              "note": "CPU restatement of the reference's MinkowskiEngine-CPU algorithm (hash maps, per-offset index_select -> "
                                      f"mm -> index_add_) + stock PyTorch decoder; torch threads = {torch.get_num_threads()}"},
@@ -223,7 +230,7 @@ def main_ours(args):
     import torch
     import torch.distributed as dist
 
-    from room_instance_segmentation_mask3d_b200 import lib, mask3d_model, me_api, ops, scenes, weights
+    from room_instance_segmentation_mask3d_b200 import lib, mask3d_model, me_api, ops, parallel, scenes, weights
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -235,11 +242,18 @@ def main_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib.load()
-    lib.reserve_device_pool(8.0, dev)  # one splittable segment instead of cudaMalloc stalls while the allocator grows
     ops.set_compute_mode(args.mode)
     voxel = args.voxel_cm / 100.0
-    n_scenes = 3
-    host_scenes = [scenes.collate([scenes.floor_plan(1000 + rank * 16 + i, voxel_m=voxel)]) for i in range(n_scenes)]
+    B = max(1, args.scenes_per_step)
+    n_scenes = 3  # batches cycled
+    # B + 2 distinct scenes per rank; batch i = scenes i .. i + B - 1 (cyclic): every step sees a different batch
+    n_distinct = B + 2
+    if args.workload == "building":
+        gen = lambda i: scenes.building(2000 + rank * 64 + i, voxel_m=voxel)
+    else:
+        gen = lambda i: scenes.floor_plan(1000 + rank * 64 + i, voxel_m=voxel)
+    distinct = [gen(i) for i in range(n_distinct)]
+    host_scenes = [scenes.collate([distinct[(i + j) % n_distinct] for j in range(B)]) for i in range(n_scenes)]
     model = mask3d_model.Mask3D().eval()
     weights.load_synth(model, seed=0)
     model = model.to(dev)
@@ -247,20 +261,23 @@ def main_ours(args):
     pinned = [(torch.from_numpy(c).pin_memory(), torch.from_numpy(f).pin_memory()) for c, f in host_scenes]
     resident = [(c.to(dev), f.to(dev)) for c, f in pinned]
     nvox = [c.shape[0] for c, _ in host_scenes]
+    gb_per_mvox = 6.0  # caching-allocator segment per lane, per million voxels of a batch (maps + activations), measured ~4.5
+    lane_gb = max(8.0, gb_per_mvox * max(nvox) / 1e6)
+    lib.reserve_device_pool(4.0, dev)  # one splittable segment instead of cudaMalloc stalls while the allocator grows
 
-    # Both loops hand the NEXT scene's inputs to the forward call (`prefetch=`): its coordinate phase (H2D in the e2e loop,
+    # Both loops hand the NEXT batch's inputs to the forward call (`prefetch=`): its coordinate phase (H2D in the e2e loop,
     # hashing, strided maps, kernel maps, tile plans: all the host round trips) runs on a side stream behind the current
-    # scene's backbone instead of in front of an idle GPU.  Every scene still gets its own full coordinate phase inside the
-    # timed region (step i prepares scene i+1; the first timed step consumes what the last warm-up step prepared).
-    # Consecutive scenes alternate between two streams ("lanes"): a scene's decoder is a chain of small latency-bound kernels, the
-    # next scene's backbone a sequence of kernels that fill the GPU, and the two overlap.  Each lane has its own pinned result
+    # batch's backbone instead of in front of an idle GPU.  Every batch still gets its own full coordinate phase inside the
+    # timed region (step i prepares batch i+1; the first timed step consumes what the last warm-up step prepared).
+    # Consecutive batches alternate between two streams ("lanes"): a batch's decoder is a chain of small latency-bound kernels, the
+    # next batch's backbone a sequence of kernels that fill the GPU, and the two overlap.  Each lane has its own pinned result
     # buffers; the timed region ends when BOTH lanes have drained (see `timed`).
     n_lanes = 1 if args.lanes < 2 else 2
     lanes = [torch.cuda.Stream(device=dev) for _ in range(n_lanes)]
     for st_ in lanes:  # the caching allocator keeps blocks per stream: one up-front segment for every stream a forward runs on
-        lib.reserve_device_pool(12.0, dev, stream=st_)
-    lib.reserve_device_pool(6.0, dev, stream=model.side_stream(dev))
-    h_cls = [torch.empty((13, 1, 25, 2), dtype=torch.float32).pin_memory() for _ in range(n_lanes)]
+        lib.reserve_device_pool(lane_gb, dev, stream=st_)
+    lib.reserve_device_pool(lane_gb / 2, dev, stream=model.side_stream(dev))
+    h_cls = [torch.empty((13, B, 25, 2), dtype=torch.float32).pin_memory() for _ in range(n_lanes)]
     h_mask = [[torch.empty((n, 25), dtype=torch.float32).pin_memory() for n in nvox] for _ in range(n_lanes)]
     state = {"res": None, "e2e": None, "g_res": 0, "g_e2e": 0, "vox": 0}
 
@@ -315,13 +332,14 @@ def main_ours(args):
     gc.collect()
     gc.freeze()
     gc.disable()
-    # nvidia-smi is started BEFORE the warm-up: its start-up (NVML initialisation, first query) takes driver locks for tens of
-    # milliseconds, which used to land inside the first timed region; the rows that fall inside the timed region are the ones
-    # reported (ClockSampler.window)
+    # the clock sampler is started BEFORE the warm-up: its start-up (NVML initialisation, first query) takes driver locks for tens of
+    # milliseconds, which used to land inside the first timed region; the rows that fall inside the timed region are the ones reported
     sampler = ClockSampler(local)
     if rank == 0 and not args.no_clocks:
         sampler.start()
-    n_warm = max(args.warmup, 2 * n_scenes)  # every scene twice: CUDA-graph capture, allocator growth, weight images
+    # warm-up: at least every batch twice (CUDA-graph capture, allocator growth, weight images) -- the line reports the --warmup
+    # argument as `warmup` and the steps actually run as `warmup_run`
+    n_warm = max(args.warmup, 2 * n_scenes)
     for i in range(n_warm):
         step_resident(i)
     sampler.mark()
@@ -330,7 +348,7 @@ def main_ours(args):
     ms = timed(step_resident, args.steps)
     launches = lib.kernel_launches - launches0
     clocks = sampler.stop() if rank == 0 else None
-    vox_per_step = state["vox"] / args.steps  # the scenes actually processed inside the timed region
+    vox_per_step = state["vox"] / args.steps  # the voxels actually processed inside the timed region
     value = world * vox_per_step * args.steps / (ms * 1e-3)
 
     gc.collect()
@@ -353,11 +371,13 @@ def main_ours(args):
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
         ops.USE_COMPOSITE = False  # time the conv launches on their own (the composite call also enqueues the norm kernels)
+        state["one_lane"] = True  # per-launch events must not see the other lane's kernels interleaved
+        for i in range(2):  # warm the instrumented configuration (separate conv / norm calls allocate differently) before timing it
+            step_resident(i)
+        torch.cuda.synchronize()
         ev = lib.instrument(["mk_conv_fwd_bf16"])
         isteps = min(args.steps, 3)
-        torch.cuda.synchronize()
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-        state["one_lane"] = True  # per-launch events must not see the other lane's kernels interleaved
         with torch.cuda.stream(lanes[0]):
             t0.record()
         for i in range(isteps):
@@ -384,7 +404,6 @@ def main_ours(args):
             a = by_shape.setdefault(k, [0.0, 0.0, 0])
             a[0] += t[0]; a[1] += s.elapsed_time(e); a[2] += 1
         top = sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:8]
-        achieved = tot_flops / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
         # launch classes of the same kernel: the gather-GEMM proper (K = 27 / 8 offsets, tensor-bound by design) and the
         # K = 1 launches (1x1 convs, K/V projections, mask-logit product: one pass over [N, C], HBM-bound)
         g_ms, g_fl, g_n = summarize(lambda t: t[1] > 1)
@@ -395,11 +414,17 @@ def main_ours(args):
         # 25-column mask logits and the fp32 `src` of the key projection) -- taken as 2 B in, 2 or 4 B out per element
         o_bytes = sum(t[4] * (2 * t[2] + (4 if (t[3] <= 32 or t[2] != t[3]) else 2) * min(t[3], 128)) for s, e, t in recs if t[1] == 1)
         tf = lambda fl, ms_: fl / (ms_ * 1e-3) / 1e12 if ms_ > 0 else 0.0
-        roofline = {"kernel": "k_conv_umma (tcgen05 gather-GEMM sparse conv), all launches of the step", "bound": "tensor", "achieved": achieved,
+        achieved = tf(g_fl, g_ms)
+        roofline = {"kernel": "k_conv_umma (tcgen05 gather-GEMM sparse conv): the K > 1 launches of the step (3^3, 2^3 and transposed 2^3 "
+                              "convolutions); the K = 1 launches of the same kernel are HBM-bound and reported under classes",
+                    "bound": "tensor", "achieved": achieved,
                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC.get("bytes_per_launch"),
                     "traffic_note": NCU_TRAFFIC.get("note"), "peak_source": peak_src,
-                    "launches_per_step": n_launch / isteps, "flops_per_launch_avg": tot_flops / max(n_launch, 1),
-                    "ms_per_launch_avg": tot_ms / max(n_launch, 1), "share_of_step": tot_ms / step_ms,
+                    "launches_per_step": g_n / isteps, "flops_per_launch_avg": g_fl / max(g_n, 1),
+                    "ms_per_launch_avg": g_ms / max(g_n, 1), "share_of_step": g_ms / step_ms,
+                    "all_launches": {"launches_per_step": n_launch / isteps, "ms_per_step": tot_ms / isteps,
+                                     "achieved_tflops": tf(tot_flops, tot_ms), "frac_of_tensor_peak": tf(tot_flops, tot_ms) / peak,
+                                     "share_of_step": tot_ms / step_ms},
                     "classes": {
                         "gather_gemm_K>1": {"launches_per_step": g_n / isteps, "ms_per_step": g_ms / isteps, "achieved_tflops": tf(g_fl, g_ms),
                                             "frac_of_tensor_peak": tf(g_fl, g_ms) / peak},
@@ -420,13 +445,16 @@ def main_ours(args):
 
     # first clause of BASELINE.json's metric: Res16UNet34C forward + backward voxels/s (fused training path, bf16 tensor cores),
     # on the same scene generator; reported beside the headline, not part of the timed regions above
+    Bt = max(1, min(B, args.train_scenes))
+    c_t, f_t = (torch.from_numpy(x).to(dev) for x in scenes.collate([distinct[j] for j in range(Bt)]))
+    n_t = int(c_t.shape[0])
+    sizes_t = [len(distinct[j]) for j in range(Bt)]
     train = None
     if rank == 0 and world == 1 and not args.no_train:
         try:
             bb = mask3d_model.Res16UNet34C()
             weights.load_synth(bb, seed=0)
             bb = bb.to(dev).train()
-            c_t, f_t = resident[0]
 
             def tstep():
                 for prm in bb.parameters():
@@ -434,89 +462,116 @@ def main_ours(args):
                 out, fm = bb.forward_train(me_api.SparseTensor(features=f_t, coordinates=c_t))
                 (out.F.float().square().mean() + sum(t.F.float().square().mean() for t in fm[:-1])).backward()
 
-            for _ in range(8):
+            for _ in range(6):
                 tstep()
             tsteps = 5
             t_ms = timed(lambda i: tstep(), tsteps) / tsteps
             train = {"what": "Res16UNet34C forward + backward, fused training path (bf16 activations, tcgen05 fwd/dgrad/wgrad), maps and "
-                             "plans rebuilt every step, one scene per step", "voxels": nvox[0], "ms_fwd_bwd": t_ms,
-                     "voxels_per_s": nvox[0] / (t_ms * 1e-3)}
+                             f"plans rebuilt every step, {Bt} scene(s) per step", "voxels": n_t, "ms_fwd_bwd": t_ms,
+                     "voxels_per_s": n_t / (t_ms * 1e-3)}
             del bb
         except Exception as exc:  # the headline line must survive a failure here
             train = {"error": repr(exc)[:200]}
 
-    # loss side on the outputs of one inference step: matcher cost matrices of all 13 decoder outputs, the
-    # Hungarian assignments (scipy on the host, as in the reference), losses and the gradient w.r.t. all 13 logit tensors
+    # BASELINE.json configs[2]: the training step, data-parallel over the N GPUs (one process per GPU, every rank its own scenes):
+    # Mask3D.forward_train -> SetCriterion (incl. the reference's all_reduce(num_masks), criterion.py:244-246) -> backward with the
+    # bucketed NCCL gradient all-reduce OVERLAPPED with it (parallel.GradientBuckets) -> AdamW (lr 1e-4).  Runs at every N.
     loss_side = None
-    if rank == 0 and world == 1 and not args.no_train:
+    train_step = None
+    if not args.no_train:
         try:
             from types import SimpleNamespace
 
             from room_instance_segmentation_mask3d_b200 import criterion as CR
 
-            with torch.no_grad():
-                o = model(model.prepare(*resident[0]))
-            n0, T = int(o["pred_mask_all_decoders"][-1].shape[0]), 24
-            seg = torch.div(torch.arange(n0, device=dev) * T, n0, rounding_mode="floor")  # 24 instances = runs of voxel rows
-            tgt = [SimpleNamespace(instances_labels=torch.zeros(T, dtype=torch.long, device=dev),
-                                   instances_masks=torch.stack([seg == t for t in range(T)]))]
-            pm = [t.detach().clone().requires_grad_(True) for t in o["pred_mask_all_decoders"]]
-            pc = [t.detach().clone().requires_grad_(True) for t in o["pred_class_all_decoders"]]
-            D = len(pm)
+            T = 24  # instances per scene = runs of voxel rows
+            tgt = []
+            for nb in sizes_t:
+                seg = torch.div(torch.arange(nb, device=dev) * T, nb, rounding_mode="floor")
+                tgt.append(SimpleNamespace(instances_labels=torch.zeros(T, dtype=torch.long, device=dev),
+                                           instances_masks=torch.stack([seg == t for t in range(T)])))
             wts = {"loss_ce": 2.0, "loss_mask": 5.0, "loss_dice": 2.0}
             wd = dict(wts)
-            for d in range(D - 1):
+            for d in range(12):
                 wd.update({k + f"_mask_module_{d}": v for k, v in wts.items()})
-            crit = CR.SetCriterion(pc[0].shape[-1] - 1, CR.HungarianMatcher(2.0, 5.0, 2.0, -1), wd, 0.1, ["labels", "masks"], -1, 3.0, 0.75,
-                                   -1).to(dev)
-            mo = dict(pred_class=pc[-1], pred_class_all_decoders=pc, pred_mask=pm[-1], pred_mask_all_decoders=pm)
+            crit = CR.SetCriterion(1, CR.HungarianMatcher(2.0, 5.0, 2.0, -1), wd, 0.1, ["labels", "masks"], -1, 3.0, 0.75, -1).to(dev)
 
-            def lstep():
-                for t in pm + pc:
-                    t.grad = None
-                ls = crit(mo, tgt)
-                sum(ls[k] * wd[k] for k in ls).backward()
+            if rank == 0 and world == 1:
+                # loss side alone on the outputs of one inference step of the training batch
+                with torch.no_grad():
+                    o = model(model.prepare(c_t, f_t))
+                pm = [t.detach().clone().requires_grad_(True) for t in o["pred_mask_all_decoders"]]
+                pc = [t.detach().clone().requires_grad_(True) for t in o["pred_class_all_decoders"]]
+                mo = dict(pred_class=pc[-1], pred_class_all_decoders=pc, pred_mask=pm[-1], pred_mask_all_decoders=pm)
 
-            for _ in range(3):
-                lstep()
-            l_ms = timed(lambda i: lstep(), 5) / 5
-            loss_side = {"what": "SetCriterion forward + backward (matcher costs, Hungarian on the host, mask/dice/class losses, gradients of all "
-                                 "decoder outputs' mask logits) on the outputs of one inference step", "voxels": n0, "decoder_outputs": D,
-                         "instances": T, "ms_fwd_bwd": l_ms}
-            del pm, pc, mo, o
+                def lstep():
+                    for t in pm + pc:
+                        t.grad = None
+                    ls = crit(mo, tgt)
+                    sum(ls[k] * wd[k] for k in ls).backward()
 
-            # whole training step: Mask3D.forward_train -> SetCriterion -> backward -> AdamW (lr 1e-4)
+                for _ in range(3):
+                    lstep()
+                l_ms = timed(lambda i: lstep(), 5) / 5
+                loss_side = {"what": "SetCriterion forward + backward (matcher costs, Hungarian on the host, mask/dice/class losses, gradients of "
+                                     "all decoder outputs' mask logits) on the outputs of one inference step", "voxels": n_t,
+                             "decoder_outputs": len(pm), "instances": T * Bt, "ms_fwd_bwd": l_ms}
+                del pm, pc, mo, o
+
             model.train()
-            opt = torch.optim.AdamW([p_ for n_, p_ in model.named_parameters() if not n_.startswith("backbone.final")], lr=1e-4)
-            c_t, f_t = resident[0]
+            params = [p_ for n_, p_ in model.named_parameters() if not n_.startswith("backbone.final")]
+            gbk = parallel.GradientBuckets(params)
+            opt = torch.optim.AdamW(params, lr=1e-4)
+            ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            exposed = []
 
-            def wstep():
-                opt.zero_grad(set_to_none=True)
+            def wstep(record=False):
+                gbk.zero()
                 out_t = model.forward_train(me_api.SparseTensor(features=f_t, coordinates=c_t))
                 ls = crit(out_t, tgt)
                 sum(ls[k] * wd[k] for k in ls).backward()
+                ev_b[0].record()
+                gbk.finish()  # the compute stream waits here for whatever part of the all-reduce backward did not hide
+                ev_b[1].record()
                 opt.step()
+                if record:
+                    torch.cuda.synchronize()
+                    exposed.append(ev_b[0].elapsed_time(ev_b[1]))
 
-            for _ in range(10):  # the caching allocator keeps growing (cudaMalloc) for the first handful of training steps
+            for _ in range(8):  # the caching allocator keeps growing (cudaMalloc) for the first handful of training steps
                 wstep()
-            w_ms = timed(lambda i: wstep(), 5) / 5
-            loss_side["train_step"] = {"what": "Mask3D.forward_train + SetCriterion + backward + AdamW on the same scene (maps and plans "
-                                               "rebuilt every step)", "ms_step": w_ms, "voxels_per_s": n0 / (w_ms * 1e-3)}
+            wsteps = 5
+            w_ms = timed(lambda i: wstep(), wsteps) / wsteps
+            for _ in range(3):
+                wstep(record=True)
+            n_par = sum(p_.numel() for p_ in params)
+            train_step = {"what": "BASELINE.json configs[2]: Mask3D.forward_train + SetCriterion + backward + bucketed gradient all-reduce "
+                                  "(NCCL, overlapped with backward) + AdamW; maps and plans rebuilt every step; every rank its own "
+                                  f"{Bt} scene(s) of the workload", "n_gpus": world, "scenes_per_step_per_gpu": Bt, "voxels_per_gpu": n_t,
+                          "ms_step": w_ms, "voxels_per_s": world * n_t / (w_ms * 1e-3), "scenes_per_s": world * Bt / (w_ms * 1e-3),
+                          "allreduce": {"parameters": n_par, "bytes": 4 * n_par, "buckets": len(gbk.buckets),
+                                        "collectives_per_step": gbk.collectives // max(1, 8 + wsteps + 3) if world > 1 else 0,
+                                        "exposed_ms": float(np.median(exposed)) if exposed else None,
+                                        "note": "exposed = time the compute stream waits in GradientBuckets.finish() after backward "
+                                                "(CUDA events); at N = 1 no collective runs"}}
+            gbk.remove()
             model.eval()
             for p_ in model.parameters():
                 p_.grad = None
-            del opt
+            del opt, gbk
         except Exception as exc:
-            loss_side = dict(loss_side or {}, error=repr(exc)[:200])
+            train_step = {"error": repr(exc)[:300]}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic", "config": workload_config(voxel, n_scenes),
-                "scenes_per_sec": world * args.steps / (ms * 1e-3), "voxels_per_scene": vox_per_step,
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "warmup_run": n_warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
+                "config": workload_config(voxel, n_scenes, B, args.workload),
+                "scenes_per_sec": world * B * args.steps / (ms * 1e-3), "voxels_per_step_per_gpu": vox_per_step,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "train_fwd_bwd": train, "loss_side": loss_side}
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "train_fwd_bwd": train,
+                "loss_side": loss_side, "train_step": train_step}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -553,6 +608,10 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--voxel-cm", type=float, default=2.0)
+    ap.add_argument("--scenes-per-step", type=int, default=4, help="scenes batched per step per GPU (the reference batches 16 small scenes, "
+                    "conf/data/indoor.yaml:21; 4 x 0.9 M voxels fills the coarse U-Net levels and keeps every index below 2^31)")
+    ap.add_argument("--train-scenes", type=int, default=2, help="scenes per training step per GPU")
+    ap.add_argument("--workload", default="floor", choices=["floor", "building"], help="floor: configs[1] single-floor scenes; building: configs[3] multi-floor buildings")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=2, help="streams consecutive scenes alternate between (1 = a single stream)")
     ap.add_argument("--no-train", action="store_true", help="skip the backbone forward+backward measurement")

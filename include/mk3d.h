@@ -116,6 +116,15 @@ int mk_conv_weight_image_bf16(const float* W, int K, int cin, int cout, int tran
 int mk_conv_fwd_bf16(const void* in, int64_t n_in, int cin, const void* wimg, int cout, const int32_t* nbr, int K, int64_t n_slots,
                      const int32_t* out_rows, const uint32_t* tile_kmask, const int32_t* kidx, int64_t n_out,
                      const float* bias, void* out, int out_dtype, int out_cols, int out_stride, void* stream);
+/* TF32 tensor-core mode = the reference's own precision (fp32 tensors with torch.set_float32_matmul_precision("high"),
+ * mask3d/main_instance_segmentation.py:52): same kernel, fp32 rows gathered as 128-byte chunks of 32 channels,
+ * tcgen05.mma.kind::tf32 (K = 8 per instruction), fp32 accumulation.  `in` fp32 [n_in,cin] (cin % 8 == 0), `wimg` from
+ * mk_conv_weight_image_tf32 (fp32, 32-channel chunks); everything else as mk_conv_fwd_bf16. */
+int64_t mk_conv_weight_image_tf32_elems(int K, int cin, int cout, int transpose);
+int mk_conv_weight_image_tf32(const float* W, int K, int cin, int cout, int transpose, void* img, void* stream);
+int mk_conv_fwd_tf32(const void* in, int64_t n_in, int cin, const void* wimg, int cout, const int32_t* nbr, int K, int64_t n_slots,
+                     const int32_t* out_rows, const uint32_t* tile_kmask, const int32_t* kidx, int64_t n_out,
+                     const float* bias, void* out, int out_dtype, int out_cols, int out_stride, void* stream);
 /* A-operand producer of mk_conv_fwd_bf16: 0 = LSU (16-byte cp.async into the swizzled tile, default), 1 = TMA gather4. */
 int mk_set_gather_mode(int mode);
 /* 1: results are bit-identical from run to run (the reference trains with `deterministic: true`,
@@ -194,6 +203,8 @@ int mk_conv_instnorm_bf16(const void* in, int64_t n_in, int cin, const void* wim
  * out[o] = sum over existing children / (#children if average).  nbr int32 [K,n_out].
  * ------------------------------------------------------------------------------------------- */
 int mk_pool_fwd(const float* in, int C, const int32_t* nbr, int K, int64_t n_out, int average, float* out, void* stream);
+/* same, input fp32 or bf16 (in_dtype), output fp32: pools the bf16 mask features without a cast pass */
+int mk_pool_fwd_dt(const void* in, int in_dtype, int C, const int32_t* nbr, int K, int64_t n_out, int average, float* out, void* stream);
 int mk_pool_bwd(const float* dout, int C, const int32_t* nbr, int K, int64_t n_out, int average, int64_t n_in, float* din,
                 void* stream);
 
@@ -213,6 +224,9 @@ int mk_scene_minmax(const float* xyz, int64_t n, const int32_t* scene_offsets, i
  * gauss_B fp32 [3, D/2]; base / out [n, D]. */
 int mk_fourier_pe(const float* xyz, int64_t n, const int32_t* scene_offsets, int B, const float* cmin, const float* cmax,
                   const float* gauss_B, int D, const void* base, int base_dtype, void* out, int out_dtype, void* stream);
+/* 1: force the CUDA-core forward kernel of the masked cross-attention (A/B measurements); default 0: bf16 keys / values with
+ * D = 128, H = 8, Q <= 32 run on the tensor-core kernel (mma.sync, warp-level online softmax). */
+int mk_set_xattn_simt(int on);
 int64_t mk_xattn_workspace_bytes(int B, int Q, int H, int64_t n_keys);
 /* Masked cross-attention core of one decoder layer, all scenes, no padding (varlen over scene_offsets):
  *   ctx[b,q,h,:] = softmax_k( scale * qp[b,q,h,:] . kp[k,h,:]  masked ) @ vp[k,h,:]

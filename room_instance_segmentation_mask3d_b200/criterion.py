@@ -354,6 +354,18 @@ class SetCriterion(nn.Module):
             for d in range(D):
                 mask_costs(logits[d], tg, sels[d], out=buf[d], n_rows=nr[d])
             stats = MaskStats(buf, nr, None, sels)
+        else:
+            rs = stats.row_select if isinstance(stats.row_select, (list, tuple)) else [stats.row_select]
+            if any(r is not None for r in rs):
+                # the matcher sub-sampled rows (matcher.num_points != -1) but the criterion must not (num_points == -1): the loss
+                # is taken over ALL points, as in the reference (criterion.py:181-196), so the statistics are recomputed on all rows
+                D, dev = len(logits), logits[0].device
+                buf = torch.empty((D, 3, tg.B, logits[0].shape[1], 32 * tg.W), dtype=torch.float32, device=dev)
+                nr = torch.empty((D, tg.B), dtype=torch.float32, device=dev)
+                for d in range(D):
+                    mask_costs(logits[d], tg, None, out=buf[d], n_rows=nr[d])
+                stats = MaskStats(buf, nr)
+        # NB: a scene without targets contributes 0 to the mask / dice losses here; the reference divides 0 by 0 there (NaN)
         return _MaskLossFn.apply(tg, stats, match, inv_m, *logits)
 
     def _losses(self, cls_stack, logits, tg, stats, matches_all):

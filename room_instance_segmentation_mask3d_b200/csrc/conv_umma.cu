@@ -54,68 +54,53 @@ __device__ __forceinline__ uint32_t split_bits(uint32_t m, int part, int ksplit)
 
 // Work enumeration of one CTA, identical in every role.  A "super-tile" is G consecutive 128-slot tiles (G = 2 when cout <= 128:
 // the two accumulators share every weight chunk, and mask-sorted plans give neighbouring tiles the same offset set).  An
-// iteration is (super-tile, 64-channel chunk c, offset k in the union of the member tiles' masks), ordered super-tile, chunk,
-// offset: all offsets of chunk 0, then all offsets of chunk 1 (the rows a compact tile re-gathers across its offsets are then
-// re-touched within ~10 iterations on half the bytes, which fits the L1 left next to the pipeline stages).
-// One step is ~10 instructions; the masks of the NEXT super-tile are loaded when the current one is entered.
-struct Walk {
-  const uint32_t* __restrict__ km;
-  int st, stride, num_st, num_tiles, nch, c, part, ks;
-  uint32_t m0, m1, mall, mu, n0, n1;
-  bool two;
-  __device__ __forceinline__ void fetch(int s, uint32_t& a, uint32_t& b) const {
-    a = 0u;
-    b = 0u;
-    if (s < num_st) {
-      const int t = two ? 2 * s : s;
-      a = __ldg(km + t);
-      if (two && t + 1 < num_tiles) b = __ldg(km + t + 1);
-    }
-  }
-  __device__ __forceinline__ void enter() {
-    mall = m0 | m1;
-    if (ks > 1) mall = split_bits(mall, part, ks);
-    mu = mall;
-    c = 0;
-  }
-  __device__ __forceinline__ void next_st() {
-    st += stride;
-    m0 = n0;
-    m1 = n1;
-    fetch(st + stride, n0, n1);
-    enter();
-  }
-  __device__ __forceinline__ void skip() {
-    while (st < num_st && mall == 0u) next_st();
-  }
-  __device__ Walk(const uint32_t* km_, int G, int first, int stride_, int num_tiles_, int nch_, int part_, int ks_)
-      : km(km_), st(first), stride(stride_), num_tiles(num_tiles_), nch(nch_), part(part_), ks(ks_), two(G == 2) {
-    num_st = two ? (num_tiles + 1) >> 1 : num_tiles;
-    fetch(st, m0, m1);
-    fetch(st + stride, n0, n1);
-    enter();
-    skip();
-  }
-  __device__ __forceinline__ bool valid() const { return st < num_st; }
-  __device__ __forceinline__ int k() const { return __ffs(mu) - 1; }
-  __device__ __forceinline__ uint32_t has() const {
-    const int kk = __ffs(mu) - 1;
-    return ((m0 >> kk) & 1u) | (((m1 >> kk) & 1u) << 1);
-  }
-  // true on the last iteration of the super-tile (its accumulators are complete after it)
-  __device__ __forceinline__ bool last() const { return (mu & (mu - 1)) == 0u && c == nch - 1; }
-  __device__ __forceinline__ void step() {
-    mu &= mu - 1;
-    if (mu == 0u) {
-      if (++c < nch) {
-        mu = mall;
-      } else {
-        next_st();
-        skip();
-      }
-    }
-  }
+// iteration is (super-tile, 64-channel chunk c, offset k of the union of the member tiles' masks), ordered super-tile, chunk,
+// offset.  Inside a chunk pass the offsets of a 3^3 kernel are visited x-plane by x-plane (all offsets with dx = -1, then
+// dx = 0, then dx = +1): voxel rows are in lexicographic (x, y, z) order, so the 9 offsets of one dx gather (nearly) the SAME
+// input rows, shifted by a few rows -- consecutive iterations then re-read rows that are still in the L1 left next to the
+// pipeline stages, instead of re-fetching them from L2 (the kernel is bound by L2 -> SM bandwidth once its issue overheads
+// are gone: ncu l1tex__m_xbar2l1tex_read_bytes, profiles/r02_ncu_conv96_summary.txt).
+//
+// The order is materialised once per super-tile and warp as a per-lane vector: lane j holds the j-th offset (`kvec`), so an
+// iteration costs one shuffle + a handful of ALU instructions and no data-dependent loop (the first version of this kernel
+// spent ~190 cycles per step in a bit-walking cursor, 4 steps per producer stage).
+struct SuperTile {
+  uint32_t m0, m1;  // member tile masks
+  int n;            // offsets of this CTA's share of the union
+  int kvec;         // lane j < n: j-th offset in visiting order
 };
+__device__ __forceinline__ void load_masks(const uint32_t* __restrict__ km, int s, int num_st, int num_tiles, bool two, uint32_t& a, uint32_t& b) {
+  a = 0u;
+  b = 0u;
+  if (s < num_st) {
+    const int t = two ? 2 * s : s;
+    a = __ldg(km + t);
+    if (two && t + 1 < num_tiles) b = __ldg(km + t + 1);
+  }
+}
+__device__ __forceinline__ SuperTile make_super(uint32_t m0, uint32_t m1, int K, int part, int ks, int lane) {
+  SuperTile t;
+  t.m0 = m0;
+  t.m1 = m1;
+  uint32_t mall = m0 | m1;
+  if (ks > 1) mall = split_bits(mall, part, ks);
+  const uint32_t M0 = K == 27 ? 0x1249249u : 0xFFFFFFFFu;  // ix == 0 (k = ix + 3 * iy + 9 * iz)
+  const uint32_t M1 = K == 27 ? 0x2492492u : 0u;           // ix == 1
+  const uint32_t g0 = mall & M0, g1 = mall & M1, g2 = mall & ~(M0 | M1);
+  const int n0 = __popc(g0), n1 = __popc(g1);
+  t.n = __popc(mall);
+  uint32_t g = g2;
+  int r = lane - n0 - n1;
+  if (lane < n0) {
+    g = g0;
+    r = lane;
+  } else if (lane < n0 + n1) {
+    g = g1;
+    r = lane - n0;
+  }
+  t.kvec = lane < t.n ? (int)__fns(g, 0, r + 1) : 0;
+  return t;
+}
 
 template <typename TOut, bool kDbg>
 __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const ConvParams p) {
@@ -134,7 +119,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const ConvParams p)
   uint64_t* tmem_full = bars + 2 * kMaxStages;     // [2]  one tcgen05.commit per MMA issuer
   uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;  // [2]  128 epilogue threads
   uint32_t* tmem_base_slot = (uint32_t*)(bars + 2 * kMaxStages + 4);
-  float* out_stage = (float*)(bars + 2 * kMaxStages + 6);  // [4 epilogue warps][32 rows x out_cols] when p.stage_out (16-byte aligned)
+  int32_t* idx_stage = (int32_t*)(bars + 2 * kMaxStages + 6);  // [8 producer warps][2][4 units][32] neighbour-table entries (8 KB)
+  float* out_stage = (float*)(idx_stage + kCvProducerWarps * 2 * 4 * 32);  // [4 epilogue warps][32 rows x out_cols] when p.stage_out
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dbg = kDbg ? p.debug : 0;
@@ -191,102 +177,152 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const ConvParams p)
       const int UW = 4 * G / split;  // units per warp: 4 or 2
       const int piece = lane & 7;    // 16-byte piece of the 128-byte row
       const int rsub = lane >> 3;    // row octet of the unit this lane copies
-      const uint32_t row_bytes = (uint32_t)p.cin * (uint32_t)sizeof(__nv_bfloat16);
-      const int cin = p.cin;
+      const uint32_t row_bytes = (uint32_t)p.cin * (uint32_t)p.elem;  // bf16 (2) or fp32 / tf32 (4) activations
+      const int cin_bytes = p.cin * p.elem;
       const int64_t n_slots = p.n_slots;
       const int32_t* __restrict__ nbr = p.nbr;
       const int32_t* __restrict__ kidx = p.kidx;
       const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
       // destination of (unit 0, jj = 0) inside a stage for this lane; row = rsub * 8 + jj => row & 7 == jj => swizzled piece = piece ^ jj
       const uint32_t dst_lane = (uint32_t)(sub * UW * 32 * 128 + rsub * 8 * 128);
-      struct It {
+      const bool two = G == 2;
+      const int num_st = two ? (p.num_tiles + 1) >> 1 : p.num_tiles;
+      const uint32_t* __restrict__ kmask = p.tile_kmask;
+      const int K = p.K;
+      const uint32_t my_idx = smem_u32(idx_stage) + (uint32_t)(warp * 2 * 4 * 128);  // this warp's [2 buffers][4 units][32 entries]
+      long long tp_wait = 0, tp_start = kDbg ? clock64() : 0;
+      // ---- lookahead walker: position of this group's NEXT own iteration (may be in a later super-tile) ----
+      struct Own {
         int st, k, ch;
         uint32_t has;
         bool valid;
       };
-      Walk la(p.tile_kmask, G, cta_first, cta_stride, p.num_tiles, nchunks, cta_part, ksplit);  // lookahead walker
-      for (int i = 0; i < gi && la.valid(); ++i) la.step();
-      auto next_it = [&]() -> It {
-        It x;
-        x.valid = la.valid();
-        x.st = la.st;
-        x.k = x.valid ? la.k() : 0;
-        x.ch = la.c;
-        x.has = x.valid ? la.has() : 0u;
-        if (x.valid && lane < UW) {  // pull the index lines of the stage after this one into L1 (lane u: unit u's 128-byte line)
-          const int gu = sub * UW + lane;
-          const int64_t slot = (int64_t)x.st * (G * kTileM) + gu * 32;
-          if (((x.has >> (gu >> 2)) & 1u) && slot < n_slots)
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(nbr + (int64_t)x.k * n_slots + slot));
+      int w_st = cta_first;   // super-tile of the walker
+      int w_i = gi;           // iteration index inside it (may exceed its total: carried into the next super-tile)
+      uint32_t nm0, nm1;
+      load_masks(kmask, cta_first, num_st, p.num_tiles, two, nm0, nm1);
+      SuperTile T = make_super(nm0, nm1, K, cta_part, ksplit, lane);
+      load_masks(kmask, cta_first + cta_stride, num_st, p.num_tiles, two, nm0, nm1);
+      auto take = [&]() -> Own {  // resolve the walker's position to an iteration, then advance it by NP
+        Own o;
+        while (w_st < num_st && w_i >= T.n * nchunks) {
+          w_i -= T.n * nchunks;
+          w_st += cta_stride;
+          T = make_super(nm0, nm1, K, cta_part, ksplit, lane);
+          load_masks(kmask, w_st + cta_stride, num_st, p.num_tiles, two, nm0, nm1);
+          if (T.n <= 2 && sub == 0) {  // short passes (1x1 convs, mask logits): the table rows stream from DRAM, pull them into L2 early
+            const int k0 = __shfl_sync(0xffffffffu, T.kvec, 0);
+            const int64_t slot = ((int64_t)w_st + 6 * cta_stride) * (G * kTileM) + lane * 32;
+            if (lane < 4 * G && slot < n_slots) asm volatile("prefetch.global.L2 [%0];" ::"l"(nbr + (int64_t)k0 * n_slots + slot));
+          }
         }
-        for (int i = 0; i < NP && la.valid(); ++i) la.step();
-        return x;
+        o.valid = w_st < num_st;
+        o.st = w_st;
+        int ch = 0, j = w_i;
+        while (o.valid && j >= T.n) {
+          j -= T.n;
+          ++ch;
+        }
+        o.ch = ch;
+        o.k = __shfl_sync(0xffffffffu, T.kvec, o.valid ? j : 0);
+        o.has = o.valid ? (((T.m0 >> o.k) & 1u) | (((T.m1 >> o.k) & 1u) << 1)) : 0u;
+        w_i += NP;
+        return o;
+      };
+      // this lane's table entry per owned unit of an iteration: slot = st * G * 128 + (sub * UW + u) * 32 + lane
+      auto stage_indices = [&](const Own& o, int buf) {
+        const int32_t* col = nbr + (int64_t)o.k * n_slots;
+        const int64_t slot_w = (int64_t)o.st * (G * kTileM) + sub * UW * 32 + lane;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (u < UW && ((o.has >> ((sub * UW + u) >> 2)) & 1u)) {  // warp-uniform
+            const int64_t slot = slot_w + u * 32;
+            const bool in = slot < n_slots;
+            cp_async_4(my_idx + (uint32_t)((buf * 4 + u) * 128 + lane * 4), col + (in ? slot : 0), in ? 4u : 0u);
+          }
+        }
+        cp_async_commit();
       };
       int stage = gi % S;
       uint32_t phase = (uint32_t)((gi / S) & 1);
-      long long tp_wait = 0, tp_start = kDbg ? clock64() : 0;
-      It cur = next_it();
+      int ibuf = 0;
+      Own cur = take();
+      if (cur.valid) stage_indices(cur, ibuf);
       while (cur.valid) {
-        const It nxt = next_it();
-        const int ch = cur.ch;
-        const int width = min(kChunkElems, cin - ch * kChunkElems);  // valid elements in this chunk
-        // this lane's 8 row indices per owned unit
-        int idx[4][8];
-        const int32_t* col = nbr + (int64_t)cur.k * n_slots;
-        const int64_t slot0 = (int64_t)cur.st * (G * kTileM) + sub * UW * 32 + rsub * 8;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const bool on = u < UW && ((cur.has >> ((sub * UW + u) >> 2)) & 1u);
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const int64_t slot = slot0 + u * 32 + jj;
-            idx[u][jj] = -1;
-            if (on && slot < n_slots) idx[u][jj] = __ldg(col + slot);
-          }
+        const Own nxt = take();
+        if (nxt.valid) {
+          stage_indices(nxt, ibuf ^ 1);
+          cp_async_wait<1>();  // everything but the group just committed: this iteration's entries have landed
+        } else {
+          cp_async_wait<0>();
         }
-        const int kw = kidx ? __ldg(kidx + cur.k) : cur.k;
-        const long long tp0 = kDbg ? clock64() : 0;
-        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-        if (kDbg) tp_wait += clock64() - tp0;
-        const uint32_t bar = smem_u32(&full_bar[stage]);
-        // lanes whose piece lies beyond a narrow chunk (or all lanes in the gather-off ablation) issue nothing
-        const bool act = piece * 8 < width && !(dbg & 1);
-        // source address = per-lane 64-bit base + row * row_bytes as ONE 32x32+64 multiply-add (IMAD.WIDE.U32)
-        uint64_t src0 = (uint64_t)p.in + (uint64_t)(ch * kChunkElems + piece * 8) * sizeof(__nv_bfloat16);
-        asm volatile("" : "+l"(src0));  // keep the base in one register pair (otherwise it is re-derived from the constant bank per copy)
-        const uint32_t a_lane = sA_u32 + (uint32_t)(stage * a_bytes) + dst_lane;
-        if (act) {
+        __syncwarp();  // the entries were written by other lanes of this warp
+        {
+          const int k = cur.k, ch = cur.ch;
+          const uint32_t has = cur.has;
+          const int64_t slot_st = (int64_t)cur.st * (G * kTileM) + sub * UW * 32;
+          const int width = min(128, cin_bytes - ch * 128);  // valid bytes of this 128-byte chunk
+          // this lane's 8 row indices per owned unit: rows rsub * 8 .. rsub * 8 + 7 of the unit = two 16-byte shared-memory reads
+          int idx[4][8];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            if (u < UW && ((cur.has >> ((sub * UW + u) >> 2)) & 1u)) {  // warp-uniform
+            if (u < UW && ((has >> ((sub * UW + u) >> 2)) & 1u)) {
+              const uint32_t a0 = my_idx + (uint32_t)((ibuf * 4 + u) * 128 + rsub * 32);
+              const int4 lo = lds_v4i(a0), hi = lds_v4i(a0 + 16u);
+              idx[u][0] = lo.x; idx[u][1] = lo.y; idx[u][2] = lo.z; idx[u][3] = lo.w;
+              idx[u][4] = hi.x; idx[u][5] = hi.y; idx[u][6] = hi.z; idx[u][7] = hi.w;
+              if (slot_st + u * 32 + 32 > n_slots) {  // last, partial unit of the plan: rows past its end gather nothing
 #pragma unroll
-              for (int jj = 0; jj < 8; ++jj) {
-                const int i = idx[u][jj];
-                const uint32_t dst = a_lane + (uint32_t)(u * 32 * 128 + jj * 128) + (uint32_t)((piece ^ jj) << 4);
-                cp_async_16(dst, (const void*)(src0 + (uint64_t)(i < 0 ? 0u : (uint32_t)i) * row_bytes), i < 0 ? 0u : 16u);
+                for (int jj = 0; jj < 8; ++jj)
+                  if (slot_st + u * 32 + rsub * 8 + jj >= n_slots) idx[u][jj] = -1;
               }
             }
           }
-        }
-        // completion-triggered arrive: no wait_group / fence in the producer; the proxy hand-over is completed by the MMA
-        // thread's acquire fence after it has observed the barrier phase
-        cp_async_arrive_noinc(bar);
-        if (sub == 0) {
-          if (elect_one_sync()) {
-            if (kDbg && (dbg & 2)) {
-              mbar_arrive(bar);
-            } else {
-              mbar_arrive_expect_tx(bar, (uint32_t)b_bytes);
-              const __nv_bfloat16* wsrc = p.wimg + ((int64_t)kw * nchunks + ch) * (int64_t)p.cout * kChunkElems;
-              bulk_copy_g2s(sB_u32 + (uint32_t)(stage * b_bytes), wsrc, (uint32_t)b_bytes, bar);
+          ibuf ^= 1;
+          const int kw = kidx ? __ldg(kidx + k) : k;
+          const long long tp0 = kDbg ? clock64() : 0;
+          mbar_wait_hint(smem_u32(&empty_bar[stage]), phase ^ 1, 20000u);
+          if (kDbg) tp_wait += clock64() - tp0;
+          const uint32_t bar = smem_u32(&full_bar[stage]);
+          // lanes whose piece lies beyond a narrow chunk (or all lanes in the gather-off ablation) issue nothing
+          const bool act = piece * 16 < width && !(dbg & 1);
+          // source address = per-lane 64-bit base + row * row_bytes as ONE 32x32+64 multiply-add (IMAD.WIDE.U32)
+          uint64_t src0 = (uint64_t)p.in + (uint64_t)(ch * 128 + piece * 16);
+          asm volatile("" : "+l"(src0));  // keep the base in one register pair (otherwise it is re-derived from the constant bank per copy)
+          const uint32_t a_lane = sA_u32 + (uint32_t)(stage * a_bytes) + dst_lane;
+          if (act) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (u < UW && ((has >> ((sub * UW + u) >> 2)) & 1u)) {  // warp-uniform
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                  const int r = idx[u][jj];
+                  const uint32_t dst = a_lane + (uint32_t)(u * 32 * 128 + jj * 128) + (uint32_t)((piece ^ jj) << 4);
+                  cp_async_16(dst, (const void*)(src0 + (uint64_t)(r < 0 ? 0u : (uint32_t)r) * row_bytes), r < 0 ? 0u : 16u);
+                }
+              }
             }
           }
-          __syncwarp();
-        }
-        stage += NP;
-        while (stage >= S) {
-          stage -= S;
-          phase ^= 1;
+          // completion-triggered arrive: no wait_group / fence in the producer; the proxy hand-over is completed by the MMA
+          // thread's acquire fence after it has observed the barrier phase
+          cp_async_arrive_noinc(bar);
+          if (sub == 0) {
+            if (elect_one_sync()) {
+              if (kDbg && (dbg & 2)) {
+                mbar_arrive(bar);
+              } else {
+                mbar_arrive_expect_tx(bar, (uint32_t)b_bytes);
+                const uint8_t* wsrc = (const uint8_t*)p.wimg + ((int64_t)kw * nchunks + ch) * (int64_t)b_bytes;
+                bulk_copy_g2s(sB_u32 + (uint32_t)(stage * b_bytes), wsrc, (uint32_t)b_bytes, bar);
+              }
+            }
+            __syncwarp();
+          }
+          stage += NP;
+          while (stage >= S) {
+            stage -= S;
+            phase ^= 1;
+          }
         }
         cur = nxt;
       }
@@ -305,8 +341,9 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const ConvParams p)
     // 384 cycles the 8 MMAs of a 96-column iteration take on the tensor pipe; split over two warps both halves overlap.  Both
     // wait on the stage's full barrier and both commit to its empty barrier (count = number of issuers).
     const int mg = warp == kCvMmaWarp ? 0 : 1;  // member tile this warp issues for (G == 1: the only one)
-    const uint32_t idesc = make_idesc(kTileM, p.cout);
-    const int cin = p.cin;
+    const bool tf32 = p.elem == 4;
+    const uint32_t idesc = tf32 ? make_idesc_tf32(kTileM, p.cout) : make_idesc(kTileM, p.cout);
+    const int cin_bytes = p.cin * p.elem;
     const uint32_t a_lo_base = smem_desc_lo(smem_u32(sA)), b_lo_base = smem_desc_lo(smem_u32(sB));
     const uint32_t a_step = (uint32_t)(a_bytes >> 4), b_step = (uint32_t)(b_bytes >> 4);
     const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), tfull0 = smem_u32(tmem_full), tempty0 = smem_u32(tmem_empty);
@@ -315,58 +352,67 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const ConvParams p)
     int acc_buf = 0;
     uint32_t acc_phase = 0;
     long long tw_full = 0, tw_tmem = 0, t_start = kDbg ? clock64() : 0, n_it = 0;
-    Walk w(p.tile_kmask, G, cta_first, cta_stride, p.num_tiles, nchunks, cta_part, ksplit);
-    while (w.valid()) {
+    const bool two = G == 2;
+    const int num_st = two ? (p.num_tiles + 1) >> 1 : p.num_tiles;
+    const uint32_t* __restrict__ kmask = p.tile_kmask;
+    const int K = p.K;
+    uint32_t nm0, nm1;
+    load_masks(kmask, cta_first, num_st, p.num_tiles, two, nm0, nm1);
+    for (int st = cta_first; st < num_st; st += cta_stride) {
+      const SuperTile T = make_super(nm0, nm1, K, cta_part, ksplit, lane);
+      load_masks(kmask, st + cta_stride, num_st, p.num_tiles, two, nm0, nm1);
+      if (T.n == 0) continue;
       {
         const long long t0 = kDbg ? clock64() : 0;
-        mbar_wait(tempty0 + 8u * acc_buf, acc_phase ^ 1);
+        mbar_wait_hint(tempty0 + 8u * acc_buf, acc_phase ^ 1, 20000u);
         if (kDbg) tw_tmem += clock64() - t0;
         tc_fence_after();
       }
       uint32_t started = 0;  // 1: this warp's accumulator holds a partial sum
       const uint32_t tmem_d = tmem_base + (uint32_t)((acc_buf * G + mg) * acc_cols);
-      bool last;
-      do {
-        const uint32_t has = w.has();
-        last = w.last();
-        const int nk = min(kChunkElems, cin - w.c * kChunkElems) >> 4;
-        const long long t1 = kDbg ? clock64() : 0;
-        mbar_wait(full0 + 8u * slot, ph);
-        if (kDbg) {
-          tw_full += clock64() - t1;
-          ++n_it;
-        }
-        fence_proxy_async_acquire();  // producers' cp.async (generic proxy) writes -> visible to tcgen05.mma (async proxy)
-        tc_fence_after();
-        const uint32_t b_lo = b_lo_base + (uint32_t)slot * b_step;
-        const uint32_t a_lo = a_lo_base + (uint32_t)slot * a_step + (uint32_t)(mg * (kABytes >> 4));
-        const uint32_t mine = (has >> mg) & 1u;
-        if (elect_one_sync()) {
-          if (mine) {
-            if (kDbg && (dbg & 4)) {
-              if (!started) umma_bf16_lohi(tmem_d, a_lo, b_lo, kSmemDescHi, idesc, 0u);
-            } else if (nk == 4) {
-              // +32 bytes along K inside the 128-byte swizzle row == +2 in the (addr >> 4) field
-              umma_bf16_lohi(tmem_d, a_lo, b_lo, kSmemDescHi, idesc, started);
-              umma_bf16_lohi(tmem_d, a_lo + 2u, b_lo + 2u, kSmemDescHi, idesc, 1u);
-              umma_bf16_lohi(tmem_d, a_lo + 4u, b_lo + 4u, kSmemDescHi, idesc, 1u);
-              umma_bf16_lohi(tmem_d, a_lo + 6u, b_lo + 6u, kSmemDescHi, idesc, 1u);
-            } else {
-              for (int kk = 0; kk < nk; ++kk)
-                umma_bf16_lohi(tmem_d, a_lo + 2u * kk, b_lo + 2u * kk, kSmemDescHi, idesc, (kk > 0) ? 1u : started);
-            }
+      const uint32_t mym = mg ? T.m1 : T.m0;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int nk = min(128, cin_bytes - ch * 128) >> 5;  // one MMA per 32 bytes of K (16 bf16 / 8 tf32)
+        for (int j = 0; j < T.n; ++j) {
+          const int k = __shfl_sync(0xffffffffu, T.kvec, j);
+          const uint32_t mine = (mym >> k) & 1u;
+          const bool last = ch == nchunks - 1 && j == T.n - 1;
+          const long long t1 = kDbg ? clock64() : 0;
+          mbar_wait_hint(full0 + 8u * slot, ph, 5000u);
+          if (kDbg) {
+            tw_full += clock64() - t1;
+            ++n_it;
           }
-          umma_commit(empty0 + 8u * slot);  // frees the stage when these MMAs (and the other issuer's) retire
-          if (last) umma_commit(tfull0 + 8u * acc_buf);
+          fence_proxy_async_acquire();  // producers' cp.async (generic proxy) writes -> visible to tcgen05.mma (async proxy)
+          tc_fence_after();
+          const uint32_t b_lo = b_lo_base + (uint32_t)slot * b_step;
+          const uint32_t a_lo = a_lo_base + (uint32_t)slot * a_step + (uint32_t)(mg * (kABytes >> 4));
+          if (elect_one_sync()) {
+            if (mine) {
+              if (kDbg && (dbg & 4)) {
+                if (!started) umma_lohi(tf32, tmem_d, a_lo, b_lo, kSmemDescHi, idesc, 0u);
+              } else if (nk == 4) {
+                // +32 bytes along K inside the 128-byte swizzle row == +2 in the (addr >> 4) field
+                umma_lohi(tf32, tmem_d, a_lo, b_lo, kSmemDescHi, idesc, started);
+                umma_lohi(tf32, tmem_d, a_lo + 2u, b_lo + 2u, kSmemDescHi, idesc, 1u);
+                umma_lohi(tf32, tmem_d, a_lo + 4u, b_lo + 4u, kSmemDescHi, idesc, 1u);
+                umma_lohi(tf32, tmem_d, a_lo + 6u, b_lo + 6u, kSmemDescHi, idesc, 1u);
+              } else {
+                for (int kk = 0; kk < nk; ++kk)
+                  umma_lohi(tf32, tmem_d, a_lo + 2u * kk, b_lo + 2u * kk, kSmemDescHi, idesc, (kk > 0) ? 1u : started);
+              }
+            }
+            umma_commit(empty0 + 8u * slot);  // frees the stage when these MMAs (and the other issuer's) retire
+            if (last) umma_commit(tfull0 + 8u * acc_buf);
+          }
+          __syncwarp();
+          started |= mine;
+          if (++slot == S) {
+            slot = 0;
+            ph ^= 1;
+          }
         }
-        __syncwarp();
-        started |= mine;
-        if (++slot == S) {
-          slot = 0;
-          ph ^= 1;
-        }
-        w.step();
-      } while (!last);
+      }
       if (++acc_buf == 2) {
         acc_buf = 0;
         acc_phase ^= 1;
@@ -423,7 +469,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const ConvParams p)
       const bool any = (km[0] | km[1]) != 0u;
       if (any) {
         const long long t0 = kDbg ? clock64() : 0;
-        mbar_wait(smem_u32(&tmem_full[acc_buf]), acc_phase);
+        mbar_wait_hint(smem_u32(&tmem_full[acc_buf]), acc_phase, 100000u);
         if (kDbg) te_wait += clock64() - t0;
         tc_fence_after();
       }
@@ -566,9 +612,33 @@ __global__ void __launch_bounds__(256) k_weight_image(const float* __restrict__ 
   }
 }
 
+// fp32 (tf32) weight image: 32-element (128-byte) chunks, same 16-byte-piece XOR (row & 7) swizzle:
+// img[((k * nchunks + ch) * rows + n) * 32 + swz(n, e)] = W'[k][ch*32 + e][n]
+__global__ void __launch_bounds__(256) k_weight_image_tf32(const float* __restrict__ W, int K, int cin, int cout, int transpose,
+                                                           float* __restrict__ img) {
+  const int red = transpose ? cout : cin;
+  const int rows = transpose ? cin : cout;
+  const int nchunks = (red + 31) / 32;
+  const int64_t total = (int64_t)K * nchunks * rows * 32;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int e = (int)(i % 32);
+    int64_t t = i / 32;
+    const int n = (int)(t % rows);
+    t /= rows;
+    const int ch = (int)(t % nchunks);
+    const int k = (int)(t / nchunks);
+    const int r = ch * 32 + e;
+    float v = 0.f;
+    if (r < red) v = transpose ? W[((int64_t)k * cin + n) * cout + r] : W[((int64_t)k * cin + r) * cout + n];
+    const int piece = e >> 2, within = e & 3;  // 16-byte piece = 4 fp32
+    const int64_t dst = ((int64_t)(k * nchunks + ch) * rows + n) * 32 + (((piece ^ (n & 7)) << 2) | within);
+    img[dst] = v;
+  }
+}
+
 inline size_t conv_smem_bytes(int cout, int stages, int group = 1, int stage_out_cols = 0) {
   return 1024 + (size_t)stages * ((size_t)group * kABytes + (size_t)cout * 128) + (2 * kMaxStages + 6) * sizeof(uint64_t) + 16 +
-         (size_t)4 * 32 * stage_out_cols * sizeof(float);
+         (size_t)8 * 2 * 4 * 32 * sizeof(int32_t) + (size_t)4 * 32 * stage_out_cols * sizeof(float);
 }
 
 int conv_tma_launch(const ConvParams& p, int64_t n_in, int out_dtype, cudaStream_t st);  // conv_tma.cu
@@ -638,11 +708,14 @@ int mk_conv_weight_image_bf16(const float* W, int K, int cin, int cout, int tran
   return check_launch(__func__);
 }
 
-int mk_conv_fwd_bf16(const void* in, int64_t n_in, int cin, const void* wimg, int cout, const int32_t* nbr, int K, int64_t n_slots,
-                     const int32_t* out_rows, const uint32_t* tile_kmask, const int32_t* kidx, int64_t n_out,
-                     const float* bias, void* out, int out_dtype, int out_cols, int out_stride, void* stream_) {
+}  // extern "C"
+
+// shared launcher of mk_conv_fwd_bf16 / mk_conv_fwd_tf32 (`in_dtype`: MK_BF16 -> kind::f16 on bf16 rows, MK_F32 -> kind::tf32 on fp32 rows)
+static int conv_fwd_launch(const void* in, int in_dtype, int64_t n_in, int cin, const void* wimg, int cout, const int32_t* nbr, int K,
+                           int64_t n_slots, const int32_t* out_rows, const uint32_t* tile_kmask, const int32_t* kidx, int64_t n_out,
+                           const float* bias, void* out, int out_dtype, int out_cols, int out_stride, void* stream_) {
   MK_REQUIRE(mk_device_supported(), "tcgen05 path needs an sm_100 device (B200)");
-  MK_REQUIRE(cin % 16 == 0 && cin >= 16, "cin must be a multiple of 16");
+  MK_REQUIRE(in_dtype == MK_F32 ? (cin % 8 == 0 && cin >= 8) : (cin % 16 == 0 && cin >= 16), "cin must be a multiple of 16 (bf16) / 8 (tf32)");
   MK_REQUIRE(cout % 16 == 0 && cout >= 16 && cout <= 256, "cout must be a multiple of 16 in [16,256]");
   MK_REQUIRE(K >= 1 && K <= 32, "K must be <= 32 (per-tile offset bitmask)");
   if (out_cols <= 0) out_cols = cout;
@@ -653,6 +726,7 @@ int mk_conv_fwd_bf16(const void* in, int64_t n_in, int cin, const void* wimg, in
   ConvParams p;
   p.in = (const __nv_bfloat16*)in;
   p.wimg = (const __nv_bfloat16*)wimg;
+  p.elem = in_dtype == MK_F32 ? 4 : 2;
   p.nbr = nbr;
   p.out_rows = out_rows;
   p.tile_kmask = tile_kmask;
@@ -665,7 +739,7 @@ int mk_conv_fwd_bf16(const void* in, int64_t n_in, int cin, const void* wimg, in
   p.cout = cout;
   p.K = K;
   p.num_tiles = (int)ceil_div(n_slots, kTileM);
-  p.nchunks = (cin + kChunkElems - 1) / kChunkElems;
+  p.nchunks = (cin * p.elem + 127) / 128;
   p.out_cols = out_cols;
   p.out_stride = out_stride;
   const int elem = out_dtype == MK_F32 ? 4 : 2;
@@ -675,7 +749,7 @@ int mk_conv_fwd_bf16(const void* in, int64_t n_in, int cin, const void* wimg, in
   p.debug = tn.debug;
   p.trace = nullptr;
   p.chunk_major = 1;
-  if (gather_mode() == 1) return conv_tma_launch(p, n_in, out_dtype, (cudaStream_t)stream_);
+  if (gather_mode() == 1 && p.elem == 2) return conv_tma_launch(p, n_in, out_dtype, (cudaStream_t)stream_);
   // super-tiles of two tiles when both accumulators fit next to their double buffer (4 x 128 TMEM columns) and there are
   // enough tiles to keep every SM busy with the coarser work unit
   int group = (cout <= 128 && p.num_tiles >= 4 * num_sms()) ? 2 : 1;
@@ -761,6 +835,35 @@ int mk_conv_fwd_bf16(const void* in, int64_t n_in, int cin, const void* wimg, in
   else MK_LAUNCH(__nv_bfloat16, false);
 #endif
 #undef MK_LAUNCH
+  return check_launch(__func__);
+}
+
+extern "C" {
+
+int mk_conv_fwd_bf16(const void* in, int64_t n_in, int cin, const void* wimg, int cout, const int32_t* nbr, int K, int64_t n_slots,
+                     const int32_t* out_rows, const uint32_t* tile_kmask, const int32_t* kidx, int64_t n_out,
+                     const float* bias, void* out, int out_dtype, int out_cols, int out_stride, void* stream_) {
+  return conv_fwd_launch(in, MK_BF16, n_in, cin, wimg, cout, nbr, K, n_slots, out_rows, tile_kmask, kidx, n_out, bias, out, out_dtype, out_cols,
+                         out_stride, stream_);
+}
+
+int mk_conv_fwd_tf32(const void* in, int64_t n_in, int cin, const void* wimg, int cout, const int32_t* nbr, int K, int64_t n_slots,
+                     const int32_t* out_rows, const uint32_t* tile_kmask, const int32_t* kidx, int64_t n_out,
+                     const float* bias, void* out, int out_dtype, int out_cols, int out_stride, void* stream_) {
+  return conv_fwd_launch(in, MK_F32, n_in, cin, wimg, cout, nbr, K, n_slots, out_rows, tile_kmask, kidx, n_out, bias, out, out_dtype, out_cols,
+                         out_stride, stream_);
+}
+
+int64_t mk_conv_weight_image_tf32_elems(int K, int cin, int cout, int transpose) {
+  const int red = transpose ? cout : cin, rows = transpose ? cin : cout;
+  return (int64_t)K * ((red + 31) / 32) * rows * 32;
+}
+
+int mk_conv_weight_image_tf32(const float* W, int K, int cin, int cout, int transpose, void* img, void* stream_) {
+  const int64_t total = mk_conv_weight_image_tf32_elems(K, cin, cout, transpose);
+  int64_t blocks = ceil_div(total, 256);
+  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+  k_weight_image_tf32<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(W, K, cin, cout, transpose, (float*)img);
   return check_launch(__func__);
 }
 

@@ -110,6 +110,9 @@ __global__ void k_hash_insert(const int4* __restrict__ coords, int64_t n, int sx
   int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   int4 c = coords[r];
+  // status bit 1: the batch column is not ascending -- the scene row ranges (scene_offsets, decomposed_*, the instance-norm
+  // segments) assume batch-sorted rows, which is what sparse_collate produces (datasets/utils.py:126)
+  if (r > 0 && coords[r - 1].x > c.x) atomicOr(status, 2);
   if (sx > 1) c.y = floor_div(c.y, sx) * sx;
   if (sy > 1) c.z = floor_div(c.z, sy) * sy;
   if (sz > 1) c.w = floor_div(c.w, sz) * sz;

@@ -267,6 +267,241 @@ __global__ void __launch_bounds__(1024) k_xattn_partial(const float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Tensor-core form of k_xattn_partial for the shapes the model runs (bf16 keys / values, D = 128, H = 8 heads of 16 channels,
+// Q <= 32 queries): a flash-attention style kernel with warp-level softmax.  The SIMT kernel above spends ~60 instructions per
+// (key, query, head) triple on CUDA cores (1.0-1.8 ms per launch on the 865 k keys of level 1 of a 4-scene batch, 15-25x above
+// the time HBM needs for the 443 MB of keys and values); here a warp owns one head for all (padded to 32) queries:
+//   S[32 q x 64 keys] = Q_h K_h^T   16 x mma.sync.m16n8k16 (bf16, fp32 accumulate), scores in log2 units (scale * log2e folded into Q)
+//   mask (blocked bits, "all blocked => unblock" rule through any_open), online softmax in the accumulator fragments (row
+//   max / sum by quad shuffles), P re-used in registers as the A operand of
+//   O[32 q x 16] += P V_h       16 x mma.sync, V fragments by ldmatrix.trans
+// K / V tiles (64 keys x 128 channels, rows of a scene are contiguous) arrive by 16-byte cp.async, double buffered.  The op is
+// HBM-bound (Q = 25: <= 25 FLOP per key / value byte), so mma.sync is enough to get the arithmetic out
+// of the way of the memory system; partial records and k_xattn_combine are those of the SIMT kernel.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kXmKeys = 64;            // keys per tile
+constexpr int kXmPitch = 136;          // bf16 elements per staged row (128 + 8: consecutive rows shift by 4 banks -> conflict-free fragments)
+constexpr int kXmThreads = 256;        // 8 warps = 8 heads
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+__global__ void __launch_bounds__(kXmThreads) k_xattn_partial_mma(const float* __restrict__ qp, const __nv_bfloat16* __restrict__ kp,
+                                                                  const __nv_bfloat16* __restrict__ vp, const uint8_t* __restrict__ blocked,
+                                                                  const int32_t* __restrict__ any_open,
+                                                                  const int32_t* __restrict__ scene_offsets, int Q, float scale,
+                                                                  int keys_per_split, float* __restrict__ partial) {
+  constexpr int D = 128, H = 8, HD = 16;
+  extern __shared__ __align__(16) uint8_t xm_smem[];
+  __nv_bfloat16* sK = (__nv_bfloat16*)xm_smem;                          // [2][64][136]
+  __nv_bfloat16* sV = sK + 2 * kXmKeys * kXmPitch;                      // [2][64][136]
+  uint32_t* sM = (uint32_t*)(sV + 2 * kXmKeys * kXmPitch);              // [2][64] blocked bits per key (bit q)
+  const int b = blockIdx.y, split = blockIdx.x, nsplit = gridDim.x;
+  const int64_t s0 = (int64_t)scene_offsets[b] + (int64_t)split * keys_per_split;
+  const int64_t s1 = min((int64_t)scene_offsets[b + 1], s0 + keys_per_split);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int h = warp;                 // head of this warp
+  const int g = lane >> 2, tq = lane & 3;
+
+  // Q_h as A fragments (2 m-tiles of 16 queries), scaled into log2 units, bf16
+  uint32_t qa[2][4];
+  const float qs = scale * 1.4426950408889634f;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int q = mt * 16 + g + (r & 1) * 8;      // a0,a2: row g; a1,a3: row g + 8
+      const int d = tq * 2 + (r >> 1) * 8;          // a0,a1: cols 2t..; a2,a3: cols 2t + 8..
+      float x0 = 0.f, x1 = 0.f;
+      if (q < Q) {
+        const float* src = qp + ((int64_t)b * Q + q) * D + h * HD + d;
+        x0 = src[0] * qs;
+        x1 = src[1] * qs;
+      }
+      qa[mt][r] = pack_bf16x2(x0, x1);
+    }
+  }
+  // per row (query) flags: rows g, g+8 of each m-tile
+  uint32_t row_use_mask = 0;  // bit (mt*2 + hi): the query's mask is applied (some key of the scene is open for it)
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi) {
+      const int q = mt * 16 + g + hi * 8;
+      if (q < Q && any_open[b * Q + q] != 0) row_use_mask |= 1u << (mt * 2 + hi);
+    }
+
+  float m_run[2][2], l_run[2][2], o[2][2][4];  // [m-tile][row half]; o[m-tile][d-block][4]
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    m_run[mt][0] = m_run[mt][1] = -INFINITY;
+    l_run[mt][0] = l_run[mt][1] = 0.f;
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[mt][nb][j] = 0.f;
+  }
+
+  const int64_t ntiles = s1 > s0 ? (s1 - s0 + kXmKeys - 1) / kXmKeys : 0;
+  auto load_tile = [&](int64_t tile, int buf) {
+    const int64_t k0 = s0 + tile * kXmKeys;
+    // 64 rows x 16 pieces of 16 B per matrix = 1024 pieces: 4 per thread and matrix
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int pidx = t + i * kXmThreads;
+      const int r = pidx >> 4, c = (pidx & 15) * 8;
+      const bool in = k0 + r < s1;
+      const int64_t src = (in ? (k0 + r) : s0) * D + c;
+      const uint32_t dk = (uint32_t)__cvta_generic_to_shared(sK + ((size_t)buf * kXmKeys + r) * kXmPitch + c);
+      const uint32_t dv = (uint32_t)__cvta_generic_to_shared(sV + ((size_t)buf * kXmKeys + r) * kXmPitch + c);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dk), "l"(kp + src), "r"(in ? 16u : 0u) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dv), "l"(vp + src), "r"(in ? 16u : 0u) : "memory");
+    }
+    // blocked bits of the tile's keys: 4 threads per key, 8 queries each, OR-ed by quad shuffles
+    {
+      const int r = t >> 2, part = t & 3;
+      uint32_t w = 0;
+      if (k0 + r < s1) {
+        const uint8_t* src = blocked + (k0 + r) * Q;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int q = part * 8 + j;
+          if (q < Q && src[q]) w |= 1u << q;
+        }
+      }
+      w |= __shfl_xor_sync(0xffffffffu, w, 1);
+      w |= __shfl_xor_sync(0xffffffffu, w, 2);
+      if (part == 0) sM[buf * kXmKeys + r] = w;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  if (ntiles > 0) load_tile(0, 0);
+  for (int64_t tile = 0; tile < ntiles; ++tile) {
+    const int buf = (int)(tile & 1);
+    if (tile + 1 < ntiles) {
+      load_tile(tile + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const __nv_bfloat16* tK = sK + (size_t)buf * kXmKeys * kXmPitch;
+    const __nv_bfloat16* tV = sV + (size_t)buf * kXmKeys * kXmPitch;
+    const uint32_t* tM = sM + buf * kXmKeys;
+    const int nvalid = (int)min((int64_t)kXmKeys, s1 - (s0 + tile * kXmKeys));  // keys of this tile inside the split
+
+    // ---- S = Q_h K_h^T for the 64 keys: 8 n-blocks of 8 keys ----
+    float sc[2][8][4];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      // B fragment: B[k = d][n = key]: b0 = K[key nb*8 + g][h*16 + 2t, +1], b1 = same row, d + 8
+      const uint32_t* row = reinterpret_cast<const uint32_t*>(tK + (size_t)(nb * 8 + g) * kXmPitch + h * HD);
+      const uint32_t b0 = row[tq], b1 = row[tq + 4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        sc[mt][nb][0] = sc[mt][nb][1] = sc[mt][nb][2] = sc[mt][nb][3] = 0.f;
+        mma_bf16_16816(sc[mt][nb], qa[mt], b0, b1);
+      }
+    }
+    // ---- mask + online softmax (rows g / g+8 of each m-tile; this thread's keys: nb*8 + 2t, +1) ----
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      float tmax[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        const uint32_t w0 = tM[nb * 8 + tq * 2], w1 = tM[nb * 8 + tq * 2 + 1];
+#pragma unroll
+        for (int hi = 0; hi < 2; ++hi) {
+          const int q = mt * 16 + g + hi * 8;
+          const bool um = (row_use_mask >> (mt * 2 + hi)) & 1u;
+          // the blocked bit applies only while the query's mask is in use; keys past the end of the split never take part
+          const int key = nb * 8 + tq * 2;
+          const bool x0 = key >= nvalid || (um && ((w0 >> q) & 1u));
+          const bool x1 = key + 1 >= nvalid || (um && ((w1 >> q) & 1u));
+          if (x0) sc[mt][nb][hi * 2] = -INFINITY;
+          if (x1) sc[mt][nb][hi * 2 + 1] = -INFINITY;
+          tmax[hi] = fmaxf(tmax[hi], fmaxf(sc[mt][nb][hi * 2], sc[mt][nb][hi * 2 + 1]));
+        }
+      }
+#pragma unroll
+      for (int hi = 0; hi < 2; ++hi) {
+        tmax[hi] = fmaxf(tmax[hi], __shfl_xor_sync(0xffffffffu, tmax[hi], 1));
+        tmax[hi] = fmaxf(tmax[hi], __shfl_xor_sync(0xffffffffu, tmax[hi], 2));
+        const float mn = fmaxf(m_run[mt][hi], tmax[hi]);
+        const float ms = mn == -INFINITY ? 0.f : mn;           // all keys so far excluded: keep everything at zero
+        const float corr = exp2f(m_run[mt][hi] - ms);          // m_run = -inf -> 0
+        float rs = 0.f;
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+          const float p0 = exp2f(sc[mt][nb][hi * 2] - ms), p1 = exp2f(sc[mt][nb][hi * 2 + 1] - ms);
+          sc[mt][nb][hi * 2] = p0;
+          sc[mt][nb][hi * 2 + 1] = p1;
+          rs += p0 + p1;
+        }
+        rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+        rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+        l_run[mt][hi] = l_run[mt][hi] * corr + rs;
+        m_run[mt][hi] = mn;
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+          o[mt][nb][hi * 2] *= corr;
+          o[mt][nb][hi * 2 + 1] *= corr;
+        }
+      }
+    }
+    // ---- O += P V_h: 4 k-steps of 16 keys, 2 d-blocks of 8 channels ----
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t pa[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        pa[mt][0] = pack_bf16x2(sc[mt][2 * ks][0], sc[mt][2 * ks][1]);
+        pa[mt][1] = pack_bf16x2(sc[mt][2 * ks][2], sc[mt][2 * ks][3]);
+        pa[mt][2] = pack_bf16x2(sc[mt][2 * ks + 1][0], sc[mt][2 * ks + 1][1]);
+        pa[mt][3] = pack_bf16x2(sc[mt][2 * ks + 1][2], sc[mt][2 * ks + 1][3]);
+      }
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) {
+        // B[k = key][n = d]: V rows (keys) ks*16 .. +15, channels h*16 + nb*8 .. +7, transposed on load
+        const uint32_t addr = (uint32_t)__cvta_generic_to_shared(tV + (size_t)(ks * 16 + (lane & 15)) * kXmPitch + h * HD + nb * 8);
+        uint32_t b0, b1;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(addr));
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) mma_bf16_16816(o[mt][nb], pa[mt], b0, b1);
+      }
+    }
+    __syncthreads();  // the buffer is refilled by the load issued in the next iteration
+  }
+
+  // partial record of (query, head): {m, l, acc[16]} at partial[((b * nsplit + split) * Q * H + q * H + h) * (2 + 32)]
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi) {
+      const int q = mt * 16 + g + hi * 8;
+      if (q >= Q) continue;
+      float* rec = partial + (((int64_t)b * nsplit + split) * Q * H + (int64_t)q * H + h) * (2 + kXaMaxHd);
+      if (tq == 0) {
+        rec[0] = m_run[mt][hi];
+        rec[1] = l_run[mt][hi];
+      }
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) {
+        rec[2 + nb * 8 + tq * 2] = o[mt][nb][hi * 2];
+        rec[2 + nb * 8 + tq * 2 + 1] = o[mt][nb][hi * 2 + 1];
+      }
+    }
+}
+
 // grid (ceil(Q*H / 8), B), block 256: warp w handles (query, head) pair 8*blockIdx.x + w; its 32 lanes fold the splits
 // lane, lane+32, ... in ascending order (online-softmax merge), then the lanes are merged by a fixed shuffle tree.
 __global__ void __launch_bounds__(256) k_xattn_combine(const float* __restrict__ partial, int nsplit, int Q, int D, int H,
@@ -507,6 +742,8 @@ __global__ void __launch_bounds__(256) k_xattn_bwd_q_combine(const float* __rest
   dq[i] = a * scale;
 }
 
+int g_xattn_simt = 0;  // 1: force the CUDA-core forward kernel (A/B measurements, mk_set_xattn_simt)
+
 inline int xattn_splits(int64_t n, int B) {
   // ~6 resident blocks (7 warps each, 34 KB of shared memory) per SM over the batch so that one block's tile load /
   // barrier hides behind the others' arithmetic; at least 128 keys per split
@@ -572,6 +809,11 @@ int mk_fourier_pe(const float* xyz, int64_t n, const int32_t* scene_offsets, int
   return check_launch(__func__);
 }
 
+int mk_set_xattn_simt(int on) {
+  g_xattn_simt = on ? 1 : 0;
+  return 0;
+}
+
 int64_t mk_xattn_workspace_bytes(int B, int Q, int H, int64_t n_keys) {
   const int splits = xattn_splits(n_keys, B);
   return ((int64_t)B * splits * Q * H * (2 + kXaMaxHd)) * (int64_t)sizeof(float) + (int64_t)B * Q * sizeof(int32_t) + 256;
@@ -608,7 +850,17 @@ int mk_masked_xattn_fwd_lse(const float* qp, const void* kp, const void* vp, int
   k_xattn_partial<T, HD><<<grid, threads, smem, st>>>(qp, (const T*)kp, (const T*)vp, blocked, any_open, scene_offsets, Q, D, H, \
                                                       scale, keys_per_split, partial)
   const bool hd16 = D / H <= 16;
-  if (kv_dtype == MK_F32) {
+  if (kv_dtype == MK_BF16 && D == 128 && H == 8 && Q <= 32 && !g_xattn_simt) {
+    // tensor-core path (flash-attention style, warp-level softmax); same partial records, same combine
+    const size_t smem_mma = (size_t)4 * kXmKeys * kXmPitch * sizeof(__nv_bfloat16) + 2 * kXmKeys * sizeof(uint32_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(k_xattn_partial_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
+      attr_set = true;
+    }
+    k_xattn_partial_mma<<<grid, kXmThreads, smem_mma, st>>>(qp, (const __nv_bfloat16*)kp, (const __nv_bfloat16*)vp, blocked, any_open,
+                                                            scene_offsets, Q, scale, keys_per_split, partial);
+  } else if (kv_dtype == MK_F32) {
     if (hd16) MK_XA(float, 16); else MK_XA(float, 32);
   } else {
     if (hd16) MK_XA(__nv_bfloat16, 16); else MK_XA(__nv_bfloat16, 32);

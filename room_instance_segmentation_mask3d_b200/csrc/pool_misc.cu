@@ -7,7 +7,8 @@
 
 namespace mk {
 
-__global__ void __launch_bounds__(256) k_pool_fwd(const float* __restrict__ in, int C, const int32_t* __restrict__ nbr, int K,
+template <typename TIn>
+__global__ void __launch_bounds__(256) k_pool_fwd(const TIn* __restrict__ in, int C, const int32_t* __restrict__ nbr, int K,
                                                   int64_t n_out, int average, float* __restrict__ out) {
   const int CV = (C + 3) >> 2;
   const int64_t total = n_out * CV;
@@ -22,7 +23,7 @@ __global__ void __launch_bounds__(256) k_pool_fwd(const float* __restrict__ in, 
       ++cnt;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (c + j < C) acc[j] += in[(int64_t)r * C + c + j];
+        if (c + j < C) acc[j] += to_f32<TIn>(in[(int64_t)r * C + c + j]);
     }
     const float inv = (average && cnt > 0) ? 1.f / (float)cnt : 1.f;
 #pragma unroll
@@ -91,7 +92,17 @@ extern "C" {
 
 int mk_pool_fwd(const float* in, int C, const int32_t* nbr, int K, int64_t n_out, int average, float* out, void* stream_) {
   if (n_out == 0) return 0;
-  k_pool_fwd<<<grid_for(n_out * ((C + 3) / 4)), 256, 0, (cudaStream_t)stream_>>>(in, C, nbr, K, n_out, average, out);
+  k_pool_fwd<float><<<grid_for(n_out * ((C + 3) / 4)), 256, 0, (cudaStream_t)stream_>>>(in, C, nbr, K, n_out, average, out);
+  return check_launch(__func__);
+}
+
+int mk_pool_fwd_dt(const void* in, int in_dtype, int C, const int32_t* nbr, int K, int64_t n_out, int average, float* out, void* stream_) {
+  if (n_out == 0) return 0;
+  if (in_dtype == MK_BF16)
+    k_pool_fwd<__nv_bfloat16><<<grid_for(n_out * ((C + 3) / 4)), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)in, C, nbr, K, n_out,
+                                                                                                    average, out);
+  else
+    k_pool_fwd<float><<<grid_for(n_out * ((C + 3) / 4)), 256, 0, (cudaStream_t)stream_>>>((const float*)in, C, nbr, K, n_out, average, out);
   return check_launch(__func__);
 }
 

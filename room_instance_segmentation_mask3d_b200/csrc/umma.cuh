@@ -46,6 +46,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// Same, with a suspend-time hint (ns): the hardware may park the thread until the phase completes or the limit passes.  Without
+// a hint try_wait returns after a few tens of cycles, and the 6 waiting warps of k_conv_umma (4 epilogue, 2 MMA) then spin
+// through ~10 M try_wait + branch instructions per launch (ncu source view), stealing issue slots and MIO bandwidth from
+// the producers.
+__device__ __forceinline__ void mbar_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+      "@P1 bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity), "r"(ns)
+      : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // Consumer-side (acquire) half of the generic -> async proxy hand-over: executed by the MMA thread after it has observed the
@@ -90,6 +107,14 @@ __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
   return v;
 }
 
+__device__ __forceinline__ int4 lds_v4i(uint32_t addr) {
+  int4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
   // .ca: allocate in L1 — a tile is a compact spatial patch (mask + Z-curve sorted), so the neighbour rows gathered for its
   // different offsets overlap heavily and are re-read from L1 instead of L2
@@ -149,6 +174,27 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, u
       "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// tf32 x tf32 -> fp32 (fp32 operands in shared memory, K = 8 per instruction): the reference's own precision
+// (torch.set_float32_matmul_precision("high"), mask3d/main_instance_segmentation.py:52)
+__device__ __forceinline__ void umma_tf32_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %3};\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_lohi(bool tf32, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                          uint32_t accumulate) {
+  if (tf32) umma_tf32_lohi(tmem_d, a_lo, b_lo, desc_hi, idesc, accumulate);
+  else umma_bf16_lohi(tmem_d, a_lo, b_lo, desc_hi, idesc, accumulate);
+}
 __device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
 constexpr uint32_t kSmemDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // SBO 1024 B, version 1, SWIZZLE_128B
 
@@ -182,6 +228,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// instruction descriptor, kind::tf32: D fp32, A/B tf32 (format 2), both K-major
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 struct ConvParams {
   const __nv_bfloat16* in;
   const __nv_bfloat16* wimg;
@@ -196,6 +247,7 @@ struct ConvParams {
   int cin;
   int cout;
   int K;
+  int elem;        // bytes per operand element: 2 = bf16 (kind::f16), 4 = fp32 read as tf32 (kind::tf32)
   int num_tiles;
   int num_stages;
   int group;       // member tiles per super-tile (1 or 2)

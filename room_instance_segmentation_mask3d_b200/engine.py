@@ -213,8 +213,11 @@ class CoordinateManager:
                  lib.p(out_coords), lib.p(uniq), lib.p(inv), ctypes.c_void_p(meta.data_ptr()), ctypes.c_void_p(meta.data_ptr() + 4),
                  lib.p(ws), wsb, lib.stream())
         n_out, status = meta.tolist()  # one host sync per map: sizes are data-dependent
-        if status != 0:
+        if status & 1:
             raise RuntimeError("coordinate out of the packable range [-2^17, 2^17) or batch index >= 1023")
+        if status & 2:
+            raise RuntimeError("rows are not sorted by batch index: this backend keeps every scene's rows contiguous (what "
+                               "ME.utils.sparse_collate produces, mask3d/datasets/utils.py:126); sort the rows by coordinates[:, 0] first")
         return CoordMap(out_coords[:n_out], keys, vals, cap), uniq[:n_out], inv
 
     def insert_and_map(self, coords: torch.Tensor, tensor_stride=1, string_id: str = ""):

