@@ -277,9 +277,12 @@ def main_ours(args):
     for st_ in lanes:  # the caching allocator keeps blocks per stream: one up-front segment for every stream a forward runs on
         lib.reserve_device_pool(lane_gb, dev, stream=st_)
     lib.reserve_device_pool(lane_gb / 2, dev, stream=model.side_stream(dev))
+    compact = args.e2e_results == "compact"
     h_cls = [torch.empty((13, B, 25, 2), dtype=torch.float32).pin_memory() for _ in range(n_lanes)]
     h_mask = [[torch.empty((n, 25), dtype=torch.float32).pin_memory() for n in nvox] for _ in range(n_lanes)]
-    state = {"res": None, "e2e": None, "g_res": 0, "g_e2e": 0, "vox": 0}
+    h_bits = [[torch.empty(n, dtype=torch.int32).pin_memory() for n in nvox] for _ in range(n_lanes)]
+    h_score = [torch.empty((B, 25), dtype=torch.float32).pin_memory() for _ in range(n_lanes)]
+    state = {"res": None, "e2e": None, "g_res": 0, "g_e2e": 0, "vox": 0, "compact": compact}
 
     def step_resident(_i=None):
         g = state["g_res"]
@@ -296,9 +299,13 @@ def main_ours(args):
         x = state["e2e"] if state["e2e"] is not None else model.prepare(*pinned[g % n_scenes])
         ln = g % n_lanes
         with torch.cuda.stream(lanes[ln]):
-            o = model(x, prefetch=pinned[(g + 1) % n_scenes])
+            o = model(x, prefetch=pinned[(g + 1) % n_scenes], compact=state["compact"])
             h_cls[ln].copy_(torch.stack(o["pred_class_all_decoders"]), non_blocking=True)
-            h_mask[ln][g % n_scenes].copy_(o["pred_mask_all_decoders"][-1], non_blocking=True)
+            if state["compact"]:  # the binary masks (one bit word per voxel) + per-query mask scores, what the post-processing keeps
+                h_bits[ln][g % n_scenes].copy_(o["mask_bits"], non_blocking=True)
+                h_score[ln].copy_(o["mask_score"], non_blocking=True)
+            else:                 # the final fp32 mask logits [N, 25]
+                h_mask[ln][g % n_scenes].copy_(o["pred_mask_all_decoders"][-1], non_blocking=True)
         state["e2e"] = o.pop("prefetched")
         state["g_e2e"] = g + 1
         state["vox"] += nvox[g % n_scenes]
@@ -358,7 +365,19 @@ def main_ours(args):
     ms_e2e = timed(step_e2e, args.steps)
     e2e_value = world * state["vox"] / (ms_e2e * 1e-3)
     h2d = int(np.mean([c.numel() * 4 + f.numel() * 4 for c, f in pinned]))
-    d2h = int(h_cls[0].numel() * 4 + np.mean([m.numel() * 4 for m in h_mask[0]]))
+    d2h_logits = int(h_cls[0].numel() * 4 + np.mean([m.numel() * 4 for m in h_mask[0]]))
+    d2h_compact = int(h_cls[0].numel() * 4 + h_score[0].numel() * 4 + np.mean([m.numel() * 4 for m in h_bits[0]]))
+    d2h = d2h_compact if compact else d2h_logits
+    # the other result form, for comparison (fewer steps): full fp32 mask logits vs bit-packed masks + scores
+    state["compact"] = not compact
+    for i in range(n_scenes):
+        step_e2e(i)
+    state["vox"] = 0
+    osteps = max(3, args.steps // 3)
+    ms_other = timed(step_e2e, osteps)
+    e2e_other = {"results": "logits" if compact else "compact", "value": world * state["vox"] / (ms_other * 1e-3), "unit": UNIT,
+                 "d2h_bytes_per_step": d2h_logits if compact else d2h_compact, "ms_per_step": ms_other / osteps, "steps": osteps}
+    state["compact"] = compact
 
     # per-launch CUDA events around the dominant kernel (k_conv_umma) over extra instrumented steps
     roofline = None
@@ -399,24 +418,29 @@ def main_ours(args):
 
         tot_ms, tot_flops, n_launch = summarize(lambda t: True)
         by_shape = {}
+        # t = (algorithmic FLOPs, K, cin, cout, rows, kind): kind "conv" = gather-GEMM over a spatial kernel map (3^3, 2^3, transposed
+        # 2^3); "dense" = one input row per output row (1x1 convs, K / V projections, and the mask-logit product, whose "offsets"
+        # are the scenes of the batch: K = B there)
+        is_conv = lambda t: (t[5] == "conv") if len(t) > 5 else t[1] > 1
         for s, e, t in recs:
-            k = f"K{t[1]}_{t[2]}x{t[3]}"
+            k = ("K" if is_conv(t) else "dense_K") + f"{t[1]}_{t[2]}x{t[3]}"
             a = by_shape.setdefault(k, [0.0, 0.0, 0])
             a[0] += t[0]; a[1] += s.elapsed_time(e); a[2] += 1
-        top = sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:8]
+        top = sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:24]
         # launch classes of the same kernel: the gather-GEMM proper (K = 27 / 8 offsets, tensor-bound by design) and the
         # K = 1 launches (1x1 convs, K/V projections, mask-logit product: one pass over [N, C], HBM-bound)
-        g_ms, g_fl, g_n = summarize(lambda t: t[1] > 1)
-        big_ms, big_fl, big_n = summarize(lambda t: t[1] > 1 and t[4] >= 128 * 148 * 4)   # enough tiles to fill 148 SMs
-        o_ms, o_fl, o_n = summarize(lambda t: t[1] == 1)
+        g_ms, g_fl, g_n = summarize(is_conv)
+        big_ms, big_fl, big_n = summarize(lambda t: is_conv(t) and t[4] >= 128 * 148 * 4)   # enough tiles to fill 148 SMs
+        o_ms, o_fl, o_n = summarize(lambda t: not is_conv(t))
         hbm_peak = float(peaks.get("hbm_gbs", 6455.0))
         # algorithmic bytes of a K = 1 launch: read [N, Cin] bf16, write [N, Cout_stored] (bf16 activations; fp32 for the
         # 25-column mask logits and the fp32 `src` of the key projection) -- taken as 2 B in, 2 or 4 B out per element
-        o_bytes = sum(t[4] * (2 * t[2] + (4 if (t[3] <= 32 or t[2] != t[3]) else 2) * min(t[3], 128)) for s, e, t in recs if t[1] == 1)
+        o_bytes = sum(t[4] * (2 * t[2] + (4 if (t[3] <= 32 or t[2] != t[3]) else 2) * min(t[3], 128)) for s, e, t in recs if not is_conv(t))
         tf = lambda fl, ms_: fl / (ms_ * 1e-3) / 1e12 if ms_ > 0 else 0.0
         achieved = tf(g_fl, g_ms)
-        roofline = {"kernel": "k_conv_umma (tcgen05 gather-GEMM sparse conv): the K > 1 launches of the step (3^3, 2^3 and transposed 2^3 "
-                              "convolutions); the K = 1 launches of the same kernel are HBM-bound and reported under classes",
+        roofline = {"kernel": "k_conv_umma (tcgen05 gather-GEMM sparse conv): the launches over spatial kernel maps (3^3, 2^3 and transposed "
+                              "2^3 convolutions); the dense launches of the same kernel (1x1 convs, K / V projections, mask-logit product) "
+                              "are HBM-bound and reported under classes.K=1_hbm_bound",
                     "bound": "tensor", "achieved": achieved,
                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC.get("bytes_per_launch"),
                     "traffic_note": NCU_TRAFFIC.get("note"), "peak_source": peak_src,
@@ -569,7 +593,11 @@ def main_ours(args):
                 "config": workload_config(voxel, n_scenes, B, args.workload),
                 "scenes_per_sec": world * B * args.steps / (ms * 1e-3), "voxels_per_step_per_gpu": vox_per_step,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": ms_e2e / args.steps},
+                        "ms_per_step": ms_e2e / args.steps,
+                        "results": ("compact: class logits of all 13 decoder outputs + binary masks of the final output as one bit word per "
+                                    "voxel + per-query mask scores (what trainer/trainer.py:373-402 derives from the logits), built on the "
+                                    "device") if compact else "class logits of all 13 decoder outputs + final fp32 mask logits [N, 25]",
+                        "other_result_form": e2e_other},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "train_fwd_bwd": train,
                 "loss_side": loss_side, "train_step": train_step}
         print(json.dumps(line))
@@ -612,6 +640,9 @@ if __name__ == "__main__":
                     "conf/data/indoor.yaml:21; 4 x 0.9 M voxels fills the coarse U-Net levels and keeps every index below 2^31)")
     ap.add_argument("--train-scenes", type=int, default=2, help="scenes per training step per GPU")
     ap.add_argument("--workload", default="floor", choices=["floor", "building"], help="floor: configs[1] single-floor scenes; building: configs[3] multi-floor buildings")
+    ap.add_argument("--e2e-results", default="compact", choices=["compact", "logits"],
+                    help="what the end-to-end loop copies back per step: compact = bit-packed binary masks + mask scores + class logits "
+                         "(default), logits = the final fp32 mask logits [N, 25] + class logits; the other form is measured beside it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=2, help="streams consecutive scenes alternate between (1 = a single stream)")
     ap.add_argument("--no-train", action="store_true", help="skip the backbone forward+backward measurement")

@@ -216,6 +216,12 @@ int mk_pool_bwd(const float* dout, int C, const int32_t* nbr, int K, int64_t n_o
 int mk_mask_logits(const void* feat, int x_dtype, int64_t n, int C, const int32_t* scene_offsets, int B,
                    const float* embed, int Q, float* logits, void* stream);
 /* One pooling step on logits followed (optionally) by the threshold: blocked[o,q] = sigmoid(pooled) < 0.5. */
+/* Compact inference result of one decoder output (what trainer/trainer.py:373-402 derives from the mask logits): bits uint32 [n]
+ * (bit q = logit[n, q] > 0, i.e. sigmoid > 0.5; Q <= 32) and score fp32 [B, Q] = sum_n sigmoid(x) [x > 0] / (sum_n [x > 0] + 1e-6) per
+ * scene, in ONE pass over logits fp32 [n, Q]; deterministic (fixed-order merge of per-block partial sums). */
+int64_t mk_mask_compact_workspace_bytes(int64_t n, int B);
+int mk_mask_compact(const float* logits, int64_t n, int Q, const int32_t* scene_offsets, int B, uint32_t* bits, float* score, void* workspace,
+                    int64_t workspace_bytes, void* stream);
 int mk_pool_threshold(const float* pooled, int64_t n, int Q, uint8_t* blocked, void* stream);
 /* Per-scene min / max of fp32 [n,3] coordinates (input_range of the fourier embedding, mask3d.py:267-268,323-328). */
 int mk_scene_minmax(const float* xyz, int64_t n, const int32_t* scene_offsets, int B, float* cmin, float* cmax, void* stream);

@@ -102,7 +102,7 @@ __device__ __forceinline__ SuperTile make_super(uint32_t m0, uint32_t m1, int K,
   return t;
 }
 
-template <typename TOut, bool kDbg>
+template <typename TOut, bool kDbg, bool kTf32>
 __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x G x A 16 KB][stages x B cout*128][barriers]
@@ -245,11 +245,29 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const ConvParams p)
       };
       int stage = gi % S;
       uint32_t phase = (uint32_t)((gi / S) & 1);
+      // pull the table lines of an iteration into L1 (not tracked by cp.async groups / the stage barrier: see below)
+      auto prefetch_indices = [&](const Own& o) {
+        if (o.valid && lane < UW) {  // lane u: unit u's 128-byte line of the table row
+          const int gu = sub * UW + lane;
+          const int64_t slot = (int64_t)o.st * (G * kTileM) + gu * 32;
+          if (((o.has >> (gu >> 2)) & 1u) && slot < n_slots)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nbr + (int64_t)o.k * n_slots + slot));
+        }
+      };
       int ibuf = 0;
+      // Three iterations are in flight per producer: `cur` is gathered now; the table entries of `nxt` are copied to shared memory
+      // (cp.async, 4 B per lane and unit) while cur's rows are gathered; the table LINES of `nx2` are prefetched into L1 one
+      // iteration earlier still.  The cp.async of nxt's entries precede cur's gathers in this thread's cp.async order, so the
+      // stage's completion-triggered mbarrier arrive also waits for them: they must be L1 hits (~50 cycles), not L2 / DRAM round
+      // trips (ncu + MK3D_TRACE: with the entries fetched from L2 every stage completed ~one memory latency late, and with only 4
+      // ring slots that latency is paid once per 4 iterations by the whole pipeline).
       Own cur = take();
+      Own nxt = take();
+      prefetch_indices(nxt);
       if (cur.valid) stage_indices(cur, ibuf);
       while (cur.valid) {
-        const Own nxt = take();
+        const Own nx2 = take();
+        prefetch_indices(nx2);
         if (nxt.valid) {
           stage_indices(nxt, ibuf ^ 1);
           cp_async_wait<1>();  // everything but the group just committed: this iteration's entries have landed
@@ -325,6 +343,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const ConvParams p)
           }
         }
         cur = nxt;
+        nxt = nx2;
       }
       if (kDbg && p.trace && warp == 0 && lane == 0) {
         p.trace[blockIdx.x * 16 + 0] = (unsigned long long)tp_wait;
@@ -341,12 +360,12 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const ConvParams p)
     // 384 cycles the 8 MMAs of a 96-column iteration take on the tensor pipe; split over two warps both halves overlap.  Both
     // wait on the stage's full barrier and both commit to its empty barrier (count = number of issuers).
     const int mg = warp == kCvMmaWarp ? 0 : 1;  // member tile this warp issues for (G == 1: the only one)
-    const bool tf32 = p.elem == 4;
-    const uint32_t idesc = tf32 ? make_idesc_tf32(kTileM, p.cout) : make_idesc(kTileM, p.cout);
+    const uint32_t idesc = kTf32 ? make_idesc_tf32(kTileM, p.cout) : make_idesc(kTileM, p.cout);
     const int cin_bytes = p.cin * p.elem;
-    const uint32_t a_lo_base = smem_desc_lo(smem_u32(sA)), b_lo_base = smem_desc_lo(smem_u32(sB));
+    const uint32_t a_lo_base = smem_desc_lo(smem_u32(sA)) + (uint32_t)(mg * (kABytes >> 4)), b_lo_base = smem_desc_lo(smem_u32(sB));
     const uint32_t a_step = (uint32_t)(a_bytes >> 4), b_step = (uint32_t)(b_bytes >> 4);
     const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), tfull0 = smem_u32(tmem_full), tempty0 = smem_u32(tmem_empty);
+    const int nk_last = min(128, cin_bytes - (nchunks - 1) * 128) >> 5;  // MMAs of the last chunk (one per 32 bytes of K: 16 bf16 / 8 tf32)
     int slot = 0;
     uint32_t ph = 0;
     int acc_buf = 0;
@@ -356,6 +375,42 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const ConvParams p)
     const int num_st = two ? (p.num_tiles + 1) >> 1 : p.num_tiles;
     const uint32_t* __restrict__ kmask = p.tile_kmask;
     const int K = p.K;
+    uint32_t tmem_d = 0, started = 0, tfull_bar = 0;
+    // one pipeline stage: wait for it, issue this member tile's MMAs, free it.  Called with a LITERAL slot in the 4-stage loop
+    // below, so that barrier addresses and descriptor bases are base + immediate (the issuing warp is a serial chain of
+    // ~8-cycle uniform-datapath instructions: every instruction removed from an iteration is ~8 cycles of issue latency)
+    auto issue = [&](const int s, const uint32_t phs, const uint32_t mine, const int nk, const bool last) {
+      const long long t1 = kDbg ? clock64() : 0;
+      mbar_wait_hint(full0 + 8u * s, phs, 5000u);
+      if (kDbg) {
+        tw_full += clock64() - t1;
+        ++n_it;
+      }
+      fence_proxy_async_acquire();  // producers' cp.async (generic proxy) writes -> visible to tcgen05.mma (async proxy)
+      tc_fence_after();
+      const uint32_t b_lo = b_lo_base + (uint32_t)s * b_step;
+      const uint32_t a_lo = a_lo_base + (uint32_t)s * a_step;
+      if (elect_one_sync()) {
+        if (mine) {
+          if (kDbg && (dbg & 4)) {
+            if (!started) umma_lohi<kTf32>(tmem_d, a_lo, b_lo, kSmemDescHi, idesc, 0u);
+          } else if (nk == 4) {
+            // +32 bytes along K inside the 128-byte swizzle row == +2 in the (addr >> 4) field
+            umma_lohi<kTf32>(tmem_d, a_lo, b_lo, kSmemDescHi, idesc, started);
+            umma_lohi<kTf32>(tmem_d, a_lo + 2u, b_lo + 2u, kSmemDescHi, idesc, 1u);
+            umma_lohi<kTf32>(tmem_d, a_lo + 4u, b_lo + 4u, kSmemDescHi, idesc, 1u);
+            umma_lohi<kTf32>(tmem_d, a_lo + 6u, b_lo + 6u, kSmemDescHi, idesc, 1u);
+          } else {
+            for (int kk = 0; kk < nk; ++kk)
+              umma_lohi<kTf32>(tmem_d, a_lo + 2u * kk, b_lo + 2u * kk, kSmemDescHi, idesc, (kk > 0) ? 1u : started);
+          }
+        }
+        umma_commit(empty0 + 8u * s);  // frees the stage when these MMAs (and the other issuer's) retire
+        if (last) umma_commit(tfull_bar);
+      }
+      __syncwarp();
+      started |= mine;
+    };
     uint32_t nm0, nm1;
     load_masks(kmask, cta_first, num_st, p.num_tiles, two, nm0, nm1);
     for (int st = cta_first; st < num_st; st += cta_stride) {
@@ -368,51 +423,57 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const ConvParams p)
         if (kDbg) tw_tmem += clock64() - t0;
         tc_fence_after();
       }
-      uint32_t started = 0;  // 1: this warp's accumulator holds a partial sum
-      const uint32_t tmem_d = tmem_base + (uint32_t)((acc_buf * G + mg) * acc_cols);
-      const uint32_t mym = mg ? T.m1 : T.m0;
-      for (int ch = 0; ch < nchunks; ++ch) {
-        const int nk = min(128, cin_bytes - ch * 128) >> 5;  // one MMA per 32 bytes of K (16 bf16 / 8 tf32)
-        for (int j = 0; j < T.n; ++j) {
-          const int k = __shfl_sync(0xffffffffu, T.kvec, j);
-          const uint32_t mine = (mym >> k) & 1u;
-          const bool last = ch == nchunks - 1 && j == T.n - 1;
-          const long long t1 = kDbg ? clock64() : 0;
-          mbar_wait_hint(full0 + 8u * slot, ph, 5000u);
-          if (kDbg) {
-            tw_full += clock64() - t1;
-            ++n_it;
-          }
-          fence_proxy_async_acquire();  // producers' cp.async (generic proxy) writes -> visible to tcgen05.mma (async proxy)
-          tc_fence_after();
-          const uint32_t b_lo = b_lo_base + (uint32_t)slot * b_step;
-          const uint32_t a_lo = a_lo_base + (uint32_t)slot * a_step + (uint32_t)(mg * (kABytes >> 4));
-          if (elect_one_sync()) {
-            if (mine) {
-              if (kDbg && (dbg & 4)) {
-                if (!started) umma_lohi(tf32, tmem_d, a_lo, b_lo, kSmemDescHi, idesc, 0u);
-              } else if (nk == 4) {
-                // +32 bytes along K inside the 128-byte swizzle row == +2 in the (addr >> 4) field
-                umma_lohi(tf32, tmem_d, a_lo, b_lo, kSmemDescHi, idesc, started);
-                umma_lohi(tf32, tmem_d, a_lo + 2u, b_lo + 2u, kSmemDescHi, idesc, 1u);
-                umma_lohi(tf32, tmem_d, a_lo + 4u, b_lo + 4u, kSmemDescHi, idesc, 1u);
-                umma_lohi(tf32, tmem_d, a_lo + 6u, b_lo + 6u, kSmemDescHi, idesc, 1u);
-              } else {
-                for (int kk = 0; kk < nk; ++kk)
-                  umma_lohi(tf32, tmem_d, a_lo + 2u * kk, b_lo + 2u * kk, kSmemDescHi, idesc, (kk > 0) ? 1u : started);
+      started = 0;  // 1: this warp's accumulator holds a partial sum
+      tmem_d = tmem_base + (uint32_t)((acc_buf * G + mg) * acc_cols);
+      tfull_bar = tfull0 + 8u * acc_buf;
+      // bit j: this warp's member tile has the j-th offset of the pass
+      const uint32_t mine_vec = __ballot_sync(0xffffffffu, lane < T.n && (((mg ? T.m1 : T.m0) >> T.kvec) & 1u));
+      const int total = T.n * nchunks;
+      const int full_its = total - T.n;  // iterations before the last chunk (4 MMAs each)
+      int i = 0, j = 0;
+#define MK_STEP(SLOT)                                                              \
+  {                                                                                \
+    issue(SLOT, ph, (mine_vec >> j) & 1u, i < full_its ? 4 : nk_last, i == total - 1); \
+    ++i;                                                                           \
+    if (++j == T.n) j = 0;                                                         \
+  }
+      if (S == 4) {
+        while (i < total) {
+          switch (slot) {
+            case 0:
+              MK_STEP(0);
+              if (i == total) {
+                slot = 1;
+                break;
               }
-            }
-            umma_commit(empty0 + 8u * slot);  // frees the stage when these MMAs (and the other issuer's) retire
-            if (last) umma_commit(tfull0 + 8u * acc_buf);
+            case 1:
+              MK_STEP(1);
+              if (i == total) {
+                slot = 2;
+                break;
+              }
+            case 2:
+              MK_STEP(2);
+              if (i == total) {
+                slot = 3;
+                break;
+              }
+            default:
+              MK_STEP(3);
+              slot = 0;
+              ph ^= 1;
           }
-          __syncwarp();
-          started |= mine;
+        }
+      } else {
+        while (i < total) {
+          MK_STEP(slot);
           if (++slot == S) {
             slot = 0;
             ph ^= 1;
           }
         }
       }
+#undef MK_STEP
       if (++acc_buf == 2) {
         acc_buf = 0;
         acc_phase ^= 1;
@@ -796,15 +857,20 @@ static int conv_fwd_launch(const void* in, int in_dtype, int64_t n_in, int cin, 
     cudaMemset2DAsync(out, (size_t)out_stride * sizeof(float), 0, (size_t)out_cols * sizeof(float), (size_t)n_out, (cudaStream_t)stream_);
   }
   cudaStream_t st = (cudaStream_t)stream_;
-#define MK_LAUNCH(T, D)                                                                                     \
+#define MK_LAUNCH1(T, D, F)                                                                                  \
   do {                                                                                                      \
-    static size_t smem_set_##D = 0; /* per instantiation: raise the limit only when a launch needs more */  \
-    if (smem > smem_set_##D) {                                                                              \
-      cudaFuncSetAttribute(k_conv_umma<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
-      smem_set_##D = smem;                                                                                  \
+    static size_t smem_set = 0; /* per instantiation: raise the limit only when a launch needs more */      \
+    if (smem > smem_set) {                                                                                  \
+      cudaFuncSetAttribute(k_conv_umma<T, D, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+      smem_set = smem;                                                                                      \
     }                                                                                                       \
-    if (tn.carveout >= 0) cudaFuncSetAttribute(k_conv_umma<T, D>, cudaFuncAttributePreferredSharedMemoryCarveout, tn.carveout); \
-    k_conv_umma<T, D><<<grid, kCvThreads, smem, st>>>(p);                                                   \
+    if (tn.carveout >= 0) cudaFuncSetAttribute(k_conv_umma<T, D, F>, cudaFuncAttributePreferredSharedMemoryCarveout, tn.carveout); \
+    k_conv_umma<T, D, F><<<grid, kCvThreads, smem, st>>>(p);                                                \
+  } while (0)
+#define MK_LAUNCH(T, D)                 \
+  do {                                  \
+    if (p.elem == 4) MK_LAUNCH1(T, D, true); \
+    else MK_LAUNCH1(T, D, false);       \
   } while (0)
 #ifdef MK3D_TUNING
   if (tn.trace) {
@@ -835,6 +901,7 @@ static int conv_fwd_launch(const void* in, int in_dtype, int64_t n_in, int cin, 
   else MK_LAUNCH(__nv_bfloat16, false);
 #endif
 #undef MK_LAUNCH
+#undef MK_LAUNCH1
   return check_launch(__func__);
 }
 

@@ -61,6 +61,81 @@ __global__ void __launch_bounds__(256) k_threshold(const float* __restrict__ x, 
   }
 }
 
+// Compact inference result of one decoder output (trainer/trainer.py:373-402 needs exactly this of the mask logits): per voxel the
+// binary masks of all Q <= 32 queries as one bit word (bit q = logit > 0 <=> sigmoid > 0.5), per (scene, query) the mask score
+// sum_n sigmoid(x) [x > 0] / (sum_n [x > 0] + 1e-6).  One pass over the [N, Q] fp32 logits (4 Q bytes read, 4 bytes written
+// per voxel instead of 4 Q bytes copied to the host).  Block = 256 rows of one scene segment; lane = row; the per-query sums are
+// reduced by shuffles inside the warp, through shared memory across the 8 warps, and merged per block in a fixed order by
+// k_mask_compact_final (deterministic: no floating-point atomics).
+__global__ void __launch_bounds__(256) k_mask_compact(const float* __restrict__ logits, int64_t n, int Q,
+                                                      const int32_t* __restrict__ scene_offsets, int B, uint32_t* __restrict__ bits,
+                                                      float* __restrict__ part /* [blocks][2][32] */, int32_t* __restrict__ block_scene) {
+  __shared__ float s_sum[8][2][32];
+  // blocks are laid out per scene: block -> (scene, chunk) by scanning the (tiny) offsets table
+  int blk = blockIdx.x, b = 0;
+  while (b < B) {
+    const int nb = (scene_offsets[b + 1] - scene_offsets[b] + 255) / 256;
+    if (blk < nb) break;
+    blk -= nb;
+    ++b;
+  }
+  if (b >= B) {
+    if (threadIdx.x == 0) block_scene[blockIdx.x] = -1;
+    return;
+  }
+  const int64_t row = (int64_t)scene_offsets[b] + (int64_t)blk * 256 + threadIdx.x;
+  const bool in = row < scene_offsets[b + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t w = 0;
+  float hs = 0.f, cs = 0.f;  // this lane's query column sums after the transpose-reduce below
+  // every lane walks the Q columns of its own row; column q's partial sums are reduced across the warp with one xor-butterfly
+  for (int q = 0; q < Q; ++q) {
+    float h = 0.f, c = 0.f;
+    if (in) {
+      const float x = logits[row * Q + q];
+      if (x > 0.f) {
+        w |= 1u << q;
+        h = 1.f / (1.f + __expf(-x));
+        c = 1.f;
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      h += __shfl_xor_sync(0xffffffffu, h, d);
+      c += __shfl_xor_sync(0xffffffffu, c, d);
+    }
+    if (lane == q) {
+      hs = h;
+      cs = c;
+    }
+  }
+  if (in) bits[row] = w;
+  s_sum[warp][0][lane] = hs;
+  s_sum[warp][1][lane] = cs;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int k = threadIdx.x >> 5, q = threadIdx.x & 31;
+    float a = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) a += s_sum[ww][k][q];
+    part[((int64_t)blockIdx.x * 2 + k) * 32 + q] = a;
+  }
+  if (threadIdx.x == 0) block_scene[blockIdx.x] = b;
+}
+
+// score[b, q] = sum of the scene's block partials in block order
+__global__ void __launch_bounds__(32) k_mask_compact_final(const float* __restrict__ part, const int32_t* __restrict__ block_scene, int nblocks,
+                                                          int Q, float* __restrict__ score /* [B][Q] */) {
+  const int b = blockIdx.x, q = threadIdx.x;
+  float h = 0.f, c = 0.f;
+  for (int i = 0; i < nblocks; ++i) {
+    if (block_scene[i] != b) continue;
+    h += part[((int64_t)i * 2 + 0) * 32 + q];
+    c += part[((int64_t)i * 2 + 1) * 32 + q];
+  }
+  if (q < Q) score[b * Q + q] = h / (c + 1e-6f);
+}
+
 template <typename TS, typename TD>
 __global__ void __launch_bounds__(256) k_cast(const TS* __restrict__ s, TD* __restrict__ d, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -118,6 +193,25 @@ int mk_pool_bwd(const float* dout, int C, const int32_t* nbr, int K, int64_t n_o
 int mk_pool_threshold(const float* pooled, int64_t n, int Q, uint8_t* blocked, void* stream_) {
   if (n == 0) return 0;
   k_threshold<<<grid_for(n * Q), 256, 0, (cudaStream_t)stream_>>>(pooled, n * Q, blocked);
+  return check_launch(__func__);
+}
+
+int64_t mk_mask_compact_workspace_bytes(int64_t n, int B) {
+  const int64_t nblocks = (n + 255) / 256 + B;
+  return nblocks * (2 * 32 * (int64_t)sizeof(float) + (int64_t)sizeof(int32_t)) + 256;
+}
+
+int mk_mask_compact(const float* logits, int64_t n, int Q, const int32_t* scene_offsets, int B, uint32_t* bits, float* score, void* workspace,
+                    int64_t workspace_bytes, void* stream_) {
+  MK_REQUIRE(Q >= 1 && Q <= 32, "compact results pack one bit per query into a 32-bit word: Q <= 32");
+  MK_REQUIRE(workspace_bytes >= mk_mask_compact_workspace_bytes(n, B), "workspace too small");
+  if (B <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream_;
+  const int nblocks = (int)((n + 255) / 256 + B);  // upper bound of sum_b ceil(n_b / 256)
+  float* part = (float*)workspace;
+  int32_t* block_scene = (int32_t*)(part + (int64_t)nblocks * 64);
+  k_mask_compact<<<nblocks, 256, 0, st>>>(logits, n, Q, scene_offsets, B, bits, part, block_scene);
+  k_mask_compact_final<<<B, 32, 0, st>>>(part, block_scene, nblocks, Q, score);
   return check_launch(__func__);
 }
 

@@ -190,9 +190,9 @@ __device__ __forceinline__ void umma_tf32_lohi(uint32_t tmem_d, uint32_t a_lo, u
       "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void umma_lohi(bool tf32, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
-                                          uint32_t accumulate) {
-  if (tf32) umma_tf32_lohi(tmem_d, a_lo, b_lo, desc_hi, idesc, accumulate);
+template <bool kTf32>
+__device__ __forceinline__ void umma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kTf32) umma_tf32_lohi(tmem_d, a_lo, b_lo, desc_hi, idesc, accumulate);
   else umma_bf16_lohi(tmem_d, a_lo, b_lo, desc_hi, idesc, accumulate);
 }
 __device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }

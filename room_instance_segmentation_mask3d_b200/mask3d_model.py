@@ -484,7 +484,7 @@ class Mask3D(nn.Module):
         return side
 
     @torch.no_grad()
-    def forward(self, x: ME.SparseTensor, is_eval: bool = True, prefetch=None) -> dict:
+    def forward(self, x: ME.SparseTensor, is_eval: bool = True, prefetch=None, compact: bool = False) -> dict:
         """Fused inference forward.  Returns the fields of the reference's ModelOutput (mask3d.py:28-47).
 
         `prefetch = (coordinates, features)` of the NEXT scene (host pinned or device tensors): its coordinate phase is
@@ -505,6 +505,13 @@ class Mask3D(nn.Module):
             x.C.record_stream(cur)
         with lib.stream_scope():
             out = self._forward(x)
+            if compact:
+                # what the reference's post-processing keeps of the final mask logits (trainer/trainer.py:373-402): the binary masks
+                # (bit q of word n = voxel n belongs to query q) and the per-query mask scores, built on the device in one pass --
+                # 4 bytes per voxel to copy to the host instead of 4 * Q
+                off0 = x.coordinate_manager.scene_offsets(out["backbone_features"].coordinate_map_key)
+                B = x.coordinate_manager.number_of_unique_batch_indices()
+                out["mask_bits"], out["mask_score"] = ops.mask_compact(out["pred_mask_all_decoders"][-1], off0, B)
         if prefetch is not None:
             out["prefetched"] = self.prepare(prefetch[0], prefetch[1], wait_event=self._ev_backbone)
         return out
@@ -616,8 +623,11 @@ class Mask3D(nn.Module):
                 Wsq = self._d(sq.weight, "T", lambda w: w.t())                                  # [C_l, D]
                 Wk = self._d(mha.in_proj_weight, "k", lambda w: w[D:2 * D].t())                   # [D, D] (in, out)
                 Wv = self._d(mha.in_proj_weight, "v", lambda w: w[2 * D:].t())
-            src = lin(fmaps[hl].F, Wsq, kml, sq.bias, torch.float32)
-            kin = ops.fourier_pe(cf[hl], offs[hl], B, rng[hl][0], rng[hl][1], gB, base=src, out_dtype=torch.float32)  # src + pos
+            # inference: `src` and `src + pos` directly in the activation dtype the K / V projections read (bf16 on the tensor-core
+            # path): no fp32 round trip + cast pass over [N_l, 128]; training keeps fp32 (autograd through the PE add)
+            sdt = torch.float32 if train else act
+            src = lin(fmaps[hl].F, Wsq, kml, sq.bias, sdt)
+            kin = ops.fourier_pe(cf[hl], offs[hl], B, rng[hl][0], rng[hl][1], gB, base=src, out_dtype=sdt)  # src + pos
             kv[i] = (lin(kin, Wk, kml, mha.in_proj_bias[D:2 * D], act), lin(src, Wv, kml, mha.in_proj_bias[2 * D:], act))
         max_rows = None
         if train:

@@ -136,7 +136,7 @@ def conv_forward(x: torch.Tensor, W: torch.Tensor, km: KernelMap, bias: Optional
     ocols = out_cols or cout
     out = torch.empty((km.n_out, ocols), dtype=out_dtype, device=x.device)
     if lib._timed is not None:  # bench.py instrumentation: algorithmic FLOPs = 2 * P * Cin * Cout
-        lib.set_tag((2 * km.num_pairs * cin * ocols, K, cin, cout, km.n_out))
+        lib.set_tag((2 * km.num_pairs * cin * ocols, K, cin, cout, km.n_out, "dense" if (K == 1 or out_cols) else "conv"))
     plan = km.sorted_plan() if SORT_TILES else km
     lib.call("mk_conv_fwd_tf32" if tf32 else "mk_conv_fwd_bf16", lib.p(xb), xb.shape[0], cin, lib.p(img), cout, lib.p(plan.nbr), K, plan.n_slots, lib.p(plan.out_rows), lib.p(plan.tile_kmask),
              lib.p(kidx), km.n_out, lib.p(bias_flat), lib.p(out), lib.dt(out), ocols, ocols, lib.stream())
@@ -172,7 +172,7 @@ def conv_wgrad_bf16(x: torch.Tensor, dout: torch.Tensor, km: KernelMap, K: int, 
     plan = km.sorted_plan() if SORT_TILES else km
     dW = torch.empty((K, cin, cout), dtype=torch.float32, device=x.device)
     if lib._timed is not None:
-        lib.set_tag((2 * km.num_pairs * cin * cout, K, cin, cout, km.n_out))
+        lib.set_tag((2 * km.num_pairs * cin * cout, K, cin, cout, km.n_out, "dense" if K == 1 else "conv"))
     lib.call("mk_conv_wgrad_bf16", lib.p(xb), xb.shape[0], cin, lib.p(db), cout, lib.p(plan.nbr), K, plan.n_slots, lib.p(plan.out_rows),
              lib.p(plan.wgrad_plan), km.n_out, lib.p(dW), lib.stream())
     return dW
@@ -200,7 +200,7 @@ def conv_instnorm_bf16(x: torch.Tensor, W: torch.Tensor, km: KernelMap, scene_of
     if residual is not None:
         assert residual.dtype == out_dtype and residual.is_contiguous()
     if lib._timed is not None:
-        lib.set_tag((2 * km.num_pairs * cin * cout, K, cin, cout, n))
+        lib.set_tag((2 * km.num_pairs * cin * cout, K, cin, cout, n, "dense" if K == 1 else "conv"))
     base = ws.data_ptr()
     lib.call("mk_conv_instnorm_bf16", x.data_ptr(), x.shape[0], cin, img.data_ptr(), cout, plan.nbr.data_ptr(), K, plan.n_slots,
              lib.p(plan.out_rows), plan.tile_kmask.data_ptr(), None, n, lib.p(_flat32(bias)), scene_offsets.data_ptr(), B, eps,
@@ -250,7 +250,7 @@ def conv_instnorm_fast(x: torch.Tensor, lp: tuple, km: KernelMap, scene_offsets:
     ws = lib.scratch(tmp_bytes + stats_bytes + wsb, x.device)
     base = ws.data_ptr()
     if lib._timed is not None:
-        lib.set_tag((2 * km.num_pairs * cin * cout, K, cin, cout, n))
+        lib.set_tag((2 * km.num_pairs * cin * cout, K, cin, cout, n, "dense" if K == 1 else "conv"))
     out_rows = plan.out_rows
     lib.call("mk_conv_instnorm_bf16", x.data_ptr(), x.shape[0], cin, img.data_ptr(), cout, plan.nbr.data_ptr(), K, plan.n_slots,
              out_rows.data_ptr() if out_rows is not None else None, plan.tile_kmask.data_ptr(), None, n, None, scene_offsets.data_ptr(), B, eps,
@@ -425,10 +425,22 @@ def mask_logits_from_image(feat: torch.Tensor, img: torch.Tensor, select: Kernel
     assert feat.dtype == torch.bfloat16 and feat.is_contiguous()
     out = torch.empty((n, Q), dtype=torch.float32, device=feat.device)
     if lib._timed is not None:
-        lib.set_tag((2 * n * C * Q, select.K, C, Qp, n))
+        lib.set_tag((2 * n * C * Q, select.K, C, Qp, n, "dense"))
     lib.call("mk_conv_fwd_bf16", lib.p(feat), n, C, lib.p(img), Qp, lib.p(select.nbr), select.K, select.n_slots, lib.p(select.out_rows),
              lib.p(select.tile_kmask), None, n, None, lib.p(out), lib.F32, Q, Q, lib.stream())
     return out
+
+
+def mask_compact(logits: torch.Tensor, scene_offsets: torch.Tensor, B: int):
+    """Compact result of a decoder output: (bits int32 [n]: bit q = logits[n, q] > 0, score fp32 [B, Q]: the per-query mask score
+    of the reference's post-processing, trainer/trainer.py:389-392) in one pass over the fp32 logits [n, Q], Q <= 32."""
+    n, Q = logits.shape
+    bits = torch.empty(n, dtype=torch.int32, device=logits.device)
+    score = torch.empty((B, Q), dtype=torch.float32, device=logits.device)
+    ws = lib.scratch(lib.query("mk_mask_compact_workspace_bytes", n, B), logits.device)
+    lib.call("mk_mask_compact", lib.p(logits.contiguous()), n, Q, lib.p(scene_offsets), B, lib.p(bits), lib.p(score), lib.p(ws), ws.numel(),
+             lib.stream())
+    return bits, score
 
 
 def threshold_blocked(pooled: torch.Tensor) -> torch.Tensor:

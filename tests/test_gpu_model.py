@@ -273,3 +273,46 @@ def test_mask3d_forward_train_gradients_vs_oracle(setup):
           f"backbone kernels median {bb[len(bb) // 2]:.4f} min {bb[0]:.4f} ({len(bb)}); worst {worst}")
     assert dec[len(dec) // 2] >= 0.99 and dec[0] >= 0.95
     assert bb[len(bb) // 2] >= 0.85 and bb[0] >= 0.75
+
+
+@pytest.mark.timeout(900)
+def test_bf16_tensor_core_mode_binary_masks_vs_fp32_oracle_on_a_room_scene():
+    """Parity of the BENCHMARKED mode (bf16 tensor cores) where it matters: the binary instance masks.  One S200k-class room
+    (223 648 voxels at 2 cm) through the fused bf16 path against the fp32 CPU oracle of the reference's
+    algorithm: FPS queries identical, per-query binary-mask IoU and the fraction of flipped (voxel, query) bits of the final
+    output and of the first decoder output (which has no data-dependent threshold upstream), tf32 mode beside it."""
+    from oracle import mask3d_oracle, me_oracle
+    from room_instance_segmentation_mask3d_b200 import mask3d_model, me_api, ops, scenes, weights
+
+    coords, feats = scenes.collate([scenes.box_room()])
+    model = mask3d_model.Mask3D().eval()
+    weights.load_synth(model, seed=0)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        ref = mask3d_oracle.mask3d_forward(sd, me_oracle.SparseTensor(features=torch.from_numpy(feats), coordinates=torch.from_numpy(coords)))
+    model = model.cuda()
+
+    def stats(got, want):
+        g, w = got > 0, want > 0
+        flipped = float((g != w).float().mean())
+        inter, union = (g & w).sum(0).float(), (g | w).sum(0).float()
+        iou = torch.where(union > 0, inter / union.clamp_min(1), torch.ones_like(union))
+        return flipped, float(iou.min()), float(iou.mean())
+
+    res = {}
+    try:
+        for mode in ("bf16", "tf32"):
+            ops.set_compute_mode(mode)
+            o = model(me_api.SparseTensor(features=torch.from_numpy(feats).cuda(), coordinates=torch.from_numpy(coords).cuda()))
+            assert np.array_equal(o["sampled_coords"].cpu().numpy(), ref["sampled_coords"].numpy()), "FPS picked different queries"
+            first = stats(o["pred_mask_all_decoders"][0].float().cpu(), torch.cat(ref["pred_masks"][0]))
+            last = stats(o["pred_mask_all_decoders"][-1].float().cpu(), torch.cat(ref["pred_masks"][-1]))
+            res[mode] = (first, last)
+            print(f"{mode}: first output flipped {first[0]:.4%} IoU min {first[1]:.4f} mean {first[2]:.4f} | final output flipped "
+                  f"{last[0]:.4%} IoU min {last[1]:.4f} mean {last[2]:.4f}")
+    finally:
+        ops.set_compute_mode("bf16")
+    for mode, lim_flip, lim_iou in (("bf16", 0.01, 0.98), ("tf32", 0.002, 0.995)):
+        first, last = res[mode]
+        assert first[0] <= lim_flip and first[2] >= lim_iou, (mode, "first decoder output", first)
+        assert last[0] <= lim_flip and last[2] >= lim_iou, (mode, "final output", last)

@@ -651,3 +651,23 @@ def test_fps_matches_reference_tie_breaking(R):
                 continue
             ref = fps_oracle.furthest_point_sample(s.astype(np.float32), m)
             assert np.array_equal(idx[b], ref), f"scene {b}, m {m}"
+
+
+def test_mask_compact_bits_and_scores(R):
+    """mk_mask_compact: bit q of word n == logits[n, q] > 0; score == sum sigmoid(x)[x>0] / (sum [x>0] + 1e-6) per scene and query
+    (trainer/trainer.py:389-392); ragged scenes incl. an empty one, two runs bit-identical."""
+    torch.manual_seed(3)
+    sizes = [700, 0, 1300, 5]
+    Q = 25
+    off = torch.tensor([0] + list(np.cumsum(sizes)), dtype=torch.int32)
+    x = torch.randn(sum(sizes), Q) * 2
+    bits, score = R.ops.mask_compact(x.cuda(), off.cuda(), len(sizes))
+    bits2, score2 = R.ops.mask_compact(x.cuda(), off.cuda(), len(sizes))
+    assert torch.equal(bits, bits2) and torch.equal(score, score2)
+    want_bits = ((x > 0).long() << torch.arange(Q)).sum(1).to(torch.int32)
+    assert torch.equal(bits.cpu(), want_bits)
+    for b, n in enumerate(sizes):
+        xs = x[int(off[b]):int(off[b + 1])].double()
+        m = xs > 0
+        want = (torch.sigmoid(xs) * m).sum(0) / (m.sum(0) + 1e-6)
+        assert rel_err(score[b].cpu().double(), want) < 1e-5 or float(want.abs().max()) == 0
