@@ -589,7 +589,7 @@ def main_ours(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "warmup_run": n_warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
+                "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[args.mode], "data": "synthetic",
                 "config": workload_config(voxel, n_scenes, B, args.workload),
                 "scenes_per_sec": world * B * args.steps / (ms * 1e-3), "voxels_per_step_per_gpu": vox_per_step,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -634,10 +634,11 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "tf32", "fp32"],
+                    help="bf16: the benchmarked tensor-core mode; tf32: the reference's own precision on the same tcgen05 kernel; fp32: CUDA-core checker")
     ap.add_argument("--voxel-cm", type=float, default=2.0)
-    ap.add_argument("--scenes-per-step", type=int, default=4, help="scenes batched per step per GPU (the reference batches 16 small scenes, "
-                    "conf/data/indoor.yaml:21; 4 x 0.9 M voxels fills the coarse U-Net levels and keeps every index below 2^31)")
+    ap.add_argument("--scenes-per-step", type=int, default=8, help="scenes batched per step per GPU (the reference batches 16 small scenes, "
+                    "conf/data/indoor.yaml:21; 8 x 0.9 M voxels fill the coarse U-Net levels: 208 tiles on level 4)")
     ap.add_argument("--train-scenes", type=int, default=2, help="scenes per training step per GPU")
     ap.add_argument("--workload", default="floor", choices=["floor", "building"], help="floor: configs[1] single-floor scenes; building: configs[3] multi-floor buildings")
     ap.add_argument("--e2e-results", default="compact", choices=["compact", "logits"],
