@@ -90,6 +90,13 @@ int mk_row_sort_keys(const int32_t* nbr, int K, int64_t n, const int32_t* coords
 /* keys[o] = offset bitmask of slot o only (int32).  A STABLE sort by it groups equal masks and keeps each group in row order
  * (the default plan: as fast for the gathers as the Z-curve order, half the sort). */
 int mk_row_mask_keys(const int32_t* nbr, int K, int64_t n, int32_t* keys, void* stream);
+/* Stable grouping of rows by a 32-bit key with at most 1024 distinct values (the tile-plan sort: rows grouped by their offset
+ * mask, groups in ascending key order, rows of a group in their original order -- exactly the permutation a stable sort by key
+ * gives).  keys uint32 [n] (0xFFFFFFFF is reserved), order int32 [n] out, status int32 (device, may be NULL): bit 0 set when
+ * there were more than 1024 distinct keys (order is then a permutation but not grouped).  Deterministic.  Replaces the
+ * thrust / CUB sorts of MinkowskiEngine's kernel-map construction. */
+int64_t mk_group_rows_workspace_bytes(int64_t n);
+int mk_group_rows(const uint32_t* keys, int64_t n, int32_t* order, int32_t* status, void* workspace, int64_t workspace_bytes, void* stream);
 int mk_permute_table(const int32_t* nbr, int K, int64_t n, const int32_t* order, int64_t n_slots, int32_t* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

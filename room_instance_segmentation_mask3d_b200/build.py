@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmk3d.so")
-SOURCES = ["coords.cu", "conv_simt.cu", "conv_umma.cu", "conv_wgrad_umma.cu", "conv_tma.cu", "norm.cu", "pool_misc.cu", "decoder.cu", "fps.cu", "fused.cu", "loss.cu"]
+SOURCES = ["coords.cu", "group_sort.cu", "conv_simt.cu", "conv_umma.cu", "conv_wgrad_umma.cu", "conv_tma.cu", "norm.cu", "pool_misc.cu", "decoder.cu", "fps.cu", "fused.cu", "loss.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--use_fast_math=false"]
 

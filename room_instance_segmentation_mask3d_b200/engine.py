@@ -84,6 +84,20 @@ class CoordMap:
 _SORT_MODE = os.environ.get("MK3D_SORT", "mask")
 
 
+def group_rows(keys: torch.Tensor) -> torch.Tensor:
+    """int32 [n] = the permutation a stable sort by `keys` (int32, few distinct values, all >= 0) gives, through mk_group_rows
+    (hash set of the distinct keys + counting sort: csrc/group_sort.cu).  No host sync; more than 1024 distinct keys (never seen:
+    a scene has a few hundred distinct offset masks) would leave the rows ungrouped, which only costs tile efficiency."""
+    n = keys.shape[0]
+    order = torch.empty(n, dtype=I32, device=keys.device)
+    if n == 0:
+        return order
+    wsb = lib.query("mk_group_rows_workspace_bytes", n)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=keys.device)
+    lib.call("mk_group_rows", lib.p(keys), n, lib.p(order), None, lib.p(ws), wsb, lib.stream())
+    return order
+
+
 class KernelMap:
     """Output-stationary kernel map nbr[K, n_slots] (+ what the tensor-core kernel needs)."""
 
@@ -134,7 +148,10 @@ class KernelMap:
                 else:  # default: group by offset mask, rows of a group stay in lexicographic order (32-bit stable sort)
                     keys = torch.empty(n, dtype=I32, device=dev)
                     lib.call("mk_row_mask_keys", lib.p(self.nbr), self.K, n, lib.p(keys), lib.stream())
-                order = torch.sort(keys, stable=True).indices.to(I32)
+                if _SORT_MODE == "morton":
+                    order = torch.sort(keys, stable=True).indices.to(I32)
+                else:
+                    order = group_rows(keys)
                 nbr_s = torch.empty_like(self.nbr)
                 lib.call("mk_permute_table", lib.p(self.nbr), self.K, n, lib.p(order), n, lib.p(nbr_s), lib.stream())
                 self._sorted = KernelMap(nbr_s, self.K, n, order)
@@ -335,7 +352,7 @@ class CoordinateManager:
             # slots = fine rows grouped by k (stable: ascending row inside a group), every group padded to a multiple of 128.
             # No host sync: the slot count is the upper bound ceil(n_fine / 128) + K tiles; surplus tiles have an empty offset
             # mask and are skipped by the kernel.
-            order = torch.sort(koff, stable=True).indices
+            order = group_rows((koff + 1).contiguous()).long()  # koff in [-1, K): keys >= 0
             k_sorted = koff[order].long()
             ks_ = torch.arange(K, device=self.device)
             start = torch.searchsorted(k_sorted, ks_)  # k_sorted ascends: group boundaries without a host sync

@@ -46,6 +46,8 @@ _SIGS = {
     "mk_set_deterministic": (c_int, [c_int]),
     "mk_row_sort_keys": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mk_row_mask_keys": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "mk_group_rows_workspace_bytes": (c_int64, [c_int64]),
+    "mk_group_rows": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "mk_permute_table": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "mk_conv_stem_f32": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_int, c_void_p]),
     "mk_conv_stem_wgrad_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
@@ -179,7 +181,7 @@ class stream_scope:
 
 # kernels launched per C-ABI call (memsets not counted) — bench.py reports the total as `gpu_launches`
 _KERNELS_PER_CALL = {"mk_coordmap_build": 7, "mk_instnorm_stats": 2, "mk_masked_xattn_fwd": 3, "mk_masked_xattn_fwd_lse": 3, "mk_masked_xattn_bwd": 5, "mk_instnorm_bwd": 3, "mk_instnorm_relu_bwd": 3, "mk_scene_minmax": 3,
-                     "mk_fps": 25, "mk_mask_compact": 2, "mk_mask_costs": 3, "mk_conv_instnorm_bf16": 4, "mk_conv_wgrad_plan": 3, "mk_conv_stem_wgrad_f32": 2}
+                     "mk_fps": 25, "mk_mask_compact": 2, "mk_group_rows": 6, "mk_mask_costs": 3, "mk_conv_instnorm_bf16": 4, "mk_conv_wgrad_plan": 3, "mk_conv_stem_wgrad_f32": 2}
 kernel_launches = 0
 _timed = None  # optional {entry-point name: [(start_event, end_event, tag), ...]} filled when bench.py instruments a step
 _tag = None

@@ -671,3 +671,29 @@ def test_mask_compact_bits_and_scores(R):
         m = xs > 0
         want = (torch.sigmoid(xs) * m).sum(0) / (m.sum(0) + 1e-6)
         assert rel_err(score[b].cpu().double(), want) < 1e-5 or float(want.abs().max()) == 0
+
+
+@pytest.mark.parametrize("n,distinct", [(1, 1), (31, 3), (1024, 1), (1025, 7), (100_003, 300), (889_057, 1000)])
+def test_group_rows_equals_stable_sort(R, n, distinct):
+    """mk_group_rows (hash set of distinct keys + counting sort) == the permutation of a stable sort by key."""
+    g = torch.Generator().manual_seed(n)
+    vals = torch.randint(0, 1 << 27, (distinct,), generator=g, dtype=torch.int64).to(torch.int32)
+    # runs of equal keys (as offset masks come) mixed with scattered ones
+    idx = torch.randint(0, distinct, (n,), generator=g)
+    idx[: n // 2] = torch.sort(idx[: n // 2]).values
+    keys = vals[idx].cuda()
+    got = R.engine.group_rows(keys)
+    want = torch.sort(keys, stable=True).indices.to(torch.int32)
+    assert torch.equal(got, want)
+
+
+def test_group_rows_too_many_distinct_keys_sets_status(R):
+    n = 5000
+    keys = torch.arange(n, dtype=torch.int32).cuda()  # 5000 distinct keys > 1024
+    order = torch.empty(n, dtype=torch.int32, device="cuda")
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    wsb = R.lib.query("mk_group_rows_workspace_bytes", n)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    R.lib.call("mk_group_rows", R.lib.p(keys), n, R.lib.p(order), R.lib.p(status), R.lib.p(ws), wsb, R.lib.stream())
+    assert int(status.item()) & 1
+    assert sorted(order.cpu().tolist()) == list(range(n))  # still a permutation
