@@ -166,6 +166,13 @@ int64_t mk_conv_wgrad_plan_elems(int64_t num_tiles, int K);
 int mk_conv_wgrad_plan(const uint32_t* tile_kmask, int64_t num_tiles, int K, int32_t* plan, void* stream);
 int mk_conv_wgrad_bf16(const void* x, int64_t n_in, int cin, const void* dy, int cout, const int32_t* nbr, int K, int64_t n_slots,
                        const int32_t* out_rows, const int32_t* plan, int64_t n_out, float* dW, void* stream);
+/* Same with a workspace: when mk_set_deterministic(1) is active and `workspace` holds mk_conv_wgrad_det_workspace_bytes() bytes, every
+ * (tile block, offset) work item writes its accumulator to its own slot and the slots of an offset are added in item order
+ * (run-to-run bit-identical, no floating-point REDs); otherwise identical to mk_conv_wgrad_bf16. */
+int64_t mk_conv_wgrad_det_workspace_bytes(int64_t n_slots, int K, int cin, int cout);
+int mk_conv_wgrad_bf16_ws(const void* x, int64_t n_in, int cin, const void* dy, int cout, const int32_t* nbr, int K, int64_t n_slots,
+                          const int32_t* out_rows, const int32_t* plan, int64_t n_out, float* dW, void* workspace, int64_t workspace_bytes,
+                          void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (4) Normalisation / activation.  Replaces MinkowskiInstanceNorm (global avg-pool + broadcast kernels,

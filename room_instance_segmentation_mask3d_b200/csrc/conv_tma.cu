@@ -13,6 +13,7 @@
 // Warp roles (256 threads): warp 0 TMA producer (A gathers on all lanes, weight-image bulk copy on lane 0), warp 1 MMA issuer,
 // warp 2 TMEM allocator, warps 4-7 epilogue (TMEM lane quarter = warp % 4).
 #include <cuda.h>
+#include <cstring>
 
 #include "umma.cuh"
 
@@ -249,6 +250,22 @@ static PFN_encodeTiled get_encode_fn() {
       fn = (PFN_encodeTiled)ptr;
   }
   return fn;
+}
+
+// tensor map {cin, n_in} of the rows at `base` (elem = 2: bf16, 4: fp32), box {128 bytes, 1}, SWIZZLE_128B -> 128 bytes at `out`
+int encode_rows_tmap(void* out, const void* base, int elem, int cin, int64_t n_in) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return -1;
+  const cuuint64_t gdim[2] = {(cuuint64_t)cin, (cuuint64_t)(n_in > 0 ? n_in : 1)};
+  const cuuint64_t gstride[1] = {(cuuint64_t)cin * (cuuint64_t)elem};
+  const cuuint32_t box[2] = {(cuuint32_t)(128 / elem), 1u};
+  const cuuint32_t estride[2] = {1u, 1u};
+  CUtensorMap tmap;
+  CUresult r = enc(&tmap, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, gdim, gstride, box, estride,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return -2;
+  memcpy(out, &tmap, sizeof(tmap));
+  return 0;
 }
 
 int conv_tma_launch(const ConvParams& p_in, int64_t n_in, int out_dtype, cudaStream_t st) {

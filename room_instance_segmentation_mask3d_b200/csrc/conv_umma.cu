@@ -103,7 +103,7 @@ __device__ __forceinline__ SuperTile make_super(uint32_t m0, uint32_t m1, int K,
 }
 
 template <typename TOut, bool kDbg, bool kTf32>
-__global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const ConvParams p) {
+__global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x G x A 16 KB][stages x B cout*128][barriers]
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const ConvParams p)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 32 * split + 1);
+      mbar_init(smem_u32(&full_bar[s]), p.gather4 ? 1 : 32 * split + 1);  // gather4: ONE arrive.expect_tx, the TMA engine completes the bytes
       mbar_init(smem_u32(&empty_bar[s]), G);  // one tcgen05.commit per MMA issuer
     }
     for (int b = 0; b < 2; ++b) {
@@ -164,10 +164,9 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const ConvParams p)
     // a stage has 4 * G units of 32 rows (member tile g, row quarter q), warp `sub` of the group gathers units
     // [sub * UW, (sub + 1) * UW), UW = 4 * G / split <= 4.
     //
-    // Per unit a lane issues 8 LDGSTS: lane = (rsub, piece) copies the 16-byte piece `piece` of unit rows rsub * 8 + jj, jj = 0..7,
-    // i.e. one warp instruction moves 4 rows x 128 B.  The 8 row indices a lane needs are consecutive entries of the neighbour
-    // table and are read straight from it (8 lanes share each address; the unit's 32 entries are one 128-byte line, which the
-    // previous own stage prefetched into L1) -- no index shuffles: ncu's source view of the shuffle-based version showed every
+    // Per unit a lane issues 8 LDGSTS: lane = (rsub, piece) copies the 16-byte piece `piece` of unit rows 4 * jj + rsub, jj = 0..7,
+    // i.e. one warp instruction moves 4 consecutive rows x 128 B.  The unit's 32 table entries are staged in shared memory one own
+    // stage ahead (4-byte cp.async per lane) and each lane reads its 8 entries back (broadcast LDS) -- no index shuffles: ncu's source view of the shuffle-based version showed every
     // LDGSTS waiting ~30 cycles on its own SHFL (volatile asm is not reordered), and the 64 SHFL per iteration took a quarter
     // of the LSU data pipe.
     const int NP = p.num_producers;
@@ -175,6 +174,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const ConvParams p)
     const int sub = warp - gi * split;
     if (gi < NP) {
       const int UW = 4 * G / split;  // units per warp: 4 or 2
+      const int TU = p.tma_units;    // of which the last TU are gathered by the TMA engine (0: all through LDGSTS)
       const int piece = lane & 7;    // 16-byte piece of the 128-byte row
       const int rsub = lane >> 3;    // row octet of the unit this lane copies
       const uint32_t row_bytes = (uint32_t)p.cin * (uint32_t)p.elem;  // bf16 (2) or fp32 / tf32 (4) activations
@@ -183,8 +183,11 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const ConvParams p)
       const int32_t* __restrict__ nbr = p.nbr;
       const int32_t* __restrict__ kidx = p.kidx;
       const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
-      // destination of (unit 0, jj = 0) inside a stage for this lane; row = rsub * 8 + jj => row & 7 == jj => swizzled piece = piece ^ jj
-      const uint32_t dst_lane = (uint32_t)(sub * UW * 32 * 128 + rsub * 8 * 128);
+      // One warp instruction copies unit rows 4 * jj + rsub (rsub = lane / 8): FOUR CONSECUTIVE rows.  Their swizzle phases (row & 7)
+      // differ, so the 32-byte sectors of the four rows that arrive together land in disjoint banks and share a shared-memory
+      // wavefront; with rows 8 apart (same phase) ncu counted 10.0 M LDGSTS bank conflicts per 96->96 launch instead of 5.9 M.
+      const uint32_t dst_lane = (uint32_t)(sub * UW * 32 * 128 + rsub * 128);
+      const uint32_t sw_even = (uint32_t)((piece ^ rsub) << 4), sw_odd = (uint32_t)((piece ^ (4 + rsub)) << 4);  // row & 7 = 4 * (jj & 1) + rsub
       const bool two = G == 2;
       const int num_st = two ? (p.num_tiles + 1) >> 1 : p.num_tiles;
       const uint32_t* __restrict__ kmask = p.tile_kmask;
@@ -229,6 +232,76 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const ConvParams p)
         w_i += NP;
         return o;
       };
+      if (p.gather4) {
+        // ---- TMA row gather: the owning warp (split == 1) issues, per member tile, ONE tile::gather4 per lane = rows 4 * lane .. + 3
+        // of the tile (their four table entries are one 16-byte load, issued one own iteration ahead and held in registers).  The TMA
+        // engine fetches the four 128-byte row pieces from L2, writes them in the 128B swizzle and zero-fills absent neighbours
+        // (index -1 is outside the tensor map), so the gather costs the SM 2 instructions per 4 rows instead of 8 LDGSTS + their
+        // address arithmetic, and none of the LSU data-pipe wavefronts that bounded the LDGSTS version
+        // (profiles/r02_ncu_conv96_summary.txt: l1tex lsu wavefronts 65 % with the tensor pipe at 28 %).
+        const bool vec = (n_slots & 3) == 0;
+        auto load_idx = [&](const Own& o, int g) -> int4 {
+          int4 v = make_int4(-1, -1, -1, -1);
+          if (o.valid && ((o.has >> g) & 1u)) {
+            const int64_t slot = (int64_t)o.st * (G * kTileM) + g * kTileM + 4 * lane;
+            const int32_t* col = nbr + (int64_t)o.k * n_slots;
+            if (vec) {
+              if (slot < n_slots) v = ldg_nc_v4(col + slot);
+            } else {
+              if (slot + 0 < n_slots) v.x = __ldg(col + slot + 0);
+              if (slot + 1 < n_slots) v.y = __ldg(col + slot + 1);
+              if (slot + 2 < n_slots) v.z = __ldg(col + slot + 2);
+              if (slot + 3 < n_slots) v.w = __ldg(col + slot + 3);
+            }
+          }
+          return v;
+        };
+        int stage = gi % S;
+        uint32_t phase = (uint32_t)((gi / S) & 1);
+        const int box = 128 / p.elem;  // channels per 128-byte chunk
+        Own cur = take();
+        int4 c0 = load_idx(cur, 0), c1 = two ? load_idx(cur, 1) : make_int4(-1, -1, -1, -1);
+        while (cur.valid) {
+          const Own nxt = take();
+          const int4 n0 = load_idx(nxt, 0), n1 = two ? load_idx(nxt, 1) : make_int4(-1, -1, -1, -1);
+          const int k = cur.k, ch = cur.ch;
+          const uint32_t has = cur.has;
+          const int kw = kidx ? __ldg(kidx + k) : k;
+          const long long tp0 = kDbg ? clock64() : 0;
+          mbar_wait_hint(smem_u32(&empty_bar[stage]), phase ^ 1, 20000u);
+          if (kDbg) tp_wait += clock64() - tp0;
+          const uint32_t bar = smem_u32(&full_bar[stage]);
+          const uint32_t a_dst = sA_u32 + (uint32_t)(stage * a_bytes) + (uint32_t)(lane * 512);
+          const bool gather = !(kDbg && (dbg & 1));
+          if (lane == 0) {
+            const uint32_t a_tx = gather ? (uint32_t)__popc(has) * (uint32_t)kABytes : 0u;
+            if (kDbg && (dbg & 2)) {
+              mbar_arrive_expect_tx(bar, a_tx);
+            } else {
+              mbar_arrive_expect_tx(bar, a_tx + (uint32_t)b_bytes);
+              const uint8_t* wsrc = (const uint8_t*)p.wimg + ((int64_t)kw * nchunks + ch) * (int64_t)b_bytes;
+              bulk_copy_g2s(sB_u32 + (uint32_t)(stage * b_bytes), wsrc, (uint32_t)b_bytes, bar);
+            }
+          }
+          if (gather) {
+            if (has & 1u) tma_gather4(a_dst, p.tmap, ch * box, c0.x, c0.y, c0.z, c0.w, bar);
+            if (has & 2u) tma_gather4(a_dst + (uint32_t)kABytes, p.tmap, ch * box, c1.x, c1.y, c1.z, c1.w, bar);
+          }
+          __syncwarp();
+          stage += NP;
+          while (stage >= S) {
+            stage -= S;
+            phase ^= 1;
+          }
+          cur = nxt;
+          c0 = n0;
+          c1 = n1;
+        }
+        if (kDbg && p.trace && warp == 0 && lane == 0) {
+          p.trace[blockIdx.x * 16 + 0] = (unsigned long long)tp_wait;
+          p.trace[blockIdx.x * 16 + 1] = (unsigned long long)(clock64() - tp_start);
+        }
+      } else {
       // this lane's table entry per owned unit of an iteration: slot = st * G * 128 + (sub * UW + u) * 32 + lane
       auto stage_indices = [&](const Own& o, int buf) {
         const int32_t* col = nbr + (int64_t)o.k * n_slots;
@@ -280,22 +353,22 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const ConvParams p)
           const uint32_t has = cur.has;
           const int64_t slot_st = (int64_t)cur.st * (G * kTileM) + sub * UW * 32;
           const int width = min(128, cin_bytes - ch * 128);  // valid bytes of this 128-byte chunk
-          // this lane's 8 row indices per owned unit: rows rsub * 8 .. rsub * 8 + 7 of the unit = two 16-byte shared-memory reads
+          // this lane's 8 row indices per owned unit: unit rows 4 * jj + rsub (8 lanes share each shared-memory word: broadcast)
           int idx[4][8];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            if (u < UW && ((has >> ((sub * UW + u) >> 2)) & 1u)) {
-              const uint32_t a0 = my_idx + (uint32_t)((ibuf * 4 + u) * 128 + rsub * 32);
-              const int4 lo = lds_v4i(a0), hi = lds_v4i(a0 + 16u);
-              idx[u][0] = lo.x; idx[u][1] = lo.y; idx[u][2] = lo.z; idx[u][3] = lo.w;
-              idx[u][4] = hi.x; idx[u][5] = hi.y; idx[u][6] = hi.z; idx[u][7] = hi.w;
+            if (u < UW - TU && ((has >> ((sub * UW + u) >> 2)) & 1u)) {
+              const uint32_t a0 = my_idx + (uint32_t)((ibuf * 4 + u) * 128 + rsub * 4);
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) idx[u][jj] = lds_s32(a0 + (uint32_t)(jj * 16));
               if (slot_st + u * 32 + 32 > n_slots) {  // last, partial unit of the plan: rows past its end gather nothing
 #pragma unroll
                 for (int jj = 0; jj < 8; ++jj)
-                  if (slot_st + u * 32 + rsub * 8 + jj >= n_slots) idx[u][jj] = -1;
+                  if (slot_st + u * 32 + 4 * jj + rsub >= n_slots) idx[u][jj] = -1;
               }
             }
           }
+          const int ibuf_cur = ibuf;
           ibuf ^= 1;
           const int kw = kidx ? __ldg(kidx + k) : k;
           const long long tp0 = kDbg ? clock64() : 0;
@@ -311,13 +384,27 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const ConvParams p)
           if (act) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              if (u < UW && ((has >> ((sub * UW + u) >> 2)) & 1u)) {  // warp-uniform
+              if (u < UW - TU && ((has >> ((sub * UW + u) >> 2)) & 1u)) {  // warp-uniform
 #pragma unroll
                 for (int jj = 0; jj < 8; ++jj) {
                   const int r = idx[u][jj];
-                  const uint32_t dst = a_lane + (uint32_t)(u * 32 * 128 + jj * 128) + (uint32_t)((piece ^ jj) << 4);
+                  const uint32_t dst = a_lane + (uint32_t)(u * 32 * 128 + jj * 512) + ((jj & 1) ? sw_odd : sw_even);
                   cp_async_16(dst, (const void*)(src0 + (uint64_t)(r < 0 ? 0u : (uint32_t)r) * row_bytes), r < 0 ? 0u : 16u);
                 }
+              }
+            }
+          }
+          // the last TU units of this warp go through the TMA engine instead: lanes 0-7 issue one tile::gather4 each (rows 4 * lane ..
+          // + 3 of the unit, their four staged table entries are one 16-byte shared-memory read).  The TMA unit sustains about one
+          // 128-byte row per 6.7 cycles per SM (measured, profiles/r02_conv_sweep.txt: a gather4-only producer runs 96->96 in 0.39 ms)
+          // -- too slow alone, but it runs beside the LSU path, which is the unit that bounds this kernel.
+          if (TU > 0 && lane < 8 && !(dbg & 1)) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (u >= UW - TU && u < UW && ((has >> ((sub * UW + u) >> 2)) & 1u)) {
+                const int4 r4 = lds_v4i(my_idx + (uint32_t)((ibuf_cur * 4 + u) * 128 + lane * 16));
+                tma_gather4(sA_u32 + (uint32_t)(stage * a_bytes) + (uint32_t)((sub * UW + u) * 32 * 128 + lane * 512), p.tmap, ch * (128 / p.elem), r4.x, r4.y,
+                            r4.z, r4.w, bar);
               }
             }
           }
@@ -326,10 +413,16 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const ConvParams p)
           cp_async_arrive_noinc(bar);
           if (sub == 0) {
             if (elect_one_sync()) {
+              // transaction bytes of the stage: the weight chunk + the TMA-gathered units of every warp of the group
+              uint32_t a_tx = 0;
+              if (TU > 0 && !(dbg & 1)) {
+                for (int gu = 0; gu < 4 * G; ++gu)
+                  if ((gu % UW) >= UW - TU && ((has >> (gu >> 2)) & 1u)) a_tx += 32u * 128u;
+              }
               if (kDbg && (dbg & 2)) {
-                mbar_arrive(bar);
+                mbar_arrive_expect_tx(bar, a_tx);
               } else {
-                mbar_arrive_expect_tx(bar, (uint32_t)b_bytes);
+                mbar_arrive_expect_tx(bar, a_tx + (uint32_t)b_bytes);
                 const uint8_t* wsrc = (const uint8_t*)p.wimg + ((int64_t)kw * nchunks + ch) * (int64_t)b_bytes;
                 bulk_copy_g2s(sB_u32 + (uint32_t)(stage * b_bytes), wsrc, (uint32_t)b_bytes, bar);
               }
@@ -350,6 +443,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const ConvParams p)
         p.trace[blockIdx.x * 16 + 1] = (unsigned long long)(clock64() - tp_start);
       }
       cp_async_wait<0>();
+      }  // LDGSTS gather
     }
   } else if (warp == kCvMmaWarp || (warp == kCvAllocWarp && G == 2)) {
     // ===================== MMA issuers (whole warp converged, one elected lane issues) =====================
@@ -703,6 +797,7 @@ inline size_t conv_smem_bytes(int cout, int stages, int group = 1, int stage_out
 }
 
 int conv_tma_launch(const ConvParams& p, int64_t n_in, int out_dtype, cudaStream_t st);  // conv_tma.cu
+int encode_rows_tmap(void* out, const void* base, int elem, int cin, int64_t n_in);          // conv_tma.cu
 
 // 0 = LSU producer: 16-byte cp.async (LDGSTS) into the swizzled A tile (default); 1 = TMA gather4 producer (mk_set_gather_mode(1);
 // measured ~2.5x slower on random rows, kept for A/B measurements)
@@ -752,7 +847,7 @@ int mk_set_deterministic(int on) {
 }
 
 int mk_set_gather_mode(int mode) {
-  g_gather_mode = mode ? 1 : 0;
+  g_gather_mode = mode;
   return 0;
 }
 
@@ -846,6 +941,21 @@ static int conv_fwd_launch(const void* in, int in_dtype, int64_t n_in, int cin, 
   if (tn.split >= group && tn.split <= 4) p.split = tn.split;
   p.num_producers = stages < kCvProducerWarps / p.split ? stages : kCvProducerWarps / p.split;
   if (tn.producers >= 1 && tn.producers < p.num_producers) p.num_producers = tn.producers;
+  p.tma_units = 0;
+  if (gather_mode() >= 3 && ((cin * p.elem) & 15) == 0) {  // hybrid: gather_mode - 2 units of every producer warp through the TMA engine
+    MK_REQUIRE(encode_rows_tmap(p.tmap, in, p.elem, cin, n_in) == 0, "cuTensorMapEncodeTiled failed");
+    p.tma_units = gather_mode() - 2;
+    const int uw = 4 * group / p.split;
+    if (p.tma_units > uw - 1) p.tma_units = uw - 1;
+  }
+  p.gather4 = 0;
+  if (gather_mode() == 2 && ((cin * p.elem) & 15) == 0 && ((uintptr_t)nbr & 15) == 0) {  // TMA row gather inside this kernel (A/B switch)
+    MK_REQUIRE(encode_rows_tmap(p.tmap, in, p.elem, cin, n_in) == 0, "cuTensorMapEncodeTiled failed");
+    p.gather4 = 1;
+    p.split = 1;
+    p.num_producers = stages < 4 ? stages : 4;
+    if (tn.producers >= 1 && tn.producers < p.num_producers) p.num_producers = tn.producers;
+  }
   p.num_stages = stages;
   const size_t smem = conv_smem_bytes(cout, stages, group, soc);
   int grid = num_sms();

@@ -40,6 +40,7 @@ struct WgradParams {
   const int32_t* out_rows;
   const int32_t* plan;  // see mk_conv_wgrad_plan
   float* dw;
+  float* partial;     // deterministic mode: per-item accumulators [n_items * nmb][128][cout] (plain stores, merged in item order); else nullptr
   int64_t n_slots;
   int64_t n_out;
   int cin, cout, K;
@@ -199,17 +200,26 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_wgrad_umma(const WgradP
       uint64_t dsrc = (uint64_t)p.dy + (uint64_t)(piece * 8) * 2u;
       asm volatile("" : "+l"(xsrc));
       asm volatile("" : "+l"(dsrc));
+      // all 32 index shuffles first, then the copies: `asm volatile` statements keep their order, so interleaving one SHFL per
+      // group of copies made every group wait ~30 cycles on its own shuffle (ncu source view of the forward kernel, round 2)
+      int ii[2][8], oo[2][8];
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
-          const int ii = __shfl_sync(0xffffffffu, ci.in[q], 4 * jj + rsub);
-          const int oo = __shfl_sync(0xffffffffu, ci.out[q], 4 * jj + rsub);
+          ii[q][jj] = __shfl_sync(0xffffffffu, ci.in[q], 4 * jj + rsub);
+          oo[q][jj] = __shfl_sync(0xffffffffu, ci.out[q], 4 * jj + rsub);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
           const int row = q * 32 + 4 * jj + rsub;
           const uint32_t roff = (uint32_t)(row * 128) + ((jj & 1) ? sw_odd : sw_even);
-          const uint32_t nbytes = ii < 0 ? 0u : 16u;
-          const uint64_t xs = xsrc + (uint64_t)(ii < 0 ? 0u : (uint32_t)ii) * x_row_bytes;
-          const uint64_t ds = dsrc + (uint64_t)(oo < 0 ? 0u : (uint32_t)oo) * dy_row_bytes;
+          const uint32_t nbytes = ii[q][jj] < 0 ? 0u : 16u;
+          const uint64_t xs = xsrc + (uint64_t)(ii[q][jj] < 0 ? 0u : (uint32_t)ii[q][jj]) * x_row_bytes;
+          const uint64_t ds = dsrc + (uint64_t)(oo[q][jj] < 0 ? 0u : (uint32_t)oo[q][jj]) * dy_row_bytes;
 #pragma unroll
           for (int c = 0; c < kWgAChunks; ++c)
             if (c * 64 + piece * 8 < cinb) cp_async_16(a_base + (uint32_t)(c * kWgChunkBytes) + roff, (const void*)(xs + c * 128), nbytes);
@@ -296,7 +306,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) k_conv_wgrad_umma(const WgradP
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int rr = 8 * i + rsel;
-          if (row0 + rr < p.cin) {
+          if (p.partial != nullptr) {
+            // deterministic mode: this item's accumulator goes to its own slot with plain stores; k_wg_merge adds the slots of an
+            // offset in item order (no floating-point atomics, run-to-run bit-identical)
+            const uint32_t sv = stg + (uint32_t)(rr * kWgFlushPitch + 4 * quad) * 4u;
+            float* dst = p.partial + ((int64_t)j * 128 + q * 32 + rr) * p.cout + c0 + 4 * quad;
+            *reinterpret_cast<float4*>(dst) = make_float4(lds_f32(sv), lds_f32(sv + 4u), lds_f32(sv + 8u), lds_f32(sv + 12u));
+          } else if (row0 + rr < p.cin) {
             const uint32_t sv = stg + (uint32_t)(rr * kWgFlushPitch + 4 * quad) * 4u;
             float* dst = p.dw + ((int64_t)item.k * p.cin + row0 + rr) * p.cout + c0 + 4 * quad;
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(lds_f32(sv)), "f"(lds_f32(sv + 4u)),
@@ -410,6 +426,31 @@ __global__ void __launch_bounds__(256) k_wg_fill(const uint32_t* __restrict__ km
     if ((kmask[t] >> k) & 1u) units[o++] = t;
 }
 
+// deterministic merge: dW[k][mb * 128 + r][c] = sum over the items i of offset k, in item order, of partial[mb * n_items + i][r][c]
+__global__ void __launch_bounds__(256) k_wg_merge(const float* __restrict__ partial, const int32_t* __restrict__ plan, int max_items, int K,
+                                                  int cin, int cout, int nmb, float* __restrict__ dw) {
+  const int n_items = plan[0];
+  const int32_t* items = plan + kWgPlanHeader;
+  const int k = blockIdx.y;
+  const int64_t per_k = (int64_t)cin * cout;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < per_k; e += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(e / cout), c = (int)(e - (int64_t)row * cout);
+    const int mb = row >> 7, r = row & 127;
+    float acc = 0.f;
+    for (int i = 0; i < n_items; ++i) {
+      const int2 v = __ldg(reinterpret_cast<const int2*>(items) + i);
+      if ((v.y >> kWgItemShift) == k && (v.y & ((1 << kWgItemShift) - 1)) > 0)
+        acc += partial[(((int64_t)mb * n_items + i) * 128 + r) * cout + c];
+    }
+    dw[(int64_t)k * per_k + e] = acc;
+  }
+  (void)max_items;
+  (void)K;
+  (void)nmb;
+}
+
+extern int g_deterministic;  // conv_umma.cu (mk_set_deterministic)
+
 inline int wgrad_block_tiles(int64_t num_tiles) {
   // ~2 tile blocks per SM: long enough accumulation runs (one flush per (block, offset)), enough items to balance the grid
   int64_t t = ceil_div(num_tiles, 2 * (int64_t)num_sms());
@@ -456,8 +497,23 @@ int mk_conv_wgrad_plan(const uint32_t* tile_kmask, int64_t num_tiles, int K, int
   return check_launch(__func__);
 }
 
+int64_t mk_conv_wgrad_det_workspace_bytes(int64_t n_slots, int K, int cin, int cout) {
+  const int64_t items = wgrad_max_items(ceil_div(n_slots > 0 ? n_slots : 1, kTileM), K) * ((cin + 127) / 128);
+  return items * 128 * (int64_t)cout * (int64_t)sizeof(float) + 256;
+}
+
+int mk_conv_wgrad_bf16_ws(const void* x, int64_t n_in, int cin, const void* dy, int cout, const int32_t* nbr, int K, int64_t n_slots,
+                          const int32_t* out_rows, const int32_t* plan, int64_t n_out, float* dW, void* workspace, int64_t workspace_bytes,
+                          void* stream_);
+
 int mk_conv_wgrad_bf16(const void* x, int64_t n_in, int cin, const void* dy, int cout, const int32_t* nbr, int K, int64_t n_slots,
                        const int32_t* out_rows, const int32_t* plan, int64_t n_out, float* dW, void* stream_) {
+  return mk_conv_wgrad_bf16_ws(x, n_in, cin, dy, cout, nbr, K, n_slots, out_rows, plan, n_out, dW, nullptr, 0, stream_);
+}
+
+int mk_conv_wgrad_bf16_ws(const void* x, int64_t n_in, int cin, const void* dy, int cout, const int32_t* nbr, int K, int64_t n_slots,
+                          const int32_t* out_rows, const int32_t* plan, int64_t n_out, float* dW, void* workspace, int64_t workspace_bytes,
+                          void* stream_) {
   (void)n_in;
   MK_REQUIRE(mk_device_supported(), "tcgen05 path needs an sm_100 device (B200)");
   MK_REQUIRE(cin % 8 == 0 && cin >= 8, "cin must be a multiple of 8");
@@ -474,6 +530,9 @@ int mk_conv_wgrad_bf16(const void* x, int64_t n_in, int cin, const void* dy, int
   p.out_rows = out_rows;
   p.plan = plan;
   p.dw = dW;
+  // deterministic mode (mk_set_deterministic(1)) with a workspace: per-item accumulators + fixed-order merge instead of REDs
+  const bool det = g_deterministic && workspace != nullptr && workspace_bytes >= mk_conv_wgrad_det_workspace_bytes(n_slots, K, cin, cout);
+  p.partial = det ? (float*)workspace : nullptr;
   p.n_slots = n_slots;
   p.n_out = n_out;
   p.cin = cin;
@@ -492,6 +551,11 @@ int mk_conv_wgrad_bf16(const void* x, int64_t n_in, int cin, const void* dy, int
   int grid = num_sms();
   if (grid > max_units) grid = (int)max_units;
   k_conv_wgrad_umma<<<grid, kNumThreads, smem, st>>>(p);
+  if (det) {
+    const int64_t per_k = (int64_t)cin * cout;
+    dim3 mg((unsigned)(ceil_div(per_k, 256) < 64 ? ceil_div(per_k, 256) : 64), (unsigned)K);
+    k_wg_merge<<<mg, 256, 0, st>>>(p.partial, plan, p.max_items, K, cin, cout, p.nmb, dW);
+  }
   return check_launch(__func__);
 }
 

@@ -111,26 +111,53 @@ __device__ __forceinline__ int gs_lookup(const uint32_t* __restrict__ tkeys, con
   return 0;  // more than kGsMaxGroups distinct keys (status bit set by k_gs_rank): keep indices in range
 }
 
-// block = 4 warps, warp w handles rows [(4 * blockIdx.x + w) * 1024, +1024); hist[(warp block) * kGsMaxGroups + g]
+// block = 4 warps, warp w handles rows [(4 * blockIdx.x + w) * 1024, +1024); hist[(warp block) * kGsMaxGroups + g].  The 4096-slot
+// table is copied to shared memory first: a warp makes 32 dependent steps, and with the probes going to L2 the kernel sat at
+// 6 % of the warp slots for 33 us per 889 k rows (ncu, profiles/r02_families_infer_summary.txt).
 __global__ void __launch_bounds__(128) k_gs_hist(const uint32_t* __restrict__ keys, int64_t n, const uint32_t* __restrict__ tkeys,
                                                  const uint32_t* __restrict__ tids, const int32_t* __restrict__ meta, int16_t* __restrict__ gid,
                                                  int32_t* __restrict__ hist) {
   __shared__ int s_hist[4][kGsMaxGroups];
+  __shared__ uint32_t s_tk[kGsTableCap];
+  __shared__ uint16_t s_ti[kGsTableCap];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = meta[0];
+  for (int i = threadIdx.x; i < kGsTableCap; i += 128) {
+    s_tk[i] = tkeys[i];
+    s_ti[i] = (uint16_t)tids[i];
+  }
   for (int g = lane; g < D; g += 32) s_hist[warp][g] = 0;
-  __syncwarp();
+  __syncthreads();
   const int64_t wb = (int64_t)blockIdx.x * 4 + warp;
   const int64_t r0 = wb * kGsRowsPerWarp;
   if (r0 >= n) return;
-  for (int step = 0; step < kGsRowsPerWarp / 32; ++step) {
-    const int64_t i = r0 + step * 32 + lane;
-    const bool in = i < n;
-    const int g = in ? gs_lookup(tkeys, tids, keys[i]) : -1;
-    if (in) gid[i] = (int16_t)g;
-    const unsigned peers = __match_any_sync(0xffffffffu, g);
-    if (in && (int)(__ffs(peers) - 1) == lane) s_hist[warp][g] += __popc(peers);
-    __syncwarp();
+  auto lookup = [&](uint32_t k) -> int {
+    uint32_t h = gs_hash(k) & (kGsTableCap - 1);
+    for (int probe = 0; probe < kGsTableCap; ++probe) {
+      const uint32_t cur = s_tk[h];
+      if (cur == k) return (int)s_ti[h];
+      if (cur == kGsEmpty) break;
+      h = (h + 1) & (kGsTableCap - 1);
+    }
+    return 0;  // more than kGsMaxGroups distinct keys (status bit set by k_gs_rank): keep indices in range
+  };
+  for (int step = 0; step < kGsRowsPerWarp / 32; step += 4) {
+    uint32_t kk[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = r0 + (step + u) * 32 + lane;
+      kk[u] = i < n ? keys[i] : kGsEmpty;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = r0 + (step + u) * 32 + lane;
+      const bool in = i < n;
+      const int g = in ? lookup(kk[u]) : -1;
+      if (in) gid[i] = (int16_t)g;
+      const unsigned peers = __match_any_sync(0xffffffffu, g);
+      if (in && (int)(__ffs(peers) - 1) == lane) s_hist[warp][g] += __popc(peers);
+      __syncwarp();
+    }
   }
   for (int g = lane; g < D; g += 32) hist[wb * kGsMaxGroups + g] = s_hist[warp][g];
 }
@@ -192,18 +219,27 @@ __global__ void __launch_bounds__(128) k_gs_scatter(const int16_t* __restrict__ 
   if (r0 >= n) return;
   for (int g = lane; g < D; g += 32) s_off[warp][g] = base[g] + hist[wb * kGsMaxGroups + g];
   __syncwarp();
-  for (int step = 0; step < kGsRowsPerWarp / 32; ++step) {
-    const int64_t i = r0 + step * 32 + lane;
-    const bool in = i < n;
-    const int g = in ? (int)gid[i] : -1;
-    const unsigned peers = __match_any_sync(0xffffffffu, g);
-    if (in) {
-      const int rank = __popc(peers & ((1u << lane) - 1u));  // earlier rows of this step with the same group
-      order[s_off[warp][g] + rank] = (int32_t)i;
+  for (int step = 0; step < kGsRowsPerWarp / 32; step += 4) {
+    int gg[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {  // the four loads are independent: one memory latency per four steps
+      const int64_t i = r0 + (step + u) * 32 + lane;
+      gg[u] = i < n ? (int)gid[i] : -1;
     }
-    __syncwarp();
-    if (in && (int)(__ffs(peers) - 1) == lane) s_off[warp][g] += __popc(peers);
-    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = r0 + (step + u) * 32 + lane;
+      const bool in = i < n;
+      const int g = gg[u];
+      const unsigned peers = __match_any_sync(0xffffffffu, g);
+      if (in) {
+        const int rank = __popc(peers & ((1u << lane) - 1u));  // earlier rows of this step with the same group
+        order[s_off[warp][g] + rank] = (int32_t)i;
+      }
+      __syncwarp();
+      if (in && (int)(__ffs(peers) - 1) == lane) s_off[warp][g] += __popc(peers);
+      __syncwarp();
+    }
   }
 }
 

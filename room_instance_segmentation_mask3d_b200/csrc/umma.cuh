@@ -107,6 +107,11 @@ __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
   return v;
 }
 
+__device__ __forceinline__ int lds_s32(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ int4 lds_v4i(uint32_t addr) {
   int4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
@@ -133,6 +138,20 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+
+// TMA row gather (sm_100): FOUR rows r0..r3 of a 2-D tensor map (box = {row chunk, 1}), columns [c0, c0 + box), land as four consecutive
+// box rows at dst in the map's shared-memory swizzle; rows / columns outside the tensor (r < 0: absent neighbours) are zero-filled
+// and still count towards the barrier's transaction bytes.
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const void* tmap, int c0, int r0, int r1, int r2, int r3, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
+               "l"(tmap), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ int4 ldg_nc_v4(const int32_t* p) {
+  int4 v;
+  asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
@@ -263,6 +282,9 @@ struct ConvParams {
                    // and ADDS its partial result into the (zeroed, fp32) output with vector REDs
   int debug;       // timing ablation flags (MK3D_DEBUG), 0 in production
   unsigned long long* trace;  // MK3D_TRACE: per-CTA role timers [grid][8], nullptr in production
+  int tma_units;   // > 0: the last tma_units units (32 rows) of every producer warp are gathered by the TMA engine, the rest by LDGSTS
+  int gather4;     // 1: the A rows are gathered by the TMA engine (tile::gather4 through `tmap`) instead of LDGSTS
+  alignas(64) unsigned long long tmap[16];  // CUtensorMap of the input rows: {cin, n_in}, box {128 bytes of channels, 1}, SWIZZLE_128B
 };
 
 struct Ring {

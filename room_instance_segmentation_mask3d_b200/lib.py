@@ -58,6 +58,9 @@ _SIGS = {
     "mk_conv_wgrad_plan": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "mk_conv_wgrad_bf16": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
                                    c_void_p]),
+    "mk_conv_wgrad_det_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int]),
+    "mk_conv_wgrad_bf16_ws": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
+                                      c_void_p, c_int64, c_void_p]),
     "mk_instnorm_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
     "mk_instnorm_stats": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "mk_norm_apply": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
@@ -181,7 +184,7 @@ class stream_scope:
 
 # kernels launched per C-ABI call (memsets not counted) — bench.py reports the total as `gpu_launches`
 _KERNELS_PER_CALL = {"mk_coordmap_build": 7, "mk_instnorm_stats": 2, "mk_masked_xattn_fwd": 3, "mk_masked_xattn_fwd_lse": 3, "mk_masked_xattn_bwd": 5, "mk_instnorm_bwd": 3, "mk_instnorm_relu_bwd": 3, "mk_scene_minmax": 3,
-                     "mk_fps": 25, "mk_mask_compact": 2, "mk_group_rows": 6, "mk_mask_costs": 3, "mk_conv_instnorm_bf16": 4, "mk_conv_wgrad_plan": 3, "mk_conv_stem_wgrad_f32": 2}
+                     "mk_fps": 25, "mk_mask_compact": 2, "mk_group_rows": 6, "mk_mask_costs": 3, "mk_conv_instnorm_bf16": 4, "mk_conv_wgrad_plan": 3, "mk_conv_wgrad_bf16_ws": 2, "mk_conv_stem_wgrad_f32": 2}
 kernel_launches = 0
 _timed = None  # optional {entry-point name: [(start_event, end_event, tag), ...]} filled when bench.py instruments a step
 _tag = None

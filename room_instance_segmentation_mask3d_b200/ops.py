@@ -18,6 +18,7 @@ from . import lib
 from .engine import KernelMap
 
 _MODE = "bf16"
+_DETERMINISTIC = False
 SORT_TILES = True  # mask-sorted tile plans for the tensor-core conv (engine.KernelMap.sorted_plan)
 USE_COMPOSITE = True  # conv -> instance norm -> act through one C-ABI call; bench.py turns it off to time conv launches alone
 
@@ -36,6 +37,8 @@ def set_deterministic(on: bool) -> None:
     """Run-to-run bit-identical results (what the reference's `deterministic: true`, conf/trainer/trainer.yaml:1, asks of a
     backend): the tensor-core conv stops splitting the offsets of small levels over CTAs (floating-point REDs in varying order).
     Off by default (fastest)."""
+    global _DETERMINISTIC
+    _DETERMINISTIC = bool(on)
     lib.call("mk_set_deterministic", int(bool(on)))
 
 
@@ -173,6 +176,12 @@ def conv_wgrad_bf16(x: torch.Tensor, dout: torch.Tensor, km: KernelMap, K: int, 
     dW = torch.empty((K, cin, cout), dtype=torch.float32, device=x.device)
     if lib._timed is not None:
         lib.set_tag((2 * km.num_pairs * cin * cout, K, cin, cout, km.n_out, "dense" if K == 1 else "conv"))
+    if _DETERMINISTIC:  # per-item accumulators + fixed-order merge instead of floating-point REDs
+        wsb = lib.query("mk_conv_wgrad_det_workspace_bytes", plan.n_slots, K, cin, cout)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
+        lib.call("mk_conv_wgrad_bf16_ws", lib.p(xb), xb.shape[0], cin, lib.p(db), cout, lib.p(plan.nbr), K, plan.n_slots, lib.p(plan.out_rows),
+                 lib.p(plan.wgrad_plan), km.n_out, lib.p(dW), lib.p(ws), wsb, lib.stream())
+        return dW
     lib.call("mk_conv_wgrad_bf16", lib.p(xb), xb.shape[0], cin, lib.p(db), cout, lib.p(plan.nbr), K, plan.n_slots, lib.p(plan.out_rows),
              lib.p(plan.wgrad_plan), km.n_out, lib.p(dW), lib.stream())
     return dW

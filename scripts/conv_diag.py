@@ -31,6 +31,8 @@ else:
     np.save(cache, c)
 c = torch.from_numpy(c).cuda()
 lib.load()
+if os.environ.get('MK3D_GATHER'):
+    lib.call('mk_set_gather_mode', int(os.environ['MK3D_GATHER']))
 mgr = engine.CoordinateManager(D=3)
 k0, _ = mgr.insert_and_map(c)
 km3 = mgr.neighbor_table(k0, k0, ksize, 1)

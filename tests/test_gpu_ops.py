@@ -697,3 +697,22 @@ def test_group_rows_too_many_distinct_keys_sets_status(R):
     R.lib.call("mk_group_rows", R.lib.p(keys), n, R.lib.p(order), R.lib.p(status), R.lib.p(ws), wsb, R.lib.stream())
     assert int(status.item()) & 1
     assert sorted(order.cpu().tolist()) == list(range(n))  # still a permutation
+
+
+def test_conv_wgrad_deterministic_mode_is_bit_identical_and_correct(R):
+    """mk_set_deterministic(1): the weight gradient is accumulated per work item and merged in a fixed order -- two runs give the
+    same bits (the default path adds with red.global in varying order) and the values agree with the fp64 reference."""
+    mgr, k_in, k_out, km, x, W, bias = _conv_setup(R, 96, 96, 3, 1, seed=77)
+    g = torch.Generator().manual_seed(6)
+    dy = torch.randn(km.n_out, 96, generator=g)
+    xb, dyb = x.bfloat16(), dy.bfloat16()
+    ref = _wgrad_ref(xb.float(), dyb.float(), km.nbr.cpu().numpy(), 27)
+    R.ops.set_deterministic(True)
+    try:
+        a = R.ops.conv_wgrad_bf16(xb.cuda(), dyb.cuda(), km, 27, 96, 96)
+        b = R.ops.conv_wgrad_bf16(xb.cuda(), dyb.cuda(), km, 27, 96, 96)
+        torch.cuda.synchronize()
+    finally:
+        R.ops.set_deterministic(False)
+    assert torch.equal(a, b)
+    assert rel_err(a, ref) < 1e-4
