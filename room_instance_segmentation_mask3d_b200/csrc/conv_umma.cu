@@ -35,11 +35,15 @@
 namespace mk {
 
 // ---- thread layout of k_conv_umma (448 threads = 14 warps) ----
+// A wider layout (768 threads: 16 gather warps, registers rebalanced with setmaxnreg) was measured and dropped: the same
+// times within 3 % on every shape (profiles/r02_conv_sweep.txt) -- the gather is bound by the LSU's LDGSTS rate and the
+// depth of the 4-slot ring, not by the number of warps issuing.
 constexpr int kCvProducerWarps = 8;   // warps 0-7: gather producers (stage ownership in groups of `split` warps)
 constexpr int kCvMmaWarp = 8;         // MMA issuer
 constexpr int kCvAllocWarp = 9;       // TMEM allocation; second MMA issuer when G == 2
 constexpr int kCvEpiWarp0 = 10;       // warps 10-13: epilogue (TMEM lane quarter = warp & 3)
 constexpr int kCvThreads = 448;
+constexpr int kMaxUW = 4;             // most 32-row units a producer warp gathers per stage
 
 // keep the set bits of m whose ordinal is congruent to `part` modulo `ksplit` (offset split of small problems)
 __device__ __forceinline__ uint32_t split_bits(uint32_t m, int part, int ksplit) {
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const __grid_consta
   uint64_t* tmem_full = bars + 2 * kMaxStages;     // [2]  one tcgen05.commit per MMA issuer
   uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;  // [2]  128 epilogue threads
   uint32_t* tmem_base_slot = (uint32_t*)(bars + 2 * kMaxStages + 4);
-  int32_t* idx_stage = (int32_t*)(bars + 2 * kMaxStages + 6);  // [8 producer warps][2][4 units][32] neighbour-table entries (8 KB)
+  int32_t* idx_stage = (int32_t*)(bars + 2 * kMaxStages + 6);  // [producer warps][2][4 units][32] neighbour-table entries (1 KB per warp)
   float* out_stage = (float*)(idx_stage + kCvProducerWarps * 2 * 4 * 32);  // [4 epilogue warps][32 rows x out_cols] when p.stage_out
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -174,7 +178,6 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const __grid_consta
     const int sub = warp - gi * split;
     if (gi < NP) {
       const int UW = 4 * G / split;  // units per warp: 4 or 2
-      const int TU = p.tma_units;    // of which the last TU are gathered by the TMA engine (0: all through LDGSTS)
       const int piece = lane & 7;    // 16-byte piece of the 128-byte row
       const int rsub = lane >> 3;    // row octet of the unit this lane copies
       const uint32_t row_bytes = (uint32_t)p.cin * (uint32_t)p.elem;  // bf16 (2) or fp32 / tf32 (4) activations
@@ -186,8 +189,6 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const __grid_consta
       // One warp instruction copies unit rows 4 * jj + rsub (rsub = lane / 8): FOUR CONSECUTIVE rows.  Their swizzle phases (row & 7)
       // differ, so the 32-byte sectors of the four rows that arrive together land in disjoint banks and share a shared-memory
       // wavefront; with rows 8 apart (same phase) ncu counted 10.0 M LDGSTS bank conflicts per 96->96 launch instead of 5.9 M.
-      const uint32_t dst_lane = (uint32_t)(sub * UW * 32 * 128 + rsub * 128);
-      const uint32_t sw_even = (uint32_t)((piece ^ rsub) << 4), sw_odd = (uint32_t)((piece ^ (4 + rsub)) << 4);  // row & 7 = 4 * (jj & 1) + rsub
       const bool two = G == 2;
       const int num_st = two ? (p.num_tiles + 1) >> 1 : p.num_tiles;
       const uint32_t* __restrict__ kmask = p.tile_kmask;
@@ -195,41 +196,47 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const __grid_consta
       const uint32_t my_idx = smem_u32(idx_stage) + (uint32_t)(warp * 2 * 4 * 128);  // this warp's [2 buffers][4 units][32 entries]
       long long tp_wait = 0, tp_start = kDbg ? clock64() : 0;
       // ---- lookahead walker: position of this group's NEXT own iteration (may be in a later super-tile) ----
+      // kept incrementally as (super-tile, chunk pass, offset ordinal): one iteration costs two compares, a shuffle and the table
+      // address (the first version re-derived chunk and ordinal with a division loop: ~550 cycles per iteration in MK3D_TRACE)
       struct Own {
         int st, k, ch;
         uint32_t has;
-        bool valid;
+        bool valid, tail;
+        const int32_t* col;  // table entries of this warp's first unit: nbr[k][st * G * 128 + sub * UW * 32 ...]
       };
       int w_st = cta_first;   // super-tile of the walker
-      int w_i = gi;           // iteration index inside it (may exceed its total: carried into the next super-tile)
+      int w_j = gi;           // offset ordinal inside the current chunk pass (may exceed T.n: carried on)
+      int w_ch = 0;           // chunk pass
       uint32_t nm0, nm1;
       load_masks(kmask, cta_first, num_st, p.num_tiles, two, nm0, nm1);
       SuperTile T = make_super(nm0, nm1, K, cta_part, ksplit, lane);
       load_masks(kmask, cta_first + cta_stride, num_st, p.num_tiles, two, nm0, nm1);
+      const int64_t n_full = n_slots - (int64_t)(G * kTileM);  // super-tiles starting beyond this are partial
       auto take = [&]() -> Own {  // resolve the walker's position to an iteration, then advance it by NP
         Own o;
-        while (w_st < num_st && w_i >= T.n * nchunks) {
-          w_i -= T.n * nchunks;
-          w_st += cta_stride;
-          T = make_super(nm0, nm1, K, cta_part, ksplit, lane);
-          load_masks(kmask, w_st + cta_stride, num_st, p.num_tiles, two, nm0, nm1);
-          if (T.n <= 2 && sub == 0) {  // short passes (1x1 convs, mask logits): the table rows stream from DRAM, pull them into L2 early
-            const int k0 = __shfl_sync(0xffffffffu, T.kvec, 0);
-            const int64_t slot = ((int64_t)w_st + 6 * cta_stride) * (G * kTileM) + lane * 32;
-            if (lane < 4 * G && slot < n_slots) asm volatile("prefetch.global.L2 [%0];" ::"l"(nbr + (int64_t)k0 * n_slots + slot));
+        while (w_st < num_st && w_j >= T.n) {
+          w_j -= T.n;
+          if (T.n == 0 || ++w_ch == nchunks) {
+            w_ch = 0;
+            w_st += cta_stride;
+            T = make_super(nm0, nm1, K, cta_part, ksplit, lane);
+            load_masks(kmask, w_st + cta_stride, num_st, p.num_tiles, two, nm0, nm1);
+            if (T.n <= 2 && sub == 0) {  // short passes (1x1 convs, mask logits): the table rows stream from DRAM, pull them into L2 early
+              const int k0 = __shfl_sync(0xffffffffu, T.kvec, 0);
+              const int64_t slot = ((int64_t)w_st + 6 * cta_stride) * (G * kTileM) + lane * 32;
+              if (lane < 4 * G && slot < n_slots) asm volatile("prefetch.global.L2 [%0];" ::"l"(nbr + (int64_t)k0 * n_slots + slot));
+            }
           }
         }
         o.valid = w_st < num_st;
         o.st = w_st;
-        int ch = 0, j = w_i;
-        while (o.valid && j >= T.n) {
-          j -= T.n;
-          ++ch;
-        }
-        o.ch = ch;
-        o.k = __shfl_sync(0xffffffffu, T.kvec, o.valid ? j : 0);
+        o.ch = w_ch;
+        o.k = __shfl_sync(0xffffffffu, T.kvec, o.valid ? w_j : 0);
         o.has = o.valid ? (((T.m0 >> o.k) & 1u) | (((T.m1 >> o.k) & 1u) << 1)) : 0u;
-        w_i += NP;
+        const int64_t slot0 = (int64_t)o.st * (G * kTileM);
+        o.tail = slot0 > n_full;
+        o.col = nbr + ((int64_t)o.k * n_slots + slot0 + sub * UW * 32);
+        w_j += NP;
         return o;
       };
       if (p.gather4) {
@@ -302,150 +309,186 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const __grid_consta
           p.trace[blockIdx.x * 16 + 1] = (unsigned long long)(clock64() - tp_start);
         }
       } else {
-      // this lane's table entry per owned unit of an iteration: slot = st * G * 128 + (sub * UW + u) * 32 + lane
-      auto stage_indices = [&](const Own& o, int buf) {
-        const int32_t* col = nbr + (int64_t)o.k * n_slots;
-        const int64_t slot_w = (int64_t)o.st * (G * kTileM) + sub * UW * 32 + lane;
+        // ---- LDGSTS gather ----
+        // All units of a warp belong to ONE member tile (UW <= 4), so "does this warp have work in the iteration" is one
+        // warp-uniform test, and everything inside is straight-line code: MK3D_TRACE of the previous version (per-unit predicates,
+        // 8 scalar index reads per unit, bounds checks in every unit) showed 59 % of a producer iteration outside the gather issue.
+        const int member = (sub * UW) >> 2;
+        // a lane stages the table entry of unit row L = lane at position perm(L) = (L & 3) * 8 + (L >> 2): the eight rows
+        // 4 * jj + rsub a lane copies (wide chunks) are then the 8 consecutive entries rsub * 8 .., read with two LDS.128; for
+        // chunks of <= 64 bytes (rows 8 * jj + q, q = lane >> 2) they are entries (q & 3) * 8 + 2 * jj + (q >> 2)
+        const uint32_t st_off = (uint32_t)((((lane & 3) << 3) | (lane >> 2)) << 2);
+        const int q8 = lane >> 2;
+        auto stage_indices = [&](const Own& o, int buf) {
+          if ((o.has >> member) & 1u) {
+            const uint32_t dst = my_idx + (uint32_t)(buf * 512) + st_off;
+            if (!o.tail) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (u < UW && ((o.has >> ((sub * UW + u) >> 2)) & 1u)) {  // warp-uniform
-            const int64_t slot = slot_w + u * 32;
-            const bool in = slot < n_slots;
-            cp_async_4(my_idx + (uint32_t)((buf * 4 + u) * 128 + lane * 4), col + (in ? slot : 0), in ? 4u : 0u);
-          }
-        }
-        cp_async_commit();
-      };
-      int stage = gi % S;
-      uint32_t phase = (uint32_t)((gi / S) & 1);
-      // pull the table lines of an iteration into L1 (not tracked by cp.async groups / the stage barrier: see below)
-      auto prefetch_indices = [&](const Own& o) {
-        if (o.valid && lane < UW) {  // lane u: unit u's 128-byte line of the table row
-          const int gu = sub * UW + lane;
-          const int64_t slot = (int64_t)o.st * (G * kTileM) + gu * 32;
-          if (((o.has >> (gu >> 2)) & 1u) && slot < n_slots)
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(nbr + (int64_t)o.k * n_slots + slot));
-        }
-      };
-      int ibuf = 0;
-      // Three iterations are in flight per producer: `cur` is gathered now; the table entries of `nxt` are copied to shared memory
-      // (cp.async, 4 B per lane and unit) while cur's rows are gathered; the table LINES of `nx2` are prefetched into L1 one
-      // iteration earlier still.  The cp.async of nxt's entries precede cur's gathers in this thread's cp.async order, so the
-      // stage's completion-triggered mbarrier arrive also waits for them: they must be L1 hits (~50 cycles), not L2 / DRAM round
-      // trips (ncu + MK3D_TRACE: with the entries fetched from L2 every stage completed ~one memory latency late, and with only 4
-      // ring slots that latency is paid once per 4 iterations by the whole pipeline).
-      Own cur = take();
-      Own nxt = take();
-      prefetch_indices(nxt);
-      if (cur.valid) stage_indices(cur, ibuf);
-      while (cur.valid) {
-        const Own nx2 = take();
-        prefetch_indices(nx2);
-        if (nxt.valid) {
-          stage_indices(nxt, ibuf ^ 1);
-          cp_async_wait<1>();  // everything but the group just committed: this iteration's entries have landed
-        } else {
-          cp_async_wait<0>();
-        }
-        __syncwarp();  // the entries were written by other lanes of this warp
-        {
-          const int k = cur.k, ch = cur.ch;
-          const uint32_t has = cur.has;
-          const int64_t slot_st = (int64_t)cur.st * (G * kTileM) + sub * UW * 32;
-          const int width = min(128, cin_bytes - ch * 128);  // valid bytes of this 128-byte chunk
-          // this lane's 8 row indices per owned unit: unit rows 4 * jj + rsub (8 lanes share each shared-memory word: broadcast)
-          int idx[4][8];
+              for (int u = 0; u < kMaxUW; ++u)
+                if (u < UW) cp_async_4(dst + (uint32_t)(u * 128), o.col + u * 32 + lane, 4u);
+            } else {  // partial super-tile at the end of the plan: rows past its end gather nothing
+              const int64_t slot = (int64_t)o.st * (G * kTileM) + sub * UW * 32 + lane;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (u < UW - TU && ((has >> ((sub * UW + u) >> 2)) & 1u)) {
-              const uint32_t a0 = my_idx + (uint32_t)((ibuf * 4 + u) * 128 + rsub * 4);
-#pragma unroll
-              for (int jj = 0; jj < 8; ++jj) idx[u][jj] = lds_s32(a0 + (uint32_t)(jj * 16));
-              if (slot_st + u * 32 + 32 > n_slots) {  // last, partial unit of the plan: rows past its end gather nothing
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj)
-                  if (slot_st + u * 32 + 4 * jj + rsub >= n_slots) idx[u][jj] = -1;
-              }
-            }
-          }
-          const int ibuf_cur = ibuf;
-          ibuf ^= 1;
-          const int kw = kidx ? __ldg(kidx + k) : k;
-          const long long tp0 = kDbg ? clock64() : 0;
-          mbar_wait_hint(smem_u32(&empty_bar[stage]), phase ^ 1, 20000u);
-          if (kDbg) tp_wait += clock64() - tp0;
-          const uint32_t bar = smem_u32(&full_bar[stage]);
-          // lanes whose piece lies beyond a narrow chunk (or all lanes in the gather-off ablation) issue nothing
-          const bool act = piece * 16 < width && !(dbg & 1);
-          // source address = per-lane 64-bit base + row * row_bytes as ONE 32x32+64 multiply-add (IMAD.WIDE.U32)
-          uint64_t src0 = (uint64_t)p.in + (uint64_t)(ch * 128 + piece * 16);
-          asm volatile("" : "+l"(src0));  // keep the base in one register pair (otherwise it is re-derived from the constant bank per copy)
-          const uint32_t a_lane = sA_u32 + (uint32_t)(stage * a_bytes) + dst_lane;
-          if (act) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (u < UW - TU && ((has >> ((sub * UW + u) >> 2)) & 1u)) {  // warp-uniform
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                  const int r = idx[u][jj];
-                  const uint32_t dst = a_lane + (uint32_t)(u * 32 * 128 + jj * 512) + ((jj & 1) ? sw_odd : sw_even);
-                  cp_async_16(dst, (const void*)(src0 + (uint64_t)(r < 0 ? 0u : (uint32_t)r) * row_bytes), r < 0 ? 0u : 16u);
+              for (int u = 0; u < kMaxUW; ++u) {
+                if (u < UW) {
+                  if (slot + u * 32 < n_slots) cp_async_4(dst + (uint32_t)(u * 128), o.col + u * 32 + lane, 4u);
+                  else sts_s32(dst + (uint32_t)(u * 128), -1);
                 }
               }
             }
           }
-          // the last TU units of this warp go through the TMA engine instead: lanes 0-7 issue one tile::gather4 each (rows 4 * lane ..
-          // + 3 of the unit, their four staged table entries are one 16-byte shared-memory read).  The TMA unit sustains about one
-          // 128-byte row per 6.7 cycles per SM (measured, profiles/r02_conv_sweep.txt: a gather4-only producer runs 96->96 in 0.39 ms)
-          // -- too slow alone, but it runs beside the LSU path, which is the unit that bounds this kernel.
-          if (TU > 0 && lane < 8 && !(dbg & 1)) {
+          cp_async_commit();
+        };
+        // pull the table lines of an iteration into L1 (not tracked by cp.async groups / the stage barrier: see below)
+        auto prefetch_indices = [&](const Own& o) {
+          if (o.valid && !o.tail && lane < UW && ((o.has >> member) & 1u)) asm volatile("prefetch.global.L1 [%0];" ::"l"(o.col + lane * 32));
+        };
+        int stage = gi % S;
+        uint32_t phase = (uint32_t)((gi / S) & 1);
+        int ibuf = 0;
+        // Three iterations are in flight per producer: `cur` is gathered now; the table entries of `nxt` are copied to shared memory
+        // (cp.async, 4 B per lane and unit) while cur's rows are gathered; the table LINES of `nx2` are prefetched into L1 one
+        // iteration earlier still.  The cp.async of nxt's entries precede cur's gathers in this thread's cp.async order, so the
+        // stage's completion-triggered mbarrier arrive also waits for them: they must be L1 hits (~50 cycles), not L2 / DRAM round
+        // trips (ncu + MK3D_TRACE: with the entries fetched from L2 every stage completed ~one memory latency late, and with only 4
+        // ring slots that latency is paid once per 4 iterations by the whole pipeline).
+        Own cur = take();
+        Own nxt = take();
+        prefetch_indices(nxt);
+        if (cur.valid) stage_indices(cur, ibuf);
+        long long tq_take = 0, tq_stage = 0, tq_lds = 0, tq_issue = 0, tq_arr = 0, tq0 = 0;
+        // per-lane constants of the two copy shapes
+        const uint32_t a_wide = sA_u32 + (uint32_t)(sub * UW * 32 * 128 + rsub * 128);  // + stage, unit, jj * 512, swizzle
+        const uint32_t sw_even = (uint32_t)((piece ^ rsub) << 4), sw_odd = (uint32_t)((piece ^ (4 + rsub)) << 4);  // row & 7 = 4 * (jj & 1) + rsub
+        const uint32_t a_nar = sA_u32 + (uint32_t)(sub * UW * 32 * 128 + q8 * 128) + (uint32_t)(((lane & 3) ^ q8) << 4);  // row & 7 = q8 for every jj
+        const uint32_t rd_wide = my_idx + (uint32_t)(rsub * 32), rd_nar = my_idx + (uint32_t)((q8 & 3) * 32);
+        const bool odd_entry = (q8 >> 2) != 0;
+        while (cur.valid) {
+          if (kDbg) tq0 = clock64();
+          const Own nx2 = take();
+          prefetch_indices(nx2);
+          if (kDbg) {
+            const long long t = clock64();
+            tq_take += t - tq0;
+            tq0 = t;
+          }
+          if (nxt.valid) {
+            stage_indices(nxt, ibuf ^ 1);
+            cp_async_wait<1>();  // everything but the group just committed: this iteration's entries have landed
+          } else {
+            cp_async_wait<0>();
+          }
+          __syncwarp();  // the entries were written by other lanes of this warp
+          if (kDbg) {
+            const long long t = clock64();
+            tq_stage += t - tq0;
+            tq0 = t;
+          }
+          const int ch = cur.ch;
+          const bool mine = ((cur.has >> member) & 1u) != 0;
+          const int width = min(128, cin_bytes - ch * 128);  // valid bytes of this 128-byte chunk
+          // chunks of <= 64 valid bytes (32-channel layers, the second chunk of 96 channels): a warp instruction copies EIGHT
+          // consecutive rows x 64 B (lane = (row, 16-byte piece 0..3)) -- 4 LDGSTS per unit instead of 8 half-empty ones
+          const bool narrow = width <= 64;
+          const uint32_t rd = (narrow ? rd_nar : rd_wide) + (uint32_t)(ibuf * 512);
+          int4 e0[kMaxUW], e1[kMaxUW];
+          if (mine) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (u >= UW - TU && u < UW && ((has >> ((sub * UW + u) >> 2)) & 1u)) {
-                const int4 r4 = lds_v4i(my_idx + (uint32_t)((ibuf_cur * 4 + u) * 128 + lane * 16));
-                tma_gather4(sA_u32 + (uint32_t)(stage * a_bytes) + (uint32_t)((sub * UW + u) * 32 * 128 + lane * 512), p.tmap, ch * (128 / p.elem), r4.x, r4.y,
-                            r4.z, r4.w, bar);
+            for (int u = 0; u < kMaxUW; ++u) {
+              if (u < UW) {
+                e0[u] = lds_v4i(rd + (uint32_t)(u * 128));
+                e1[u] = lds_v4i(rd + (uint32_t)(u * 128 + 16));
               }
             }
+          }
+          ibuf ^= 1;
+          const long long tp0 = kDbg ? clock64() : 0;
+          if (kDbg) tq_lds += tp0 - tq0;
+          mbar_wait_hint(smem_u32(&empty_bar[stage]), phase ^ 1, 20000u);
+          if (kDbg) {
+            tq0 = clock64();
+            tp_wait += tq0 - tp0;
+          }
+          const uint32_t bar = smem_u32(&full_bar[stage]);
+          if (sub == 0 && elect_one_sync()) {  // the weight chunk first: its bulk copy runs beside the gathers
+            if (kDbg && (dbg & 2)) {
+              mbar_arrive(bar);
+            } else {
+              const int kw = kidx ? __ldg(kidx + cur.k) : cur.k;
+              mbar_arrive_expect_tx(bar, (uint32_t)b_bytes);
+              const uint8_t* wsrc = (const uint8_t*)p.wimg + (uint64_t)(uint32_t)(kw * nchunks + ch) * (uint64_t)(uint32_t)b_bytes;
+              bulk_copy_g2s(sB_u32 + (uint32_t)(stage * b_bytes), wsrc, (uint32_t)b_bytes, bar);
+            }
+          }
+          __syncwarp();
+          const int pc = narrow ? (lane & 3) : piece;
+          // lanes whose piece lies beyond a narrow chunk (or all lanes in the gather-off ablation) issue nothing
+          if (mine && pc * 16 < width && !(dbg & 1)) {
+            // source address = per-lane 64-bit base + row * row_bytes as ONE 32x32+64 multiply-add (IMAD.WIDE.U32)
+            uint64_t src0 = (uint64_t)p.in + (uint64_t)(ch * 128 + pc * 16);
+            asm volatile("" : "+l"(src0));  // keep the base in one register pair (otherwise it is re-derived from the constant bank per copy)
+            if (narrow) {
+              const uint32_t a0 = a_nar + (uint32_t)(stage * a_bytes);
+#pragma unroll
+              for (int u = 0; u < kMaxUW; ++u) {
+                if (u < UW) {
+                  const int r4[4] = {odd_entry ? e0[u].y : e0[u].x, odd_entry ? e0[u].w : e0[u].z, odd_entry ? e1[u].y : e1[u].x,
+                                     odd_entry ? e1[u].w : e1[u].z};
+#pragma unroll
+                  for (int jj = 0; jj < 4; ++jj) {
+                    const int r = r4[jj];
+                    cp_async_16(a0 + (uint32_t)(u * 32 * 128 + jj * 1024), (const void*)(src0 + (uint64_t)(r < 0 ? 0u : (uint32_t)r) * row_bytes),
+                                r < 0 ? 0u : 16u);
+                  }
+                }
+              }
+            } else {
+              const uint32_t a0 = a_wide + (uint32_t)(stage * a_bytes);
+#pragma unroll
+              for (int u = 0; u < kMaxUW; ++u) {
+                if (u < UW) {
+                  const int r8[8] = {e0[u].x, e0[u].y, e0[u].z, e0[u].w, e1[u].x, e1[u].y, e1[u].z, e1[u].w};
+#pragma unroll
+                  for (int jj = 0; jj < 8; ++jj) {
+                    const int r = r8[jj];
+                    cp_async_16(a0 + (uint32_t)(u * 32 * 128 + jj * 512) + ((jj & 1) ? sw_odd : sw_even),
+                                (const void*)(src0 + (uint64_t)(r < 0 ? 0u : (uint32_t)r) * row_bytes), r < 0 ? 0u : 16u);
+                  }
+                }
+              }
+            }
+          }
+          if (kDbg) {
+            const long long t = clock64();
+            tq_issue += t - tq0;
+            tq0 = t;
           }
           // completion-triggered arrive: no wait_group / fence in the producer; the proxy hand-over is completed by the MMA
           // thread's acquire fence after it has observed the barrier phase
           cp_async_arrive_noinc(bar);
-          if (sub == 0) {
-            if (elect_one_sync()) {
-              // transaction bytes of the stage: the weight chunk + the TMA-gathered units of every warp of the group
-              uint32_t a_tx = 0;
-              if (TU > 0 && !(dbg & 1)) {
-                for (int gu = 0; gu < 4 * G; ++gu)
-                  if ((gu % UW) >= UW - TU && ((has >> (gu >> 2)) & 1u)) a_tx += 32u * 128u;
-              }
-              if (kDbg && (dbg & 2)) {
-                mbar_arrive_expect_tx(bar, a_tx);
-              } else {
-                mbar_arrive_expect_tx(bar, a_tx + (uint32_t)b_bytes);
-                const uint8_t* wsrc = (const uint8_t*)p.wimg + ((int64_t)kw * nchunks + ch) * (int64_t)b_bytes;
-                bulk_copy_g2s(sB_u32 + (uint32_t)(stage * b_bytes), wsrc, (uint32_t)b_bytes, bar);
-              }
-            }
-            __syncwarp();
-          }
           stage += NP;
-          while (stage >= S) {
+          if (stage >= S) {  // NP <= S
             stage -= S;
             phase ^= 1;
           }
+          if (kDbg) tq_arr += clock64() - tq0;
+          cur = nxt;
+          nxt = nx2;
         }
-        cur = nxt;
-        nxt = nx2;
-      }
-      if (kDbg && p.trace && warp == 0 && lane == 0) {
-        p.trace[blockIdx.x * 16 + 0] = (unsigned long long)tp_wait;
-        p.trace[blockIdx.x * 16 + 1] = (unsigned long long)(clock64() - tp_start);
-      }
-      cp_async_wait<0>();
+        if (kDbg && p.trace && warp == 0 && lane == 0) {
+          p.trace[blockIdx.x * 16 + 0] = (unsigned long long)tp_wait;
+          p.trace[blockIdx.x * 16 + 1] = (unsigned long long)(clock64() - tp_start);
+          p.trace[blockIdx.x * 16 + 8] = (unsigned long long)tq_take;
+          p.trace[blockIdx.x * 16 + 9] = (unsigned long long)tq_stage;
+          p.trace[blockIdx.x * 16 + 10] = (unsigned long long)tq_lds;
+          p.trace[blockIdx.x * 16 + 11] = (unsigned long long)tq_issue;
+          p.trace[blockIdx.x * 16 + 12] = (unsigned long long)tq_arr;
+        }
+        cp_async_wait<0>();
       }  // LDGSTS gather
     }
-  } else if (warp == kCvMmaWarp || (warp == kCvAllocWarp && G == 2)) {
+  } else if (warp < kCvEpiWarp0) {
+    if (warp == kCvMmaWarp || (warp == kCvAllocWarp && G == 2)) {
     // ===================== MMA issuers (whole warp converged, one elected lane issues) =====================
     // Every lane runs the loop so that all control flow and descriptor arithmetic stays warp-uniform; only the tcgen05
     // instructions sit under elect_one_sync() (see umma.cuh).  With super-tiles (G == 2) there are TWO issuers, one per member
@@ -579,7 +622,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const __grid_consta
       p.trace[blockIdx.x * 16 + 4] = (unsigned long long)(clock64() - t_start);
       p.trace[blockIdx.x * 16 + 5] = (unsigned long long)n_it;
     }
-  } else if (warp >= kCvEpiWarp0) {
+    }  // MMA issuer warps
+  } else {
     // ===================== epilogue (4 warps) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     int acc_buf = 0;
@@ -793,7 +837,7 @@ __global__ void __launch_bounds__(256) k_weight_image_tf32(const float* __restri
 
 inline size_t conv_smem_bytes(int cout, int stages, int group = 1, int stage_out_cols = 0) {
   return 1024 + (size_t)stages * ((size_t)group * kABytes + (size_t)cout * 128) + (2 * kMaxStages + 6) * sizeof(uint64_t) + 16 +
-         (size_t)8 * 2 * 4 * 32 * sizeof(int32_t) + (size_t)4 * 32 * stage_out_cols * sizeof(float);
+         (size_t)kCvProducerWarps * 2 * 4 * 32 * sizeof(int32_t) + (size_t)4 * 32 * stage_out_cols * sizeof(float);
 }
 
 int conv_tma_launch(const ConvParams& p, int64_t n_in, int out_dtype, cudaStream_t st);  // conv_tma.cu
@@ -936,18 +980,12 @@ static int conv_fwd_launch(const void* in, int in_dtype, int64_t n_in, int cin, 
   if (tn.stages >= 2 && tn.stages < stages) stages = tn.stages;  // tuning sweeps only
   // producer groups: one per ring slot (a group may be at most one ring phase ahead); two warps per group (one per member
   // tile) when there are member tiles to split and warps to spare
+  const int pw = kCvProducerWarps;
   p.split = group;  // a producer warp gathers at most 4 units of 32 rows
-  while (p.split < 4 && 2 * p.split * stages <= kCvProducerWarps) p.split *= 2;  // 4 stages: 2 warps per stage
+  while (p.split < 4 && 2 * p.split * stages <= pw) p.split *= 2;  // 4 stages: 2 warps per stage
   if (tn.split >= group && tn.split <= 4) p.split = tn.split;
-  p.num_producers = stages < kCvProducerWarps / p.split ? stages : kCvProducerWarps / p.split;
+  p.num_producers = stages < pw / p.split ? stages : pw / p.split;
   if (tn.producers >= 1 && tn.producers < p.num_producers) p.num_producers = tn.producers;
-  p.tma_units = 0;
-  if (gather_mode() >= 3 && ((cin * p.elem) & 15) == 0) {  // hybrid: gather_mode - 2 units of every producer warp through the TMA engine
-    MK_REQUIRE(encode_rows_tmap(p.tmap, in, p.elem, cin, n_in) == 0, "cuTensorMapEncodeTiled failed");
-    p.tma_units = gather_mode() - 2;
-    const int uw = 4 * group / p.split;
-    if (p.tma_units > uw - 1) p.tma_units = uw - 1;
-  }
   p.gather4 = 0;
   if (gather_mode() == 2 && ((cin * p.elem) & 15) == 0 && ((uintptr_t)nbr & 15) == 0) {  // TMA row gather inside this kernel (A/B switch)
     MK_REQUIRE(encode_rows_tmap(p.tmap, in, p.elem, cin, n_in) == 0, "cuTensorMapEncodeTiled failed");
@@ -1005,6 +1043,8 @@ static int conv_fwd_launch(const void* in, int in_dtype, int64_t n_in, int cin, 
       for (int j = 0; j < 16; ++j) a[j] += (double)h[(size_t)b * 16 + j] / grid;
     fprintf(stderr, "[mk3d trace] cin %d cout %d K %d tiles %d stages %d producers %dx%d | producer0: wait_empty %.0f / total %.0f | mma: wait_full %.0f wait_tmem %.0f / total %.0f, iters %.0f | epilogue: wait_full %.0f / total %.0f (cycles, CTA mean)\n",
             cin, cout, K, p.num_tiles, stages, p.num_producers, p.split, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+    fprintf(stderr, "[mk3d trace]   producer0 phases: walker %.0f | index staging + wait_group %.0f | index reads %.0f | gather issue %.0f | arrive + weight copy %.0f\n",
+            a[8], a[9], a[10], a[11], a[12]);
   }
 #else
   if (out_dtype == MK_F32) MK_LAUNCH(float, false);

@@ -117,6 +117,9 @@ __device__ __forceinline__ int4 lds_v4i(uint32_t addr) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
 }
+__device__ __forceinline__ void sts_s32(uint32_t addr, int v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
@@ -282,7 +285,6 @@ struct ConvParams {
                    // and ADDS its partial result into the (zeroed, fp32) output with vector REDs
   int debug;       // timing ablation flags (MK3D_DEBUG), 0 in production
   unsigned long long* trace;  // MK3D_TRACE: per-CTA role timers [grid][8], nullptr in production
-  int tma_units;   // > 0: the last tma_units units (32 rows) of every producer warp are gathered by the TMA engine, the rest by LDGSTS
   int gather4;     // 1: the A rows are gathered by the TMA engine (tile::gather4 through `tmap`) instead of LDGSTS
   alignas(64) unsigned long long tmap[16];  // CUtensorMap of the input rows: {cin, n_in}, box {128 bytes of channels, 1}, SWIZZLE_128B
 };

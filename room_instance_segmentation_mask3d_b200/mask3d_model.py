@@ -484,7 +484,7 @@ class Mask3D(nn.Module):
         return side
 
     @torch.no_grad()
-    def forward(self, x: ME.SparseTensor, is_eval: bool = True, prefetch=None, compact: bool = False) -> dict:
+    def forward(self, x: ME.SparseTensor, is_eval: bool = True, prefetch=None, compact: bool = False, aux_outputs: bool = True) -> dict:
         """Fused inference forward.  Returns the fields of the reference's ModelOutput (mask3d.py:28-47).
 
         `prefetch = (coordinates, features)` of the NEXT scene (host pinned or device tensors): its coordinate phase is
@@ -493,7 +493,11 @@ class Mask3D(nn.Module):
 
         The forward runs on the CURRENT torch stream and keeps its static CUDA-graph buffers per stream, so consecutive scenes may
         alternate between two streams (`with torch.cuda.stream(lane[i % 2]): model(x, prefetch=...)`): the latency-bound
-        decoder chain of one scene then overlaps the bandwidth- and tensor-bound backbone of the next (bench.py does this)."""
+        decoder chain of one scene then overlaps the bandwidth- and tensor-bound backbone of the next (bench.py does this).
+
+        `aux_outputs=False`: the full-resolution mask logits of the 12 intermediate decoder outputs (the reference's `aux_outputs`,
+        mask3d.py:405-441, read by the criterion only) are not materialised -- the attention masks of those layers come from the
+        pooled mask features either way; `pred_mask_all_decoders` then holds the final prediction only."""
         ev = getattr(x, "_ready_event", None)
         if ev is not None:
             cur = torch.cuda.current_stream()
@@ -504,7 +508,7 @@ class Mask3D(nn.Module):
             x.F.record_stream(cur)
             x.C.record_stream(cur)
         with lib.stream_scope():
-            out = self._forward(x)
+            out = self._forward(x, aux_outputs=aux_outputs)
             if compact:
                 # what the reference's post-processing keeps of the final mask logits (trainer/trainer.py:373-402): the binary masks
                 # (bit q of word n = voxel n belongs to query q) and the per-query mask scores, built on the device in one pass --
@@ -525,7 +529,7 @@ class Mask3D(nn.Module):
         with lib.stream_scope():
             return self._forward(x, train=True)
 
-    def _forward(self, x: ME.SparseTensor, train: bool = False) -> dict:
+    def _forward(self, x: ME.SparseTensor, train: bool = False, aux_outputs: bool = True) -> dict:
         mgr = x.coordinate_manager
         mode = ops.get_compute_mode()
         act = torch.bfloat16 if mode == "bf16" else torch.float32
@@ -604,6 +608,8 @@ class Mask3D(nn.Module):
             cls = self.class_embed_head(qn)
             if train:
                 logits = ops._MaskLogitsFn.apply(mask_features, emb, offs[-1], B, sel0, off0_host)
+            elif want_mask and not aux_outputs:
+                logits = None
             else:
                 logits = ops.mask_logits(mask_features, offs[-1], B, emb, select=sel0)  # [N0, Q] fp32
             blocked = blocked_from(emb.detach(), hl) if want_mask else None  # the attention mask carries no gradient (mask3d.py:549)
@@ -645,7 +651,9 @@ class Mask3D(nn.Module):
 
             def masks_from_graph(hl, want_mask):
                 cls = qg.cls.clone()
-                if mode == "bf16" and sel0.K <= 32:  # more than 32 scenes: the per-tile offset mask is 32 bits -> CUDA-core kernel
+                if want_mask and not aux_outputs:
+                    logits = None
+                elif mode == "bf16" and sel0.K <= 32:  # more than 32 scenes: the per-tile offset mask is 32 bits -> CUDA-core kernel
                     logits = ops.mask_logits_from_image(mask_features, qg.img, sel0, Q)
                 elif mode == "bf16":
                     logits = ops.mask_logits(mask_features, offs[-1], B, qg.emb, select=None)
@@ -661,7 +669,8 @@ class Mask3D(nn.Module):
                     ops.masked_cross_attention(qg.qp, kp, vp, blocked, offs[hl], H, out=qg.ctx)
                     qg.layer(i)
                     pred_class.append(cls)
-                    pred_masks.append(logits)
+                    if logits is not None:
+                        pred_masks.append(logits)
             cls, logits, _ = masks_from_graph(0, False)
             queries = qg.queries.clone()
         else:
@@ -674,7 +683,8 @@ class Mask3D(nn.Module):
                     ctx = ops.masked_cross_attention(qp, kp, vp, blocked, offs[hl], H, max_scene_rows=max_rows[i] if train else None)
                     queries = self._query_update(i, queries, query_pos, ctx)
                     pred_class.append(cls)
-                    pred_masks.append(logits)
+                    if logits is not None:
+                        pred_masks.append(logits)
             cls, logits, _ = mask_module(queries, 0, False)
         pred_class.append(cls)
         pred_masks.append(logits)

@@ -151,6 +151,28 @@ def test_bf16_mode_is_run_to_run_bit_identical_when_deterministic(setup):
         ops.set_deterministic(False)
 
 
+def test_final_prediction_only_forward_matches_the_full_forward(setup):
+    """forward(aux_outputs=False) skips the intermediate outputs' full-resolution mask logits and nothing else: class logits of all 13
+    outputs, the final mask logits and the queries are bit-identical to the full forward (deterministic mode, bf16 and fp32)."""
+    g, model, ME, ops = setup
+    ops.set_deterministic(True)
+    try:
+        for mode in ("bf16", "fp32"):
+            ops.set_compute_mode(mode)
+            full = model(_input(g, ME))
+            lean = model(_input(g, ME), aux_outputs=False)
+            torch.cuda.synchronize()
+            assert len(full["pred_mask_all_decoders"]) == 13 and len(lean["pred_mask_all_decoders"]) == 1
+            assert torch.equal(full["pred_mask_all_decoders"][-1], lean["pred_mask_all_decoders"][-1])
+            assert len(lean["pred_class_all_decoders"]) == 13
+            for a, b in zip(full["pred_class_all_decoders"], lean["pred_class_all_decoders"]):
+                assert torch.equal(a, b)
+            assert torch.equal(full["queries"], lean["queries"])
+    finally:
+        ops.set_deterministic(False)
+        ops.set_compute_mode("fp32")
+
+
 def test_prefetch_on_side_stream_gives_identical_results(setup):
     """Mask3D.forward(x, prefetch=next): the coordinate phase of the next scene runs on a side stream behind the current
     scene's backbone.  Outputs must equal the plain sequential calls bit for bit (fp32 mode), over several alternating scenes."""
