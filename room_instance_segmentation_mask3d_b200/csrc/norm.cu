@@ -11,6 +11,21 @@ namespace mk {
 
 constexpr int kNormThreads = 256;
 
+// 1-D grid over the NON-EMPTY (scene, chunk) pairs of a batch (host: ceil(n / rows_per_chunk) + B blocks is an upper bound):
+// block g -> scene b and chunk g - (chunks of the scenes before b); false past the end.  A (chunks, B) grid sized for the
+// largest possible scene launches B - 1 empty blocks per useful one.
+__device__ __forceinline__ bool resolve_chunk(const int32_t* __restrict__ offs, int B, int rpc, int g, int& b, int& chunk) {
+  for (b = 0; b < B; ++b) {
+    const int nb = (offs[b + 1] - offs[b] + rpc - 1) / rpc;
+    if (g < nb) {
+      chunk = g;
+      return true;
+    }
+    g -= nb;
+  }
+  return false;
+}
+
 // partial layout: [chunk][3][C] = {count (as float), shifted sum, shifted sum of squares}, shift[chunk][C]
 template <typename T>
 __global__ void __launch_bounds__(kNormThreads) k_in_stats_partial(const T* __restrict__ x, int C,
@@ -63,18 +78,29 @@ __device__ __forceinline__ void chan_merge(double& n, double& mu, double& m2, do
   n = nt;
 }
 
-__global__ void __launch_bounds__(256) k_in_stats_final(const float* __restrict__ partial, int C, int chunks_per_scene, float eps,
-                                                        float* __restrict__ mean, float* __restrict__ rstd) {
+__global__ void __launch_bounds__(256) k_in_stats_final(const float* __restrict__ partial, int C, int chunks_per_scene_cap, float eps,
+                                                        float* __restrict__ mean, float* __restrict__ rstd,
+                                                        const int32_t* __restrict__ scene_offsets, int rows_per_chunk) {
   const int b = blockIdx.y;
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  // chunks are laid out for the largest possible scene (stride chunks_per_scene_cap); only the ones this scene fills are read
+  const int scene_rows = scene_offsets[b + 1] - scene_offsets[b];
+  if (scene_rows <= 0) {  // no chunk of an empty scene was written
+    if (c < C && lane == 0) {
+      mean[b * C + c] = 0.f;
+      rstd[b * C + c] = (float)(1.0 / sqrt((double)eps));
+    }
+    return;
+  }
+  const int chunks_per_scene = min(chunks_per_scene_cap, (scene_rows + rows_per_chunk - 1) / rows_per_chunk);
   if (c >= C) return;  // whole warp
   // Sums about ONE reference value (the first chunk's shift, a sample of the channel): per chunk
   //   sum(x - ref) = s1 + n d,  sum((x - ref)^2) = s2 + 2 d s1 + n d^2,  d = shift_chunk - ref
   // in fp64 with multiply-adds only (the pairwise Chan merge needed an fp64 division per chunk on the critical path of a
   // kernel that is pure latency: ~10 us per call, 62 calls per forward).  Fixed order: lane l folds chunks l, l+32, ...,
   // then a fixed shuffle tree => bit-reproducible run to run.
-  const float* p0 = partial + ((int64_t)(b * chunks_per_scene)) * 4 * C;
+  const float* p0 = partial + ((int64_t)(b * chunks_per_scene_cap)) * 4 * C;
   const double ref = p0[3 * C + c];
   double n = 0, S = 0, SS = 0;
   // four chunks per lane per round, all 16 loads issued before the first use (the kernel is a chain of L2 latencies)
@@ -83,7 +109,7 @@ __global__ void __launch_bounds__(256) k_in_stats_final(const float* __restrict_
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int ch = ch0 + 32 * u;
-      const float* p = partial + ((int64_t)(b * chunks_per_scene + (ch < chunks_per_scene ? ch : 0))) * 4 * C;
+      const float* p = partial + ((int64_t)(b * chunks_per_scene_cap + (ch < chunks_per_scene ? ch : 0))) * 4 * C;
       const bool ok = ch < chunks_per_scene;
       v[u][0] = ok ? p[c] : 0.f;
       v[u][1] = ok ? p[C + c] : 0.f;
@@ -120,13 +146,13 @@ __global__ void __launch_bounds__(256) k_in_stats_final(const float* __restrict_
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kNormThreads) k_in_stats(const T* __restrict__ x, int C, const int32_t* __restrict__ scene_offsets,
+__global__ void __launch_bounds__(kNormThreads) k_in_stats(const T* __restrict__ x, int C, const int32_t* __restrict__ scene_offsets, int B,
                                                            int rows_per_chunk, int chunks_per_scene, float eps,
                                                            float* __restrict__ partial, unsigned* __restrict__ counters,
                                                            float* __restrict__ mean, float* __restrict__ rstd) {
   constexpr int V = 16 / (int)sizeof(T);  // channels per 16-byte load
-  const int b = blockIdx.y;
-  const int chunk = blockIdx.x;
+  int b, chunk;
+  if (!resolve_chunk(scene_offsets, B, rows_per_chunk, (int)blockIdx.x, b, chunk)) return;
   const int64_t start = (int64_t)scene_offsets[b] + (int64_t)chunk * rows_per_chunk;
   const int64_t end = min((int64_t)scene_offsets[b + 1], start + rows_per_chunk);
   const int CV = C / V;
@@ -267,31 +293,49 @@ __device__ __forceinline__ void st_vec(T* p, const float (&v)[V]) {
   }
 }
 
-// bf16 -> bf16 apply, 8 channels (16 bytes) per thread and 32-bit index arithmetic: the generic kernel below moves 8 bytes per
-// thread and pays a 64-bit division per element group, which made this HBM-bound pass instruction-bound.
-__global__ void __launch_bounds__(256) k_norm_apply_bf16x8(const __nv_bfloat16* __restrict__ x, unsigned total, unsigned CV,
+// bf16 -> bf16 apply, 8 channels (16 bytes) per thread.  The grid-stride step is a multiple of the vectors per row (host: grid
+// rounded to a multiple of CV / gcd(CV, 256)), so a thread keeps ONE channel group for its whole life: mean / rstd / gamma / beta
+// of that group live in registers (reloaded when the thread's rows cross into the next scene) and an element costs one 16-byte
+// load, the arithmetic and one 16-byte store.  The first version re-derived (row, channel) with a division and re-read 128 bytes
+// of parameters per 16 bytes of data: ncu had it at 0.38 of the HBM rate (profiles/r02_families_infer_summary.txt).
+__global__ void __launch_bounds__(256) k_norm_apply_bf16x8(const __nv_bfloat16* __restrict__ x, unsigned n_rows, unsigned CV,
                                                           const int32_t* __restrict__ scene_offsets, int B,
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           const __nv_bfloat16* __restrict__ residual, int relu,
                                                           __nv_bfloat16* __restrict__ out) {
   const unsigned C = CV * 8u;
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const unsigned r = i / CV;
-    const unsigned c = (i - r * CV) * 8u;
-    float v[8];
-    ld_vec<__nv_bfloat16, 8>(x + (size_t)r * C + c, v);
-    const int b = scene_of_row(scene_offsets, B, (int64_t)r);
-    const float4 m0 = load4(mean + b * C + c), m1 = load4(mean + b * C + c + 4);
-    const float4 s0 = load4(rstd + b * C + c), s1 = load4(rstd + b * C + c + 4);
+  const unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned r = i0 / CV;
+  const unsigned c = (i0 - r * CV) * 8u;
+  const unsigned r_step = gridDim.x * blockDim.x / CV;  // exact by construction of the grid
+  float gg[8], ee[8], mm[8], ss[8];
+  {
     const float4 g0 = load4(gamma + c), g1 = load4(gamma + c + 4), e0 = load4(beta + c), e1 = load4(beta + c + 4);
-    const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w}, ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+    gg[0] = g0.x; gg[1] = g0.y; gg[2] = g0.z; gg[3] = g0.w; gg[4] = g1.x; gg[5] = g1.y; gg[6] = g1.z; gg[7] = g1.w;
+    ee[0] = e0.x; ee[1] = e0.y; ee[2] = e0.z; ee[3] = e0.w; ee[4] = e1.x; ee[5] = e1.y; ee[6] = e1.z; ee[7] = e1.w;
+  }
+  int b = -1;
+  unsigned next = 0;  // first row of scene b + 1
+  for (; r < n_rows; r += r_step) {
+    if (r >= next) {  // rows are grouped by scene: a thread crosses at most B - 1 boundaries
+      do {
+        ++b;
+        next = b + 1 < B ? (unsigned)scene_offsets[b + 1] : 0xFFFFFFFFu;
+      } while (r >= next);
+      const float4 m0 = load4(mean + b * C + c), m1 = load4(mean + b * C + c + 4);
+      const float4 s0 = load4(rstd + b * C + c), s1 = load4(rstd + b * C + c + 4);
+      mm[0] = m0.x; mm[1] = m0.y; mm[2] = m0.z; mm[3] = m0.w; mm[4] = m1.x; mm[5] = m1.y; mm[6] = m1.z; mm[7] = m1.w;
+      ss[0] = s0.x; ss[1] = s0.y; ss[2] = s0.z; ss[3] = s0.w; ss[4] = s1.x; ss[5] = s1.y; ss[6] = s1.z; ss[7] = s1.w;
+    }
+    const size_t off = (size_t)r * C + c;
+    float v[8];
+    ld_vec<__nv_bfloat16, 8>(x + off, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = fmaf((v[j] - mm[j]) * ss[j], gg[j], ee[j]);
     if (residual) {
       float q[8];
-      ld_vec<__nv_bfloat16, 8>(residual + (size_t)r * C + c, q);
+      ld_vec<__nv_bfloat16, 8>(residual + off, q);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] += q[j];
     }
@@ -299,7 +343,7 @@ __global__ void __launch_bounds__(256) k_norm_apply_bf16x8(const __nv_bfloat16* 
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
     }
-    st_vec<__nv_bfloat16, 8>(out + (size_t)r * C + c, v);
+    st_vec<__nv_bfloat16, 8>(out + off, v);
   }
 }
 
@@ -410,11 +454,12 @@ __global__ void __launch_bounds__(256) k_in_bwd_dx(const float* __restrict__ x, 
 template <typename T>
 __global__ void __launch_bounds__(kNormThreads) k_inr_bwd_partial(const T* __restrict__ dy, const T* __restrict__ out,
                                                                   const T* __restrict__ x, int C,
-                                                                  const int32_t* __restrict__ scene_offsets, int rows_per_chunk,
+                                                                  const int32_t* __restrict__ scene_offsets, int B, int rows_per_chunk,
                                                                   int chunks_per_scene, const float* __restrict__ mean,
                                                                   const float* __restrict__ rstd, float* __restrict__ partial) {
   constexpr int V = 16 / (int)sizeof(T);
-  const int b = blockIdx.y, chunk = blockIdx.x;
+  int b, chunk;
+  if (!resolve_chunk(scene_offsets, B, rows_per_chunk, (int)blockIdx.x, b, chunk)) return;
   const int64_t start = (int64_t)scene_offsets[b] + (int64_t)chunk * rows_per_chunk;
   const int64_t end = min((int64_t)scene_offsets[b + 1], start + rows_per_chunk);
   const int CV = C / V;
@@ -473,22 +518,24 @@ __global__ void __launch_bounds__(kNormThreads) k_inr_bwd_partial(const T* __res
 }
 
 // grid ceil(C / 8), block 256: one warp per channel, scenes in sequence (B is small), lanes over chunks, fixed merge order.
-__global__ void __launch_bounds__(256) k_inr_bwd_final(const float* __restrict__ partial, int C, int chunks_per_scene, int B,
+__global__ void __launch_bounds__(256) k_inr_bwd_final(const float* __restrict__ partial, int C, int chunks_per_scene_cap, int B,
                                                        float* __restrict__ sum_a, float* __restrict__ sum_q,
-                                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                       const int32_t* __restrict__ scene_offsets, int rows_per_chunk) {
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (c >= C) return;
   double ta = 0, tq = 0;
   for (int b = 0; b < B; ++b) {
     double sa = 0, sq = 0;
+    const int chunks_per_scene = min(chunks_per_scene_cap, (scene_offsets[b + 1] - scene_offsets[b] + rows_per_chunk - 1) / rows_per_chunk);
     for (int ch0 = lane; ch0 < chunks_per_scene; ch0 += 128) {
       float va[4], vq[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int ch = ch0 + 32 * u;
         const bool ok = ch < chunks_per_scene;
-        const float* p = partial + ((int64_t)(b * chunks_per_scene + (ok ? ch : 0))) * 2 * C;
+        const float* p = partial + ((int64_t)(b * chunks_per_scene_cap + (ok ? ch : 0))) * 2 * C;
         va[u] = ok ? p[c] : 0.f;
         vq[u] = ok ? p[C + c] : 0.f;
       }
@@ -522,43 +569,82 @@ __global__ void __launch_bounds__(256) k_inr_bwd_apply(const T* __restrict__ dy,
                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
                                                        const float* __restrict__ gamma, const float* __restrict__ sum_a,
                                                        const float* __restrict__ sum_q, TD* __restrict__ dx, T* __restrict__ dres) {
+  // same thread-keeps-its-channel-group structure as k_norm_apply_bf16x8 (grid from row_invariant_grid): per-scene constants
+  //   d = k1 * g - k0 - k2 * x   with  k1 = gamma rstd,  k2 = gamma rstd^2 sum_q / n,  k0 = gamma rstd sum_a / n - k2 mean
+  // would change the rounding of the first version, so the original expression is kept and only its operands are cached
   constexpr int V = 16 / (int)sizeof(T);
   const int CV = C / V;
-  const int64_t total = n * CV;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / CV;
-    const int c = (int)(i - r * CV) * V;
-    const int b = scene_of_row(scene_offsets, B, r);
-    const float inv_n = 1.f / (float)(scene_offsets[b + 1] - scene_offsets[b]);
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t r = i0 / CV;
+  const int c = (int)(i0 - r * CV) * V;
+  const int64_t r_step = (int64_t)gridDim.x * blockDim.x / CV;
+  float gm[V], rs[V], mu[V], sa[V], sq[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) gm[j] = gamma ? gamma[c + j] : 1.f;
+  int b = -1;
+  int64_t next = 0;
+  float inv_n = 0.f;
+  for (; r < n; r += r_step) {
+    if (r >= next) {
+      do {
+        ++b;
+        next = b + 1 < B ? (int64_t)scene_offsets[b + 1] : (int64_t)1 << 62;
+      } while (r >= next);
+      inv_n = 1.f / (float)(scene_offsets[b + 1] - scene_offsets[b]);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        rs[j] = rstd[b * C + c + j];
+        mu[j] = mean[b * C + c + j];
+        sa[j] = sum_a[b * C + c + j];
+        sq[j] = sum_q[b * C + c + j];
+      }
+    }
+    const int64_t off = r * C + c;
     float g[V], xv[V], d[V];
-    ld_vec<T, V>(dy + r * C + c, g);
-    ld_vec<T, V>(x + r * C + c, xv);
+    ld_vec<T, V>(dy + off, g);
+    ld_vec<T, V>(x + off, xv);
     if (out) {
       float o[V];
-      ld_vec<T, V>(out + r * C + c, o);
+      ld_vec<T, V>(out + off, o);
 #pragma unroll
       for (int j = 0; j < V; ++j) g[j] = o[j] > 0.f ? g[j] : 0.f;
     }
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      const float rs = rstd[b * C + c + j];
-      const float xh = (xv[j] - mean[b * C + c + j]) * rs;
-      const float gm = gamma ? gamma[c + j] : 1.f;
-      d[j] = gm * rs * (g[j] - sum_a[b * C + c + j] * inv_n - xh * sum_q[b * C + c + j] * inv_n);
+      const float xh = (xv[j] - mu[j]) * rs[j];
+      d[j] = gm[j] * rs[j] * (g[j] - sa[j] * inv_n - xh * sq[j] * inv_n);
     }
     if constexpr (sizeof(TD) == sizeof(T)) {
-      st_vec<TD, V>(dx + r * C + c, d);
+      st_vec<TD, V>(dx + off, d);
     } else {
 #pragma unroll
-      for (int j = 0; j < V; ++j) dx[r * C + c + j] = from_f32<TD>(d[j]);
+      for (int j = 0; j < V; ++j) dx[off + j] = from_f32<TD>(d[j]);
     }
-    if (dres) st_vec<T, V>(dres + r * C + c, g);
+    if (dres) st_vec<T, V>(dres + off, g);
   }
 }
 
+// grid of 256-thread blocks whose total thread count is a multiple of `cv` (vectors per row): a grid-stride thread then keeps its
+// channel group, see k_norm_apply_bf16x8
+inline int64_t row_invariant_grid(int64_t total_vecs, int cv) {
+  int g = cv, t = 256;
+  while (t) {  // gcd(cv, 256)
+    const int q = g % t;
+    g = t;
+    t = q;
+  }
+  const int64_t m = cv / g;
+  int64_t blocks = ceil_div(total_vecs, 256);
+  const int64_t cap = 16 * (int64_t)num_sms();
+  if (blocks > cap) blocks = cap;
+  return ceil_div(blocks, m) * m;
+}
+
 inline void norm_chunking(int64_t n, int B, int* rows_per_chunk, int* chunks_per_scene) {
-  // target ~4 chunks per SM over the whole batch; chunks are per scene, sized for the largest possible scene (n)
-  int64_t target = 2 * (int64_t)num_sms();
+  // Chunks are per scene, sized for the largest possible scene (all n rows): in a batch of B similar scenes only 1 / B of the
+  // (scene, chunk) blocks have rows, so the target is 8 per SM -- with 2 per SM the statistics passes ran 2 blocks of 256
+  // threads per SM, 0.39 of the HBM rate (profiles/r02_families_infer_summary.txt)
+  int64_t target = 8 * (int64_t)num_sms();
   int64_t rpc = ceil_div(n > 0 ? n : 1, target);
   if (rpc < 64) rpc = 64;
   *rows_per_chunk = (int)rpc;
@@ -591,16 +677,17 @@ int mk_instnorm_stats(const void* x, int x_dtype, int64_t n, int C, const int32_
   // on ONE SM (measured 0.115 ms per call on B200 vs ~0.01 ms for the 12-block k_in_stats_final), so it is off.
   unsigned* counters = nullptr;
   dim3 grid((unsigned)cps, (unsigned)B);
+  const unsigned grid1 = (unsigned)(ceil_div(n > 0 ? n : 1, rpc) + B);  // >= the non-empty (scene, chunk) pairs, see resolve_chunk
   const int V = x_dtype == MK_F32 ? 4 : 8;
   if (C % V == 0 && C / V <= kNormThreads && ((uintptr_t)x & 15) == 0) {
     const int RL = kNormThreads / (C / V);
     const size_t smem = (size_t)RL * 2 * C * sizeof(float);
     if (x_dtype == MK_F32)
-      k_in_stats<float><<<grid, kNormThreads, smem, st>>>((const float*)x, C, scene_offsets, rpc, cps, eps, partial, counters, mean, rstd);
+      k_in_stats<float><<<grid1, kNormThreads, smem, st>>>((const float*)x, C, scene_offsets, B, rpc, cps, eps, partial, counters, mean, rstd);
     else
-      k_in_stats<__nv_bfloat16><<<grid, kNormThreads, smem, st>>>((const __nv_bfloat16*)x, C, scene_offsets, rpc, cps, eps, partial,
-                                                                  counters, mean, rstd);
-    k_in_stats_final<<<dim3((unsigned)ceil_div(C, 8), (unsigned)B), 256, 0, st>>>(partial, C, cps, eps, mean, rstd);
+      k_in_stats<__nv_bfloat16><<<grid1, kNormThreads, smem, st>>>((const __nv_bfloat16*)x, C, scene_offsets, B, rpc, cps, eps, partial,
+                                                                   counters, mean, rstd);
+    k_in_stats_final<<<dim3((unsigned)ceil_div(C, 8), (unsigned)B), 256, 0, st>>>(partial, C, cps, eps, mean, rstd, scene_offsets, rpc);
     return check_launch(__func__);
   }
   const int CV = C / 4, RL = kNormThreads / CV;
@@ -609,7 +696,7 @@ int mk_instnorm_stats(const void* x, int x_dtype, int64_t n, int C, const int32_
     k_in_stats_partial<float><<<grid, kNormThreads, smem, st>>>((const float*)x, C, scene_offsets, rpc, cps, partial);
   else
     k_in_stats_partial<__nv_bfloat16><<<grid, kNormThreads, smem, st>>>((const __nv_bfloat16*)x, C, scene_offsets, rpc, cps, partial);
-  k_in_stats_final<<<dim3((unsigned)ceil_div(C, 8), (unsigned)B), 256, 0, st>>>(partial, C, cps, eps, mean, rstd);
+  k_in_stats_final<<<dim3((unsigned)ceil_div(C, 8), (unsigned)B), 256, 0, st>>>(partial, C, cps, eps, mean, rstd, scene_offsets, rpc);
   return check_launch(__func__);
 }
 
@@ -626,9 +713,8 @@ int mk_norm_apply(const void* x, int x_dtype, int64_t n, int C, const int32_t* s
   if (x_dtype == MK_BF16 && out_dtype == MK_BF16 && C % 8 == 0 && mean && gamma && n * (int64_t)(C / 8) < ((int64_t)1 << 31) &&
       (((uintptr_t)x | (uintptr_t)out | (uintptr_t)residual) & 15) == 0) {
     const int64_t tot8 = n * (C / 8);
-    int64_t b8 = ceil_div(tot8, 256);
-    if (b8 > 16 * (int64_t)num_sms()) b8 = 16 * (int64_t)num_sms();
-    k_norm_apply_bf16x8<<<(unsigned)b8, 256, 0, st>>>((const __nv_bfloat16*)x, (unsigned)tot8, (unsigned)(C / 8), scene_offsets, B, mean, rstd,
+    const int64_t b8 = row_invariant_grid(tot8, C / 8);
+    k_norm_apply_bf16x8<<<(unsigned)b8, 256, 0, st>>>((const __nv_bfloat16*)x, (unsigned)n, (unsigned)(C / 8), scene_offsets, B, mean, rstd,
                                                       gamma, beta, (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)out);
     return check_launch(__func__);
   }
@@ -657,21 +743,19 @@ int mk_instnorm_relu_bwd(const void* dy, const void* out, const void* x, int dty
   float* partial = (float*)workspace;
   float* sum_a = partial + (int64_t)B * cps * 4 * C;
   float* sum_q = sum_a + (int64_t)B * C;
-  dim3 grid((unsigned)cps, (unsigned)B);
+  const unsigned grid1 = (unsigned)(ceil_div(n > 0 ? n : 1, rpc) + B);
   const int RL = kNormThreads / (C / V);
   const size_t smem = (size_t)RL * 2 * C * sizeof(float);
   if (dtype == MK_F32)
-    k_inr_bwd_partial<float><<<grid, kNormThreads, smem, st>>>((const float*)dy, (const float*)out, (const float*)x, C, scene_offsets, rpc,
-                                                              cps, mean, rstd, partial);
+    k_inr_bwd_partial<float><<<grid1, kNormThreads, smem, st>>>((const float*)dy, (const float*)out, (const float*)x, C, scene_offsets, B, rpc,
+                                                               cps, mean, rstd, partial);
   else
-    k_inr_bwd_partial<__nv_bfloat16><<<grid, kNormThreads, smem, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)out,
-                                                                      (const __nv_bfloat16*)x, C, scene_offsets, rpc, cps, mean, rstd,
-                                                                      partial);
-  k_inr_bwd_final<<<(unsigned)ceil_div(C, 8), 256, 0, st>>>(partial, C, cps, B, sum_a, sum_q, dgamma, dbeta);
+    k_inr_bwd_partial<__nv_bfloat16><<<grid1, kNormThreads, smem, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)out,
+                                                                       (const __nv_bfloat16*)x, C, scene_offsets, B, rpc, cps, mean, rstd,
+                                                                       partial);
+  k_inr_bwd_final<<<(unsigned)ceil_div(C, 8), 256, 0, st>>>(partial, C, cps, B, sum_a, sum_q, dgamma, dbeta, scene_offsets, rpc);
   if (n > 0) {
-    int64_t blocks = ceil_div(n * (C / V), 256);
-    const int64_t cap = 8 * (int64_t)num_sms();
-    if (blocks > cap) blocks = cap;
+    const int64_t blocks = row_invariant_grid(n * (C / V), C / V);
     if (dtype == MK_F32)
       k_inr_bwd_apply<float, float><<<(unsigned)blocks, 256, 0, st>>>((const float*)dy, (const float*)out, (const float*)x, n, C,
                                                                       scene_offsets, B, mean, rstd, gamma, sum_a, sum_q, (float*)dx,

@@ -12,8 +12,9 @@ from room_instance_segmentation_mask3d_b200 import lib, mask3d_model, me_api, op
 
 voxel = float(sys.argv[1]) if len(sys.argv) > 1 else 0.02
 mode = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+nb = int(sys.argv[3]) if len(sys.argv) > 3 else 1  # scenes per step (one batch)
 ops.set_compute_mode(mode)
-c, f = scenes.collate([scenes.floor_plan(1000, voxel_m=voxel)])
+c, f = scenes.collate([scenes.floor_plan(1000 + i, voxel_m=voxel) for i in range(nb)])
 c, f = torch.from_numpy(c).cuda(), torch.from_numpy(f).cuda()
 model = mask3d_model.Mask3D().eval()
 weights.load_synth(model)
