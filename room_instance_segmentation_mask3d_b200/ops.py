@@ -352,8 +352,12 @@ def pool_backward(dout: torch.Tensor, km: KernelMap, n_in: int, average: bool = 
     return din
 
 
-def mask_logits(feat: torch.Tensor, scene_offsets: torch.Tensor, B: int, embed: torch.Tensor, select: Optional[KernelMap] = None) -> torch.Tensor:
+def mask_logits(feat: torch.Tensor, scene_offsets: torch.Tensor, B: int, embed: torch.Tensor, select: Optional[KernelMap] = None,
+                padded: bool = False) -> torch.Tensor:
     """logits[n, q] = feat[n] . embed[b(n), q]   (mask3d.py:534-537).
+
+    `padded` (tensor-core path only): return [n, Qp] with Qp = Q rounded up to 16 (zero columns at the end) -- a row pitch the
+    epilogue can store with 16-byte vectors; used for the stacked products of several decoder outputs (`mask_logits_stacked`).
 
     bf16 features + a scene-select table (engine.CoordinateManager.scene_select_table): the product runs on the tcgen05
     kernel as a conv with one "offset" per scene, W[b] = embed[b]^T zero-padded to 32 accumulator columns per 32 queries,
@@ -365,11 +369,27 @@ def mask_logits(feat: torch.Tensor, scene_offsets: torch.Tensor, B: int, embed: 
         Qp = ((Q + 15) // 16) * 16
         W = torch.zeros((embed.shape[0], C, Qp), dtype=torch.float32, device=feat.device)
         W[:, :, :Q] = embed.detach().float().transpose(1, 2)
-        return conv_forward(feat, W, select, mode=tc_mode, out_dtype=torch.float32, out_cols=Q)
+        return conv_forward(feat, W, select, mode=tc_mode, out_dtype=torch.float32, out_cols=Qp if padded else Q)
+    assert not padded, "padded mask logits are a tensor-core path feature"
     out = torch.empty((n, Q), dtype=torch.float32, device=feat.device)
     lib.call("mk_mask_logits", lib.p(feat.contiguous()), lib.dt(feat), n, C, lib.p(scene_offsets), B, lib.p(embed.detach().float().contiguous()),
              Q, lib.p(out), lib.stream())
     return out
+
+
+def mask_logits_stacked(feat: torch.Tensor, scene_offsets: torch.Tensor, B: int, embeds, select: KernelMap, group: int = 6):
+    """Mask logits of SEVERAL decoder outputs in one pass over the features per `group` outputs: the embeddings [B, Q, C] of a
+    group are stacked to [B, group * Q, C], one product writes [n, pad16(group * Q)] and output l is the column slice
+    [:, l * Q:(l + 1) * Q] (a strided view).  Every logit is the same K = C dot product on the same tensor-core path as in
+    `mask_logits`, so the values are bit-identical; the features (the largest tensor of the model: [N0, 128]) are read once per
+    group instead of once per output."""
+    Q = embeds[0].shape[1]
+    outs = []
+    for g0 in range(0, len(embeds), group):
+        part = embeds[g0:g0 + group]
+        big = mask_logits(feat, scene_offsets, B, torch.cat(part, dim=1), select=select, padded=True)
+        outs += [big[:, i * Q:(i + 1) * Q] for i in range(len(part))]
+    return outs
 
 
 class _MaskLogitsFn(torch.autograd.Function):

@@ -414,6 +414,32 @@ def test_mask_logits_tensor_core_path(R):
         assert rel_err(out, ref) < 2e-3
 
 
+def test_stacked_mask_logits_are_bit_identical_to_separate_products(R):
+    """mask_logits_stacked: several decoder outputs per pass over the features, every output bit-identical to its own product
+    (bf16 features on the tcgen05 kernel; 13 outputs in groups of 6 as the inference forward uses them, and a tf32 group)."""
+    coords = make_batch(37)
+    mgr = R.engine.CoordinateManager(D=3)
+    key, _ = mgr.insert_and_map(torch.from_numpy(coords).cuda())
+    off, B = mgr.scene_offsets(key), mgr.number_of_unique_batch_indices()
+    sel = mgr.scene_select_table(key)
+    g = torch.Generator().manual_seed(8)
+    feat = torch.randn(len(coords), 128, generator=g).cuda()
+    embs = [torch.randn(B, 25, 128, generator=g).cuda() for _ in range(13)]
+    fb = feat.bfloat16()
+    stacked = R.ops.mask_logits_stacked(fb, off, B, embs, sel)
+    assert len(stacked) == 13
+    for e, o in zip(embs, stacked):
+        assert o.shape == (len(coords), 25)
+        assert torch.equal(o, R.ops.mask_logits(fb, off, B, e, select=sel))
+    R.ops.set_compute_mode("tf32")
+    try:
+        st32 = R.ops.mask_logits_stacked(feat, off, B, embs[:6], sel)
+        for e, o in zip(embs[:6], st32):
+            assert torch.equal(o, R.ops.mask_logits(feat, off, B, e, select=sel))
+    finally:
+        R.ops.set_compute_mode("fp32")
+
+
 def test_sorted_tile_plan_is_a_permutation(R):
     coords = make_batch(31)
     mgr = R.engine.CoordinateManager(D=3)
