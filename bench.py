@@ -286,6 +286,8 @@ def main_ours(args):
 
     def step_resident(_i=None):
         g = state["g_res"]
+        if os.environ.get("MK3D_BENCH_STEP_DEBUG"):
+            state.setdefault("t_calls", []).append(time.perf_counter())
         x = state["res"] if state["res"] is not None else model.prepare(*resident[g % n_scenes])
         with torch.cuda.stream(lanes[0 if state.get("one_lane") else g % n_lanes]):
             o = model(x, prefetch=resident[(g + 1) % n_scenes], aux_outputs=state.get("aux", True))
@@ -352,7 +354,26 @@ def main_ours(args):
     sampler.mark()
     launches0 = lib.kernel_launches
     state["vox"] = 0
+    mallocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
+    if os.environ.get("MK3D_BENCH_ALLOC_DEBUG"):
+        torch.cuda.memory._record_memory_history(max_entries=200000)
     ms = timed(step_resident, args.steps)
+    if os.environ.get("MK3D_BENCH_STEP_DEBUG"):
+        tc = state["t_calls"][-args.steps:]
+        print("[step debug] host ms between step calls in the timed region: " + " ".join(f"{(b - a) * 1e3:.1f}" for a, b in zip(tc, tc[1:])), file=sys.stderr)
+    if os.environ.get("MK3D_BENCH_ALLOC_DEBUG"):
+        snap = torch.cuda.memory._snapshot()
+        for tr in snap.get("device_traces", []):
+            for ev in tr:
+                if ev.get("action") in ("segment_alloc", "segment_free", "oom", "snapshot"):
+                    print(f"[alloc debug] {ev.get('action')} size {ev.get('size', 0) / 2**20:.1f} MiB stream {ev.get('stream')}", file=sys.stderr)
+        torch.cuda.memory._record_memory_history(enabled=None)
+        st_ = torch.cuda.memory_stats(dev)
+        print(f"[alloc debug] reserved {st_['reserved_bytes.all.current'] / 2**30:.1f} GiB, allocated peak {st_['allocated_bytes.all.peak'] / 2**30:.1f} GiB, "
+              f"inactive split {st_['inactive_split_bytes.all.current'] / 2**30:.1f} GiB", file=sys.stderr)
+    # cudaMalloc calls inside the timed region (0 when the caching allocator's pools were large enough: a cudaMalloc of a multi-GB
+    # block stalls the enqueueing thread for milliseconds)
+    mallocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs0
     launches = lib.kernel_launches - launches0
     clocks = sampler.stop() if rank == 0 else None
     vox_per_step = state["vox"] / args.steps  # the voxels actually processed inside the timed region
@@ -609,7 +630,7 @@ def main_ours(args):
                                     "voxel + per-query mask scores (what trainer/trainer.py:373-402 derives from the logits), built on the "
                                     "device") if compact else "class logits of all 13 decoder outputs + final fp32 mask logits [N, 25]",
                         "other_result_form": e2e_other},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "train_fwd_bwd": train,
+                "gpu_launches": launches, "cuda_mallocs_in_timed_region": mallocs, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "train_fwd_bwd": train,
                 "loss_side": loss_side, "train_step": train_step, "final_prediction_only": final_only}
         print(json.dumps(line))
     if world > 1:

@@ -75,6 +75,11 @@ int mk_kernel_map(const uint64_t* in_keys, const int32_t* in_vals, int64_t cap, 
  * both entries.  Bit-identical to mk_kernel_map. */
 int mk_kernel_map_same(const uint64_t* keys, const int32_t* vals, int64_t cap, const int32_t* coords, int64_t n, const int32_t* offsets,
                        int K, int32_t* nbr, void* stream);
+/* The 5x5x5 table of a map onto itself composed from its 3x3x3 table `nbr3` [27, n] (same offset step: `step3` = the three
+ * host ints dilation * tensor stride): two table reads per entry wherever an intermediate voxel exists, a hash probe otherwise.
+ * Bit-identical to mk_kernel_map_same with the 125 x-fastest offsets. */
+int mk_kernel_map_compose5(const uint64_t* keys, const int32_t* vals, int64_t cap, const int32_t* coords, int64_t n, const int32_t* step3,
+                           const int32_t* nbr3, int32_t* nbr5, void* stream);
 /* Per 128-slot tile, bit k set iff some slot of the tile has a neighbour for offset k (K <= 32); also the
  * total pair count (device int64).  `n_slots` is the slot count of nbr (row stride of the table). */
 int mk_tile_kmask(const int32_t* nbr, int K, int64_t n_slots, uint32_t* tile_kmask, int64_t* pair_count, void* stream);

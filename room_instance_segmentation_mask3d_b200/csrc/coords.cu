@@ -246,6 +246,56 @@ __global__ void __launch_bounds__(256) k_kernel_map_sym(const unsigned long long
   }
 }
 
+// 5^3 same-map kernel map COMPOSED from the 3^3 table of the same map: a target d with |d|_inf = 2 is reached through an
+// intermediate voxel o + s (|s|_inf = 1, s takes the sign of every axis with |d_a| = 2) and the remainder r = d - s (|r|_inf <= 1):
+// if the intermediate exists, nbr5[d][o] = nbr3[r][nbr3[s][o]] EXACTLY (also when that is -1), two array reads instead of a hash
+// probe.  The axes with |d_a| = 1 may go into s or into r, which gives up to four intermediates to try; only when none of them
+// exists is the hash table probed.  Same symmetric half / reverse write scheme as k_kernel_map_sym, bit-identical result.  On
+// surface scenes > 90 % of the 62 probes per voxel of the stem's 5^3 map become table reads (the probes are random DRAM sector
+// reads once the table of a batch no longer fits in L2: 5.4 of the 7.2 ms of kernel-map time in a batch-of-8 step).
+__global__ void __launch_bounds__(256) k_kernel_map_compose5(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ vals,
+                                                             uint64_t mask, const int4* __restrict__ coords, int64_t n, int sx, int sy, int sz,
+                                                             const int32_t* __restrict__ nbr3, int32_t* __restrict__ nbr5) {
+  const int k = blockIdx.y;  // 0 .. 62: lower half of the 125 offsets + the centre
+  const int ix = k % 5 - 2, iy = (k / 5) % 5 - 2, iz = k / 25 - 2;
+  const int ax = ix < 0 ? -ix : ix, ay = iy < 0 ? -iy : iy, az = iz < 0 ? -iz : iz;
+  auto k3 = [](int x, int y, int z) { return (x + 1) + 3 * (y + 1) + 9 * (z + 1); };
+  // forced part of the intermediate step (axes at distance 2) and the optional axes (distance 1)
+  const int fx = ax == 2 ? (ix > 0 ? 1 : -1) : 0, fy = ay == 2 ? (iy > 0 ? 1 : -1) : 0, fz = az == 2 ? (iz > 0 ? 1 : -1) : 0;
+  const int ox = ax == 1 ? ix : 0, oy = ay == 1 ? iy : 0, oz = az == 1 ? iz : 0;
+  const bool direct = ax <= 1 && ay <= 1 && az <= 1;
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
+    if (k == 62) {
+      nbr5[(int64_t)k * n + o] = (int)o;
+      continue;
+    }
+    int row = -1;
+    if (direct) {
+      row = nbr3[(int64_t)k3(ix, iy, iz) * n + o];
+    } else {
+      bool resolved = false;
+#pragma unroll
+      for (int c = 0; c < 8 && !resolved; ++c) {  // subsets of the optional axes that go into the intermediate step
+        const int tx = (c & 1) ? ox : 0, ty = (c & 2) ? oy : 0, tz = (c & 4) ? oz : 0;
+        if (((c & 1) && !ox) || ((c & 2) && !oy) || ((c & 4) && !oz)) continue;  // not a distinct subset
+        const int s0 = fx + tx, s1 = fy + ty, s2 = fz + tz;
+        const int m = nbr3[(int64_t)k3(s0, s1, s2) * n + o];
+        if (m >= 0) {
+          row = nbr3[(int64_t)k3(ix - s0, iy - s1, iz - s2) * n + m];
+          resolved = true;
+        }
+      }
+      if (!resolved) {
+        const int4 cc = coords[o];
+        const int x = cc.y + ix * sx, y = cc.z + iy * sy, z = cc.w + iz * sz;
+        if (coord_in_range(cc.x, x, y, z)) row = hash_lookup(keys, vals, mask, pack_key(cc.x, x, y, z));
+      }
+    }
+    nbr5[(int64_t)k * n + o] = row;
+    if (row >= 0) nbr5[(int64_t)(124 - k) * n + row] = (int)o;
+  }
+}
+
 __global__ void __launch_bounds__(MK_TILE_ROWS) k_tile_kmask(const int32_t* __restrict__ nbr, int K, int64_t n_slots,
                                                              uint32_t* __restrict__ tile_kmask,
                                                              unsigned long long* __restrict__ pair_count) {
@@ -438,6 +488,19 @@ int mk_kernel_map_same(const uint64_t* keys, const int32_t* vals, int64_t cap, c
   if (bx > 8 * num_sms()) bx = 8 * num_sms();
   dim3 grid((unsigned)bx, (unsigned)ceil_div(half + 1, kSymK));
   k_kernel_map_sym<<<grid, 256, 0, st>>>((const unsigned long long*)keys, vals, (uint64_t)(cap - 1), (const int4*)coords, n, offsets, K, nbr);
+  return check_launch(__func__);
+}
+
+int mk_kernel_map_compose5(const uint64_t* keys, const int32_t* vals, int64_t cap, const int32_t* coords, int64_t n, const int32_t* step3_host,
+                           const int32_t* nbr3, int32_t* nbr5, void* stream_) {
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream_;
+  cudaMemsetAsync(nbr5 + (int64_t)63 * n, 0xFF, (size_t)62 * n * sizeof(int32_t), st);
+  int64_t bx = ceil_div(n, 256);
+  if (bx > 8 * num_sms()) bx = 8 * num_sms();
+  dim3 grid((unsigned)bx, 63u);
+  k_kernel_map_compose5<<<grid, 256, 0, st>>>((const unsigned long long*)keys, vals, (uint64_t)(cap - 1), (const int4*)coords, n, step3_host[0],
+                                              step3_host[1], step3_host[2], nbr3, nbr5);
   return check_launch(__func__);
 }
 

@@ -305,8 +305,16 @@ class CoordinateManager:
             nbr = torch.empty((K, om.n), dtype=I32, device=self.device)
             offs = self._offsets_dev(ks, dl, in_key.tensor_stride)
             same = in_key == out_key and all(k % 2 == 1 for k in ks) and os.environ.get("MK3D_KMAP_SYM", "1") != "0"
-            lib.call("mk_kernel_map_same" if same else "mk_kernel_map", lib.p(im.keys), lib.p(im.vals), im.cap, lib.p(om.coords), om.n,
-                     lib.p(offs), K, lib.p(nbr), lib.stream())
+            if same and ks == (5, 5, 5) and len(set(dl)) == 1 and os.environ.get("MK3D_KMAP_COMPOSE", "1") != "0":
+                # the stem's 5^3 table composed from the 3^3 table of the same map (which the last decoder stage needs anyway):
+                # table reads instead of 62 hash probes per voxel, bit-identical (csrc/coords.cu k_kernel_map_compose5)
+                km3 = self.neighbor_table(in_key, out_key, 3, dl)
+                step = (ctypes.c_int32 * 3)(*[d * t for d, t in zip(dl, in_key.tensor_stride)])
+                lib.call("mk_kernel_map_compose5", lib.p(im.keys), lib.p(im.vals), im.cap, lib.p(om.coords), om.n,
+                         ctypes.cast(step, ctypes.c_void_p), lib.p(km3.nbr), lib.p(nbr), lib.stream())
+            else:
+                lib.call("mk_kernel_map_same" if same else "mk_kernel_map", lib.p(im.keys), lib.p(im.vals), im.cap, lib.p(om.coords), om.n,
+                         lib.p(offs), K, lib.p(nbr), lib.stream())
             km = KernelMap(nbr, K, om.n, out_coords=om.coords, out_stride=out_key.tensor_stride)
             self._kmaps[ck] = km
         return km

@@ -414,6 +414,34 @@ def test_mask_logits_tensor_core_path(R):
         assert rel_err(out, ref) < 2e-3
 
 
+@pytest.mark.parametrize("kind", ["scene", "sparse_random", "strided"])
+def test_composed_5x5x5_kernel_map_is_bit_identical_to_probing(R, kind, monkeypatch):
+    """mk_kernel_map_compose5 (5^3 table from the 3^3 table of the same map, hash probes only where no intermediate voxel exists)
+    == mk_kernel_map_same == the oracle; on surface scenes, on sparse random voxels (most intermediates missing: the fallback
+    probes carry the result) and on a stride-2 map (offset step 2)."""
+    if kind == "sparse_random":
+        rng = np.random.default_rng(5)
+        xyz = np.unique(rng.integers(0, 14, size=(900, 3)), axis=0)
+        coords = np.concatenate([np.concatenate([np.full((len(xyz), 1), b), xyz + 3 * b], 1) for b in range(2)]).astype(np.int32)
+    else:
+        coords = make_batch(41)
+    outs = []
+    for compose in ("1", "0"):
+        monkeypatch.setenv("MK3D_KMAP_COMPOSE", compose)
+        mgr = R.engine.CoordinateManager(D=3)
+        key, _ = mgr.insert_and_map(torch.from_numpy(coords).cuda())
+        if kind == "strided":
+            key = mgr.stride(key, 2)
+        km = mgr.neighbor_table(key, key, 5, 1)
+        outs.append((km.nbr.cpu().numpy(), mgr.get_coordinates(key).cpu().numpy()))
+    assert np.array_equal(outs[0][0], outs[1][0])
+    c = outs[0][1]
+    ts = 2 if kind == "strided" else 1
+    ref = O.neighbor_table(c, c, O.kernel_offsets((5, 5, 5), (1, 1, 1), (ts, ts, ts)))
+    assert np.array_equal(outs[0][0], ref)
+    assert (outs[0][0] >= 0).sum() > len(c)  # not a trivial map
+
+
 def test_stacked_mask_logits_are_bit_identical_to_separate_products(R):
     """mask_logits_stacked: several decoder outputs per pass over the features, every output bit-identical to its own product
     (bf16 features on the tcgen05 kernel; 13 outputs in groups of 6 as the inference forward uses them, and a tf32 group)."""
