@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_conv_umma launch from an `ncu --set full` capture (profiles/), next to the
 # algorithmic bytes of that launch; filled in from the capture named in `note` (None until a capture of the current kernel exists)
-NCU_TRAFFIC = {"bytes_per_launch": 227360512 + 133211392,
+NCU_TRAFFIC = {"bytes_per_launch": 227673856 + 133283072,
                "note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE k_conv_umma launch of the dominant shape (3^3 96->96 on the "
                        "889057-voxel level-0 map: 155.2 GFLOP, algorithmic minimum 437.9 MB incl. the 96 MB neighbour table, part of which "
                        "is L2-resident), ncu --set full, profiles/r02_ncu_conv96_summary.txt"}
