@@ -34,15 +34,16 @@
 
 namespace mk {
 
-// ---- thread layout of k_conv_umma (448 threads = 14 warps) ----
+// ---- thread layout of k_conv_umma (576 threads = 18 warps) ----
 // A wider layout (768 threads: 16 gather warps, registers rebalanced with setmaxnreg) was measured and dropped: the same
 // times within 3 % on every shape (profiles/r02_conv_sweep.txt) -- the gather is bound by the LSU's LDGSTS rate and the
 // depth of the 4-slot ring, not by the number of warps issuing.
 constexpr int kCvProducerWarps = 8;   // warps 0-7: gather producers (stage ownership in groups of `split` warps)
 constexpr int kCvMmaWarp = 8;         // MMA issuer
 constexpr int kCvAllocWarp = 9;       // TMEM allocation; second MMA issuer when G == 2
-constexpr int kCvEpiWarp0 = 10;       // warps 10-13: epilogue (TMEM lane quarter = warp & 3)
-constexpr int kCvThreads = 448;
+constexpr int kCvEpiWarp0 = 10;       // warps 10-17: epilogue (TMEM lane quarter = warp & 3), two warps per quarter
+constexpr int kCvEpiWarps = 8;        // set 0 = warps 10-13, set 1 = warps 14-17: member tile 1 of a super-tile, or the upper columns when G == 1
+constexpr int kCvThreads = 576;
 constexpr int kMaxUW = 4;             // most 32-row units a producer warp gathers per stage
 
 // keep the set bits of m whose ordinal is congruent to `part` modulo `ksplit` (offset split of small problems)
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const __grid_consta
   uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;  // [2]  128 epilogue threads
   uint32_t* tmem_base_slot = (uint32_t*)(bars + 2 * kMaxStages + 4);
   int32_t* idx_stage = (int32_t*)(bars + 2 * kMaxStages + 6);  // [producer warps][2][4 units][32] neighbour-table entries (1 KB per warp)
-  float* out_stage = (float*)(idx_stage + kCvProducerWarps * 2 * 4 * 32);  // [4 epilogue warps][32 rows x out_cols] when p.stage_out
+  float* out_stage = (float*)(idx_stage + kCvProducerWarps * 2 * 4 * 32);  // [8 epilogue warps][32 rows x out_cols] when p.stage_out
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dbg = kDbg ? p.debug : 0;
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const __grid_consta
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&tmem_full[b]), G);
-      mbar_init(smem_u32(&tmem_empty[b]), 4 * 32);
+      mbar_init(smem_u32(&tmem_empty[b]), kCvEpiWarps * 32);
     }
     fence_barrier_init();
   }
@@ -625,7 +626,15 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const __grid_consta
     }  // MMA issuer warps
   } else {
     // ===================== epilogue (4 warps) =====================
+    // MK3D_DEBUG=8 (no stores) showed the dense launches (1x1 convs, mask logits) bound by the epilogue: one warp per TMEM lane
+    // quarter walked both member tiles and all columns as ONE serial chain of TMEM load -> convert -> store (96->128: 0.130 ms
+    // with stores, 0.072 without; the MMA issuers waited 64 % of their time for a free accumulator).  Two warps per quarter halve
+    // the chain: set 1 takes member tile 1 of a super-tile, or the upper half of the columns when there is one tile per stage.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int eset = (warp - kCvEpiWarp0) >> 2;
+    const int col_half = ((p.out_cols + 31) >> 5) << 4;  // G == 1: columns [0, col_half) to set 0, the rest to set 1
+    const int c_lo = (G == 1 && eset == 1) ? col_half : 0;
+    const int c_hi = (G == 1 && eset == 0) ? min(col_half, p.out_cols) : p.out_cols;
     int acc_buf = 0;
     uint32_t acc_phase = 0;
     const int num_st = (p.num_tiles + G - 1) / G;
@@ -675,13 +684,15 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const __grid_consta
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
         if (g >= G || st * G + g >= p.num_tiles) continue;
+        if (G == 2 && g != eset) continue;
         TOut* optr = orow[g] >= 0 ? (TOut*)p.out + orow[g] * p.out_stride : nullptr;
         const uint32_t tcol = (uint32_t)((acc_buf * G + g) * acc_cols);
         if (p.stage_out) {
           // Row pitch of e.g. 25 fp32 (mask logits): per-thread row stores would touch 32 sectors per instruction.  The
           // warp's 32 rows are one contiguous run of 32 * out_cols elements in global memory, so transpose through shared
           // memory (odd pitch => conflict free) and store the run with fully coalesced 128-byte instructions.
-          const uint32_t stg = smem_u32(out_stage) + (uint32_t)(q * 32 * p.out_cols) * 4u;  // this warp's staging block
+          if (G == 1 && eset == 1) continue;  // whole rows are staged by one warp
+          const uint32_t stg = smem_u32(out_stage) + (uint32_t)(((eset << 2) + q) * 32 * p.out_cols) * 4u;  // this warp's staging block
           const uint32_t my_row = stg + (uint32_t)(lane * p.out_cols) * 4u;
           for (int c0 = 0; c0 < p.out_cols; c0 += 16) {
             uint32_t r[16];
@@ -721,14 +732,85 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const __grid_consta
           __syncwarp();
           continue;
         }
-        for (int c0 = 0; c0 < p.out_cols; c0 += 16) {
+        if (p.epi_stage) {
+          // Rows in slot order (dense launches: 1x1 convs, mask logits): per-thread row stores put 16 bytes per lane into 32
+          // different rows, i.e. 32 half-filled sectors per instruction, and the MK3D_TRACE / MK3D_DEBUG=8 runs showed these
+          // launches bound by exactly that (96->128: 0.130 ms with stores, 0.072 without; with 8 epilogue warps the gather
+          // producers then stalled behind the store traffic in the LSU).  Blocks of 32 rows x 64 bytes go through shared memory
+          // (row pitch 80 B) and are stored 8 rows x 64 contiguous bytes per instruction: whole sectors, half the L2 write
+          // transactions.
+          const int EB = p.epi_stage;                 // bytes of a row per block: 64 or 128 (what the shared-memory budget allows)
+          const int CB = EB / (int)sizeof(TOut);      // columns per block
+          const int pitch_s = EB + 16;                // staging row pitch: conflict-free 16-byte accesses both ways
+          const uint32_t stg = smem_u32(out_stage) + (uint32_t)(((eset << 2) + q) * 32 * pitch_s);
+          const uint32_t my_row = stg + (uint32_t)(lane * pitch_s);
+          const int64_t row0 = ((int64_t)(st * G + g)) * kTileM + q * 32;
+          const int lpr = EB >> 4;                    // lanes per row of a store instruction (4 or 8)
+          const int rsub = lane / lpr, piece = lane - rsub * lpr, rpi = 32 / lpr;  // rows per instruction (8 or 4)
+          const int64_t pitch = (int64_t)p.out_stride * (int)sizeof(TOut);
+          for (int c0 = c_lo; c0 < c_hi; c0 += CB) {
+            const int width = min(CB, c_hi - c0);  // a multiple of 16 columns (host)
+            for (int h = 0; h < width; h += 32) {  // two TMEM loads in flight per wait
+              uint32_t r[2][16];
+              const bool second = h + 16 < width;
+              if (km[g] != 0u) {
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + tcol + (uint32_t)(c0 + h), r[0]);
+                if (second) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + tcol + (uint32_t)(c0 + h + 16), r[1]);
+                tmem_ld_wait();
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) r[0][j] = r[1][j] = 0u;
+              }
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                if (u == 0 || second) {
+                  const int cb = h + 16 * u;
+                  float v[16];
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[u][j]) + (p.bias ? s_bias[c0 + cb + j] : 0.f);
+                  if constexpr (sizeof(TOut) == 4) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) sts_v4(my_row + (uint32_t)((cb + j) * 4), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 8) {
+                      uint32_t w[4];
+#pragma unroll
+                      for (int t = 0; t < 4; ++t) {
+                        __nv_bfloat162 b2 = __floats2bfloat162_rn(v[j + 2 * t], v[j + 2 * t + 1]);
+                        w[t] = *reinterpret_cast<uint32_t*>(&b2);
+                      }
+                      sts_v4(my_row + (uint32_t)((cb + j) * 2),
+                             make_float4(__uint_as_float(w[0]), __uint_as_float(w[1]), __uint_as_float(w[2]), __uint_as_float(w[3])));
+                    }
+                  }
+                }
+              }
+            }
+            __syncwarp();
+            if (piece * 16 < width * (int)sizeof(TOut) && !(dbg & 8)) {
+              uint8_t* dst0 = (uint8_t*)p.out + ((int64_t)c0 * (int)sizeof(TOut) + piece * 16);
+              for (int rr = rsub; rr < 32; rr += rpi) {
+                if (row0 + rr < p.n_out) {
+                  const float4 w4 = lds_v4(stg + (uint32_t)(rr * pitch_s + piece * 16));
+                  *reinterpret_cast<float4*>(dst0 + (row0 + rr) * pitch) = w4;
+                }
+              }
+            }
+            __syncwarp();
+          }
+          continue;
+        }
+        // the TMEM load of the next 16 columns is in flight while these 16 are converted and stored
+        uint32_t rn[16];
+        if (km[g] != 0u && c_lo < c_hi) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + tcol + (uint32_t)c_lo, rn);
+        for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
           float v[16];
           if (km[g] != 0u) {
-            uint32_t r[16];
-            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + tcol + (uint32_t)c0, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rn[j]);
+            if (c0 + 16 < c_hi) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + tcol + (uint32_t)(c0 + 16), rn);
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = 0.f;
@@ -835,9 +917,10 @@ __global__ void __launch_bounds__(256) k_weight_image_tf32(const float* __restri
   }
 }
 
-inline size_t conv_smem_bytes(int cout, int stages, int group = 1, int stage_out_cols = 0) {
+inline size_t conv_smem_bytes(int cout, int stages, int group = 1, int stage_out_cols = 0, int epi_stage = 0) {
+  const size_t out_stage = epi_stage ? (size_t)kCvEpiWarps * 32 * (epi_stage + 16) : (size_t)kCvEpiWarps * 32 * stage_out_cols * sizeof(float);
   return 1024 + (size_t)stages * ((size_t)group * kABytes + (size_t)cout * 128) + (2 * kMaxStages + 6) * sizeof(uint64_t) + 16 +
-         (size_t)kCvProducerWarps * 2 * 4 * 32 * sizeof(int32_t) + (size_t)4 * 32 * stage_out_cols * sizeof(float);
+         (size_t)kCvProducerWarps * 2 * 4 * 32 * sizeof(int32_t) + out_stage;
 }
 
 int conv_tma_launch(const ConvParams& p, int64_t n_in, int out_dtype, cudaStream_t st);  // conv_tma.cu
@@ -854,7 +937,7 @@ inline int gather_mode() { return g_gather_mode; }
 //   MK3D_DEBUG bit mask (results are wrong when non-zero): 1 skip gathers, 2 skip weight copies, 4 one MMA per tile, 8 skip stores
 //   MK3D_TRACE=1 per-role cycle counters; MK3D_GROUP, MK3D_KSPLIT, MK3D_STAGES, MK3D_PRODUCERS, MK3D_SPLIT, MK3D_CARVEOUT shape overrides
 struct Tuning {
-  int debug = 0, trace = 0, group = 0, ksplit = 0, stages = 0, producers = 0, split = 0, carveout = -1;
+  int debug = 0, trace = 0, group = 0, ksplit = 0, stages = 0, producers = 0, split = 0, carveout = -1, epi_stage = 1;
 };
 inline const Tuning& tuning() {
   static Tuning t;
@@ -870,6 +953,7 @@ inline const Tuning& tuning() {
     t.producers = geti("MK3D_PRODUCERS", 0);
     t.split = geti("MK3D_SPLIT", 0);
     t.carveout = geti("MK3D_CARVEOUT", -1);
+    t.epi_stage = geti("MK3D_EPI_STAGE", 1);
     init = true;
   }
 #endif
@@ -945,6 +1029,8 @@ static int conv_fwd_launch(const void* in, int in_dtype, int64_t n_in, int cin, 
   const int elem = out_dtype == MK_F32 ? 4 : 2;
   p.stage_out = (out_rows == nullptr && out_stride == out_cols && ((out_stride * elem) & 15) != 0 && out_cols <= 64) ? 1 : 0;
   const int soc = p.stage_out ? out_cols : 0;
+  // coalescing epilogue for launches whose rows are in slot order (dense: 1x1 convs, mask logits, unsorted plans)
+  p.epi_stage = (!p.stage_out && out_rows == nullptr && (out_cols & 15) == 0 && ((out_stride * elem) & 15) == 0 && tuning().epi_stage != 0) ? 1 : 0;
   const Tuning& tn = tuning();
   p.debug = tn.debug;
   p.trace = nullptr;
@@ -971,12 +1057,21 @@ static int conv_fwd_launch(const void* in, int in_dtype, int64_t n_in, int cin, 
       p.ksplit = ks;
     }
   }
+  if (p.ksplit > 1) p.epi_stage = 0;  // partial sums are added with REDs from registers
+  if (p.epi_stage) {
+    // 128-byte blocks, for rows that are whole blocks: measured on the 889 k-voxel map (profiles/r02_conv_ablation.txt) 96->128
+    // 0.149 -> 0.113 ms, 256->128 0.195 -> 0.133, 384->256 0.362 -> 0.251, 128->160 fp32 0.284 -> 0.199 -- also where the larger
+    // staging area costs the ring its fourth slot; 64-byte blocks gain a third of that, and rows of 192 bytes (96 bf16 channels)
+    // are 13 % slower than with direct stores, so they keep those.
+    p.epi_stage = ((out_cols * elem) & 127) == 0 ? 128 : 0;
+    if (tuning().epi_stage == 64 || tuning().epi_stage == 128) p.epi_stage = tuning().epi_stage;
+  }
   int stages = kMaxStages;
-  while (stages > 2 && conv_smem_bytes(cout, stages, group, soc) > 222 * 1024) --stages;
+  while (stages > 2 && conv_smem_bytes(cout, stages, group, soc, p.epi_stage) > 222 * 1024) --stages;
   // Super-tiles: 4 stages (<= 176 KB) instead of the 5 that fit: the smaller carve-out leaves ~50 KB of L1 for the neighbour
   // rows a compact tile re-gathers across offsets (L1 sector hit rate 13 % -> 50+ %).
   if (group == 2 && stages > 4) stages = 4;
-  MK_REQUIRE(conv_smem_bytes(cout, stages, group, soc) <= 227 * 1024, "shared memory budget exceeded");
+  MK_REQUIRE(conv_smem_bytes(cout, stages, group, soc, p.epi_stage) <= 227 * 1024, "shared memory budget exceeded");
   if (tn.stages >= 2 && tn.stages < stages) stages = tn.stages;  // tuning sweeps only
   // producer groups: one per ring slot (a group may be at most one ring phase ahead); two warps per group (one per member
   // tile) when there are member tiles to split and warps to spare
@@ -995,7 +1090,7 @@ static int conv_fwd_launch(const void* in, int in_dtype, int64_t n_in, int cin, 
     if (tn.producers >= 1 && tn.producers < p.num_producers) p.num_producers = tn.producers;
   }
   p.num_stages = stages;
-  const size_t smem = conv_smem_bytes(cout, stages, group, soc);
+  const size_t smem = conv_smem_bytes(cout, stages, group, soc, p.epi_stage);
   int grid = num_sms();
   const int num_super = (p.num_tiles + group - 1) / group;
   if (grid > num_super) grid = num_super;

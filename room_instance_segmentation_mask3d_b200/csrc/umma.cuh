@@ -101,6 +101,9 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
   return v;
 }
+__device__ __forceinline__ void sts_v4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
@@ -285,6 +288,7 @@ struct ConvParams {
                    // and ADDS its partial result into the (zeroed, fp32) output with vector REDs
   int debug;       // timing ablation flags (MK3D_DEBUG), 0 in production
   unsigned long long* trace;  // MK3D_TRACE: per-CTA role timers [grid][8], nullptr in production
+  int epi_stage;   // 1: epilogue transposes 32 x 64-byte blocks through shared memory and stores whole sectors (rows in slot order)
   int gather4;     // 1: the A rows are gathered by the TMA engine (tile::gather4 through `tmap`) instead of LDGSTS
   alignas(64) unsigned long long tmap[16];  // CUtensorMap of the input rows: {cin, n_in}, box {128 bytes of channels, 1}, SWIZZLE_128B
 };
