@@ -255,8 +255,8 @@ __global__ void __launch_bounds__(256) k_kernel_map_sym(const unsigned long long
 // reads once the table of a batch no longer fits in L2: 5.4 of the 7.2 ms of kernel-map time in a batch-of-8 step).
 __global__ void __launch_bounds__(256) k_kernel_map_compose5(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ vals,
                                                              uint64_t mask, const int4* __restrict__ coords, int64_t n, int sx, int sy, int sz,
-                                                             const int32_t* __restrict__ nbr3, int32_t* __restrict__ nbr5) {
-  const int k = blockIdx.y;  // 0 .. 62: lower half of the 125 offsets + the centre
+                                                             const int32_t* __restrict__ nbr3, int32_t* __restrict__ nbr5, int sym) {
+  const int k = blockIdx.y;  // sym: 0 .. 62 = lower half of the 125 offsets + the centre, hits also write the mirrored entry; else all 125
   const int ix = k % 5 - 2, iy = (k / 5) % 5 - 2, iz = k / 25 - 2;
   const int ax = ix < 0 ? -ix : ix, ay = iy < 0 ? -iy : iy, az = iz < 0 ? -iz : iz;
   auto k3 = [](int x, int y, int z) { return (x + 1) + 3 * (y + 1) + 9 * (z + 1); };
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(256) k_kernel_map_compose5(const unsigned long
       }
     }
     nbr5[(int64_t)k * n + o] = row;
-    if (row >= 0) nbr5[(int64_t)(124 - k) * n + row] = (int)o;
+    if (sym && row >= 0) nbr5[(int64_t)(124 - k) * n + row] = (int)o;
   }
 }
 
@@ -495,12 +495,16 @@ int mk_kernel_map_compose5(const uint64_t* keys, const int32_t* vals, int64_t ca
                            const int32_t* nbr3, int32_t* nbr5, void* stream_) {
   if (n == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream_;
-  cudaMemsetAsync(nbr5 + (int64_t)63 * n, 0xFF, (size_t)62 * n * sizeof(int32_t), st);
+  // lower half + mirrored writes (sym = 1): computing all 125 entries independently (no mirrored scatter, no pre-fill) was measured
+  // at 7.9 ms against 4.1 ms for a batch of 7.1 M voxels -- the fallback probes of the directions normal to the surfaces dominate
+  // and they double
+  const int sym = 1;
+  if (sym) cudaMemsetAsync(nbr5 + (int64_t)63 * n, 0xFF, (size_t)62 * n * sizeof(int32_t), st);
   int64_t bx = ceil_div(n, 256);
   if (bx > 8 * num_sms()) bx = 8 * num_sms();
-  dim3 grid((unsigned)bx, 63u);
+  dim3 grid((unsigned)bx, sym ? 63u : 125u);
   k_kernel_map_compose5<<<grid, 256, 0, st>>>((const unsigned long long*)keys, vals, (uint64_t)(cap - 1), (const int4*)coords, n, step3_host[0],
-                                              step3_host[1], step3_host[2], nbr3, nbr5);
+                                              step3_host[1], step3_host[2], nbr3, nbr5, sym);
   return check_launch(__func__);
 }
 
