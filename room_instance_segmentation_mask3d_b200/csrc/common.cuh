@@ -116,6 +116,32 @@ __device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
   *reinterpret_cast<uint2*>(p) = r;
 }
 
+// 32-byte store (sm_100: STG.256): a whole sector per lane, p 32-byte aligned
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]),
+               "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+// 16 consecutive channels as whole sectors: 2 x 32-byte stores (fp32) or 1 (bf16); p 32-byte aligned
+__device__ __forceinline__ void store16_sectors(float* p, const float (&v)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; j += 8) {
+    uint32_t w[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) w[t] = __float_as_uint(v[j + t]);
+    stg256(p + j, w);
+  }
+}
+__device__ __forceinline__ void store16_sectors(__nv_bfloat16* p, const float (&v)[16]) {
+  uint32_t w[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    w[j] = *reinterpret_cast<uint32_t*>(&t);
+  }
+  stg256(p, w);
+}
+
 // 16 consecutive channels from fp32 registers: 4 x 16-byte stores (fp32) or 2 x 16-byte stores (bf16)
 __device__ __forceinline__ void store16(float* p, const float (&v)[16]) {
 #pragma unroll

@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(256) k_conv_stem_rows(const float* __restrict_
     }
     if (valid) {
       TOut* dst = out + o * cout;
+      const bool sectors = ((((uintptr_t)out) | (uintptr_t)(cout * sizeof(TOut))) & 31) == 0;
       if ((cout & 15) == 0) {
 #pragma unroll
         for (int c0 = 0; c0 < CO; c0 += 16) {
@@ -145,7 +146,8 @@ __global__ void __launch_bounds__(256) k_conv_stem_rows(const float* __restrict_
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = acc[c0 + j];
-            store16(dst + c0, v);
+            if (sectors) store16_sectors(dst + c0, v);  // thread = row: a whole 32-byte sector per store instead of two halves
+            else store16(dst + c0, v);
           }
         }
       } else {

@@ -834,7 +834,9 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_umma(const __grid_consta
               }
             }
           } else if (optr && !(dbg & 8)) {
-            if (vec_ok && c0 + 16 <= p.out_cols) {
+            if (p.vec32 && c0 + 16 <= p.out_cols) {
+              store16_sectors(optr + c0, v);  // a whole 32-byte sector per lane: half the L2 write transactions of 16-byte stores
+            } else if (vec_ok && c0 + 16 <= p.out_cols) {
               store16(optr + c0, v);
             } else {
 #pragma unroll
@@ -937,7 +939,7 @@ inline int gather_mode() { return g_gather_mode; }
 //   MK3D_DEBUG bit mask (results are wrong when non-zero): 1 skip gathers, 2 skip weight copies, 4 one MMA per tile, 8 skip stores
 //   MK3D_TRACE=1 per-role cycle counters; MK3D_GROUP, MK3D_KSPLIT, MK3D_STAGES, MK3D_PRODUCERS, MK3D_SPLIT, MK3D_CARVEOUT shape overrides
 struct Tuning {
-  int debug = 0, trace = 0, group = 0, ksplit = 0, stages = 0, producers = 0, split = 0, carveout = -1, epi_stage = 1;
+  int debug = 0, trace = 0, group = 0, ksplit = 0, stages = 0, producers = 0, split = 0, carveout = -1, epi_stage = 1, vec32 = 1;
 };
 inline const Tuning& tuning() {
   static Tuning t;
@@ -954,6 +956,7 @@ inline const Tuning& tuning() {
     t.split = geti("MK3D_SPLIT", 0);
     t.carveout = geti("MK3D_CARVEOUT", -1);
     t.epi_stage = geti("MK3D_EPI_STAGE", 1);
+    t.vec32 = geti("MK3D_VEC32", 1);
     init = true;
   }
 #endif
@@ -1029,6 +1032,7 @@ static int conv_fwd_launch(const void* in, int in_dtype, int64_t n_in, int cin, 
   const int elem = out_dtype == MK_F32 ? 4 : 2;
   p.stage_out = (out_rows == nullptr && out_stride == out_cols && ((out_stride * elem) & 15) != 0 && out_cols <= 64) ? 1 : 0;
   const int soc = p.stage_out ? out_cols : 0;
+  p.vec32 = ((((uintptr_t)out) & 31) == 0 && ((out_stride * elem) & 31) == 0 && tuning().vec32 != 0) ? 1 : 0;
   // coalescing epilogue for launches whose rows are in slot order (dense: 1x1 convs, mask logits, unsorted plans)
   p.epi_stage = (!p.stage_out && out_rows == nullptr && (out_cols & 15) == 0 && ((out_stride * elem) & 15) == 0 && tuning().epi_stage != 0) ? 1 : 0;
   const Tuning& tn = tuning();

@@ -288,6 +288,7 @@ struct ConvParams {
                    // and ADDS its partial result into the (zeroed, fp32) output with vector REDs
   int debug;       // timing ablation flags (MK3D_DEBUG), 0 in production
   unsigned long long* trace;  // MK3D_TRACE: per-CTA role timers [grid][8], nullptr in production
+  int vec32;       // 1: output rows are 32-byte aligned: the direct epilogue stores whole sectors (STG.256)
   int epi_stage;   // 1: epilogue transposes 32 x 64-byte blocks through shared memory and stores whole sectors (rows in slot order)
   int gather4;     // 1: the A rows are gathered by the TMA engine (tile::gather4 through `tmap`) instead of LDGSTS
   alignas(64) unsigned long long tmap[16];  // CUtensorMap of the input rows: {cin, n_in}, box {128 bytes of channels, 1}, SWIZZLE_128B
