@@ -1067,7 +1067,9 @@ static int conv_fwd_launch(const void* in, int in_dtype, int64_t n_in, int cin, 
     // 0.149 -> 0.113 ms, 256->128 0.195 -> 0.133, 384->256 0.362 -> 0.251, 128->160 fp32 0.284 -> 0.199 -- also where the larger
     // staging area costs the ring its fourth slot; 64-byte blocks gain a third of that, and rows of 192 bytes (96 bf16 channels)
     // are 13 % slower than with direct stores, so they keep those.
-    p.epi_stage = ((out_cols * elem) & 127) == 0 ? 128 : 0;
+    // Against direct stores of whole sectors (STG.256, added later): still ahead for bf16 rows of >= 256 bytes (96->128 0.113 vs
+    // 0.120 ms, 256->128 0.133 vs 0.161, 384->256 0.248 vs 0.297), behind for fp32 rows (128->160: 0.199 vs 0.185) and 128-byte rows.
+    p.epi_stage = (((out_cols * elem) & 127) == 0 && elem == 2 && out_cols * elem >= 256) ? 128 : 0;
     if (tuning().epi_stage == 64 || tuning().epi_stage == 128) p.epi_stage = tuning().epi_stage;
   }
   int stages = kMaxStages;
