@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_conv_umma launch from an `ncu --set full` capture (profiles/), next to the
 # algorithmic bytes of that launch; filled in from the capture named in `note` (None until a capture of the current kernel exists)
-NCU_TRAFFIC = {"bytes_per_launch": 227673856 + 133283072,
+NCU_TRAFFIC = {"bytes_per_launch": 229788416 + 139122176,
                "note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE k_conv_umma launch of the dominant shape (3^3 96->96 on the "
                        "889057-voxel level-0 map: 155.2 GFLOP, algorithmic minimum 437.9 MB incl. the 96 MB neighbour table, part of which "
                        "is L2-resident), ncu --set full, profiles/r02_ncu_conv96_summary.txt"}
@@ -380,10 +380,12 @@ def main_ours(args):
     value = world * vox_per_step * args.steps / (ms * 1e-3)
 
     gc.collect()
-    for i in range(n_scenes):
+    for i in range(max(args.warmup, 2 * n_scenes)):  # as many warm-up steps as the resident loop: the e2e path allocates its own result buffers
         step_e2e(i)
     state["vox"] = 0
+    mallocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
     ms_e2e = timed(step_e2e, args.steps)
+    mallocs_e2e = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs0
     e2e_value = world * state["vox"] / (ms_e2e * 1e-3)
     h2d = int(np.mean([c.numel() * 4 + f.numel() * 4 for c, f in pinned]))
     d2h_logits = int(h_cls[0].numel() * 4 + np.mean([m.numel() * 4 for m in h_mask[0]]))
@@ -630,7 +632,7 @@ def main_ours(args):
                                     "voxel + per-query mask scores (what trainer/trainer.py:373-402 derives from the logits), built on the "
                                     "device") if compact else "class logits of all 13 decoder outputs + final fp32 mask logits [N, 25]",
                         "other_result_form": e2e_other},
-                "gpu_launches": launches, "cuda_mallocs_in_timed_region": mallocs, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "train_fwd_bwd": train,
+                "gpu_launches": launches, "cuda_mallocs_in_timed_region": mallocs, "cuda_mallocs_in_e2e_region": mallocs_e2e, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "train_fwd_bwd": train,
                 "loss_side": loss_side, "train_step": train_step, "final_prediction_only": final_only}
         print(json.dumps(line))
     if world > 1:
