@@ -279,8 +279,12 @@ def main_ours(args):
     lib.reserve_device_pool(lane_gb / 2, dev, stream=model.side_stream(dev))
     compact = args.e2e_results == "compact"
     h_cls = [torch.empty((13, B, 25, 2), dtype=torch.float32).pin_memory() for _ in range(n_lanes)]
-    h_mask = [[torch.empty((n, 25), dtype=torch.float32).pin_memory() for n in nvox] for _ in range(n_lanes)]
-    h_bits = [[torch.empty(n, dtype=torch.int32).pin_memory() for n in nvox] for _ in range(n_lanes)]
+    # one pinned result buffer per lane, sized for the largest batch and sliced per batch (a buffer per (lane, batch) pinned 4 GB of
+    # host memory per rank at 8 scenes per step)
+    h_mask_buf = [torch.empty((max(nvox), 25), dtype=torch.float32).pin_memory() for _ in range(n_lanes)]
+    h_bits_buf = [torch.empty(max(nvox), dtype=torch.int32).pin_memory() for _ in range(n_lanes)]
+    h_mask = [[h_mask_buf[ln][:n] for n in nvox] for ln in range(n_lanes)]
+    h_bits = [[h_bits_buf[ln][:n] for n in nvox] for ln in range(n_lanes)]
     h_score = [torch.empty((B, 25), dtype=torch.float32).pin_memory() for _ in range(n_lanes)]
     state = {"res": None, "e2e": None, "g_res": 0, "g_e2e": 0, "vox": 0, "compact": compact}
 

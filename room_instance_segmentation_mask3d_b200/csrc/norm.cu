@@ -104,10 +104,11 @@ __global__ void __launch_bounds__(256) k_in_stats_final(const float* __restrict_
   const double ref = p0[3 * C + c];
   double n = 0, S = 0, SS = 0;
   // four chunks per lane per round, all 16 loads issued before the first use (the kernel is a chain of L2 latencies)
-  for (int ch0 = lane; ch0 < chunks_per_scene; ch0 += 128) {
-    float v[4][4];
+  constexpr int U = 8;  // chunks per lane and round: all 4 * U loads are issued before the first use
+  for (int ch0 = lane; ch0 < chunks_per_scene; ch0 += 32 * U) {
+    float v[U][4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int ch = ch0 + 32 * u;
       const float* p = partial + ((int64_t)(b * chunks_per_scene_cap + (ch < chunks_per_scene ? ch : 0))) * 4 * C;
       const bool ok = ch < chunks_per_scene;
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(256) k_in_stats_final(const float* __restrict_
       v[u][3] = ok ? p[3 * C + c] : 0.f;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {  // ascending chunk order per lane, as before
+    for (int u = 0; u < U; ++u) {  // ascending chunk order per lane, as before
       const double nb = v[u][0];
       if (nb <= 0) continue;
       const double s1 = v[u][1], s2 = v[u][2], d = (double)v[u][3] - ref;
@@ -529,10 +530,11 @@ __global__ void __launch_bounds__(256) k_inr_bwd_final(const float* __restrict__
   for (int b = 0; b < B; ++b) {
     double sa = 0, sq = 0;
     const int chunks_per_scene = min(chunks_per_scene_cap, (scene_offsets[b + 1] - scene_offsets[b] + rows_per_chunk - 1) / rows_per_chunk);
-    for (int ch0 = lane; ch0 < chunks_per_scene; ch0 += 128) {
-      float va[4], vq[4];
+    constexpr int U = 8;
+    for (int ch0 = lane; ch0 < chunks_per_scene; ch0 += 32 * U) {
+      float va[U], vq[U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int ch = ch0 + 32 * u;
         const bool ok = ch < chunks_per_scene;
         const float* p = partial + ((int64_t)(b * chunks_per_scene_cap + (ok ? ch : 0))) * 2 * C;
@@ -540,7 +542,7 @@ __global__ void __launch_bounds__(256) k_inr_bwd_final(const float* __restrict__
         vq[u] = ok ? p[C + c] : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         sa += va[u];
         sq += vq[u];
       }

@@ -184,6 +184,25 @@ class stream_scope:
 
 
 # kernels launched per C-ABI call (memsets not counted) — bench.py reports the total as `gpu_launches`
+def cache_built():
+    """Guard of a cached device tensor built on the current stream: [event behind its producer, that stream, streams that have waited].
+    Cached weight images / derived layouts are handed to whichever stream runs the next forward (bench.py alternates two): a
+    consumer on another stream must not read an image the building stream is still writing."""
+    cur = torch.cuda.current_stream()
+    ev = torch.cuda.Event()
+    ev.record(cur)
+    return [ev, cur.cuda_stream, set()]
+
+
+def cache_use(guard) -> None:
+    """Make the current stream wait (once) for the producer of a cached tensor built on another stream."""
+    cur = torch.cuda.current_stream()
+    sid = cur.cuda_stream
+    if sid != guard[1] and sid not in guard[2]:
+        cur.wait_event(guard[0])
+        guard[2].add(sid)
+
+
 _KERNELS_PER_CALL = {"mk_coordmap_build": 7, "mk_instnorm_stats": 2, "mk_masked_xattn_fwd": 3, "mk_masked_xattn_fwd_lse": 3, "mk_masked_xattn_bwd": 5, "mk_instnorm_bwd": 3, "mk_instnorm_relu_bwd": 3, "mk_scene_minmax": 3,
                      "mk_fps": 25, "mk_mask_compact": 2, "mk_group_rows": 6, "mk_mask_costs": 3, "mk_conv_instnorm_bf16": 4, "mk_conv_wgrad_plan": 3, "mk_conv_wgrad_bf16_ws": 2, "mk_conv_stem_wgrad_f32": 2}
 kernel_launches = 0

@@ -415,8 +415,10 @@ class Mask3D(nn.Module):
         k = (p.data_ptr(), tag)
         e = self._derived.get(k)
         if e is None or e[0] != p._version:
-            e = (p._version, fn(p.detach()).contiguous())
+            e = (p._version, fn(p.detach()).contiguous(), lib.cache_built())
             self._derived[k] = e
+        else:
+            lib.cache_use(e[2])  # built on another stream (two-lane inference): wait for its producer once
         return e[1]
 
     def _query_update(self, i: int, queries, query_pos, ctx):

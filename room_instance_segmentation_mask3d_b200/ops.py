@@ -53,6 +53,7 @@ def weight_image(W: torch.Tensor, transpose: bool = False, tf32: bool = False) -
     key = (W.data_ptr(), int(transpose) + 2 * int(tf32), tuple(W.shape))
     ent = _wimg_cache.get(key)
     if ent is not None and ent[0] == W._version and ent[2]() is not None:
+        lib.cache_use(ent[3])
         return ent[1]
     W3 = W.detach()
     if W3.dim() == 2:
@@ -69,7 +70,7 @@ def weight_image(W: torch.Tensor, transpose: bool = False, tf32: bool = False) -
         lib.call("mk_conv_weight_image_bf16", lib.p(W3), K, cin, cout, int(transpose), lib.p(img), lib.stream())
     if len(_wimg_cache) > 4096:
         _wimg_cache.clear()
-    _wimg_cache[key] = (W._version, img, weakref.ref(W))
+    _wimg_cache[key] = (W._version, img, weakref.ref(W), lib.cache_built())
     return img
 
 
@@ -230,13 +231,14 @@ def layer_plan(W: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor):
     ver = (W._version, gamma._version, beta._version, W.data_ptr(), gamma.data_ptr())
     ent = _layer_plans.get(key)
     if ent is not None and ent[0] == ver:
+        lib.cache_use(ent[2])
         return ent[1]
     W3 = W if W.dim() == 3 else W.unsqueeze(0)
     K, cin, cout = W3.shape
     lp = (weight_image(W), _flat32(gamma), _flat32(beta), K, cin, cout)
     if len(_layer_plans) > 4096:
         _layer_plans.clear()
-    _layer_plans[key] = (ver, lp)
+    _layer_plans[key] = (ver, lp, lib.cache_built())
     return lp
 
 
