@@ -412,8 +412,8 @@ def main_ours(args):
     for i in range(max(4, n_scenes)):  # the allocator sees a new pattern of block sizes: let it settle outside the timed region
         step_resident(i)
     state["vox"] = 0
-    ms_fo = timed(step_resident, osteps)
-    final_only = {"value": world * state["vox"] / (ms_fo * 1e-3), "unit": UNIT, "ms_per_step": ms_fo / osteps, "steps": osteps,
+    ms_fo = timed(step_resident, args.steps)
+    final_only = {"value": world * state["vox"] / (ms_fo * 1e-3), "unit": UNIT, "ms_per_step": ms_fo / args.steps, "steps": args.steps,
                   "note": "forward(aux_outputs=False): final prediction only, the intermediate decoder outputs' full-resolution mask logits are not materialised"}
     state["aux"] = True
 
