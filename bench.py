@@ -427,12 +427,16 @@ def main_ours(args):
             pass
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+        if args.mode == "tf32":  # tcgen05 kind::tf32 runs at half the bf16 rate; no measured tf32 figure exists in MEASURED_PEAKS.json
+            peak *= 0.5
+            peak_src = "half of " + peak_src + ": the dense tf32 rate of the tensor pipe"
         ops.USE_COMPOSITE = False  # time the conv launches on their own (the composite call also enqueues the norm kernels)
         state["one_lane"] = True  # per-launch events must not see the other lane's kernels interleaved
         for i in range(2):  # warm the instrumented configuration (separate conv / norm calls allocate differently) before timing it
             step_resident(i)
         torch.cuda.synchronize()
-        ev = lib.instrument(["mk_conv_fwd_bf16"])
+        conv_entry = "mk_conv_fwd_tf32" if args.mode == "tf32" else "mk_conv_fwd_bf16"
+        ev = lib.instrument([conv_entry])
         isteps = min(args.steps, 3)
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(lanes[0]):
@@ -445,7 +449,7 @@ def main_ours(args):
         torch.cuda.synchronize()
         lib.instrument(None)
         ops.USE_COMPOSITE = True
-        recs = ev["mk_conv_fwd_bf16"]
+        recs = ev[conv_entry]
         step_ms = t0.elapsed_time(t1)
 
         def summarize(sel):
