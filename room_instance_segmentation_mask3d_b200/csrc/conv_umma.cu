@@ -1,32 +1,27 @@
-// tcgen05 gather-GEMM sparse convolution (bf16 operands, fp32 accumulation in TMEM) for sm_100a.
+// tcgen05 gather-GEMM sparse convolution (bf16 or tf32 operands, fp32 accumulation in TMEM) for sm_100a.
 //
 // Replaces ME's per-offset gather -> GEMM -> atomic scatter launches (K launches x 3 per conv, SURVEY.md
 // section 3.4) with ONE persistent, warp-specialised, output-stationary kernel:
 //
-//   tile      = 128 output slots (rows of the accumulator = TMEM lanes)
-//   iteration = (kernel offset k with at least one neighbour in the tile, 64-channel chunk of Cin) = one pipeline stage
-//   A operand = the 128 gathered input rows of the chunk, staged with 16-byte cp.async (LDGSTS, zero-fill for absent
-//               neighbours) straight into the 128B-swizzled K-major shared-memory layout that tcgen05.mma reads
-//   B operand = W[k] chunk, pre-swizzled on the device once per weight ("weight image"), so a stage is one
-//               linear cp.async.bulk (TMA engine, UBLKCP) completing on the stage's mbarrier
-//   D         = fp32 accumulator in TMEM, two buffers of `cout` columns: the epilogue of tile t
-//               (tcgen05.ld -> bias -> cast -> 16-byte stores, each output row written exactly once,
-//               no atomics) overlaps the MMAs of tile t+1
+//   tile       = 128 output slots (rows of the accumulator = TMEM lanes); a SUPER-TILE is G = 2 consecutive tiles when
+//                cout <= 128 (two accumulators share every weight chunk)
+//   iteration  = (super-tile, 128-byte chunk of the input row, kernel offset k with a neighbour in the super-tile)
+//              = one ring slot
+//   A operand  = the gathered input rows of the chunk, staged with 16-byte cp.async (LDGSTS, zero-fill for absent
+//                neighbours) straight into the 128B-swizzled K-major shared-memory layout that tcgen05.mma reads
+//   B operand  = W[k] chunk, pre-swizzled on the device once per weight ("weight image"), so a slot's weights are one
+//                linear cp.async.bulk (TMA engine, UBLKCP) completing on the slot's mbarrier
+//   D          = fp32 accumulators in TMEM, double-buffered: the epilogue of super-tile t (tcgen05.ld -> bias -> cast ->
+//                whole-sector stores, each output row written exactly once, no atomics) overlaps the MMAs of t + 1
 //
-// Offsets whose neighbour column is empty for the whole tile are skipped via the per-tile bitmask from
-// mk_tile_kmask, which is what keeps the MMA work close to the algorithmic 2*P*Cin*Cout on surface data.
+// Offsets whose neighbour column is empty for the whole tile are skipped via the per-tile bitmask from mk_tile_kmask, which
+// is what keeps the MMA work close to the algorithmic 2*P*Cin*Cout on surface data (mask-sorted tile plans: engine.py).
 //
-// Warp roles (320 threads): warps 0-3 and 5 are PRODUCERS, warp 4 the MMA issuer (one elected lane), warps 6-9 the
-// epilogue (TMEM lane quarter = warp % 4); warp 5 also owns the TMEM allocation.
-//
-// Producers own whole stages round-robin (stage i belongs to producer i mod 5): ncu's per-instruction stall samples of the
-// previous design (all 4 producer warps cooperating on EVERY stage, profiles/r01_conv96_*) showed the producer loop —
-// mbarrier try_wait, index shuffles, LDGSTS issue throttling, exposed index loads — at ~1100 cycles per stage on every
-// producer warp, i.e. the gather front-end, not the tensor pipe or L2, bounded the kernel.  With stage ownership the same
-// fixed costs overlap across five stages in flight.  Per stage the owning warp: waits for the stage to be free, gathers
-// 128 rows x 128 B with 32 LDGSTS per lane (neighbour indices held 4 per lane, distributed by shuffle, prefetched two of its
-// own stages ahead), lets the copies arrive on the stage's full barrier (cp.async.mbarrier.arrive.noinc: no thread-side
-// wait), and lane 0 adds the weight-image bulk copy with its expect_tx on the same barrier.
+// Warp roles (576 threads): warps 0-7 gather PRODUCERS (a group of `split` warps owns every NP-th iteration; a warp owns the
+// 32-row units of one member tile), warps 8-9 MMA ISSUERS (one per member tile, one elected lane each; warp 9 also owns the
+// TMEM allocation), warps 10-17 EPILOGUE (two per TMEM lane quarter: member tile 1 / upper column half go to the second set).
+// DESIGN.md section 5 has the measurements behind every one of these choices (role timers, ncu, ablations, and the A/B
+// records of the alternatives: TMA tile::gather4, hybrid gathers, 16 producer warps, blocked vs direct epilogue stores).
 #include <cstdlib>
 #include <vector>
 
