@@ -163,6 +163,86 @@ __global__ void __launch_bounds__(256) k_fourier_pe(const float* __restrict__ xy
   }
 }
 
+// Eight frequencies per thread: the three normalised coordinates (three fp32 divisions, the scene lookup, the coordinate loads) are
+// computed once per 8 outputs instead of once per output, and sine / cosine halves go out as 16-byte (bf16) or 32-byte (fp32)
+// vectors instead of 2- / 4-byte scalars.  Same expressions in the same order per element => bit-identical to k_fourier_pe.
+template <typename T>
+__device__ __forceinline__ void pe_load8(const T* p, float (&v)[8]) {
+  if constexpr (sizeof(T) == 2) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+      v[2 * j] = f.x;
+      v[2 * j + 1] = f.y;
+    }
+  } else {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void pe_store8(T* p, const float (&v)[8]) {
+  if constexpr (sizeof(T) == 2) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      w[j] = *reinterpret_cast<uint32_t*>(&t);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  } else {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+template <typename TB, typename TO>
+__global__ void __launch_bounds__(256) k_fourier_pe8(const float* __restrict__ xyz, int64_t n, const int32_t* __restrict__ scene_offsets,
+                                                     int B, const float* __restrict__ cmin, const float* __restrict__ cmax,
+                                                     const float* __restrict__ gauss_B, int D, const TB* __restrict__ base,
+                                                     TO* __restrict__ out) {
+  const int half = D >> 1, groups = half >> 3;  // groups of 8 frequencies per row
+  const int64_t total = n * groups;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / groups;
+    const int j0 = (int)(i - r * groups) * 8;
+    const int b = scene_of_row(scene_offsets, B, r);
+    float x[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float lo = cmin[b * 3 + a], hi = cmax[b * 3 + a];
+      x[a] = ((xyz[r * 3 + a] - lo) * 1.0f) / (hi - lo) + 0.0f;
+      x[a] *= 6.283185307179586f;
+    }
+    float s[8], c[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float p = 0.f;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) p = fmaf(x[a], gauss_B[a * half + j0 + j], p);
+      const float kq = rintf(p * 0.15915494309189535f);
+      float rr = fmaf(kq, -6.2831854820251465f, p);
+      rr = fmaf(kq, 1.7484555314695172e-07f, rr);
+      s[j] = __sinf(rr);
+      c[j] = __cosf(rr);
+    }
+    if (base) {
+      float bs[8], bc[8];
+      pe_load8<TB>(base + r * D + j0, bs);
+      pe_load8<TB>(base + r * D + half + j0, bc);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += bs[j];
+        c[j] += bc[j];
+      }
+    }
+    pe_store8<TO>(out + r * D + j0, s);
+    pe_store8<TO>(out + r * D + half + j0, c);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // masked cross-attention core
 // ---------------------------------------------------------------------------------------------------
@@ -799,8 +879,14 @@ int mk_fourier_pe(const float* xyz, int64_t n, const int32_t* scene_offsets, int
   if (n == 0) return 0;
   int64_t blocks = ceil_div(n * (D / 2), 256);
   if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
-#define MK_PE(TB, TO) \
-  k_fourier_pe<TB, TO><<<(unsigned)blocks, 256, 0, st>>>(xyz, n, scene_offsets, B, cmin, cmax, gauss_B, D, (const TB*)base, (TO*)out)
+  const bool vec8 = (D % 16) == 0 && (((uintptr_t)out | (uintptr_t)base) & 15) == 0;
+  int64_t blocks8 = ceil_div(n * (D / 16), 256);
+  if (blocks8 > 16 * num_sms()) blocks8 = 16 * num_sms();
+#define MK_PE(TB, TO)                                                                                                                    \
+  do {                                                                                                                                  \
+    if (vec8) k_fourier_pe8<TB, TO><<<(unsigned)blocks8, 256, 0, st>>>(xyz, n, scene_offsets, B, cmin, cmax, gauss_B, D, (const TB*)base, (TO*)out); \
+    else k_fourier_pe<TB, TO><<<(unsigned)blocks, 256, 0, st>>>(xyz, n, scene_offsets, B, cmin, cmax, gauss_B, D, (const TB*)base, (TO*)out);        \
+  } while (0)
   if (base_dtype == MK_F32 && out_dtype == MK_F32) MK_PE(float, float);
   else if (base_dtype == MK_F32 && out_dtype == MK_BF16) MK_PE(float, __nv_bfloat16);
   else if (base_dtype == MK_BF16 && out_dtype == MK_F32) MK_PE(__nv_bfloat16, float);
