@@ -249,12 +249,34 @@ __global__ void __launch_bounds__(256) k_fourier_pe8(const float* __restrict__ x
 // any_open[b, q] = 1 iff some key of scene b is not blocked for query q
 __global__ void __launch_bounds__(256) k_any_open(const uint8_t* __restrict__ blocked, int64_t n, int Q,
                                                   const int32_t* __restrict__ scene_offsets, int B, int32_t* __restrict__ any_open) {
+  // 16 mask bytes per thread: most are "blocked" (non-zero), so the common case is one 16-byte load and four compares; only open
+  // entries pay the division / scene lookup, and only while their flag is still clear
   const int64_t total = n * Q;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t nvec = (((uintptr_t)blocked & 15) == 0) ? total >> 4 : 0;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 w4 = reinterpret_cast<const uint4*>(blocked)[v];
+    const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      // a zero byte somewhere in the word?  (classic has-zero-byte test)
+      if (((w[u] - 0x01010101u) & ~w[u] & 0x80808080u) == 0u) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (((w[u] >> (8 * j)) & 0xffu) == 0u) {
+          const int64_t i = (v << 4) + 4 * u + j;
+          const int64_t r = i / Q;
+          const int q = (int)(i - r * Q);
+          int32_t* f = any_open + scene_of_row(scene_offsets, B, r) * Q + q;
+          if (*f == 0) *f = 1;  // benign race: every writer stores 1
+        }
+      }
+    }
+  }
+  for (int64_t i = (nvec << 4) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     if (!blocked[i]) {
       const int64_t r = i / Q;
       const int q = (int)(i - r * Q);
-      any_open[scene_of_row(scene_offsets, B, r) * Q + q] = 1;  // benign race: every writer stores 1
+      any_open[scene_of_row(scene_offsets, B, r) * Q + q] = 1;
     }
   }
 }
@@ -924,7 +946,7 @@ int mk_masked_xattn_fwd_lse(const float* qp, const void* kp, const void* vp, int
   float* partial = (float*)((uint8_t*)workspace + (((int64_t)B * Q * sizeof(int32_t) + 255) / 256) * 256);
   cudaMemsetAsync(any_open, 0, (size_t)B * Q * sizeof(int32_t), st);
   if (n > 0) {
-    int64_t blocks = ceil_div(n * Q, 256);
+    int64_t blocks = ceil_div(ceil_div(n * Q, 16), 256);
     if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
     k_any_open<<<(unsigned)blocks, 256, 0, st>>>(blocked, n, Q, scene_offsets, B, any_open);
   }
@@ -980,7 +1002,7 @@ int mk_masked_xattn_bwd(const float* qp, const void* kp, const void* vp, int kv_
   float* partial = (float*)w;
   cudaMemsetAsync(any_open, 0, (size_t)B * Q * sizeof(int32_t), st);
   if (n > 0) {
-    int64_t blocks = ceil_div(n * Q, 256);
+    int64_t blocks = ceil_div(ceil_div(n * Q, 16), 256);
     if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
     k_any_open<<<(unsigned)blocks, 256, 0, st>>>(blocked, n, Q, scene_offsets, B, any_open);
   }

@@ -33,6 +33,53 @@ __global__ void __launch_bounds__(256) k_pool_fwd(const TIn* __restrict__ in, in
   }
 }
 
+// Eight channels per thread: one 16-byte (bf16) / two 16-byte (fp32) loads per child row instead of four scalar ones, 32-bit index
+// arithmetic, 32 bytes of output per thread.  Same summation order per channel (k ascending) => bit-identical to k_pool_fwd.
+template <typename TIn>
+__global__ void __launch_bounds__(256) k_pool_fwd8(const TIn* __restrict__ in, unsigned CV, const int32_t* __restrict__ nbr, int K,
+                                                   unsigned n_out, int average, float* __restrict__ out) {
+  const unsigned C = CV * 8u;
+  const unsigned total = n_out * CV;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned o = i / CV;
+    const unsigned c = (i - o * CV) * 8u;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    int cnt = 0;
+    for (int k = 0; k < K; ++k) {
+      const int r = nbr[(size_t)k * n_out + o];
+      if (r < 0) continue;
+      ++cnt;
+      float v[8];
+      const TIn* src = in + (size_t)r * C + c;
+      if constexpr (sizeof(TIn) == 2) {
+        const uint4 q = *reinterpret_cast<const uint4*>(src);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+          v[2 * j] = f.x;
+          v[2 * j + 1] = f.y;
+        }
+      } else {
+        const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+    if (average) {
+      const float d = (float)(cnt > 0 ? cnt : 1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = acc[j] / d;
+    }
+    float* dst = out + (size_t)o * C + c;
+    *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+}
+
 // din[child] = dout[parent] / cnt(parent): every child has exactly one parent in a stride-2 2^3 map, so this is a
 // scatter with unique targets (no atomics).  Rows of `din` without a parent entry are zeroed by the caller.
 __global__ void __launch_bounds__(256) k_pool_bwd(const float* __restrict__ dout, int C, const int32_t* __restrict__ nbr, int K,
@@ -52,7 +99,20 @@ __global__ void __launch_bounds__(256) k_pool_bwd(const float* __restrict__ dout
 }
 
 __global__ void __launch_bounds__(256) k_threshold(const float* __restrict__ x, int64_t n, uint8_t* __restrict__ blocked) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  // four elements per thread (16-byte load, 4-byte store); same expression per element as the scalar tail below
+  const int64_t nvec = ((((uintptr_t)x & 15) | ((uintptr_t)blocked & 3)) == 0) ? n >> 2 : 0;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+    const float4 f = reinterpret_cast<const float4*>(x)[v];
+    const float e[4] = {f.x, f.y, f.z, f.w};
+    uint32_t w = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float s = 1.f / (1.f + expf(-e[j]));
+      w |= (s < 0.5f ? 1u : 0u) << (8 * j);
+    }
+    reinterpret_cast<uint32_t*>(blocked)[v] = w;
+  }
+  for (int64_t i = (nvec << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     // reference: sigmoid(x) < 0.5 in fp32 (mask3d.py:550).  sigmoid is monotone with sigmoid(0) = 0.5 exactly, and
     // fp32 sigmoid(x) rounds to exactly 0.5 only for |x| below ~6e-8 where 1/(1+exp(-x)) is within half an ulp of 0.5;
     // evaluate the same expression so the tie region matches bit for bit.
@@ -189,6 +249,14 @@ int mk_pool_fwd(const float* in, int C, const int32_t* nbr, int K, int64_t n_out
 
 int mk_pool_fwd_dt(const void* in, int in_dtype, int C, const int32_t* nbr, int K, int64_t n_out, int average, float* out, void* stream_) {
   if (n_out == 0) return 0;
+  if (C % 8 == 0 && n_out * (int64_t)(C / 8) < ((int64_t)1 << 31) && (((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
+    const unsigned g = grid_for(n_out * (C / 8));
+    if (in_dtype == MK_BF16)
+      k_pool_fwd8<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)in, (unsigned)(C / 8), nbr, K, (unsigned)n_out, average, out);
+    else
+      k_pool_fwd8<float><<<g, 256, 0, (cudaStream_t)stream_>>>((const float*)in, (unsigned)(C / 8), nbr, K, (unsigned)n_out, average, out);
+    return check_launch(__func__);
+  }
   if (in_dtype == MK_BF16)
     k_pool_fwd<__nv_bfloat16><<<grid_for(n_out * ((C + 3) / 4)), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)in, C, nbr, K, n_out,
                                                                                                     average, out);
@@ -208,7 +276,7 @@ int mk_pool_bwd(const float* dout, int C, const int32_t* nbr, int K, int64_t n_o
 
 int mk_pool_threshold(const float* pooled, int64_t n, int Q, uint8_t* blocked, void* stream_) {
   if (n == 0) return 0;
-  k_threshold<<<grid_for(n * Q), 256, 0, (cudaStream_t)stream_>>>(pooled, n * Q, blocked);
+  k_threshold<<<grid_for((n * Q + 3) / 4), 256, 0, (cudaStream_t)stream_>>>(pooled, n * Q, blocked);
   return check_launch(__func__);
 }
 
