@@ -302,6 +302,8 @@ def main_ours(args):
 
     def step_e2e(_i=None):
         g = state["g_e2e"]
+        if os.environ.get("MK3D_BENCH_ALLOC_DEBUG"):
+            state.setdefault("t_calls", []).append(time.perf_counter())
         x = state["e2e"] if state["e2e"] is not None else model.prepare(*pinned[g % n_scenes])
         ln = g % n_lanes
         with torch.cuda.stream(lanes[ln]):
@@ -350,9 +352,10 @@ def main_ours(args):
     sampler = ClockSampler(local)
     if rank == 0 and not args.no_clocks:
         sampler.start()
-    # warm-up: at least every batch twice (CUDA-graph capture, allocator growth, weight images) -- the line reports the --warmup
+    # warm-up: at least every batch four times (CUDA-graph capture, weight images, and the caching allocator, which was still adding
+    # multi-GB segments in the 7th-9th step of a leg: MK3D_BENCH_ALLOC_DEBUG=1) -- the line reports the --warmup
     # argument as `warmup` and the steps actually run as `warmup_run`
-    n_warm = max(args.warmup, 2 * n_scenes)
+    n_warm = max(args.warmup, 4 * n_scenes)
     for i in range(n_warm):
         step_resident(i)
     sampler.mark()
@@ -384,12 +387,23 @@ def main_ours(args):
     value = world * vox_per_step * args.steps / (ms * 1e-3)
 
     gc.collect()
-    for i in range(max(args.warmup, 2 * n_scenes)):  # as many warm-up steps as the resident loop: the e2e path allocates its own result buffers
+    for i in range(max(args.warmup, 4 * n_scenes)):  # as many warm-up steps as the resident loop: the e2e path allocates its own result buffers
         step_e2e(i)
     state["vox"] = 0
     mallocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
+    if os.environ.get("MK3D_BENCH_ALLOC_DEBUG"):
+        torch.cuda.memory._record_memory_history(max_entries=200000)
+        state["t_calls"] = []
     ms_e2e = timed(step_e2e, args.steps)
     mallocs_e2e = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs0
+    if os.environ.get("MK3D_BENCH_ALLOC_DEBUG"):
+        for tr in torch.cuda.memory._snapshot().get("device_traces", []):
+            for ev in tr:
+                if ev.get("action") in ("segment_alloc", "segment_free", "oom"):
+                    print(f"[alloc debug e2e] {ev.get('action')} size {ev.get('size', 0) / 2**20:.1f} MiB stream {ev.get('stream')}", file=sys.stderr)
+        torch.cuda.memory._record_memory_history(enabled=None)
+        tc = state.get("t_calls", [])
+        print("[step debug e2e] host ms between e2e step calls: " + " ".join(f"{(b - a) * 1e3:.1f}" for a, b in zip(tc, tc[1:])), file=sys.stderr)
     e2e_value = world * state["vox"] / (ms_e2e * 1e-3)
     h2d = int(np.mean([c.numel() * 4 + f.numel() * 4 for c, f in pinned]))
     d2h_logits = int(h_cls[0].numel() * 4 + np.mean([m.numel() * 4 for m in h_mask[0]]))
