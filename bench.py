@@ -300,20 +300,40 @@ def main_ours(args):
         state["vox"] += nvox[g % n_scenes]
         return o
 
+    # e2e input path: the H2D copy of batch g + 1 (from pinned host memory, every step, inside the timed region) is issued on a copy
+    # stream at the START of step g into a persistent device buffer of that batch, so that it runs under step g's backbone instead
+    # of inside the coordinate phase the host waits for (`prepare` then sees device tensors).  A buffer is overwritten only after
+    # the forward that last read it has finished (ev_done).
+    copy_stream = torch.cuda.Stream(device=dev)
+    dev_c = [torch.empty_like(c, device=dev) for c, _ in pinned]
+    dev_f = [torch.empty_like(f, device=dev) for _, f in pinned]
+    ev_done = [None] * n_scenes
+
     def step_e2e(_i=None):
         g = state["g_e2e"]
         if os.environ.get("MK3D_BENCH_ALLOC_DEBUG"):
             state.setdefault("t_calls", []).append(time.perf_counter())
         x = state["e2e"] if state["e2e"] is not None else model.prepare(*pinned[g % n_scenes])
         ln = g % n_lanes
+        s_next = (g + 1) % n_scenes
+        if ev_done[s_next] is not None:
+            copy_stream.wait_event(ev_done[s_next])
+        with torch.cuda.stream(copy_stream):
+            dev_c[s_next].copy_(pinned[s_next][0], non_blocking=True)
+            dev_f[s_next].copy_(pinned[s_next][1], non_blocking=True)
+            ev_h2d = torch.cuda.Event()
+            ev_h2d.record(copy_stream)
+        model.side_stream(dev).wait_event(ev_h2d)
         with torch.cuda.stream(lanes[ln]):
-            o = model(x, prefetch=pinned[(g + 1) % n_scenes], compact=state["compact"])
+            o = model(x, prefetch=(dev_c[s_next], dev_f[s_next]), compact=state["compact"])
             h_cls[ln].copy_(torch.stack(o["pred_class_all_decoders"]), non_blocking=True)
             if state["compact"]:  # the binary masks (one bit word per voxel) + per-query mask scores, what the post-processing keeps
                 h_bits[ln][g % n_scenes].copy_(o["mask_bits"], non_blocking=True)
                 h_score[ln].copy_(o["mask_score"], non_blocking=True)
             else:                 # the final fp32 mask logits [N, 25]
                 h_mask[ln][g % n_scenes].copy_(o["pred_mask_all_decoders"][-1], non_blocking=True)
+            ev_done[g % n_scenes] = torch.cuda.Event()
+            ev_done[g % n_scenes].record(lanes[ln])  # everything that reads this step's input buffer is enqueued before this point
         state["e2e"] = o.pop("prefetched")
         state["g_e2e"] = g + 1
         state["vox"] += nvox[g % n_scenes]
