@@ -137,7 +137,9 @@ int mk_conv_weight_image_tf32(const float* W, int K, int cin, int cout, int tran
 int mk_conv_fwd_tf32(const void* in, int64_t n_in, int cin, const void* wimg, int cout, const int32_t* nbr, int K, int64_t n_slots,
                      const int32_t* out_rows, const uint32_t* tile_kmask, const int32_t* kidx, int64_t n_out,
                      const float* bias, void* out, int out_dtype, int out_cols, int out_stride, void* stream);
-/* A-operand producer of mk_conv_fwd_bf16: 0 = LSU (16-byte cp.async into the swizzled tile, default), 1 = TMA gather4. */
+/* A-operand producer of mk_conv_fwd_bf16 / _tf32, for A/B measurements (bit-identical results): 0 = LSU (16-byte cp.async into the
+ * swizzled tile, default), 1 = the round-1 TMA tile::gather4 kernel (bf16 only), 2 = tile::gather4 producers inside the current
+ * kernel.  Both TMA forms measured slower on B200 (profiles/r02_gather_mechanisms.txt). */
 int mk_set_gather_mode(int mode);
 /* 1: results are bit-identical from run to run (the reference trains with `deterministic: true`,
  * mask3d/conf/trainer/trainer.yaml:1): no offset split with floating-point REDs in mk_conv_fwd_bf16 (forward / dgrad), fixed-order
